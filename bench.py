@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""PM-VAE hot-path benchmark (contract: one JSON line on rank 0).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                  [--config power] [--batch ROWS_PER_GPU] [--precision auto|fp32|bf16]
+
+A "step" is one training step of train_pm_vae.py on one batch of synthetic rows of the
+config's shape: device mask draw (threefry), eps draw, forward, loss, backward, gradient
+all-reduce (N > 1), AdamW.  `value` = rows of all ranks / max-over-ranks device time with
+the inputs resident in HBM; `e2e` = the same step fed from pinned host memory with the
+H2D copy of x and a D2H read of the step's metrics inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "PM-VAE train samples/s"
+UNIT = "samples/s"
+TRAIN_MFLOP = {"gas": 5.259, "power": 5.247, "hepmass": 5.339, "bsds": 18.868}   # SURVEY §8 (6 x sum in*out)
+CONDLL_GFLOP = {"gas": 0.5507, "power": 0.5496, "hepmass": 0.5575, "bsds": 1.4137}  # is_log_prob, K = 512
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="power", choices=sorted(TRAIN_MFLOP))
+    ap.add_argument("--batch", type=int, default=0, help="rows per GPU per step (0 = default for the precision)")
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--eval-rows", type=int, default=2048, help="rows per cond-LL eval call (K = 512)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eval", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d["hbm_gbs"], "source": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_x(name, B, seed):
+    import numpy as np
+    from posterior_matching_b200.config import DATASET_FEATURES
+    rng = np.random.default_rng(seed)
+    D = DATASET_FEATURES[name]
+    x = rng.standard_normal((B, D)).astype(np.float32)
+    x += (1e-3 * rng.standard_normal((B, D))).astype(np.float32)   # training_noise folded once (utils.py:108-116)
+    return x
+
+
+def conditioned_init(model, seed):
+    """Haiku-default init with the two TriL head matrices scaled by 0.1 (well-conditioned
+    triangular solves; same weights the parity tests use)."""
+    model.init(seed)
+    for hn in ("posterior_dist/linear", "partial_posterior_dist/linear"):
+        model.params[hn]["w"].mul_(0.1)
+    model.mark_params_changed()
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_train_baseline(name, rows, min_seconds=8.0, max_iters=20):
+    """The oracle restatement (PyTorch CPU float32, all host threads) doing the same train
+    step (forward + backward + AdamW) on a bounded sample."""
+    import numpy as np
+    import torch
+    from oracle import model as M
+    from posterior_matching_b200.config import pm_vae_config
+    cfg = pm_vae_config(name)
+    spec = M.spec_from_config(cfg.model.to_dict())
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p = M.cast_params(M.init_params(spec, 3), torch.float32)
+    for hn in ("posterior_dist/linear", "partial_posterior_dist/linear"):
+        p[hn]["w"] *= 0.1
+    m, v = M.zeros_like_params(p), M.zeros_like_params(p)
+    x = torch.tensor(synthetic_x(name, rows, 0))
+    rng = np.random.default_rng(1)
+    b = torch.tensor((rng.random(x.shape) < 0.5).astype(np.float32))
+    eps = torch.tensor(rng.standard_normal((rows, spec.d)).astype(np.float32))
+
+    def step(i):
+        _, _, g = M.loss_and_grads(p, spec, x, b, eps, 0.5)
+        M.adamw_update(p, g, m, v, count=i, lr=1e-3, wd=1e-5)
+
+    step(0)
+    times = []
+    t_all = time.perf_counter()
+    i = 1
+    while (time.perf_counter() - t_all < min_seconds or len(times) < 3) and len(times) < max_iters:
+        t0 = time.perf_counter()
+        step(i)
+        times.append(time.perf_counter() - t0)
+        i += 1
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": rows / med, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(times)} train steps of {rows} rows ({name}), PyTorch CPU float32 oracle, median",
+            "ms_per_step": med * 1e3}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own implementation of the path is JAX and cannot
+    be installed here, so this arm times the oracle port on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = 4096
+    steps = max(1, min(args.steps, 20))
+    import torch
+    import numpy as np
+    from oracle import model as M
+    from posterior_matching_b200.config import pm_vae_config
+    cfg = pm_vae_config(args.config)
+    spec = M.spec_from_config(cfg.model.to_dict())
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p = M.cast_params(M.init_params(spec, 3), torch.float32)
+    for hn in ("posterior_dist/linear", "partial_posterior_dist/linear"):
+        p[hn]["w"] *= 0.1
+    m, v = M.zeros_like_params(p), M.zeros_like_params(p)
+    x = torch.tensor(synthetic_x(args.config, rows, 0))
+    rng = np.random.default_rng(1)
+    b = torch.tensor((rng.random(x.shape) < 0.5).astype(np.float32))
+    eps = torch.tensor(rng.standard_normal((rows, spec.d)).astype(np.float32))
+    for i in range(max(1, min(args.warmup, 3))):
+        _, _, g = M.loss_and_grads(p, spec, x, b, eps, 0.5)
+        M.adamw_update(p, g, m, v, count=i, lr=1e-3, wd=1e-5)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        _, _, g = M.loss_and_grads(p, spec, x, b, eps, 0.5)
+        M.adamw_update(p, g, m, v, count=i, lr=1e-3, wd=1e-5)
+    dt = time.perf_counter() - t0
+    val = rows * steps / dt
+    sample = (f"{steps} train steps of {rows} rows ({args.config}); oracle port (PyTorch CPU float32): the JAX "
+              "reference is not installable in this image")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"pm_vae_{args.config} train step (fwd+bwd+AdamW)", "rows_per_step": rows},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from posterior_matching_b200 import PosteriorMatchingVAE, Trainer, _lib, pm_vae_config
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    name = args.config
+    cfg = pm_vae_config(name)
+    precision = args.precision
+    if precision == "auto":
+        probe = _lib.make_config(8, 16, 256, 2, 2, 2, 0, 0, 0, 1, _lib.PREC_BF16)
+        precision = "bf16" if _lib.lib.pmvae_workspace_bytes(C.byref(probe), 128, 0) > 0 else "fp32"
+    B = args.batch or (131072 if precision == "bf16" else 65536)
+    K, W = args.steps, max(args.warmup, 3)
+
+    model = PosteriorMatchingVAE.from_config(cfg.model, precision=precision)
+    conditioned_init(model, 3)
+    tr = Trainer(cfg, seed=0, precision=precision, model=model)
+    D = model.num_features
+    x_host = torch.from_numpy(synthetic_x(name, B, 100 + rank)).pin_memory()
+    x_dev = x_host.cuda()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing
+    for _ in range(W):
+        tr.train_step(x_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = int(_lib.lib.pmvae_launch_count())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        tr.train_step(x_dev)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = int(_lib.lib.pmvae_launch_count()) - l0
+    clocks = sampler.stop() if rank == 0 else None
+    metrics = tr.metrics()
+    value = world * B * K / (ms * 1e-3)
+
+    # ---- end-to-end: host buffers, H2D of x and D2H of the metrics every step
+    for _ in range(2):
+        x_dev.copy_(x_host, non_blocking=True); tr.train_step(x_dev); tr.metrics()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        x_dev.copy_(x_host, non_blocking=True)
+        tr.train_step(x_dev)
+        tr.metrics()            # D2H of the three batch sums (synchronises the step)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": 12,
+           "ms_per_step": e2e_s / K * 1e3}
+
+    # ---- dominant kernel alone: one hidden hk.Linear [B,256] x [256,256] (90% of the MACs)
+    peaks = measured_peaks()
+    H = 256
+    xin = torch.randn(B, H, device="cuda")
+    w = torch.randn(H, H, device="cuda") / 16
+    bias = torch.zeros(H, device="cuda")
+    y = torch.empty(B, H, device="cuda")
+    lws = torch.empty(max(1, int(_lib.lib.pmvae_workspace_bytes(model._cfgp, B, 0))), dtype=torch.uint8, device="cuda") \
+        if precision == "bf16" else torch.empty(1, dtype=torch.uint8, device="cuda")
+    prec_id = _lib.PREC_BF16 if precision == "bf16" else _lib.PREC_F32
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def lin():
+        _lib.check(_lib.lib.pmvae_linear(prec_id, xin.data_ptr(), w.data_ptr(), bias.data_ptr(), B, H, H, 1,
+                                         y.data_ptr(), lws.data_ptr(), lws.numel(), stream), "pmvae_linear")
+    for _ in range(3):
+        lin()
+    torch.cuda.synchronize()
+    reps = 20
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(reps):
+        lin()
+    k1.record()
+    torch.cuda.synchronize()
+    k_ms = k0.elapsed_time(k1) / reps
+    k_tflops = 2.0 * B * H * H / (k_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get(precision, {}).get("dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            traffic = None
+    step_tflops = TRAIN_MFLOP[name] * 1e6 * world * B / (ms / K * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": k_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": k_tflops / peaks["bf16_tflops"], "traffic": traffic,
+                "kernel": f"hidden hk.Linear {B}x{H}x{H} ({precision}) via pmvae_linear, timed alone ({reps} launches)",
+                "kernel_ms": k_ms, "peak_source": peaks["source"] + " (bf16 burst)",
+                "step_tflops_per_gpu": step_tflops / world,
+                "step_frac_of_sustained_peak": step_tflops / world / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"])}
+    del xin, y, lws
+
+    # ---- cond-LL evaluation throughput (eval_pm_vae_uci.py eval_fn's is_log_prob, K = 512)
+    cond = None
+    if not args.no_eval:
+        Be, Ke = args.eval_rows, 512
+        xe = x_dev[:Be].contiguous()
+        be = (torch.rand(Be, D, device="cuda") < 0.5).float()
+        for _ in range(2):
+            model.is_log_prob(xe, be, Ke, keys=((1, 2), (3, 4)), row_start=rank * Be, total_rows=world * Be)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_eval = 3
+        c0.record()
+        for _ in range(n_eval):
+            model.is_log_prob(xe, be, Ke, keys=((1, 2), (3, 4)), row_start=rank * Be, total_rows=world * Be)
+        c1.record()
+        barrier()
+        cms = max_over_ranks(c0.elapsed_time(c1)) / n_eval
+        cval = world * Be / (cms * 1e-3)
+        cond = {"metric": "PM-VAE cond-LL eval samples/s", "value": cval, "unit": UNIT, "K": Ke, "rows_per_call": Be,
+                "ms_per_call": cms, "tflops_per_gpu": CONDLL_GFLOP[name] * 1e9 * cval / world / 1e12,
+                "frac_of_tensor_peak": CONDLL_GFLOP[name] * 1e9 * cval / world / 1e12 / peaks["bf16_tflops"]}
+
+    # ---- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_train_baseline(name, 4096)
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"configs/pm_vae_{name}.py train step (mask+eps draw, fwd, bwd, "
+                                   f"{'NCCL grad all-reduce, ' if world > 1 else ''}AdamW)",
+                       "rows_per_gpu_per_step": B, "global_batch": world * B, "features": D,
+                       "parallelism": f"dp{world}", "accumulate": "fp32",
+                       "l2": "saved activations of one step exceed the 126 MB L2 (no explicit flush)",
+                       "weights": "Haiku-default init, TriL heads x0.1"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "train_metrics": metrics,
+        }
+        if cond is not None:
+            out["cond_ll_eval"] = cond
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

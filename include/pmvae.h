@@ -1,0 +1,159 @@
+/* pmvae.h -- C ABI of libpmvae.so: the B200 (sm_100a) PM-VAE hot path.
+ *
+ * The reference (lupalab/posterior-matching) is pure Python/JAX and exposes a Haiku
+ * module class, not an FFI.  These entry points are what a
+ * jax.ffi / XLA custom-call (or ctypes) binding for that path would bind; each one
+ * cites the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; the message is
+ *     available from pmvae_last_error() (thread-local);
+ *   - all data pointers are DEVICE pointers owned by the caller unless the name says
+ *     `host`; outputs are pre-allocated by the caller; nothing is retained;
+ *   - every device function only ENQUEUES work on `stream` (no sync, no allocation);
+ *     scratch comes from the caller (`ws`, sized by pmvae_workspace_bytes);
+ *   - all tensors are float32 row-major; masks are float32 0/1 (masking.py:11,17);
+ *   - keys are the two uint32 words of a JAX threefry PRNGKey, passed by value from
+ *     the host.
+ */
+#ifndef PMVAE_H_
+#define PMVAE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* pmvae_stream_t; /* cudaStream_t */
+
+/* What PosteriorMatchingVAE.from_config (posterior_matching/models/vae.py:61-118)
+ * resolves a `config.model` mapping to, for the ResidualMLP/TriLGaussian/
+ * IdentityGaussian family of configs/pm_vae_{gas,power,hepmass,bsds}.py. */
+typedef struct pmvae_config {
+  int32_t D;        /* features (decoder_dist_config.event_size)            */
+  int32_t d;        /* latent_dim                                            */
+  int32_t H;        /* hidden_units (256 in every config)                    */
+  int32_t R_enc;    /* encoder_net_config.residual_blocks                    */
+  int32_t R_dec;    /* decoder_net_config.residual_blocks                    */
+  int32_t R_part;   /* partial_encoder_net_config (defaults to the encoder's)*/
+  int32_t ln_enc;   /* layer_norm flags (networks.py:117-118,123-124,128-129)*/
+  int32_t ln_dec;
+  int32_t ln_part;
+  int32_t stop_grad;/* matching_ll_stop_gradients (vae.py:136-137)           */
+  int32_t precision;/* PMVAE_PREC_*: arithmetic of the dense contractions    */
+  int32_t reserved[5];
+} pmvae_config;
+
+enum { PMVAE_PREC_F32 = 0,  /* fp32 FMA tiles (exact-parity path)                    */
+       PMVAE_PREC_BF16 = 1  /* bf16 operands, fp32 accumulate, tcgen05/TMEM tiles    */ };
+
+/* One Haiku parameter leaf pair (SURVEY §3.3 order): w[rows, cols] and b[cols] inside
+ * the flat float32 parameter arena.  The scalar decoder_dist/log_scale is reported as
+ * rows = cols = 0 with w_off = its offset. */
+typedef struct pmvae_leaf {
+  char name[64];
+  int32_t rows, cols;
+  uint64_t w_off, b_off; /* offsets in floats */
+} pmvae_leaf;
+
+const char* pmvae_last_error(void);
+int pmvae_version(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t pmvae_launch_count(void);
+
+/* ---- parameter arena ------------------------------------------------------------ */
+/* Number of floats in the (padded) flat arena; gradients and both Adam moments use
+ * the same layout. */
+uint64_t pmvae_param_count(const pmvae_config* cfg);
+/* Fills up to `cap` leaves, returns how many the config has (or <0 on error). */
+int pmvae_layout(const pmvae_config* cfg, pmvae_leaf* out, int cap);
+
+/* ---- PRNG (jax.random threefry2x32 stream; reference draws via hk.next_rng_key():
+ *      vae.py:124,162,192-195) ------------------------------- */
+/* host: jax.random.split / fold_in / haiku PRNGSequence.next (key <- row 0, sub = row 1) */
+int pmvae_key_split_host(const uint32_t key[2], int n, uint32_t* out_keys /* [n,2] */);
+int pmvae_key_fold_in_host(const uint32_t key[2], uint32_t data, uint32_t out_key[2]);
+/* device: elements [start, start+count) of the n_total-element draw */
+int pmvae_random_bits(const uint32_t key[2], uint64_t n_total, uint64_t start, uint64_t count,
+                      uint32_t* out, pmvae_stream_t stream);
+int pmvae_uniform(const uint32_t key[2], uint64_t n_total, uint64_t start, uint64_t count,
+                  float* out, pmvae_stream_t stream);
+int pmvae_normal(const uint32_t key[2], uint64_t n_total, uint64_t start, uint64_t count,
+                 float* out, pmvae_stream_t stream);
+
+/* ---- masks (masking.py:84-91 BernoulliMaskGenerator; :235-249 MNISTMaskGenerator),
+ *      redefined on the JAX stream: b = uniform(key,[B_total,D]) < p -------------- */
+int pmvae_mask_bernoulli(const uint32_t key[2], float p, uint64_t B_total, uint64_t row_start,
+                         uint64_t rows, int32_t D, float* out, pmvae_stream_t stream);
+int pmvae_mask_mnist(const uint32_t key[2], uint64_t B_total, uint64_t row_start, uint64_t rows,
+                     float* out /* [rows,28,28,1] */, pmvae_stream_t stream);
+
+/* ---- one hk.Linear (networks.py:116,122,127; distributions.py:44,104) ------------------
+ * y[B,N] = relu?(x[B,K]) @ w[K,N] + bias[N] in the given PMVAE_PREC_* arithmetic: the
+ * dominant kernel of the path, exposed for parity tests and bench.py's roofline leg.
+ * `ws` is scratch for the bf16 operand images (may be NULL for PMVAE_PREC_F32). */
+int pmvae_linear(int32_t precision, const float* x, const float* w, const float* bias, int64_t B,
+                 int32_t K, int32_t N, int32_t relu_in, float* y, void* ws, uint64_t ws_bytes,
+                 pmvae_stream_t stream);
+
+/* ---- model ------------------------------------------------------------------------ */
+/* Bytes of scratch for a batch of B rows (training forward+backward keeps its saved
+ * activations here) and, for the evaluators, K importance samples per row. */
+uint64_t pmvae_workspace_bytes(const pmvae_config* cfg, int64_t B, int64_t K);
+
+/* Must be called after the float32 parameters change and before the next
+ * forward/eval when precision == PMVAE_PREC_BF16: refreshes the bf16 operand images
+ * kept at the head of `ws` (no-op for PMVAE_PREC_F32). */
+int pmvae_prepare_params(const pmvae_config* cfg, const float* params, void* ws, uint64_t ws_bytes,
+                         pmvae_stream_t stream);
+
+/* PosteriorMatchingVAE.__call__ (vae.py:120-144).  eps [B,d] is the N(0,I) draw behind
+ * posterior.sample (z = mu + L eps).  Writes the three per-row terms and leaves what
+ * pmvae_backward needs in `ws`. */
+int pmvae_forward(const pmvae_config* cfg, const float* params, const float* x, const float* b,
+                  const float* eps, int64_t B, float* out_rec, float* out_kl, float* out_match,
+                  void* ws, uint64_t ws_bytes, pmvae_stream_t stream);
+
+/* Vector-Jacobian product of pmvae_forward: cotangents g_* [B] for the three outputs ->
+ * gradient arena (overwritten).  (Replaces jax.value_and_grad through the module in
+ * bax.Trainer, train_pm_vae.py:85,96.) */
+int pmvae_backward(const pmvae_config* cfg, const float* params, const float* x, const float* b,
+                   const float* eps, int64_t B, const float* g_rec, const float* g_kl,
+                   const float* g_match, float* grads, void* ws, uint64_t ws_bytes,
+                   pmvae_stream_t stream);
+
+/* loss_fn (train_pm_vae.py:58-72): cotangents of loss = -mean(rec - beta*kl) - coef*mean(match)
+ * over B_global rows, and the batch sums of the three terms (out_sums[3], accumulated
+ * with atomics after being zeroed here). */
+int pmvae_loss_cotangents(int64_t B, int64_t B_global, float beta, float coef, const float* rec,
+                          const float* kl, const float* match, float* g_rec, float* g_kl,
+                          float* g_match, float* out_sums, pmvae_stream_t stream);
+
+/* optax chain of train_pm_vae.py:74-83: Adam (b1,b2,eps) -> + wd*p on leaves with
+ * ndim != 1 -> * lr -> * -1.  `count` = updates already applied. */
+int pmvae_adamw(const pmvae_config* cfg, float* params, const float* grads, float* m, float* v,
+                int64_t count, float lr, float wd, float b1, float b2, float eps,
+                pmvae_stream_t stream);
+
+/* PosteriorMatchingVAE.is_log_prob (vae.py:171-226) with K samples per row; eps drawn
+ * on device from key_z / key_zxo as normal(key, [K, B_total, d]) restricted to rows
+ * [row_start, row_start+B).  Either output may be NULL. */
+int pmvae_is_log_prob(const pmvae_config* cfg, const float* params, const float* x, const float* b,
+                      int64_t B, int64_t K, const uint32_t key_z[2], const uint32_t key_zxo[2],
+                      int64_t B_total, int64_t row_start, float* out_log_p_x,
+                      float* out_log_p_xu_given_xo, void* ws, uint64_t ws_bytes,
+                      pmvae_stream_t stream);
+
+/* mean over K of PosteriorMatchingVAE.impute (vae.py:146-169; the mean is what
+ * eval_pm_vae_uci.py:88-89 keeps). */
+int pmvae_impute_mean(const pmvae_config* cfg, const float* params, const float* x, const float* b,
+                      int64_t B, int64_t K, const uint32_t key[2], int64_t B_total,
+                      int64_t row_start, float* out /* [B,D] */, void* ws, uint64_t ws_bytes,
+                      pmvae_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMVAE_H_ */

@@ -1,0 +1,106 @@
+"""ctypes binding of libpmvae.so (the C ABI in include/pmvae.h).
+
+There is no CPU fallback: importing this module without the built library, or
+calling a device entry point without a CUDA device, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpmvae.so")
+
+PREC_F32, PREC_BF16 = 0, 1
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("D", "d", "H", "R_enc", "R_dec", "R_part", "ln_enc", "ln_dec", "ln_part", "stop_grad", "precision")]
+    _fields_.append(("reserved", C.c_int32 * 5))
+
+
+class Leaf(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("rows", C.c_int32), ("cols", C.c_int32),
+                ("w_off", C.c_uint64), ("b_off", C.c_uint64)]
+
+
+class PmvaeError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python posterior_matching_b200/csrc/build.py` "
+            "(nvcc, sm_100a).  The PM-VAE hot path has no CPU fallback.")
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+_u32p = C.POINTER(C.c_uint32)
+_vp = C.c_void_p
+_cfgp = C.POINTER(Config)
+_i64, _u64, _f32, _i32 = C.c_int64, C.c_uint64, C.c_float, C.c_int32
+
+_SIGS = {
+    "pmvae_last_error": (C.c_char_p, []),
+    "pmvae_version": (_i32, []),
+    "pmvae_launch_count": (_u64, []),
+    "pmvae_linear": (_i32, [_i32, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _u64, _vp]),
+    "pmvae_param_count": (_u64, [_cfgp]),
+    "pmvae_layout": (_i32, [_cfgp, C.POINTER(Leaf), _i32]),
+    "pmvae_key_split_host": (_i32, [_u32p, _i32, _u32p]),
+    "pmvae_key_fold_in_host": (_i32, [_u32p, C.c_uint32, _u32p]),
+    "pmvae_random_bits": (_i32, [_u32p, _u64, _u64, _u64, _vp, _vp]),
+    "pmvae_uniform": (_i32, [_u32p, _u64, _u64, _u64, _vp, _vp]),
+    "pmvae_normal": (_i32, [_u32p, _u64, _u64, _u64, _vp, _vp]),
+    "pmvae_mask_bernoulli": (_i32, [_u32p, _f32, _u64, _u64, _u64, _i32, _vp, _vp]),
+    "pmvae_mask_mnist": (_i32, [_u32p, _u64, _u64, _u64, _vp, _vp]),
+    "pmvae_workspace_bytes": (_u64, [_cfgp, _i64, _i64]),
+    "pmvae_prepare_params": (_i32, [_cfgp, _vp, _vp, _u64, _vp]),
+    "pmvae_forward": (_i32, [_cfgp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "pmvae_backward": (_i32, [_cfgp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "pmvae_loss_cotangents": (_i32, [_i64, _i64, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pmvae_adamw": (_i32, [_cfgp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _vp]),
+    "pmvae_is_log_prob": (_i32, [_cfgp, _vp, _vp, _vp, _i64, _i64, _u32p, _u32p, _i64, _i64, _vp, _vp, _vp, _u64, _vp]),
+    "pmvae_impute_mean": (_i32, [_cfgp, _vp, _vp, _vp, _i64, _i64, _u32p, _i64, _i64, _vp, _vp, _u64, _vp]),
+}
+EXPORTS = tuple(_SIGS)
+
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)  # AttributeError here = the library does not export the header's symbol
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib.pmvae_last_error()
+        raise PmvaeError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def key_arg(key):
+    """(k0, k1) -> ctypes uint32[2]."""
+    arr = (C.c_uint32 * 2)(int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF)
+    return arr
+
+
+def make_config(D, d, H, R_enc, R_dec, R_part, ln_enc, ln_dec, ln_part, stop_grad, precision) -> Config:
+    c = Config()
+    c.D, c.d, c.H = int(D), int(d), int(H)
+    c.R_enc, c.R_dec, c.R_part = int(R_enc), int(R_dec), int(R_part)
+    c.ln_enc, c.ln_dec, c.ln_part = int(bool(ln_enc)), int(bool(ln_dec)), int(bool(ln_part))
+    c.stop_grad = int(bool(stop_grad))
+    c.precision = int(precision)
+    return c
+
+
+def layout(cfg: Config):
+    n = lib.pmvae_layout(C.byref(cfg), None, 0)
+    if n < 0:
+        check(1, "pmvae_layout")
+    arr = (Leaf * n)()
+    lib.pmvae_layout(C.byref(cfg), arr, n)
+    return [(l.name.decode(), l.rows, l.cols, int(l.w_off), int(l.b_off)) for l in arr]

@@ -1,0 +1,319 @@
+// Row-wise and elementwise kernels of the PM-VAE path (all fp32, coalesced).
+//
+// Reference sites: networks.py:117-118 (LayerNorm), vae.py:127-128 (Normal log-prob
+// row-sum), vae.py:132-133 ([x*b, b]), vae.py:222-223 (reduce_logmeanexp),
+// vae.py:165-167 (impute where), train_pm_vae.py:58-83 (loss weights, optax chain).
+#include "kernels.h"
+
+namespace pmvae {
+
+static int grid1d(int64_t work, int block, int per_sm = 8) {
+  int64_t g = ceil_div(work, block);
+  const int64_t cap = 148ll * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ---------------------------------------------------------------- [x*b, b]
+__global__ void __launch_bounds__(256) concat_masked_kernel(const float* __restrict__ x, const float* __restrict__ b,
+                                                            float* __restrict__ out, int64_t B, int D) {
+  const int64_t n = B * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / D;
+    const int c = (int)(i - r * D);
+    const float bv = b[i];
+    out[r * 2 * D + c] = x[i] * bv;
+    out[r * 2 * D + D + c] = bv;
+  }
+}
+int concat_masked(const float* x, const float* b, float* out, int64_t B, int D, cudaStream_t s) {
+  if (B == 0) return 0;
+  concat_masked_kernel<<<grid1d(B * D, 256), 256, 0, s>>>(x, b, out, B, D);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- LayerNorm (warp per row)
+__global__ void __launch_bounds__(256) ln_fwd_kernel(float* __restrict__ y, float* __restrict__ rstd,
+                                                     const float* __restrict__ resid, float* __restrict__ out_sum,
+                                                     int64_t B, int N) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < B; r += nwarps) {
+    float* row = y + r * N;
+    float s = 0.f;
+    for (int c = lane; c < N; c += 32) s += row[c];
+    const float mean = warp_sum(s) / N;
+    float q = 0.f;
+    for (int c = lane; c < N; c += 32) { const float t = row[c] - mean; q += t * t; }
+    const float rs = rsqrtf(warp_sum(q) / N + 1e-5f);
+    for (int c = lane; c < N; c += 32) {
+      const float xh = (row[c] - mean) * rs;
+      row[c] = xh;
+      if (out_sum) out_sum[r * N + c] = resid[r * N + c] + xh;
+    }
+    if (lane == 0) rstd[r] = rs;
+  }
+}
+int ln_fwd(float* y, float* rstd, const float* resid, float* out_sum, int64_t B, int N, cudaStream_t s) {
+  if (B == 0) return 0;
+  ln_fwd_kernel<<<grid1d(B * 32, 256), 256, 0, s>>>(y, rstd, resid, out_sum, B, N);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ xhat,
+                                                     const float* __restrict__ rstd, float* __restrict__ dx, int64_t B,
+                                                     int N) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < B; r += nwarps) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < N; c += 32) {
+      const float g = dy[r * N + c];
+      s1 += g;
+      s2 += g * xhat[r * N + c];
+    }
+    s1 = warp_sum(s1) / N;
+    s2 = warp_sum(s2) / N;
+    const float rs = rstd[r];
+    for (int c = lane; c < N; c += 32) dx[r * N + c] = rs * (dy[r * N + c] - s1 - xhat[r * N + c] * s2);
+  }
+}
+int ln_bwd(const float* dy, const float* xhat, const float* rstd, float* dx, int64_t B, int N, cudaStream_t s) {
+  if (B == 0) return 0;
+  ln_bwd_kernel<<<grid1d(B * 32, 256), 256, 0, s>>>(dy, xhat, rstd, dx, B, N);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- column sums (bias grads)
+// block (32 x 8): 32 columns, 8 row lanes; grid.x over column groups, grid.y over row chunks
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dY, int64_t ld, float* __restrict__ out,
+                                                     int64_t B, int N) {
+  __shared__ float sm[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < N)
+    for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < B; r += (int64_t)gridDim.y * 8) acc += dY[r * ld + c];
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    atomicAdd(out + c, t);
+  }
+}
+int colsum_add(const float* dY, int64_t ld, float* out, int64_t B, int N, cudaStream_t s) {
+  if (B == 0) return 0;
+  dim3 block(32, 8);
+  int64_t gy = ceil_div(B, 8 * 16);
+  const int64_t gx = ceil_div(N, 32);
+  const int64_t cap = ceil_div(148 * 8, gx);
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  colsum_kernel<<<dim3((unsigned)gx, (unsigned)gy), block, 0, s>>>(dY, ld, out, B, N);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- Normal log-prob row sums
+__global__ void __launch_bounds__(256) rec_ll_kernel(const float* __restrict__ x, const float* __restrict__ loc,
+                                                     const float* __restrict__ log_scale, const float* __restrict__ w,
+                                                     float* __restrict__ out, int64_t B, int D) {
+  const float ls = *log_scale;
+  const float inv = expf(-ls);
+  const float cst = -ls - 0.5f * kLog2Pi;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < B; r += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < D; ++j) {
+      const float t = (x[r * D + j] - loc[r * D + j]) * inv;
+      const float ll = -0.5f * t * t + cst;
+      acc += w ? ll * w[r * D + j] : ll;
+    }
+    out[r] = acc;
+  }
+}
+int rec_ll(const float* x, const float* loc, const float* log_scale, const float* w, float* out, int64_t B, int D,
+           cudaStream_t s) {
+  if (B == 0) return 0;
+  rec_ll_kernel<<<grid1d(B, 256), 256, 0, s>>>(x, loc, log_scale, w, out, B, D);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) rec_ll_bwd_kernel(const float* __restrict__ x, const float* __restrict__ loc,
+                                                         const float* __restrict__ log_scale,
+                                                         const float* __restrict__ g, float* __restrict__ dloc,
+                                                         float* __restrict__ dls, int64_t B, int D) {
+  const float ls = *log_scale;
+  const float inv2 = expf(-2.0f * ls);
+  float part = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < B; r += (int64_t)gridDim.x * blockDim.x) {
+    const float gr = g[r];
+    float acc = 0.f;
+    for (int j = 0; j < D; ++j) {
+      const float df = x[r * D + j] - loc[r * D + j];
+      dloc[r * D + j] = gr * df * inv2;
+      acc += df * df * inv2 - 1.0f;
+    }
+    part += gr * acc;
+  }
+  part = warp_sum(part);
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sm[i];
+    atomicAdd(dls, t);
+  }
+}
+int rec_ll_bwd(const float* x, const float* loc, const float* log_scale, const float* g, float* dloc, float* dls,
+               int64_t B, int D, cudaStream_t s) {
+  if (B == 0) return 0;
+  rec_ll_bwd_kernel<<<grid1d(B, 256, 4), 256, 0, s>>>(x, loc, log_scale, g, dloc, dls, B, D);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- loss weights + batch sums
+__global__ void __launch_bounds__(256) loss_cot_kernel(int64_t B, float a, float k, float m,
+                                                       const float* __restrict__ rec, const float* __restrict__ kl,
+                                                       const float* __restrict__ match, float* __restrict__ g_rec,
+                                                       float* __restrict__ g_kl, float* __restrict__ g_match,
+                                                       float* __restrict__ sums) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < B; r += (int64_t)gridDim.x * blockDim.x) {
+    s0 += rec[r]; s1 += kl[r]; s2 += match[r];
+    g_rec[r] = a; g_kl[r] = k; g_match[r] = m;
+  }
+  s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+  __shared__ float sm[3][8];
+  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = s0; sm[1][threadIdx.x >> 5] = s1; sm[2][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sm[threadIdx.x][i];
+    atomicAdd(sums + threadIdx.x, t);
+  }
+}
+int loss_cotangents(int64_t B, int64_t B_global, float beta, float coef, const float* rec, const float* kl,
+                    const float* match, float* g_rec, float* g_kl, float* g_match, float* out_sums, cudaStream_t s) {
+  PMVAE_CHECK(B_global > 0, "B_global must be positive");
+  PMVAE_CUDA(cudaMemsetAsync(out_sums, 0, 3 * sizeof(float), s));
+  if (B == 0) return 0;
+  const float inv = 1.0f / (float)B_global;
+  loss_cot_kernel<<<grid1d(B, 256, 2), 256, 0, s>>>(B, -inv, beta * inv, -coef * inv, rec, kl, match, g_rec, g_kl,
+                                                    g_match, out_sums);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- AdamW over the flat arena
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v, uint64_t n,
+                                                    AdamSegs nd, float lr, float wd, float b1, float b2, float eps,
+                                                    float bc1, float bc2) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    float u = (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    bool decay = true;
+    for (int s = 0; s < nd.n; ++s) if (i >= nd.beg[s] && i < nd.end[s]) { decay = false; break; }
+    const float pi = p[i];
+    if (decay) u += wd * pi;
+    p[i] = pi - lr * u;
+  }
+}
+int adamw(float* p, const float* g, float* m, float* v, uint64_t n, const AdamSegs& nodecay, float lr, float wd,
+          float b1, float b2, float eps, float bc1, float bc2, cudaStream_t s) {
+  adamw_kernel<<<grid1d((int64_t)n, 256), 256, 0, s>>>(p, g, m, v, n, nodecay, lr, wd, b1, b2, eps, bc1, bc2);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- evaluators
+__global__ void __launch_bounds__(256) eval_rows_ll_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ loc,
+                                                           const float* __restrict__ log_scale,
+                                                           const float* __restrict__ base, float* __restrict__ out,
+                                                           int64_t B, int64_t K, int D) {
+  const float ls = *log_scale;
+  const float inv = expf(-ls);
+  const float cst = -ls - 0.5f * kLog2Pi;
+  const int64_t n = B * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i % B;
+    float acc = 0.f;
+    for (int j = 0; j < D; ++j) {
+      const float t = (x[r * D + j] - loc[i * D + j]) * inv;
+      const float ll = -0.5f * t * t + cst;
+      acc += w ? ll * w[r * D + j] : ll;
+    }
+    out[i] = acc + base[i];
+  }
+}
+int eval_rows_ll(const float* x, const float* w, const float* loc, const float* log_scale, const float* base,
+                 float* out, int64_t B, int64_t K, int D, cudaStream_t s) {
+  if (B * K == 0) return 0;
+  eval_rows_ll_kernel<<<grid1d(B * K, 256), 256, 0, s>>>(x, w, loc, log_scale, base, out, B, K, D);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) logmeanexp_kernel(const float* __restrict__ a, const float* __restrict__ c,
+                                                         float* __restrict__ out, int64_t B, int64_t K) {
+  const float logK = logf((float)K);
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < B; r += (int64_t)gridDim.x * blockDim.x) {
+    float res[2] = {0.f, 0.f};
+    for (int t = 0; t < (c ? 2 : 1); ++t) {
+      const float* src = t ? c : a;
+      float mx = -INFINITY;
+      for (int64_t k = 0; k < K; ++k) mx = fmaxf(mx, src[k * B + r]);
+      float sum = 0.f;
+      if (mx > -INFINITY && mx < INFINITY)
+        for (int64_t k = 0; k < K; ++k) sum += expf(src[k * B + r] - mx);
+      res[t] = (mx > -INFINITY && mx < INFINITY) ? (mx + logf(sum) - logK) : mx;
+    }
+    out[r] = res[0] - res[1];
+  }
+}
+int logmeanexp_rows(const float* a, const float* c, float* out, int64_t B, int64_t K, cudaStream_t s) {
+  if (B == 0) return 0;
+  logmeanexp_kernel<<<grid1d(B, 128), 128, 0, s>>>(a, c, out, B, K);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) impute_mean_kernel(const float* __restrict__ x, const float* __restrict__ b,
+                                                          const float* __restrict__ loc, float* __restrict__ out,
+                                                          int64_t B, int64_t K, int D) {
+  const int64_t n = B * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float bv = b[i];
+    float acc = 0.f;
+    if (bv != 0.f) {
+      acc = x[i] * bv;  // where(b, x_o, x_hat): every sample equals x_o
+    } else {
+      for (int64_t k = 0; k < K; ++k) acc += loc[k * n + i];
+      acc /= (float)K;
+    }
+    out[i] = acc;
+  }
+}
+int impute_mean(const float* x, const float* b, const float* loc, float* out, int64_t B, int64_t K, int D,
+                cudaStream_t s) {
+  if (B == 0) return 0;
+  impute_mean_kernel<<<grid1d(B * D, 256), 256, 0, s>>>(x, b, loc, out, B, K, D);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace pmvae

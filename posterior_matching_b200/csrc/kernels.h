@@ -1,0 +1,62 @@
+// Internal launchers shared between the translation units of libpmvae.
+#pragma once
+#include "common.cuh"
+
+namespace pmvae {
+
+// ---- gemm_f32.cu
+struct GemmF32Args {
+  int64_t M, N, K;
+  const float* A; int64_t lda;
+  const float* B; int64_t ldb;
+  float* C; int64_t ldc;
+  const float* bias = nullptr;
+  const float* mask = nullptr; int64_t ldmask = 0;   // out *= (mask > 0)
+  const float* resid = nullptr; int64_t ldresid = 0; // out += resid
+  int relu_a = 0;
+  int atomic = 0;   // atomicAdd the raw product into C (split-K over gridDim.z)
+  int split_k = 1;
+};
+int gemm_f32(const GemmF32Args& a, bool ta, bool tb, cudaStream_t stream);
+
+// ---- elementwise.cu
+int concat_masked(const float* x, const float* b, float* out, int64_t B, int D, cudaStream_t s);
+// y <- LN(y) in place (hk.LayerNorm(-1,False,False), eps 1e-5), rstd[B] saved;
+// if resid: out_sum = resid + LN(y)
+int ln_fwd(float* y, float* rstd, const float* resid, float* out_sum, int64_t B, int N, cudaStream_t s);
+// dx = rstd * (dy - mean(dy) - xhat * mean(dy * xhat)); dx may alias dy
+int ln_bwd(const float* dy, const float* xhat, const float* rstd, float* dx, int64_t B, int N, cudaStream_t s);
+// out[n] += sum_m dY[m, n]   (atomics)
+int colsum_add(const float* dY, int64_t ld, float* out, int64_t B, int N, cudaStream_t s);
+// rec[r] = sum_j w[r,j] * logN(x[r,j]; loc[r,j], exp(ls))   (w == nullptr -> 1)
+int rec_ll(const float* x, const float* loc, const float* log_scale, const float* w, float* out, int64_t B, int D,
+           cudaStream_t s);
+// dloc[r,j] = g[r] * (x - loc) * exp(-2 ls);  *dls += sum_r g[r] * sum_j ((x-loc)^2 exp(-2 ls) - 1)
+int rec_ll_bwd(const float* x, const float* loc, const float* log_scale, const float* g, float* dloc, float* dls,
+               int64_t B, int D, cudaStream_t s);
+int loss_cotangents(int64_t B, int64_t B_global, float beta, float coef, const float* rec, const float* kl,
+                    const float* match, float* g_rec, float* g_kl, float* g_match, float* out_sums, cudaStream_t s);
+struct AdamSegs { int n; uint32_t beg[48]; uint32_t end[48]; };  // no-decay (bias) ranges
+int adamw(float* p, const float* g, float* m, float* v, uint64_t n, const AdamSegs& nodecay, float lr, float wd,
+          float b1, float b2, float eps, float bc1, float bc2, cudaStream_t s);
+// evaluators
+// ll[k*B + r] = sum_j w * logN(x[r]; loc[k*B + r]) + base[k*B + r]
+int eval_rows_ll(const float* x, const float* w, const float* loc, const float* log_scale, const float* base,
+                 float* out, int64_t B, int64_t K, int D, cudaStream_t s);
+// out[r] = logsumexp_k(a[k*B + r]) - log K  [ - (logsumexp_k(c[k*B+r]) - log K) if c ]
+int logmeanexp_rows(const float* a, const float* c, float* out, int64_t B, int64_t K, cudaStream_t s);
+int impute_mean(const float* x, const float* b, const float* loc, float* out, int64_t B, int64_t K, int D,
+                cudaStream_t s);
+
+// ---- latent.cu  (par = raw TriL head output [B, P], P = d + d(d+1)/2)
+int latent_fwd(const float* par, const float* eps, float* z, float* kl, int64_t B, int d, cudaStream_t s);
+int match_fwd(const float* par_p, const float* z, float* match, int64_t B, int d, cudaStream_t s);
+int latent_bwd(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
+               const float* g_kl, const float* g_match, int stop_grad, float* dpar_e, float* dpar_p, int64_t B, int d,
+               cudaStream_t s);
+// z[k,r,:] = mu_r + L_r eps[k,r,:], eps = normal(key, [K, B_total, d]) rows row_start..;
+// base[k,r] = log N(z;0,I) - log q(z) = -0.5|z|^2 + 0.5|eps|^2 + sum log L_ii
+int sample_latents(const float* par, Key2 key, int64_t B, int64_t K, int64_t B_total, int64_t row_start, int d,
+                   float* z, float* base, cudaStream_t s);
+
+}  // namespace pmvae

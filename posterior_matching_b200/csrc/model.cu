@@ -1,0 +1,474 @@
+// Host-side orchestration of the PM-VAE hot path: parameter arena layout, workspace
+// plan, and the launch sequences behind the C ABI (include/pmvae.h).
+//
+// Reference: posterior_matching/models/vae.py:120-144 (__call__), :146-169 (impute),
+// :171-226 (is_log_prob); networks.py:111-135 (ResidualMLP); train_pm_vae.py:58-83.
+#include <math.h>
+#include <string.h>
+
+#include <atomic>
+#include <vector>
+
+#include "kernels.h"
+#include "model.h"
+
+namespace pmvae {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+const char* last_error() { return g_last_error.c_str(); }
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------- layout
+static int check_cfg(const pmvae_config* c) {
+  PMVAE_CHECK(c != nullptr, "null config");
+  PMVAE_CHECK(c->D >= 1 && c->D <= 4096, "D out of range");
+  PMVAE_CHECK(c->d >= 1 && c->d <= 64, "latent_dim must be in [1, 64]");
+  PMVAE_CHECK(c->H >= 4 && c->H % 4 == 0 && c->H <= 1024, "hidden_units must be a multiple of 4 in [4, 1024]");
+  PMVAE_CHECK(c->R_enc >= 0 && c->R_enc <= kMaxBlocks && c->R_dec >= 0 && c->R_dec <= kMaxBlocks &&
+                  c->R_part >= 0 && c->R_part <= kMaxBlocks,
+              "residual_blocks out of range");
+  PMVAE_CHECK(c->precision == PMVAE_PREC_F32 || c->precision == PMVAE_PREC_BF16, "unknown precision");
+  return 0;
+}
+
+static uint64_t pad64(uint64_t n) { return align_up(n, 64); }  // 256-byte leaf alignment
+
+int build_layout(const pmvae_config* c, Layout* L) {
+  PMVAE_TRY(check_cfg(c));
+  uint64_t off = 0;
+  auto leaf = [&](Leaf& lf, int rows, int cols) {
+    lf.rows = rows; lf.cols = cols;
+    lf.w = off; off += pad64((uint64_t)rows * cols);
+    lf.b = off; off += pad64((uint64_t)cols);
+  };
+  auto net = [&](Net& n, int in_dim, int R, int ln) {
+    n.in_dim = in_dim; n.R = R; n.ln = ln;
+    leaf(n.lin[0], in_dim, c->H);
+    for (int i = 1; i <= 2 * R; ++i) leaf(n.lin[i], c->H, c->H);
+  };
+  const int P = c->d + c->d * (c->d + 1) / 2;
+  L->P = P;
+  net(L->enc, c->D, c->R_enc, c->ln_enc);
+  leaf(L->post, c->H, P);
+  net(L->dec, c->d, c->R_dec, c->ln_dec);
+  leaf(L->ddist, c->H, c->D);
+  L->log_scale = off; off += 64;
+  net(L->part, 2 * c->D, c->R_part, c->ln_part);
+  leaf(L->ppost, c->H, P);
+  L->total = off;
+  return 0;
+}
+
+static void name_leaf(pmvae_leaf* o, const char* prefix, int i, const Leaf& lf) {
+  if (i == 0) snprintf(o->name, sizeof(o->name), "%s/linear", prefix);
+  else snprintf(o->name, sizeof(o->name), "%s/linear_%d", prefix, i);
+  o->rows = lf.rows; o->cols = lf.cols; o->w_off = lf.w; o->b_off = lf.b;
+}
+
+int export_layout(const pmvae_config* c, pmvae_leaf* out, int cap) {
+  Layout L;
+  if (build_layout(c, &L) != 0) return -1;
+  std::vector<pmvae_leaf> v;
+  auto push_net = [&](const Net& n, const char* prefix) {
+    for (int i = 0; i <= 2 * n.R; ++i) { pmvae_leaf l{}; name_leaf(&l, prefix, i, n.lin[i]); v.push_back(l); }
+  };
+  auto push_leaf = [&](const Leaf& lf, const char* prefix) { pmvae_leaf l{}; name_leaf(&l, prefix, 0, lf); v.push_back(l); };
+  push_net(L.enc, "encoder_net");
+  push_leaf(L.post, "posterior_dist");
+  push_net(L.dec, "decoder_net");
+  push_leaf(L.ddist, "decoder_dist");
+  { pmvae_leaf l{}; snprintf(l.name, sizeof(l.name), "decoder_dist"); l.rows = 0; l.cols = 0; l.w_off = L.log_scale; l.b_off = ~0ull; v.push_back(l); }
+  push_net(L.part, "partial_encoder_net");
+  push_leaf(L.ppost, "partial_posterior_dist");
+  for (int i = 0; i < (int)v.size() && i < cap; ++i) out[i] = v[i];
+  return (int)v.size();
+}
+
+// ---------------------------------------------------------------- workspace plan
+struct Bump {
+  char* base; uint64_t off = 0;
+  explicit Bump(void* b) : base(reinterpret_cast<char*>(b)) {}
+  template <typename T> T* take(uint64_t count) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += align_up(count * sizeof(T), 256);
+    return p;
+  }
+};
+
+struct NetSaved {            // fp32 path: pre-activation (post-LN) tensors, relu applied by the consumer
+  float* H[kMaxBlocks + 1];
+  float* U[kMaxBlocks];
+  float* V[kMaxBlocks];      // LN nets only (xhat of the second linear)
+  float* rstd0; float* rstdU[kMaxBlocks]; float* rstdV[kMaxBlocks];
+};
+
+struct TrainPlan {
+  NetSaved enc, dec, part;
+  float *par_e, *par_p, *z, *loc, *xob;
+  float *dH, *tmp1, *tmp2, *dpar_e, *dpar_p, *dloc, *dz;
+  uint64_t bytes;
+};
+
+static void plan_net(Bump& bp, const Net& n, int64_t B, int H, NetSaved& s, bool save_all) {
+  const uint64_t e = (uint64_t)B * H;
+  for (int r = 0; r <= n.R; ++r) s.H[r] = bp.take<float>(e);
+  for (int r = 0; r < n.R; ++r) s.U[r] = bp.take<float>(e);
+  (void)save_all;
+  if (n.ln) {
+    for (int r = 0; r < n.R; ++r) s.V[r] = bp.take<float>(e);
+    s.rstd0 = bp.take<float>(B);
+    for (int r = 0; r < n.R; ++r) { s.rstdU[r] = bp.take<float>(B); s.rstdV[r] = bp.take<float>(B); }
+  }
+}
+
+static TrainPlan plan_train(const pmvae_config* c, const Layout& L, int64_t B, void* ws) {
+  TrainPlan p{};
+  Bump bp(ws);
+  plan_net(bp, L.enc, B, c->H, p.enc, true);
+  plan_net(bp, L.dec, B, c->H, p.dec, true);
+  plan_net(bp, L.part, B, c->H, p.part, true);
+  p.par_e = bp.take<float>((uint64_t)B * L.P);
+  p.par_p = bp.take<float>((uint64_t)B * L.P);
+  p.z = bp.take<float>((uint64_t)B * c->d);
+  p.loc = bp.take<float>((uint64_t)B * c->D);
+  p.xob = bp.take<float>((uint64_t)B * 2 * c->D);
+  p.dH = bp.take<float>((uint64_t)B * c->H);
+  p.tmp1 = bp.take<float>((uint64_t)B * c->H);
+  p.tmp2 = bp.take<float>((uint64_t)B * c->H);
+  p.dpar_e = bp.take<float>((uint64_t)B * L.P);
+  p.dpar_p = bp.take<float>((uint64_t)B * L.P);
+  p.dloc = bp.take<float>((uint64_t)B * c->D);
+  p.dz = bp.take<float>((uint64_t)B * c->d);
+  p.bytes = bp.off;
+  return p;
+}
+
+constexpr int64_t kEvalChunkRows = 1 << 16;  // decoder rows (K * rows) per evaluator chunk
+
+struct EvalPlan {
+  NetSaved enc, part;           // B rows
+  float *par_e, *par_p, *xob;
+  NetSaved dec;                 // chunk rows
+  float *z, *base, *loc, *llA, *llC;
+  int64_t rows_per_chunk;       // data rows per chunk
+  uint64_t bytes;
+};
+
+static EvalPlan plan_eval(const pmvae_config* c, const Layout& L, int64_t B, int64_t K, void* ws) {
+  EvalPlan p{};
+  Bump bp(ws);
+  plan_net(bp, L.enc, B, c->H, p.enc, false);
+  plan_net(bp, L.part, B, c->H, p.part, false);
+  p.par_e = bp.take<float>((uint64_t)B * L.P);
+  p.par_p = bp.take<float>((uint64_t)B * L.P);
+  p.xob = bp.take<float>((uint64_t)B * 2 * c->D);
+  int64_t rpc = kEvalChunkRows / (K > 0 ? K : 1);
+  if (rpc < 1) rpc = 1;
+  if (rpc > B) rpc = B > 0 ? B : 1;
+  p.rows_per_chunk = rpc;
+  const int64_t M = rpc * K;
+  plan_net(bp, L.dec, M, c->H, p.dec, false);
+  p.z = bp.take<float>((uint64_t)M * c->d);
+  p.base = bp.take<float>((uint64_t)M);
+  p.loc = bp.take<float>((uint64_t)M * c->D);
+  p.llA = bp.take<float>((uint64_t)M);
+  p.llC = bp.take<float>((uint64_t)M);
+  p.bytes = bp.off;
+  return p;
+}
+
+uint64_t workspace_bytes(const pmvae_config* c, int64_t B, int64_t K) {
+  Layout L;
+  if (build_layout(c, &L) != 0) return 0;
+  if (B < 1) B = 1;
+  uint64_t t = plan_train(c, L, B, nullptr).bytes;
+  uint64_t e = K > 0 ? plan_eval(c, L, B, K, nullptr).bytes : 0;
+  return (t > e ? t : e) + 256;
+}
+
+// ---------------------------------------------------------------- fp32 network passes
+static int lin_fwd(const float* params, const Leaf& lf, const float* in, int64_t ld_in, int relu_in, int64_t B,
+                   float* out, const float* resid, cudaStream_t s) {
+  GemmF32Args a{};
+  a.M = B; a.N = lf.cols; a.K = lf.rows;
+  a.A = in; a.lda = ld_in;
+  a.B = params + lf.w; a.ldb = lf.cols;
+  a.C = out; a.ldc = lf.cols;
+  a.bias = params + lf.b;
+  a.relu_a = relu_in;
+  a.resid = resid; a.ldresid = lf.cols;
+  return gemm_f32(a, false, false, s);
+}
+
+static int net_fwd_f32(const float* params, const Net& n, const Leaf& head, int H, const float* in, int64_t B,
+                       const NetSaved& sv, float* head_out, cudaStream_t s) {
+  PMVAE_TRY(lin_fwd(params, n.lin[0], in, n.in_dim, 0, B, sv.H[0], nullptr, s));
+  if (n.ln) PMVAE_TRY(ln_fwd(sv.H[0], sv.rstd0, nullptr, nullptr, B, H, s));
+  for (int r = 0; r < n.R; ++r) {
+    PMVAE_TRY(lin_fwd(params, n.lin[2 * r + 1], sv.H[r], H, 1, B, sv.U[r], nullptr, s));
+    if (n.ln) {
+      PMVAE_TRY(ln_fwd(sv.U[r], sv.rstdU[r], nullptr, nullptr, B, H, s));
+      PMVAE_TRY(lin_fwd(params, n.lin[2 * r + 2], sv.U[r], H, 1, B, sv.V[r], nullptr, s));
+      PMVAE_TRY(ln_fwd(sv.V[r], sv.rstdV[r], sv.H[r], sv.H[r + 1], B, H, s));
+    } else {
+      PMVAE_TRY(lin_fwd(params, n.lin[2 * r + 2], sv.U[r], H, 1, B, sv.H[r + 1], sv.H[r], s));
+    }
+  }
+  return lin_fwd(params, head, sv.H[n.R], H, 1, B, head_out, nullptr, s);
+}
+
+static int split_for(int64_t out_rows, int64_t out_cols, int64_t B) {
+  const int64_t tiles = ceil_div(out_rows, 64) * ceil_div(out_cols, 64);
+  int64_t sp = ceil_div(148 * 4, tiles);
+  const int64_t maxsp = ceil_div(B, 256);
+  if (sp > maxsp) sp = maxsp;
+  if (sp < 1) sp = 1;
+  if (sp > 65535) sp = 65535;
+  return (int)sp;
+}
+
+// grads for one Linear: gW += relu?(in)^T dY ; gb += colsum(dY)
+static int lin_bwd_params(float* grads, const Leaf& lf, const float* in, int64_t ld_in, int relu_in, const float* dY,
+                          int64_t B, cudaStream_t s) {
+  GemmF32Args a{};
+  a.M = lf.rows; a.N = lf.cols; a.K = B;
+  a.A = in; a.lda = ld_in;     // A'(m,k) = in[k*ld + m]  (TA)
+  a.B = dY; a.ldb = lf.cols;   // B'(k,n) = dY[k*ld + n]
+  a.C = grads + lf.w; a.ldc = lf.cols;
+  a.relu_a = relu_in; a.atomic = 1; a.split_k = split_for(lf.rows, lf.cols, B);
+  PMVAE_TRY(gemm_f32(a, true, false, s));
+  return colsum_add(dY, lf.cols, grads + lf.b, B, lf.cols, s);
+}
+
+// dIn = (dY @ W^T) [* (mask > 0)] [+ resid]
+static int lin_bwd_input(const float* params, const Leaf& lf, const float* dY, int64_t B, float* dIn,
+                         const float* mask, const float* resid, cudaStream_t s) {
+  GemmF32Args a{};
+  a.M = B; a.N = lf.rows; a.K = lf.cols;
+  a.A = dY; a.lda = lf.cols;
+  a.B = params + lf.w; a.ldb = lf.cols;  // B'(k,n) = W[n*cols + k]  (TB)
+  a.C = dIn; a.ldc = lf.rows;
+  a.mask = mask; a.ldmask = lf.rows;
+  a.resid = resid; a.ldresid = lf.rows;
+  return gemm_f32(a, false, true, s);
+}
+
+static int net_bwd_f32(const float* params, float* grads, const Net& n, const Leaf& head, int H, const float* in,
+                       int64_t B, const NetSaved& sv, const float* dHead, float* dH, float* tmp1, float* tmp2,
+                       float* dIn, cudaStream_t s) {
+  PMVAE_TRY(lin_bwd_params(grads, head, sv.H[n.R], H, 1, dHead, B, s));
+  PMVAE_TRY(lin_bwd_input(params, head, dHead, B, dH, sv.H[n.R], nullptr, s));
+  for (int r = n.R - 1; r >= 0; --r) {
+    const float* dV = dH;
+    if (n.ln) { PMVAE_TRY(ln_bwd(dH, sv.V[r], sv.rstdV[r], tmp1, B, H, s)); dV = tmp1; }
+    PMVAE_TRY(lin_bwd_params(grads, n.lin[2 * r + 2], sv.U[r], H, 1, dV, B, s));
+    PMVAE_TRY(lin_bwd_input(params, n.lin[2 * r + 2], dV, B, tmp2, sv.U[r], nullptr, s));
+    if (n.ln) PMVAE_TRY(ln_bwd(tmp2, sv.U[r], sv.rstdU[r], tmp2, B, H, s));
+    PMVAE_TRY(lin_bwd_params(grads, n.lin[2 * r + 1], sv.H[r], H, 1, tmp2, B, s));
+    PMVAE_TRY(lin_bwd_input(params, n.lin[2 * r + 1], tmp2, B, dH, sv.H[r], dH, s));
+  }
+  if (n.ln) PMVAE_TRY(ln_bwd(dH, sv.H[0], sv.rstd0, dH, B, H, s));
+  PMVAE_TRY(lin_bwd_params(grads, n.lin[0], in, n.in_dim, 0, dH, B, s));
+  if (dIn) PMVAE_TRY(lin_bwd_input(params, n.lin[0], dH, B, dIn, nullptr, nullptr, s));
+  return 0;
+}
+
+// ---------------------------------------------------------------- public sequences
+int forward(const pmvae_config* c, const float* params, const float* x, const float* b, const float* eps, int64_t B,
+            float* out_rec, float* out_kl, float* out_match, void* ws, uint64_t ws_bytes, cudaStream_t s) {
+  Layout L;
+  PMVAE_TRY(build_layout(c, &L));
+  PMVAE_CHECK(params && x && b && eps && out_rec && out_kl && out_match && ws, "null pointer");
+  PMVAE_CHECK(B >= 0, "negative batch");
+  if (B == 0) return 0;
+  if (c->precision == PMVAE_PREC_BF16) return forward_bf16(c, L, params, x, b, eps, B, out_rec, out_kl, out_match, ws, ws_bytes, s);
+  TrainPlan p = plan_train(c, L, B, ws);
+  PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_workspace_bytes)");
+  PMVAE_TRY(net_fwd_f32(params, L.enc, L.post, c->H, x, B, p.enc, p.par_e, s));
+  PMVAE_TRY(latent_fwd(p.par_e, eps, p.z, out_kl, B, c->d, s));
+  PMVAE_TRY(net_fwd_f32(params, L.dec, L.ddist, c->H, p.z, B, p.dec, p.loc, s));
+  PMVAE_TRY(rec_ll(x, p.loc, params + L.log_scale, nullptr, out_rec, B, c->D, s));
+  PMVAE_TRY(concat_masked(x, b, p.xob, B, c->D, s));
+  PMVAE_TRY(net_fwd_f32(params, L.part, L.ppost, c->H, p.xob, B, p.part, p.par_p, s));
+  PMVAE_TRY(match_fwd(p.par_p, p.z, out_match, B, c->d, s));
+  return 0;
+}
+
+int backward(const pmvae_config* c, const float* params, const float* x, const float* b, const float* eps, int64_t B,
+             const float* g_rec, const float* g_kl, const float* g_match, float* grads, void* ws, uint64_t ws_bytes,
+             cudaStream_t s) {
+  Layout L;
+  PMVAE_TRY(build_layout(c, &L));
+  PMVAE_CHECK(params && x && b && eps && g_rec && g_kl && g_match && grads && ws, "null pointer");
+  PMVAE_CUDA(cudaMemsetAsync(grads, 0, L.total * sizeof(float), s));
+  if (B <= 0) return 0;
+  if (c->precision == PMVAE_PREC_BF16) return backward_bf16(c, L, params, x, b, eps, B, g_rec, g_kl, g_match, grads, ws, ws_bytes, s);
+  TrainPlan p = plan_train(c, L, B, ws);
+  PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_workspace_bytes)");
+  PMVAE_TRY(rec_ll_bwd(x, p.loc, params + L.log_scale, g_rec, p.dloc, grads + L.log_scale, B, c->D, s));
+  PMVAE_TRY(net_bwd_f32(params, grads, L.dec, L.ddist, c->H, p.z, B, p.dec, p.dloc, p.dH, p.tmp1, p.tmp2, p.dz, s));
+  PMVAE_TRY(latent_bwd(p.par_e, p.par_p, eps, p.z, p.dz, g_kl, g_match, c->stop_grad, p.dpar_e, p.dpar_p, B, c->d, s));
+  PMVAE_TRY(net_bwd_f32(params, grads, L.enc, L.post, c->H, x, B, p.enc, p.dpar_e, p.dH, p.tmp1, p.tmp2, nullptr, s));
+  PMVAE_TRY(net_bwd_f32(params, grads, L.part, L.ppost, c->H, p.xob, B, p.part, p.dpar_p, p.dH, p.tmp1, p.tmp2, nullptr, s));
+  return 0;
+}
+
+int adamw_step(const pmvae_config* c, float* params, const float* grads, float* m, float* v, int64_t count, float lr,
+               float wd, float b1, float b2, float eps, cudaStream_t s) {
+  Layout L;
+  PMVAE_TRY(build_layout(c, &L));
+  PMVAE_CHECK(params && grads && m && v && count >= 0, "bad arguments");
+  AdamSegs seg{};
+  auto add = [&](const Leaf& lf) { seg.beg[seg.n] = (uint32_t)lf.b; seg.end[seg.n] = (uint32_t)(lf.b + pad64(lf.cols)); ++seg.n; };
+  auto addnet = [&](const Net& n) { for (int i = 0; i <= 2 * n.R; ++i) add(n.lin[i]); };
+  addnet(L.enc); add(L.post); addnet(L.dec); add(L.ddist); addnet(L.part); add(L.ppost);
+  const double t = (double)count + 1.0;
+  const float bc1 = (float)(1.0 - pow((double)b1, t)), bc2 = (float)(1.0 - pow((double)b2, t));
+  return adamw(params, grads, m, v, L.total, seg, lr, wd, b1, b2, eps, bc1, bc2, s);
+}
+
+// evaluators (fp32 path): decoder over K*rows latent samples in chunks
+static int eval_common(const pmvae_config* c, const Layout& L, const float* params, const float* x, const float* b,
+                       int64_t B, const EvalPlan& p, bool need_enc, cudaStream_t s) {
+  if (need_enc) PMVAE_TRY(net_fwd_f32(params, L.enc, L.post, c->H, x, B, p.enc, p.par_e, s));
+  PMVAE_TRY(concat_masked(x, b, p.xob, B, c->D, s));
+  PMVAE_TRY(net_fwd_f32(params, L.part, L.ppost, c->H, p.xob, B, p.part, p.par_p, s));
+  return 0;
+}
+
+int is_log_prob(const pmvae_config* c, const float* params, const float* x, const float* b, int64_t B, int64_t K,
+                const uint32_t key_z[2], const uint32_t key_zxo[2], int64_t B_total, int64_t row_start,
+                float* out_log_p_x, float* out_cond, void* ws, uint64_t ws_bytes, cudaStream_t s) {
+  Layout L;
+  PMVAE_TRY(build_layout(c, &L));
+  PMVAE_CHECK(params && x && b && key_z && key_zxo && ws, "null pointer");
+  PMVAE_CHECK(K >= 1 && B >= 0 && row_start >= 0 && row_start + B <= B_total, "bad K / row range");
+  if (B == 0) return 0;
+  if (c->precision == PMVAE_PREC_BF16)
+    return is_log_prob_bf16(c, L, params, x, b, B, K, key_z, key_zxo, B_total, row_start, out_log_p_x, out_cond, ws, ws_bytes, s);
+  EvalPlan p = plan_eval(c, L, B, K, ws);
+  PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_workspace_bytes)");
+  PMVAE_TRY(eval_common(c, L, params, x, b, B, p, true, s));
+  const float* ls = params + L.log_scale;
+  for (int64_t r0 = 0; r0 < B; r0 += p.rows_per_chunk) {
+    const int64_t nb = (B - r0 < p.rows_per_chunk) ? (B - r0) : p.rows_per_chunk;
+    const int64_t M = nb * K;
+    // z ~ q(z|x)
+    PMVAE_TRY(sample_latents(p.par_e + r0 * L.P, Key2{key_z[0], key_z[1]}, nb, K, B_total, row_start + r0, c->d, p.z, p.base, s));
+    PMVAE_TRY(net_fwd_f32(params, L.dec, L.ddist, c->H, p.z, M, p.dec, p.loc, s));
+    PMVAE_TRY(eval_rows_ll(x + r0 * c->D, nullptr, p.loc, ls, p.base, p.llA, nb, K, c->D, s));
+    if (out_log_p_x) PMVAE_TRY(logmeanexp_rows(p.llA, nullptr, out_log_p_x + r0, nb, K, s));
+    if (out_cond) {
+      // z' ~ q(z|x_o), observed dims only
+      PMVAE_TRY(sample_latents(p.par_p + r0 * L.P, Key2{key_zxo[0], key_zxo[1]}, nb, K, B_total, row_start + r0, c->d, p.z, p.base, s));
+      PMVAE_TRY(net_fwd_f32(params, L.dec, L.ddist, c->H, p.z, M, p.dec, p.loc, s));
+      PMVAE_TRY(eval_rows_ll(x + r0 * c->D, b + r0 * c->D, p.loc, ls, p.base, p.llC, nb, K, c->D, s));
+      PMVAE_TRY(logmeanexp_rows(p.llA, p.llC, out_cond + r0, nb, K, s));
+    }
+  }
+  return 0;
+}
+
+int impute_mean_seq(const pmvae_config* c, const float* params, const float* x, const float* b, int64_t B, int64_t K,
+                    const uint32_t key[2], int64_t B_total, int64_t row_start, float* out, void* ws, uint64_t ws_bytes,
+                    cudaStream_t s) {
+  Layout L;
+  PMVAE_TRY(build_layout(c, &L));
+  PMVAE_CHECK(params && x && b && key && out && ws, "null pointer");
+  PMVAE_CHECK(K >= 1 && B >= 0 && row_start >= 0 && row_start + B <= B_total, "bad K / row range");
+  if (B == 0) return 0;
+  if (c->precision == PMVAE_PREC_BF16)
+    return impute_mean_bf16(c, L, params, x, b, B, K, key, B_total, row_start, out, ws, ws_bytes, s);
+  EvalPlan p = plan_eval(c, L, B, K, ws);
+  PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_workspace_bytes)");
+  PMVAE_TRY(eval_common(c, L, params, x, b, B, p, false, s));
+  for (int64_t r0 = 0; r0 < B; r0 += p.rows_per_chunk) {
+    const int64_t nb = (B - r0 < p.rows_per_chunk) ? (B - r0) : p.rows_per_chunk;
+    PMVAE_TRY(sample_latents(p.par_p + r0 * L.P, Key2{key[0], key[1]}, nb, K, B_total, row_start + r0, c->d, p.z, p.base, s));
+    PMVAE_TRY(net_fwd_f32(params, L.dec, L.ddist, c->H, p.z, nb * K, p.dec, p.loc, s));
+    PMVAE_TRY(impute_mean(x + r0 * c->D, b + r0 * c->D, p.loc, out + r0 * c->D, nb, K, c->D, s));
+  }
+  return 0;
+}
+
+}  // namespace pmvae
+
+using namespace pmvae;
+
+extern "C" {
+
+const char* pmvae_last_error(void) { return pmvae::last_error(); }
+int pmvae_version(void) { return 1; }
+uint64_t pmvae_launch_count(void) { return g_launches.load(); }
+
+int pmvae_linear(int32_t precision, const float* x, const float* w, const float* bias, int64_t B, int32_t K, int32_t N,
+                 int32_t relu_in, float* y, void* ws, uint64_t ws_bytes, pmvae_stream_t stream) {
+  PMVAE_CHECK(x && w && y && B >= 0 && K > 0 && N > 0, "bad arguments");
+  if (precision == PMVAE_PREC_BF16) return linear_bf16(x, w, bias, B, K, N, relu_in, y, ws, ws_bytes, as_stream(stream));
+  PMVAE_CHECK(precision == PMVAE_PREC_F32, "unknown precision");
+  GemmF32Args a{};
+  a.M = B; a.N = N; a.K = K;
+  a.A = x; a.lda = K; a.B = w; a.ldb = N; a.C = y; a.ldc = N;
+  a.bias = bias; a.relu_a = relu_in;
+  return gemm_f32(a, false, false, as_stream(stream));
+}
+
+uint64_t pmvae_param_count(const pmvae_config* cfg) {
+  Layout L;
+  return build_layout(cfg, &L) == 0 ? L.total : 0;
+}
+int pmvae_layout(const pmvae_config* cfg, pmvae_leaf* out, int cap) { return export_layout(cfg, out, cap); }
+
+uint64_t pmvae_workspace_bytes(const pmvae_config* cfg, int64_t B, int64_t K) {
+  if (cfg && cfg->precision == PMVAE_PREC_BF16) return workspace_bytes_bf16(cfg, B, K);
+  return workspace_bytes(cfg, B, K);
+}
+
+int pmvae_prepare_params(const pmvae_config* cfg, const float* params, void* ws, uint64_t ws_bytes,
+                         pmvae_stream_t stream) {
+  PMVAE_CHECK(cfg && params && ws, "null pointer");
+  if (cfg->precision == PMVAE_PREC_BF16) return prepare_params_bf16(cfg, params, ws, ws_bytes, as_stream(stream));
+  return 0;
+}
+
+int pmvae_forward(const pmvae_config* cfg, const float* params, const float* x, const float* b, const float* eps,
+                  int64_t B, float* out_rec, float* out_kl, float* out_match, void* ws, uint64_t ws_bytes,
+                  pmvae_stream_t stream) {
+  return forward(cfg, params, x, b, eps, B, out_rec, out_kl, out_match, ws, ws_bytes, as_stream(stream));
+}
+
+int pmvae_backward(const pmvae_config* cfg, const float* params, const float* x, const float* b, const float* eps,
+                   int64_t B, const float* g_rec, const float* g_kl, const float* g_match, float* grads, void* ws,
+                   uint64_t ws_bytes, pmvae_stream_t stream) {
+  return backward(cfg, params, x, b, eps, B, g_rec, g_kl, g_match, grads, ws, ws_bytes, as_stream(stream));
+}
+
+int pmvae_loss_cotangents(int64_t B, int64_t B_global, float beta, float coef, const float* rec, const float* kl,
+                          const float* match, float* g_rec, float* g_kl, float* g_match, float* out_sums,
+                          pmvae_stream_t stream) {
+  PMVAE_CHECK(out_sums && (B == 0 || (rec && kl && match && g_rec && g_kl && g_match)), "null pointer");
+  return loss_cotangents(B, B_global, beta, coef, rec, kl, match, g_rec, g_kl, g_match, out_sums, as_stream(stream));
+}
+
+int pmvae_adamw(const pmvae_config* cfg, float* params, const float* grads, float* m, float* v, int64_t count, float lr,
+                float wd, float b1, float b2, float eps, pmvae_stream_t stream) {
+  return adamw_step(cfg, params, grads, m, v, count, lr, wd, b1, b2, eps, as_stream(stream));
+}
+
+int pmvae_is_log_prob(const pmvae_config* cfg, const float* params, const float* x, const float* b, int64_t B,
+                      int64_t K, const uint32_t key_z[2], const uint32_t key_zxo[2], int64_t B_total,
+                      int64_t row_start, float* out_log_p_x, float* out_log_p_xu_given_xo, void* ws, uint64_t ws_bytes,
+                      pmvae_stream_t stream) {
+  return is_log_prob(cfg, params, x, b, B, K, key_z, key_zxo, B_total, row_start, out_log_p_x, out_log_p_xu_given_xo,
+                     ws, ws_bytes, as_stream(stream));
+}
+
+int pmvae_impute_mean(const pmvae_config* cfg, const float* params, const float* x, const float* b, int64_t B,
+                      int64_t K, const uint32_t key[2], int64_t B_total, int64_t row_start, float* out, void* ws,
+                      uint64_t ws_bytes, pmvae_stream_t stream) {
+  return impute_mean_seq(cfg, params, x, b, B, K, key, B_total, row_start, out, ws, ws_bytes, as_stream(stream));
+}
+
+}  // extern "C"

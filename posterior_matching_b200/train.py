@@ -1,0 +1,134 @@
+"""Training step of train_pm_vae.py on the device: loss_fn (:58-72), the beta schedules
+(:28-43, utils.py:124-136), the optax chain (:74-83) and the step/pmean semantics of
+bax.Trainer, with the batch sharded by rows across ranks and one
+all-reduce (NCCL through torch.distributed) of the flat gradient arena.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Callable, Dict, Mapping, Optional
+
+import torch
+
+from . import _lib, prng
+from .masking import get_mask_generator
+from .vae import PosteriorMatchingVAE, _stream
+
+
+def cyclical_annealing_schedule(low_value: float, high_value: float, period: int, delay: int = 0) -> Callable:
+    """utils.py:124-136."""
+    def schedule(count):
+        true_count = count
+        count = count - delay
+        count = min(max(count % period, 0), period // 2)
+        frac = 1 - count / (period // 2)
+        x = (low_value - high_value) * frac + high_value
+        return x * (1.0 if true_count >= delay else 0.0)
+    return schedule
+
+
+def linear_schedule(init_value, end_value, transition_steps, transition_begin=0) -> Callable:
+    """optax.linear_schedule."""
+    def schedule(count):
+        frac = min(max((count - transition_begin) / transition_steps, 0.0), 1.0)
+        return init_value + (end_value - init_value) * frac
+    return schedule
+
+
+def exponential_decay(init_value, transition_steps, decay_rate) -> Callable:
+    """optax.exponential_decay (continuous)."""
+    return lambda count: init_value * decay_rate ** (count / transition_steps)
+
+
+def get_beta_schedule(config: Mapping[str, Any]) -> Callable:
+    """train_pm_vae.py:28-43."""
+    if "schedule" not in config:
+        return lambda x: 1.0
+    if config["schedule"] == "monotonic":
+        return linear_schedule(config["low_value"], config["high_value"], config["transition_steps"],
+                               config["transition_begin"])
+    if config["schedule"] == "cyclic":
+        return cyclical_annealing_schedule(config["low_value"], config["high_value"], config["period"],
+                                           config["delay"])
+    raise ValueError(config["schedule"])
+
+
+class Trainer:
+    """One object per rank.  `train_step(x)` = mask draw, eps draw, forward, loss
+    cotangents, backward, gradient all-reduce, AdamW -- every launch on the current CUDA
+    stream, no host sync; metrics stay on the device until `metrics()` is called."""
+
+    def __init__(self, config: Mapping[str, Any], *, seed: int = 0, precision: str = "bf16", device=None,
+                 process_group=None, model: Optional[PosteriorMatchingVAE] = None):
+        self.config = config
+        self.model = model or PosteriorMatchingVAE.from_config(config["model"], precision=precision, device=device)
+        if model is None:
+            self.model.init(seed)
+        self.device = self.model.device
+        self.beta_schedule = get_beta_schedule(config.get("beta", {}) or {})
+        self.matching_coef = float(config.get("matching_coef", 1.0))
+        ls = config["lr_schedule"]
+        self.lr_schedule = exponential_decay(ls["init_value"], ls["transition_steps"], ls["decay_rate"])
+        self.weight_decay = float(config.get("weight_decay", 0.0))
+        adam = dict(config.get("adam", {}) or {})
+        self.b1, self.b2, self.adam_eps = adam.get("b1", 0.9), adam.get("b2", 0.999), adam.get("eps", 1e-8)
+        self.m = torch.zeros_like(self.model.arena)
+        self.v = torch.zeros_like(self.model.arena)
+        self.step = 0
+        self.pg = process_group
+        self.world = 1
+        self.rank = 0
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+            self.rank = torch.distributed.get_rank(process_group)
+        data = config.get("data", {}) or {}
+        self.mask_generator = get_mask_generator(data.get("mask_generator", "BernoulliMaskGenerator"),
+                                                 seed=seed + 1, device=self.device)
+        self._rng = prng.PRNGSequence(prng.PRNGKey(seed + 2))
+        self._cot = None
+        self._sums = torch.zeros(3, dtype=torch.float32, device=self.device)
+        self.last_beta = 1.0
+
+    def _buffers(self, B):
+        if self._cot is None or self._cot.shape[1] < B:
+            self._cot = torch.empty((3, B), dtype=torch.float32, device=self.device)
+        return self._cot
+
+    def train_step(self, x: torch.Tensor, b: Optional[torch.Tensor] = None, eps: Optional[torch.Tensor] = None):
+        """x: this rank's rows [B_local, D] of a global batch of world*B_local rows."""
+        mdl = self.model
+        B = x.shape[0]
+        Bg = B * self.world
+        row0 = self.rank * B
+        step_key = self._rng.next()     # the per-step key bax hands to the transformed loss_fn
+        if b is None:
+            b = self.mask_generator((B, mdl.num_features), row_start=row0, total_rows=Bg)
+        out = mdl(x, b, is_training=True, rng=step_key if eps is None else None, eps=eps,
+                  row_start=row0, total_rows=Bg)
+        beta = float(self.beta_schedule(self.step))
+        self.last_beta = beta
+        cot = self._buffers(B)
+        _lib.check(_lib.lib.pmvae_loss_cotangents(
+            B, Bg, beta, self.matching_coef, out["reconstruction_ll"].data_ptr(), out["kl"].data_ptr(),
+            out["matching_ll"].data_ptr(), cot[0].data_ptr(), cot[1].data_ptr(), cot[2].data_ptr(),
+            self._sums.data_ptr(), _stream()), "pmvae_loss_cotangents")
+        mdl.backward(cot[0, :B], cot[1, :B], cot[2, :B])
+        if self.world > 1:
+            # mean of per-rank mean-gradients == sum of the 1/B_global-scaled shard gradients
+            torch.distributed.all_reduce(mdl.grad_arena, group=self.pg)
+            torch.distributed.all_reduce(self._sums, group=self.pg)
+        lr = float(self.lr_schedule(self.step))
+        _lib.check(_lib.lib.pmvae_adamw(mdl._cfgp, mdl.arena.data_ptr(), mdl.grad_arena.data_ptr(),
+                                        self.m.data_ptr(), self.v.data_ptr(), self.step, lr, self.weight_decay,
+                                        self.b1, self.b2, self.adam_eps, _stream()), "pmvae_adamw")
+        mdl.mark_params_changed()
+        self.step += 1
+        self._last_Bg = Bg
+        return self._sums
+
+    def metrics(self) -> Dict[str, float]:
+        """Batch means of the last step (one D2H read): the aux dict of train_pm_vae.py:72."""
+        s = (self._sums / float(self._last_Bg)).tolist()
+        rec, kl, match = s
+        return {"reconstruction_ll": rec, "kl": kl, "matching_ll": match, "beta": self.last_beta,
+                "loss": -(rec - self.last_beta * kl) + self.matching_coef * (-match)}
