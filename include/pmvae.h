@@ -98,6 +98,16 @@ int pmvae_linear(int32_t precision, const float* x, const float* w, const float*
                  int32_t K, int32_t N, int32_t relu_in, float* y, void* ws, uint64_t ws_bytes,
                  pmvae_stream_t stream);
 
+/* The two tcgen05 kernels behind PMVAE_PREC_BF16, on raw bf16 operands (uint16 storage):
+ *   nt: y[M,N] (fp32) = A[M,K] . Bt[N,K]^T + bias[N]      (forward / input-gradient shape)
+ *   tn: y[M,N] (fp32) += A[rows,M]^T . B[rows,N]          (weight-gradient shape; y must be
+ *       zeroed by the caller, the contraction is split over CTAs and summed with atomics)
+ * Row pitches lda/ldb are in elements and must be multiples of 8; N % 8 == 0. */
+int pmvae_tc_gemm_nt(const void* A, int64_t lda, const void* Bt, int64_t ldb, const float* bias,
+                     int64_t M, int32_t N, int32_t K, float* y, pmvae_stream_t stream);
+int pmvae_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N,
+                     int64_t rows, float* y, pmvae_stream_t stream);
+
 /* ---- model ------------------------------------------------------------------------ */
 /* Bytes of scratch for a batch of B rows (training forward+backward keeps its saved
  * activations here) and, for the evaluators, K importance samples per row. */

@@ -49,6 +49,8 @@ _SIGS = {
     "pmvae_version": (_i32, []),
     "pmvae_launch_count": (_u64, []),
     "pmvae_linear": (_i32, [_i32, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _u64, _vp]),
+    "pmvae_tc_gemm_nt": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "pmvae_tc_gemm_tn": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i64, _vp, _vp]),
     "pmvae_param_count": (_u64, [_cfgp]),
     "pmvae_layout": (_i32, [_cfgp, C.POINTER(Leaf), _i32]),
     "pmvae_key_split_host": (_i32, [_u32p, _i32, _u32p]),

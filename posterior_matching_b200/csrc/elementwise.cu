@@ -3,6 +3,8 @@
 // Reference sites: networks.py:117-118 (LayerNorm), vae.py:127-128 (Normal log-prob
 // row-sum), vae.py:132-133 ([x*b, b]), vae.py:222-223 (reduce_logmeanexp),
 // vae.py:165-167 (impute where), train_pm_vae.py:58-83 (loss weights, optax chain).
+#include <cuda_bf16.h>
+
 #include "kernels.h"
 
 namespace pmvae {
@@ -123,32 +125,34 @@ int colsum_add(const float* dY, int64_t ld, float* out, int64_t B, int N, cudaSt
 
 // ---------------------------------------------------------------- Normal log-prob row sums
 __global__ void __launch_bounds__(256) rec_ll_kernel(const float* __restrict__ x, const float* __restrict__ loc,
-                                                     const float* __restrict__ log_scale, const float* __restrict__ w,
-                                                     float* __restrict__ out, int64_t B, int D) {
+                                                     int64_t ld_loc, const float* __restrict__ log_scale,
+                                                     const float* __restrict__ w, float* __restrict__ out, int64_t B,
+                                                     int D) {
   const float ls = *log_scale;
   const float inv = expf(-ls);
   const float cst = -ls - 0.5f * kLog2Pi;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < B; r += (int64_t)gridDim.x * blockDim.x) {
     float acc = 0.f;
     for (int j = 0; j < D; ++j) {
-      const float t = (x[r * D + j] - loc[r * D + j]) * inv;
+      const float t = (x[r * D + j] - loc[r * ld_loc + j]) * inv;
       const float ll = -0.5f * t * t + cst;
       acc += w ? ll * w[r * D + j] : ll;
     }
     out[r] = acc;
   }
 }
-int rec_ll(const float* x, const float* loc, const float* log_scale, const float* w, float* out, int64_t B, int D,
-           cudaStream_t s) {
+int rec_ll(const float* x, const float* loc, int64_t ld_loc, const float* log_scale, const float* w, float* out,
+           int64_t B, int D, cudaStream_t s) {
   if (B == 0) return 0;
-  rec_ll_kernel<<<grid1d(B, 256), 256, 0, s>>>(x, loc, log_scale, w, out, B, D);
+  rec_ll_kernel<<<grid1d(B, 256), 256, 0, s>>>(x, loc, ld_loc, log_scale, w, out, B, D);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void __launch_bounds__(256) rec_ll_bwd_kernel(const float* __restrict__ x, const float* __restrict__ loc,
-                                                         const float* __restrict__ log_scale,
+                                                         int64_t ld_loc, const float* __restrict__ log_scale,
                                                          const float* __restrict__ g, float* __restrict__ dloc,
+                                                         __nv_bfloat16* __restrict__ dloc_bf16, int64_t ld_dloc,
                                                          float* __restrict__ dls, int64_t B, int D) {
   const float ls = *log_scale;
   const float inv2 = expf(-2.0f * ls);
@@ -157,10 +161,14 @@ __global__ void __launch_bounds__(256) rec_ll_bwd_kernel(const float* __restrict
     const float gr = g[r];
     float acc = 0.f;
     for (int j = 0; j < D; ++j) {
-      const float df = x[r * D + j] - loc[r * D + j];
-      dloc[r * D + j] = gr * df * inv2;
+      const float df = x[r * D + j] - loc[r * ld_loc + j];
+      const float dv = gr * df * inv2;
+      if (dloc) dloc[r * ld_dloc + j] = dv;
+      if (dloc_bf16) dloc_bf16[r * ld_dloc + j] = __float2bfloat16(dv);
       acc += df * df * inv2 - 1.0f;
     }
+    if (dloc_bf16)
+      for (int j = D; j < ld_dloc; ++j) dloc_bf16[r * ld_dloc + j] = __float2bfloat16(0.f);
     part += gr * acc;
   }
   part = warp_sum(part);
@@ -173,10 +181,10 @@ __global__ void __launch_bounds__(256) rec_ll_bwd_kernel(const float* __restrict
     atomicAdd(dls, t);
   }
 }
-int rec_ll_bwd(const float* x, const float* loc, const float* log_scale, const float* g, float* dloc, float* dls,
-               int64_t B, int D, cudaStream_t s) {
+int rec_ll_bwd(const float* x, const float* loc, int64_t ld_loc, const float* log_scale, const float* g, float* dloc,
+               __nv_bfloat16* dloc_bf16, int64_t ld_dloc, float* dls, int64_t B, int D, cudaStream_t s) {
   if (B == 0) return 0;
-  rec_ll_bwd_kernel<<<grid1d(B, 256, 4), 256, 0, s>>>(x, loc, log_scale, g, dloc, dls, B, D);
+  rec_ll_bwd_kernel<<<grid1d(B, 256, 4), 256, 0, s>>>(x, loc, ld_loc, log_scale, g, dloc, dloc_bf16, ld_dloc, dls, B, D);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -241,7 +249,7 @@ int adamw(float* p, const float* g, float* m, float* v, uint64_t n, const AdamSe
 
 // ---------------------------------------------------------------- evaluators
 __global__ void __launch_bounds__(256) eval_rows_ll_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                           const float* __restrict__ loc,
+                                                           const float* __restrict__ loc, int64_t ld_loc,
                                                            const float* __restrict__ log_scale,
                                                            const float* __restrict__ base, float* __restrict__ out,
                                                            int64_t B, int64_t K, int D) {
@@ -253,17 +261,17 @@ __global__ void __launch_bounds__(256) eval_rows_ll_kernel(const float* __restri
     const int64_t r = i % B;
     float acc = 0.f;
     for (int j = 0; j < D; ++j) {
-      const float t = (x[r * D + j] - loc[i * D + j]) * inv;
+      const float t = (x[r * D + j] - loc[i * ld_loc + j]) * inv;
       const float ll = -0.5f * t * t + cst;
       acc += w ? ll * w[r * D + j] : ll;
     }
     out[i] = acc + base[i];
   }
 }
-int eval_rows_ll(const float* x, const float* w, const float* loc, const float* log_scale, const float* base,
-                 float* out, int64_t B, int64_t K, int D, cudaStream_t s) {
+int eval_rows_ll(const float* x, const float* w, const float* loc, int64_t ld_loc, const float* log_scale,
+                 const float* base, float* out, int64_t B, int64_t K, int D, cudaStream_t s) {
   if (B * K == 0) return 0;
-  eval_rows_ll_kernel<<<grid1d(B * K, 256), 256, 0, s>>>(x, w, loc, log_scale, base, out, B, K, D);
+  eval_rows_ll_kernel<<<grid1d(B * K, 256), 256, 0, s>>>(x, w, loc, ld_loc, log_scale, base, out, B, K, D);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -293,8 +301,8 @@ int logmeanexp_rows(const float* a, const float* c, float* out, int64_t B, int64
 }
 
 __global__ void __launch_bounds__(256) impute_mean_kernel(const float* __restrict__ x, const float* __restrict__ b,
-                                                          const float* __restrict__ loc, float* __restrict__ out,
-                                                          int64_t B, int64_t K, int D) {
+                                                          const float* __restrict__ loc, int64_t ld_loc,
+                                                          float* __restrict__ out, int64_t B, int64_t K, int D) {
   const int64_t n = B * D;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float bv = b[i];
@@ -302,16 +310,18 @@ __global__ void __launch_bounds__(256) impute_mean_kernel(const float* __restric
     if (bv != 0.f) {
       acc = x[i] * bv;  // where(b, x_o, x_hat): every sample equals x_o
     } else {
-      for (int64_t k = 0; k < K; ++k) acc += loc[k * n + i];
+      const int64_t r = i / D;
+      const int j = (int)(i - r * D);
+      for (int64_t k = 0; k < K; ++k) acc += loc[(k * B + r) * ld_loc + j];
       acc /= (float)K;
     }
     out[i] = acc;
   }
 }
-int impute_mean(const float* x, const float* b, const float* loc, float* out, int64_t B, int64_t K, int D,
-                cudaStream_t s) {
+int impute_mean(const float* x, const float* b, const float* loc, int64_t ld_loc, float* out, int64_t B, int64_t K,
+                int D, cudaStream_t s) {
   if (B == 0) return 0;
-  impute_mean_kernel<<<grid1d(B * D, 256), 256, 0, s>>>(x, b, loc, out, B, K, D);
+  impute_mean_kernel<<<grid1d(B * D, 256), 256, 0, s>>>(x, b, loc, ld_loc, out, B, K, D);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -1,5 +1,7 @@
 // Internal launchers shared between the translation units of libpmvae.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace pmvae {
@@ -29,11 +31,12 @@ int ln_bwd(const float* dy, const float* xhat, const float* rstd, float* dx, int
 // out[n] += sum_m dY[m, n]   (atomics)
 int colsum_add(const float* dY, int64_t ld, float* out, int64_t B, int N, cudaStream_t s);
 // rec[r] = sum_j w[r,j] * logN(x[r,j]; loc[r,j], exp(ls))   (w == nullptr -> 1)
-int rec_ll(const float* x, const float* loc, const float* log_scale, const float* w, float* out, int64_t B, int D,
-           cudaStream_t s);
+int rec_ll(const float* x, const float* loc, int64_t ld_loc, const float* log_scale, const float* w, float* out,
+           int64_t B, int D, cudaStream_t s);
 // dloc[r,j] = g[r] * (x - loc) * exp(-2 ls);  *dls += sum_r g[r] * sum_j ((x-loc)^2 exp(-2 ls) - 1)
-int rec_ll_bwd(const float* x, const float* loc, const float* log_scale, const float* g, float* dloc, float* dls,
-               int64_t B, int D, cudaStream_t s);
+// (either dloc output may be null; the bf16 one is zero-padded to its pitch)
+int rec_ll_bwd(const float* x, const float* loc, int64_t ld_loc, const float* log_scale, const float* g, float* dloc,
+               __nv_bfloat16* dloc_bf16, int64_t ld_dloc, float* dls, int64_t B, int D, cudaStream_t s);
 int loss_cotangents(int64_t B, int64_t B_global, float beta, float coef, const float* rec, const float* kl,
                     const float* match, float* g_rec, float* g_kl, float* g_match, float* out_sums, cudaStream_t s);
 struct AdamSegs { int n; uint32_t beg[48]; uint32_t end[48]; };  // no-decay (bias) ranges
@@ -41,12 +44,12 @@ int adamw(float* p, const float* g, float* m, float* v, uint64_t n, const AdamSe
           float b1, float b2, float eps, float bc1, float bc2, cudaStream_t s);
 // evaluators
 // ll[k*B + r] = sum_j w * logN(x[r]; loc[k*B + r]) + base[k*B + r]
-int eval_rows_ll(const float* x, const float* w, const float* loc, const float* log_scale, const float* base,
-                 float* out, int64_t B, int64_t K, int D, cudaStream_t s);
+int eval_rows_ll(const float* x, const float* w, const float* loc, int64_t ld_loc, const float* log_scale,
+                 const float* base, float* out, int64_t B, int64_t K, int D, cudaStream_t s);
 // out[r] = logsumexp_k(a[k*B + r]) - log K  [ - (logsumexp_k(c[k*B+r]) - log K) if c ]
 int logmeanexp_rows(const float* a, const float* c, float* out, int64_t B, int64_t K, cudaStream_t s);
-int impute_mean(const float* x, const float* b, const float* loc, float* out, int64_t B, int64_t K, int D,
-                cudaStream_t s);
+int impute_mean(const float* x, const float* b, const float* loc, int64_t ld_loc, float* out, int64_t B, int64_t K,
+                int D, cudaStream_t s);
 
 // ---- latent.cu  (par = raw TriL head output [B, P], P = d + d(d+1)/2)
 int latent_fwd(const float* par, const float* eps, float* z, float* kl, int64_t B, int d, cudaStream_t s);

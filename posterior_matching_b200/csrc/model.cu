@@ -11,6 +11,7 @@
 
 #include "kernels.h"
 #include "model.h"
+#include "tc_gemm.h"
 
 namespace pmvae {
 
@@ -289,7 +290,7 @@ int forward(const pmvae_config* c, const float* params, const float* x, const fl
   PMVAE_TRY(net_fwd_f32(params, L.enc, L.post, c->H, x, B, p.enc, p.par_e, s));
   PMVAE_TRY(latent_fwd(p.par_e, eps, p.z, out_kl, B, c->d, s));
   PMVAE_TRY(net_fwd_f32(params, L.dec, L.ddist, c->H, p.z, B, p.dec, p.loc, s));
-  PMVAE_TRY(rec_ll(x, p.loc, params + L.log_scale, nullptr, out_rec, B, c->D, s));
+  PMVAE_TRY(rec_ll(x, p.loc, c->D, params + L.log_scale, nullptr, out_rec, B, c->D, s));
   PMVAE_TRY(concat_masked(x, b, p.xob, B, c->D, s));
   PMVAE_TRY(net_fwd_f32(params, L.part, L.ppost, c->H, p.xob, B, p.part, p.par_p, s));
   PMVAE_TRY(match_fwd(p.par_p, p.z, out_match, B, c->d, s));
@@ -307,7 +308,7 @@ int backward(const pmvae_config* c, const float* params, const float* x, const f
   if (c->precision == PMVAE_PREC_BF16) return backward_bf16(c, L, params, x, b, eps, B, g_rec, g_kl, g_match, grads, ws, ws_bytes, s);
   TrainPlan p = plan_train(c, L, B, ws);
   PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_workspace_bytes)");
-  PMVAE_TRY(rec_ll_bwd(x, p.loc, params + L.log_scale, g_rec, p.dloc, grads + L.log_scale, B, c->D, s));
+  PMVAE_TRY(rec_ll_bwd(x, p.loc, c->D, params + L.log_scale, g_rec, p.dloc, nullptr, c->D, grads + L.log_scale, B, c->D, s));
   PMVAE_TRY(net_bwd_f32(params, grads, L.dec, L.ddist, c->H, p.z, B, p.dec, p.dloc, p.dH, p.tmp1, p.tmp2, p.dz, s));
   PMVAE_TRY(latent_bwd(p.par_e, p.par_p, eps, p.z, p.dz, g_kl, g_match, c->stop_grad, p.dpar_e, p.dpar_p, B, c->d, s));
   PMVAE_TRY(net_bwd_f32(params, grads, L.enc, L.post, c->H, x, B, p.enc, p.dpar_e, p.dH, p.tmp1, p.tmp2, nullptr, s));
@@ -358,13 +359,13 @@ int is_log_prob(const pmvae_config* c, const float* params, const float* x, cons
     // z ~ q(z|x)
     PMVAE_TRY(sample_latents(p.par_e + r0 * L.P, Key2{key_z[0], key_z[1]}, nb, K, B_total, row_start + r0, c->d, p.z, p.base, s));
     PMVAE_TRY(net_fwd_f32(params, L.dec, L.ddist, c->H, p.z, M, p.dec, p.loc, s));
-    PMVAE_TRY(eval_rows_ll(x + r0 * c->D, nullptr, p.loc, ls, p.base, p.llA, nb, K, c->D, s));
+    PMVAE_TRY(eval_rows_ll(x + r0 * c->D, nullptr, p.loc, c->D, ls, p.base, p.llA, nb, K, c->D, s));
     if (out_log_p_x) PMVAE_TRY(logmeanexp_rows(p.llA, nullptr, out_log_p_x + r0, nb, K, s));
     if (out_cond) {
       // z' ~ q(z|x_o), observed dims only
       PMVAE_TRY(sample_latents(p.par_p + r0 * L.P, Key2{key_zxo[0], key_zxo[1]}, nb, K, B_total, row_start + r0, c->d, p.z, p.base, s));
       PMVAE_TRY(net_fwd_f32(params, L.dec, L.ddist, c->H, p.z, M, p.dec, p.loc, s));
-      PMVAE_TRY(eval_rows_ll(x + r0 * c->D, b + r0 * c->D, p.loc, ls, p.base, p.llC, nb, K, c->D, s));
+      PMVAE_TRY(eval_rows_ll(x + r0 * c->D, b + r0 * c->D, p.loc, c->D, ls, p.base, p.llC, nb, K, c->D, s));
       PMVAE_TRY(logmeanexp_rows(p.llA, p.llC, out_cond + r0, nb, K, s));
     }
   }
@@ -388,7 +389,7 @@ int impute_mean_seq(const pmvae_config* c, const float* params, const float* x, 
     const int64_t nb = (B - r0 < p.rows_per_chunk) ? (B - r0) : p.rows_per_chunk;
     PMVAE_TRY(sample_latents(p.par_p + r0 * L.P, Key2{key[0], key[1]}, nb, K, B_total, row_start + r0, c->d, p.z, p.base, s));
     PMVAE_TRY(net_fwd_f32(params, L.dec, L.ddist, c->H, p.z, nb * K, p.dec, p.loc, s));
-    PMVAE_TRY(impute_mean(x + r0 * c->D, b + r0 * c->D, p.loc, out + r0 * c->D, nb, K, c->D, s));
+    PMVAE_TRY(impute_mean(x + r0 * c->D, b + r0 * c->D, p.loc, c->D, out + r0 * c->D, nb, K, c->D, s));
   }
   return 0;
 }
@@ -402,6 +403,21 @@ extern "C" {
 const char* pmvae_last_error(void) { return pmvae::last_error(); }
 int pmvae_version(void) { return 1; }
 uint64_t pmvae_launch_count(void) { return g_launches.load(); }
+
+int pmvae_tc_gemm_nt(const void* A, int64_t lda, const void* Bt, int64_t ldb, const float* bias, int64_t M, int32_t N,
+                     int32_t K, float* y, pmvae_stream_t stream) {
+  PMVAE_CHECK(A && Bt && y, "null pointer");
+  tc::TcGemmArgs e{};
+  e.bias = bias; e.out_f32 = y; e.ld_out_f32 = N;
+  return tc::gemm_nt(reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(Bt), ldb, M,
+                     N, K, e, as_stream(stream));
+}
+int pmvae_tc_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int64_t rows,
+                     float* y, pmvae_stream_t stream) {
+  PMVAE_CHECK(A && B && y, "null pointer");
+  return tc::gemm_tn(reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(B), ldb, M,
+                     N, rows, y, N, 1, 0, nullptr, as_stream(stream));
+}
 
 int pmvae_linear(int32_t precision, const float* x, const float* w, const float* bias, int64_t B, int32_t K, int32_t N,
                  int32_t relu_in, float* y, void* ws, uint64_t ws_bytes, pmvae_stream_t stream) {

@@ -1,0 +1,471 @@
+// tcgen05 / TMEM / TMA GEMM for the dense contractions of the PM-VAE path (sm_100a).
+//
+//   kind 0 ("NT", both operands contraction-major): C[M,N] = A[M,K] . Bt[N,K]^T
+//        hk.Linear forward  (A = activations, Bt = W^T image)      networks.py:116,122,127
+//        input gradient     (A = dY,          Bt = W image)        dX = dY @ W^T
+//   kind 1 ("TN", both operands MN-major):     C[M,N] = A[K,M]^T . B[K,N]
+//        weight gradient    (A = saved activations [rows,M], B = dY [rows,N]), the
+//        contraction runs over the batch rows and is split across CTAs.
+//
+// Structure (one CTA per SM, persistent over tiles):
+//   warp 0      : TMA producer  (cp.async.bulk.tensor 2D, SWIZZLE_128B, 4-stage mbarrier ring)
+//   warp 1      : MMA issuer    (one lane: tcgen05.mma kind::f16, M=128, N<=256, K=16, fp32 accum in TMEM)
+//   warps 2..5  : epilogue      (tcgen05.ld 32x32b.x32 -> bias / mask / residual / relu -> global)
+// Two 256-column TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "kernels.h"
+#include "tc_gemm.h"
+
+namespace pmvae {
+namespace tc {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;            // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kMaxN = 256;
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr int kThreads = 192;          // 6 warps
+constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KB
+constexpr int kBBytes = kMaxN * kBlockK * 2;        // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t kSpinLimit = 1u << 28;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) {
+      printf("pmvae tc_gemm: mbarrier wait timed out (tag %d, block %d, thread %d)\n", tag, blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start >> 4 | [16,30) LBO >> 4 | [32,46) SBO >> 4 | [46,48) version = 1 | [61,64) layout = 2
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 x bf16
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// ---------------------------------------------------------------- kernel
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcGemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + kAccStages + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 2 * kAccStages);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * kStageBytes + 8 * (2 * kStages + 2 * kAccStages));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
+  const int n_tile = p.n_tile;
+  const uint32_t stage_tx = (uint32_t)(kABytes + n_tile * kBlockK * 2);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile % p.num_m_tiles;
+        const int rest = tile / p.num_m_tiles;
+        const int nt = rest % p.num_n_tiles;
+        const int sp = rest / p.num_n_tiles;
+        const int kb0 = sp * p.kb_per_split;
+        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, 1);
+          mbar_arrive_expect_tx(full_bar(stage), stage_tx);
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sb = sa + kABytes;
+          if (KIND == 0) {
+            // A box: [64 k] x [128 rows]; B box: [64 k] x [n_tile rows]
+            tma_load_2d(sa, &map_a, full_bar(stage), kb * kBlockK, mt * kBlockM);
+            tma_load_2d(sb, &map_b, full_bar(stage), kb * kBlockK, nt * n_tile);
+          } else {
+            // MN-major: boxes of [64 m-or-n] x [64 k rows], one per 64 columns of the tile
+            for (int j = 0; j < kBlockM / 64; ++j)
+              tma_load_2d(sa + j * 8192, &map_a, full_bar(stage), mt * kBlockM + j * 64, kb * kBlockK);
+            for (int j = 0; j < n_tile / 64; ++j)
+              tma_load_2d(sb + j * 8192, &map_b, full_bar(stage), nt * n_tile + j * 64, kb * kBlockK);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(kBlockM, n_tile, KIND, KIND);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int rest = tile / p.num_m_tiles;
+        const int sp = rest / p.num_n_tiles;
+        const int kb0 = sp * p.kb_per_split;
+        const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kMaxN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            uint64_t da, db;
+            if (KIND == 0) {
+              // K-major SW128: 8-row groups 1024 B apart; a K=16 slice is 32 B inside the swizzle row
+              da = smem_desc(sa + k * 32, 16, 1024);
+              db = smem_desc(sb + k * 32, 16, 1024);
+            } else {
+              // MN-major SW128: 64-element column groups 8192 B apart (LBO), 8-k groups 1024 B apart (SBO)
+              da = smem_desc(sa + k * 2048, 8192, 1024);
+              db = smem_desc(sb + k * 2048, 8192, 1024);
+            }
+            umma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));              // accumulator ready for the epilogue
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps, one accumulator row per thread) =====================
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile % p.num_m_tiles;
+      const int rest = tile / p.num_m_tiles;
+      const int nt = rest % p.num_n_tiles;
+      const int sp = rest / p.num_n_tiles;
+      mbar_wait(tfull_bar(acc), acc_phase, 4);
+      tc_fence_after();
+      const int64_t row = (int64_t)mt * kBlockM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kMaxN);
+      for (int c0 = 0; c0 < n_tile; c0 += 32) {
+        uint32_t r[32];
+        __syncwarp();                             // tcgen05.ld is .sync.aligned: reconverge after the guards below
+        tmem_ld32(t_row + (uint32_t)c0, r);
+        tmem_ld_wait();
+        const int n0 = nt * n_tile + c0;
+        if (!row_ok || n0 >= p.N) continue;
+        if (KIND == 1) {
+          // split-K partial: fp32 tile into the partial buffer (plain stores) or atomics into C
+          float* dst = p.out_f32 + (p.atomic ? 0 : (int64_t)sp * p.M * p.ld_out_f32) + row * p.ld_out_f32 + n0;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (n0 + g * 4 >= p.N) break;
+            if (p.atomic) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) atomicAdd(dst + g * 4 + j, __uint_as_float(r[g * 4 + j]));
+            } else {
+              *reinterpret_cast<float4*>(dst + g * 4) = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]),
+                                                                    __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+            }
+          }
+          continue;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {             // 4 groups of 8 columns
+          const int n = n0 + g * 8;
+          if (n >= p.N) break;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+          if (p.bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
+          if (p.mask_bf16) {
+            const uint4 m = *reinterpret_cast<const uint4*>(p.mask_bf16 + row * p.ld_mask + n);
+            const uint32_t mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (!(bf16_lo(mm[j]) > 0.f)) v[2 * j] = 0.f;
+              if (!(bf16_hi(mm[j]) > 0.f)) v[2 * j + 1] = 0.f;
+            }
+          }
+          if (p.resid_f32) {
+            const float4 a0 = *reinterpret_cast<const float4*>(p.resid_f32 + row * p.ld_resid_f32 + n);
+            const float4 a1 = *reinterpret_cast<const float4*>(p.resid_f32 + row * p.ld_resid_f32 + n + 4);
+            v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
+            v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+          }
+          if (p.resid_bf16) {
+            const uint4 m = *reinterpret_cast<const uint4*>(p.resid_bf16 + row * p.ld_resid_bf16 + n);
+            const uint32_t mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { v[2 * j] += bf16_lo(mm[j]); v[2 * j + 1] += bf16_hi(mm[j]); }
+          }
+          if (p.out_f32) {
+            float* dst = p.out_f32 + row * p.ld_out_f32 + n;
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          }
+          if (p.out_bf16) {
+            if (p.relu_out) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            uint4 o;
+            o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+            o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+            *reinterpret_cast<uint4*>(p.out_bf16 + row * p.ld_out_bf16 + n) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] with row pitch `ld` elements; box = [box_cols (inner), box_rows]
+static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                    uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  PMVAE_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+  PMVAE_CHECK((reinterpret_cast<uintptr_t>(base) & 15u) == 0 && (ld * 2) % 16 == 0, "TMA operand must be 16-byte aligned");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PMVAE_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return 0;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int KIND>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcGemmArgs& a, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PMVAE_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = a.num_m_tiles * a.num_n_tiles * a.split_k;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  tc_gemm_kernel<KIND><<<grid, kThreads, kSmemBytes, s>>>(ma, mb, a);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+static int pick_n_tile(int N, int granule) {
+  int nt = (N + granule - 1) / granule * granule;
+  return nt > kMaxN ? kMaxN : nt;
+}
+
+// C[M,N] = A[M,K] . Bt[N,K]^T  (+ epilogue)
+int gemm_nt(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Bt, int64_t ldb, int64_t M, int N, int K,
+            TcGemmArgs ep, cudaStream_t s) {
+  PMVAE_CHECK(M >= 0 && N > 0 && K > 0, "bad gemm shape");
+  if (M == 0) return 0;
+  PMVAE_CHECK(N % 8 == 0, "tensor path needs N % 8 == 0");
+  PMVAE_CHECK(M < (1ll << 31), "M too large");
+  ep.M = (int)M; ep.N = N; ep.K = K;
+  ep.n_tile = pick_n_tile(N, 32);
+  ep.num_m_tiles = (int)ceil_div(M, kBlockM);
+  ep.num_n_tiles = (int)ceil_div(N, ep.n_tile);
+  ep.num_k_blocks = (int)ceil_div(K, kBlockK);
+  ep.split_k = 1; ep.kb_per_split = ep.num_k_blocks; ep.atomic = 0;
+  CUtensorMap ma, mb;
+  PMVAE_TRY(make_map(&ma, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBlockK, kBlockM));
+  PMVAE_TRY(make_map(&mb, Bt, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, kBlockK, (uint32_t)ep.n_tile));
+  return launch<0>(ma, mb, ep, s);
+}
+
+// C[M,N] (fp32) = A[rows,M]^T . B[rows,N], contraction over rows split across CTAs.
+// atomic = 1: atomicAdd into out (must be zeroed by the caller);
+// atomic = 0: `out` is a [split, M, ld] partial buffer; *split_out returns the split count.
+int gemm_tn(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t ldb, int M, int N, int64_t rows,
+            float* out, int64_t ld_out, int atomic, int max_split, int* split_out, cudaStream_t s) {
+  PMVAE_CHECK(M > 0 && N > 0 && rows >= 0, "bad gemm shape");
+  PMVAE_CHECK(N % 4 == 0, "tensor path needs N % 4 == 0");
+  TcGemmArgs ep{};
+  ep.M = M; ep.N = N; ep.K = (int)rows;
+  ep.n_tile = pick_n_tile(N, 64);
+  ep.num_m_tiles = (int)ceil_div(M, kBlockM);
+  ep.num_n_tiles = (int)ceil_div(N, ep.n_tile);
+  ep.num_k_blocks = (int)ceil_div(rows, kBlockK);
+  int split = num_sms() / (ep.num_m_tiles * ep.num_n_tiles);
+  if (split < 1) split = 1;
+  if (split > ep.num_k_blocks) split = ep.num_k_blocks > 0 ? ep.num_k_blocks : 1;
+  if (max_split > 0 && split > max_split) split = max_split;
+  ep.kb_per_split = (int)ceil_div(ep.num_k_blocks, split);
+  split = (int)ceil_div(ep.num_k_blocks, ep.kb_per_split);
+  if (split < 1) split = 1;
+  ep.split_k = split;
+  ep.atomic = atomic;
+  ep.out_f32 = out; ep.ld_out_f32 = ld_out;
+  if (split_out) *split_out = split;
+  if (rows == 0) return 0;
+  CUtensorMap ma, mb;
+  PMVAE_TRY(make_map(&ma, A, (uint64_t)rows, (uint64_t)M, (uint64_t)lda, 64, kBlockK));
+  PMVAE_TRY(make_map(&mb, B, (uint64_t)rows, (uint64_t)N, (uint64_t)ldb, 64, kBlockK));
+  return launch<1>(ma, mb, ep, s);
+}
+
+}  // namespace tc
+}  // namespace pmvae

@@ -1,20 +1,736 @@
-// bf16-operand tcgen05/TMEM path (placeholder until the tensor kernels land).
+// PMVAE_PREC_BF16: the PM-VAE path with bf16 operands / fp32 accumulation on tcgen05.
+//
+// Data layout in HBM (per batch of B rows, H = 256):
+//   weights   : bf16 images of every hk.Linear, W [in, out] and W^T [out, in] (row pitch
+//               padded to 8), refreshed by prepare_params after each optimizer step;
+//   A[r]      : bf16 [B, H] = relu(h_r)       operand of the next Linear, relu mask, dW operand
+//   T[r]      : bf16 [B, H] = relu(linear1)   same roles inside a residual block
+//   h         : fp32 [B, H] residual stream, updated in place by the second Linear's epilogue
+//   LN nets additionally keep the normalised pre-activations (bf16) and 1/sigma per row.
+// The 1+2R hidden contractions and the heads run on tc::gemm_nt / tc::gemm_tn; the first
+// Linear of each net (K = D, 2D or d <= 126) and its gradients are fp32 SIMT kernels that
+// also build [x*b, b] on the fly (vae.py:132-133).
+#include <cuda_bf16.h>
+
 #include "kernels.h"
 #include "model.h"
+#include "tc_gemm.h"
 
 namespace pmvae {
-#define NOT_BUILT() do { set_error("PMVAE_PREC_BF16 path is not built yet"); return 3; } while (0)
-int linear_bf16(const float*, const float*, const float*, int64_t, int, int, int, float*, void*, uint64_t,
-                cudaStream_t) { NOT_BUILT(); }
-uint64_t workspace_bytes_bf16(const pmvae_config*, int64_t, int64_t) { return 0; }
-int prepare_params_bf16(const pmvae_config*, const float*, void*, uint64_t, cudaStream_t) { NOT_BUILT(); }
-int forward_bf16(const pmvae_config*, const Layout&, const float*, const float*, const float*, const float*, int64_t,
-                 float*, float*, float*, void*, uint64_t, cudaStream_t) { NOT_BUILT(); }
-int backward_bf16(const pmvae_config*, const Layout&, const float*, const float*, const float*, const float*, int64_t,
-                  const float*, const float*, const float*, float*, void*, uint64_t, cudaStream_t) { NOT_BUILT(); }
-int is_log_prob_bf16(const pmvae_config*, const Layout&, const float*, const float*, const float*, int64_t, int64_t,
-                     const uint32_t*, const uint32_t*, int64_t, int64_t, float*, float*, void*, uint64_t,
-                     cudaStream_t) { NOT_BUILT(); }
-int impute_mean_bf16(const pmvae_config*, const Layout&, const float*, const float*, const float*, int64_t, int64_t,
-                     const uint32_t*, int64_t, int64_t, float*, void*, uint64_t, cudaStream_t) { NOT_BUILT(); }
+
+typedef __nv_bfloat16 bf16;
+__host__ __device__ static inline int pad8(int n) { return (n + 7) / 8 * 8; }
+
+static int grid1d(int64_t work, int block, int per_sm = 8) {
+  int64_t g = ceil_div(work, block);
+  const int64_t cap = 148ll * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ---------------------------------------------------------------- weight images
+struct PackLeaf { uint64_t w_off; int rows, cols, ldn, ldt; uint64_t wn_off, wt_off; int tile0; };
+struct PackTable { int n; int total_tiles; PackLeaf leaf[48]; };
+
+// One 32x32 tile per block: Wn[r, c] = bf16(W[r, c]) (pitch ldn), Wt[c, r] = bf16(W[r, c]) (pitch ldt);
+// the padding of both images is zero-filled.
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ params, bf16* __restrict__ img,
+                                                           PackTable tb) {
+  __shared__ float tile[32][33];
+  int li = 0;
+  while (li + 1 < tb.n && (int)blockIdx.x >= tb.leaf[li + 1].tile0) ++li;
+  const PackLeaf lf = tb.leaf[li];
+  const int t = blockIdx.x - lf.tile0;
+  const int tiles_c = (lf.ldn + 31) / 32;      // ldn >= cols, ldt >= rows
+  const int tr = t / tiles_c, tcn = t % tiles_c;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = tr * 32 + i, c = tcn * 32 + tx;
+    float v = 0.f;
+    if (r < lf.rows && c < lf.cols) v = params[lf.w_off + (uint64_t)r * lf.cols + c];
+    tile[i][tx] = v;
+    if (r < lf.rows && c < lf.ldn) img[lf.wn_off + (uint64_t)r * lf.ldn + c] = __float2bfloat16(v);
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = tcn * 32 + i, r = tr * 32 + tx;   // write Wt[c, r]
+    const int rows_t = pad8(lf.cols);               // image rows of W^T
+    if (c < rows_t && r < lf.ldt) img[lf.wt_off + (uint64_t)c * lf.ldt + r] = __float2bfloat16((r < lf.rows && c < lf.cols) ? tile[tx][i] : 0.f);
+  }
+}
+
+struct LeafImg { const bf16* wn; const bf16* wt; int ldn, ldt; };   // wn: [rows, ldn], wt: [pad8(cols), ldt]
+
+struct Images {
+  LeafImg enc[2 * kMaxBlocks + 1], dec[2 * kMaxBlocks + 1], part[2 * kMaxBlocks + 1], post, ddist, ppost;
+  uint64_t bytes;
+};
+
+static void plan_images(const Layout& L, void* ws, Images* im, PackTable* tb) {
+  uint64_t off = 0;  // in bf16 elements
+  int tiles = 0;
+  if (tb) { tb->n = 0; }
+  auto one = [&](const Leaf& lf, LeafImg& out) {
+    const int ldn = pad8(lf.cols), ldt = pad8(lf.rows);
+    const uint64_t wn_off = off; off += align_up((uint64_t)lf.rows * ldn, 128);
+    const uint64_t wt_off = off; off += align_up((uint64_t)pad8(lf.cols) * ldt, 128);
+    out.wn = reinterpret_cast<const bf16*>(ws) + wn_off;
+    out.wt = reinterpret_cast<const bf16*>(ws) + wt_off;
+    out.ldn = ldn; out.ldt = ldt;
+    if (tb) {
+      PackLeaf& p = tb->leaf[tb->n++];
+      p.w_off = lf.w; p.rows = lf.rows; p.cols = lf.cols; p.ldn = ldn; p.ldt = ldt;
+      p.wn_off = wn_off; p.wt_off = wt_off; p.tile0 = tiles;
+      tiles += ((ldt + 31) / 32) * ((ldn + 31) / 32);
+    }
+  };
+  auto net = [&](const Net& n, LeafImg* out) { for (int i = 0; i <= 2 * n.R; ++i) one(n.lin[i], out[i]); };
+  net(L.enc, im->enc); one(L.post, im->post);
+  net(L.dec, im->dec); one(L.ddist, im->ddist);
+  net(L.part, im->part); one(L.ppost, im->ppost);
+  im->bytes = align_up(off * 2, 1024);
+  if (tb) tb->total_tiles = tiles;
+}
+
+// ---------------------------------------------------------------- first Linear of a net (fp32 SIMT)
+// h[r, c] = sum_k in[r, k] W[k, c] + b[c];  in = x, z, or [x*b, b] built on the fly.
+// Thread = output column c, block = 16 rows.
+constexpr int kInRows = 16;
+__global__ void __launch_bounds__(256) in_layer_fwd_kernel(const float* __restrict__ in, const float* __restrict__ msk,
+                                                           int D_in, int K0, const float* __restrict__ W,
+                                                           const float* __restrict__ bias, int64_t B,
+                                                           float* __restrict__ out_h, bf16* __restrict__ out_a) {
+  extern __shared__ float in_s[];  // [kInRows][K0]
+  const int c = threadIdx.x;
+  for (int64_t r0 = (int64_t)blockIdx.x * kInRows; r0 < B; r0 += (int64_t)gridDim.x * kInRows) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kInRows * K0; i += blockDim.x) {
+      const int rr = i / K0, k = i - rr * K0;
+      const int64_t r = r0 + rr;
+      float v = 0.f;
+      if (r < B) {
+        if (msk) v = (k < D_in) ? in[r * D_in + k] * msk[r * D_in + k] : msk[r * D_in + (k - D_in)];
+        else v = in[r * D_in + k];
+      }
+      in_s[i] = v;
+    }
+    __syncthreads();
+    float acc[kInRows];
+    const float bv = bias[c];
+#pragma unroll
+    for (int rr = 0; rr < kInRows; ++rr) acc[rr] = bv;
+    for (int k = 0; k < K0; ++k) {
+      const float w = W[k * 256 + c];
+#pragma unroll
+      for (int rr = 0; rr < kInRows; ++rr) acc[rr] = fmaf(in_s[rr * K0 + k], w, acc[rr]);
+    }
+#pragma unroll
+    for (int rr = 0; rr < kInRows; ++rr) {
+      const int64_t r = r0 + rr;
+      if (r < B) {
+        if (out_h) out_h[r * 256 + c] = acc[rr];
+        if (out_a) out_a[r * 256 + c] = __float2bfloat16(fmaxf(acc[rr], 0.f));
+      }
+    }
+  }
+}
+
+// dW[k, c] += sum_r in[r, k] g[r, c];  db[c] += sum_r g[r, c]   (g bf16, atomics into the grad arena)
+constexpr int kKC = 32;
+__global__ void __launch_bounds__(256) in_layer_bwd_kernel(const float* __restrict__ in, const float* __restrict__ msk,
+                                                           int D_in, int K0, const bf16* __restrict__ g, int64_t B,
+                                                           float* __restrict__ dW, float* __restrict__ db) {
+  extern __shared__ float in_s[];  // [kInRows][kKC]
+  const int c = threadIdx.x;
+  for (int kc = 0; kc < K0; kc += kKC) {
+    const int kn = min(kKC, K0 - kc);
+    float acc[kKC];
+#pragma unroll
+    for (int k = 0; k < kKC; ++k) acc[k] = 0.f;
+    float accb = 0.f;
+    for (int64_t r0 = (int64_t)blockIdx.x * kInRows; r0 < B; r0 += (int64_t)gridDim.x * kInRows) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < kInRows * kKC; i += blockDim.x) {
+        const int rr = i / kKC, kk = i - rr * kKC;
+        const int k = kc + kk;
+        const int64_t r = r0 + rr;
+        float v = 0.f;
+        if (r < B && kk < kn) {
+          if (msk) v = (k < D_in) ? in[r * D_in + k] * msk[r * D_in + k] : msk[r * D_in + (k - D_in)];
+          else v = in[r * D_in + k];
+        }
+        in_s[i] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int rr = 0; rr < kInRows; ++rr) {
+        const int64_t r = r0 + rr;
+        const float gv = (r < B) ? __bfloat162float(g[r * 256 + c]) : 0.f;
+        accb += gv;
+#pragma unroll
+        for (int k = 0; k < kKC; ++k) acc[k] = fmaf(in_s[rr * kKC + k], gv, acc[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kKC; ++k)
+      if (k < kn) atomicAdd(dW + (kc + k) * 256 + c, acc[k]);
+    if (kc == 0) atomicAdd(db + c, accb);
+  }
+}
+
+// dIn[r, k] = sum_c g[r, c] W[k, c]   (decoder: dz), warp per row
+__global__ void __launch_bounds__(256) in_layer_dinput_kernel(const bf16* __restrict__ g, const float* __restrict__ W,
+                                                              int K0, int64_t B, float* __restrict__ dIn) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < B; r += nwarps) {
+    const uint4 gv = *reinterpret_cast<const uint4*>(g + r * 256 + lane * 8);
+    const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+    float gf[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { gf[2 * j] = __uint_as_float(gw[j] << 16); gf[2 * j + 1] = __uint_as_float(gw[j] & 0xFFFF0000u); }
+    for (int k = 0; k < K0; ++k) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + k * 256 + lane * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + k * 256 + lane * 8 + 4));
+      float s = gf[0] * w0.x + gf[1] * w0.y + gf[2] * w0.z + gf[3] * w0.w + gf[4] * w1.x + gf[5] * w1.y + gf[6] * w1.z +
+                gf[7] * w1.w;
+      s = warp_sum(s);
+      if (lane == 0) dIn[r * K0 + k] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- small bf16 helpers
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n,
+                                                        int relu) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = src[i];
+    if (relu) v = fmaxf(v, 0.f);
+    dst[i] = __float2bfloat16(v);
+  }
+}
+static int cast_bf16(const float* src, bf16* dst, int64_t n, int relu, cudaStream_t s) {
+  if (n == 0) return 0;
+  cast_bf16_kernel<<<grid1d(n, 256), 256, 0, s>>>(src, dst, n, relu);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// out[n] += sum_r g[r, n]  (bf16 g with pitch ld), block (32 x 8)
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ g, int64_t ld, float* __restrict__ out,
+                                                          int64_t B, int N) {
+  __shared__ float sm[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < N)
+    for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < B; r += (int64_t)gridDim.y * 8)
+      acc += __bfloat162float(g[r * ld + c]);
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    atomicAdd(out + c, t);
+  }
+}
+static int colsum_bf16(const bf16* g, int64_t ld, float* out, int64_t B, int N, cudaStream_t s) {
+  if (B == 0) return 0;
+  const int64_t gx = ceil_div(N, 32);
+  int64_t gy = ceil_div(B, 8 * 16);
+  const int64_t cap = ceil_div(148 * 8, gx);
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  colsum_bf16_kernel<<<dim3((unsigned)gx, (unsigned)gy), dim3(32, 8), 0, s>>>(g, ld, out, B, N);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// dst[m, n] += src[m, n] for n < N (copies a padded-pitch fp32 accumulation into the grad arena)
+__global__ void __launch_bounds__(256) add_pitched_kernel(const float* __restrict__ src, int64_t ld_src,
+                                                          float* __restrict__ dst, int64_t ld_dst, int M, int N) {
+  const int64_t n = (int64_t)M * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / N;
+    const int c = (int)(i - m * N);
+    dst[m * ld_dst + c] += src[m * ld_src + c];
+  }
+}
+
+// LayerNorm (hk.LayerNorm(-1, False, False)) on an fp32 GEMM output, warp per row:
+//   xhat -> bf16 (kept for the backward), relu(xhat) or relu(h += xhat) -> bf16 operand
+__global__ void __launch_bounds__(256) ln_fwd_bf16_kernel(const float* __restrict__ y, float* __restrict__ rstd,
+                                                          bf16* __restrict__ xhat_out, float* __restrict__ h_inout,
+                                                          int h_assign, bf16* __restrict__ a_out, int64_t B) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < B; r += nwarps) {
+    float v[8];
+    const float4 a0 = *reinterpret_cast<const float4*>(y + r * 256 + lane * 8);
+    const float4 a1 = *reinterpret_cast<const float4*>(y + r * 256 + lane * 8 + 4);
+    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+    const float mean = warp_sum(s) * (1.0f / 256.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[j] -= mean; q = fmaf(v[j], v[j], q); }
+    const float rs = rsqrtf(warp_sum(q) * (1.0f / 256.0f) + 1e-5f);
+    if (lane == 0) rstd[r] = rs;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[j] *= rs; o[j] = v[j]; }
+    if (xhat_out) {
+      uint4 pk;
+      __nv_bfloat162 t;
+      t = __floats2bfloat162_rn(v[0], v[1]); pk.x = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(v[2], v[3]); pk.y = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(v[4], v[5]); pk.z = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(v[6], v[7]); pk.w = *reinterpret_cast<uint32_t*>(&t);
+      *reinterpret_cast<uint4*>(xhat_out + r * 256 + lane * 8) = pk;
+    }
+    if (h_inout) {
+      float* hp = h_inout + r * 256 + lane * 8;
+      if (!h_assign) {
+        const float4 h0 = *reinterpret_cast<const float4*>(hp);
+        const float4 h1 = *reinterpret_cast<const float4*>(hp + 4);
+        o[0] += h0.x; o[1] += h0.y; o[2] += h0.z; o[3] += h0.w; o[4] += h1.x; o[5] += h1.y; o[6] += h1.z; o[7] += h1.w;
+      }
+      *reinterpret_cast<float4*>(hp) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(hp + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    if (a_out) {
+      uint4 pk;
+      __nv_bfloat162 t;
+      t = __floats2bfloat162_rn(fmaxf(o[0], 0.f), fmaxf(o[1], 0.f)); pk.x = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(fmaxf(o[2], 0.f), fmaxf(o[3], 0.f)); pk.y = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(fmaxf(o[4], 0.f), fmaxf(o[5], 0.f)); pk.z = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(fmaxf(o[6], 0.f), fmaxf(o[7], 0.f)); pk.w = *reinterpret_cast<uint32_t*>(&t);
+      *reinterpret_cast<uint4*>(a_out + r * 256 + lane * 8) = pk;
+    }
+  }
+}
+
+// dx = rstd * (dy - mean(dy) - xhat * mean(dy * xhat)), bf16 in / bf16 out (dx may alias dy)
+__global__ void __launch_bounds__(256) ln_bwd_bf16_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ xhat,
+                                                          const float* __restrict__ rstd, bf16* __restrict__ dx,
+                                                          int64_t B) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < B; r += nwarps) {
+    const uint4 gq = *reinterpret_cast<const uint4*>(dy + r * 256 + lane * 8);
+    const uint4 xq = *reinterpret_cast<const uint4*>(xhat + r * 256 + lane * 8);
+    const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w}, xw[4] = {xq.x, xq.y, xq.z, xq.w};
+    float g[8], x[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      g[2 * j] = __uint_as_float(gw[j] << 16); g[2 * j + 1] = __uint_as_float(gw[j] & 0xFFFF0000u);
+      x[2 * j] = __uint_as_float(xw[j] << 16); x[2 * j + 1] = __uint_as_float(xw[j] & 0xFFFF0000u);
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1 += g[j]; s2 = fmaf(g[j], x[j], s2); }
+    s1 = warp_sum(s1) * (1.0f / 256.0f);
+    s2 = warp_sum(s2) * (1.0f / 256.0f);
+    const float rs = rstd[r];
+    uint4 pk;
+    __nv_bfloat162 t;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = rs * (g[j] - s1 - x[j] * s2);
+    t = __floats2bfloat162_rn(o[0], o[1]); pk.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(o[2], o[3]); pk.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(o[4], o[5]); pk.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(o[6], o[7]); pk.w = *reinterpret_cast<uint32_t*>(&t);
+    *reinterpret_cast<uint4*>(dx + r * 256 + lane * 8) = pk;
+  }
+}
+
+// ---------------------------------------------------------------- workspace plans
+struct Bump {
+  char* base; uint64_t off;
+  Bump(void* b, uint64_t start) : base(reinterpret_cast<char*>(b)), off(start) {}
+  template <typename T> T* take(uint64_t count) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += align_up(count * sizeof(T), 1024);
+    return p;
+  }
+};
+
+struct NetSavedB {
+  bf16* A[kMaxBlocks + 1];
+  bf16* T[kMaxBlocks];
+  // LN nets: normalised pre-activations and 1/sigma
+  bf16* X0; bf16* XU[kMaxBlocks]; bf16* XV[kMaxBlocks];
+  float* rstd0; float* rstdU[kMaxBlocks]; float* rstdV[kMaxBlocks];
+};
+
+static void plan_net_b(Bump& bp, const Net& n, int64_t B, NetSavedB& s) {
+  const uint64_t e = (uint64_t)B * 256;
+  for (int r = 0; r <= n.R; ++r) s.A[r] = bp.take<bf16>(e);
+  for (int r = 0; r < n.R; ++r) s.T[r] = bp.take<bf16>(e);
+  if (n.ln) {
+    s.X0 = bp.take<bf16>(e);
+    s.rstd0 = bp.take<float>(B);
+    for (int r = 0; r < n.R; ++r) {
+      s.XU[r] = bp.take<bf16>(e); s.XV[r] = bp.take<bf16>(e);
+      s.rstdU[r] = bp.take<float>(B); s.rstdV[r] = bp.take<float>(B);
+    }
+  }
+}
+
+struct TrainPlanB {
+  Images img;
+  NetSavedB enc, dec, part;
+  float *h, *ytmp, *par_e, *par_p, *z, *loc, *dpar_e, *dpar_p, *dz, *wtmp;
+  bf16 *dH, *dU, *dG, *dpar_e_b, *dpar_p_b, *dloc_b;
+  int Dp;
+  uint64_t bytes;
+};
+
+static TrainPlanB plan_train_b(const pmvae_config* c, const Layout& L, int64_t B, void* ws) {
+  TrainPlanB p{};
+  plan_images(L, ws, &p.img, nullptr);
+  Bump bp(ws, p.img.bytes);
+  p.Dp = pad8(c->D);
+  plan_net_b(bp, L.enc, B, p.enc);
+  plan_net_b(bp, L.dec, B, p.dec);
+  plan_net_b(bp, L.part, B, p.part);
+  const bool any_ln = L.enc.ln || L.dec.ln || L.part.ln;
+  p.h = bp.take<float>((uint64_t)B * 256);
+  p.ytmp = any_ln ? bp.take<float>((uint64_t)B * 256) : nullptr;
+  p.par_e = bp.take<float>((uint64_t)B * L.P);
+  p.par_p = bp.take<float>((uint64_t)B * L.P);
+  p.z = bp.take<float>((uint64_t)B * c->d);
+  p.loc = bp.take<float>((uint64_t)B * p.Dp);
+  p.dpar_e = bp.take<float>((uint64_t)B * L.P);
+  p.dpar_p = bp.take<float>((uint64_t)B * L.P);
+  p.dz = bp.take<float>((uint64_t)B * c->d);
+  p.wtmp = bp.take<float>((uint64_t)256 * p.Dp);         // padded-pitch dW of the decoder head
+  p.dH = bp.take<bf16>((uint64_t)B * 256);
+  p.dU = bp.take<bf16>((uint64_t)B * 256);
+  p.dG = any_ln ? bp.take<bf16>((uint64_t)B * 256) : nullptr;
+  p.dpar_e_b = bp.take<bf16>((uint64_t)B * L.P);
+  p.dpar_p_b = bp.take<bf16>((uint64_t)B * L.P);
+  p.dloc_b = bp.take<bf16>((uint64_t)B * p.Dp);
+  p.bytes = bp.off;
+  return p;
+}
+
+constexpr int64_t kEvalChunkRowsB = 1 << 17;  // decoder rows (K * data rows) per evaluator chunk
+
+struct EvalPlanB {
+  Images img;
+  NetSavedB enc, part, dec;
+  float *h, *ytmp, *par_e, *par_p, *z, *base, *loc, *llA, *llC;
+  int Dp;
+  int64_t rows_per_chunk;
+  uint64_t bytes;
+};
+
+static EvalPlanB plan_eval_b(const pmvae_config* c, const Layout& L, int64_t B, int64_t K, void* ws) {
+  EvalPlanB p{};
+  plan_images(L, ws, &p.img, nullptr);
+  Bump bp(ws, p.img.bytes);
+  p.Dp = pad8(c->D);
+  int64_t rpc = kEvalChunkRowsB / (K > 0 ? K : 1);
+  if (rpc < 1) rpc = 1;
+  if (rpc > B) rpc = B > 0 ? B : 1;
+  p.rows_per_chunk = rpc;
+  const int64_t M = rpc * K;
+  const int64_t Mmax = M > B ? M : B;
+  plan_net_b(bp, L.enc, B, p.enc);
+  plan_net_b(bp, L.part, B, p.part);
+  plan_net_b(bp, L.dec, M, p.dec);
+  const bool any_ln = L.enc.ln || L.dec.ln || L.part.ln;
+  p.h = bp.take<float>((uint64_t)Mmax * 256);
+  p.ytmp = any_ln ? bp.take<float>((uint64_t)Mmax * 256) : nullptr;
+  p.par_e = bp.take<float>((uint64_t)B * L.P);
+  p.par_p = bp.take<float>((uint64_t)B * L.P);
+  p.z = bp.take<float>((uint64_t)M * c->d);
+  p.base = bp.take<float>((uint64_t)M);
+  p.loc = bp.take<float>((uint64_t)M * p.Dp);
+  p.llA = bp.take<float>((uint64_t)M);
+  p.llC = bp.take<float>((uint64_t)M);
+  p.bytes = bp.off;
+  return p;
+}
+
+uint64_t workspace_bytes_bf16(const pmvae_config* c, int64_t B, int64_t K) {
+  Layout L;
+  if (build_layout(c, &L) != 0) return 0;
+  if (c->H != 256) { set_error("the tensor path is specialised for hidden_units = 256"); return 0; }
+  if (B < 1) B = 1;
+  const uint64_t t = plan_train_b(c, L, B, nullptr).bytes;
+  const uint64_t e = K > 0 ? plan_eval_b(c, L, B, K, nullptr).bytes : 0;
+  return (t > e ? t : e) + 1024;
+}
+
+int prepare_params_bf16(const pmvae_config* c, const float* params, void* ws, uint64_t ws_bytes, cudaStream_t s) {
+  Layout L;
+  PMVAE_TRY(build_layout(c, &L));
+  PMVAE_CHECK(c->H == 256, "the tensor path is specialised for hidden_units = 256");
+  Images im;
+  PackTable tb;
+  plan_images(L, ws, &im, &tb);
+  PMVAE_CHECK(im.bytes <= ws_bytes, "workspace too small for the weight images");
+  PMVAE_CHECK((reinterpret_cast<uintptr_t>(ws) & 1023u) == 0, "workspace must be 1024-byte aligned");
+  pack_weights_kernel<<<tb.total_tiles, 256, 0, s>>>(params, reinterpret_cast<bf16*>(ws), tb);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- network passes
+static int in_layer_fwd(const float* params, const Leaf& lf, const float* in, const float* msk, int D_in, int64_t B,
+                        float* out_h, bf16* out_a, cudaStream_t s) {
+  const int K0 = lf.rows;
+  PMVAE_CHECK(K0 <= 512, "first-layer fan-in too large for the SIMT kernel");
+  int64_t g = ceil_div(B, kInRows);
+  if (g > 148 * 8) g = 148 * 8;
+  in_layer_fwd_kernel<<<(int)g, 256, kInRows * K0 * sizeof(float), s>>>(in, msk, D_in, K0, params + lf.w,
+                                                                        params + lf.b, B, out_h, out_a);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+static int net_fwd_b(const float* params, const Net& n, const LeafImg* img, const Leaf& head, const LeafImg& himg,
+                     int head_cols_pad, const float* in, const float* msk, int D_in, int64_t B, const NetSavedB& sv,
+                     float* h, float* ytmp, float* head_out, int64_t ld_head, cudaStream_t s) {
+  using tc::TcGemmArgs;
+  if (!n.ln) {
+    PMVAE_TRY(in_layer_fwd(params, n.lin[0], in, msk, D_in, B, h, sv.A[0], s));
+  } else {
+    PMVAE_TRY(in_layer_fwd(params, n.lin[0], in, msk, D_in, B, ytmp, nullptr, s));
+    ln_fwd_bf16_kernel<<<grid1d(B * 32, 256), 256, 0, s>>>(ytmp, sv.rstd0, sv.X0, h, 1, sv.A[0], B);
+    PMVAE_LAUNCH_CHECK();
+  }
+  for (int r = 0; r < n.R; ++r) {
+    const Leaf& l1 = n.lin[2 * r + 1];
+    const Leaf& l2 = n.lin[2 * r + 2];
+    if (!n.ln) {
+      TcGemmArgs e1{};
+      e1.bias = params + l1.b; e1.out_bf16 = sv.T[r]; e1.ld_out_bf16 = 256; e1.relu_out = 1;
+      PMVAE_TRY(tc::gemm_nt(sv.A[r], 256, img[2 * r + 1].wt, img[2 * r + 1].ldt, B, 256, 256, e1, s));
+      TcGemmArgs e2{};
+      e2.bias = params + l2.b; e2.resid_f32 = h; e2.ld_resid_f32 = 256; e2.out_f32 = h; e2.ld_out_f32 = 256;
+      e2.out_bf16 = sv.A[r + 1]; e2.ld_out_bf16 = 256; e2.relu_out = 1;
+      PMVAE_TRY(tc::gemm_nt(sv.T[r], 256, img[2 * r + 2].wt, img[2 * r + 2].ldt, B, 256, 256, e2, s));
+    } else {
+      TcGemmArgs e1{};
+      e1.bias = params + l1.b; e1.out_f32 = ytmp; e1.ld_out_f32 = 256;
+      PMVAE_TRY(tc::gemm_nt(sv.A[r], 256, img[2 * r + 1].wt, img[2 * r + 1].ldt, B, 256, 256, e1, s));
+      ln_fwd_bf16_kernel<<<grid1d(B * 32, 256), 256, 0, s>>>(ytmp, sv.rstdU[r], sv.XU[r], nullptr, 0, sv.T[r], B);
+      PMVAE_LAUNCH_CHECK();
+      TcGemmArgs e2{};
+      e2.bias = params + l2.b; e2.out_f32 = ytmp; e2.ld_out_f32 = 256;
+      PMVAE_TRY(tc::gemm_nt(sv.T[r], 256, img[2 * r + 2].wt, img[2 * r + 2].ldt, B, 256, 256, e2, s));
+      ln_fwd_bf16_kernel<<<grid1d(B * 32, 256), 256, 0, s>>>(ytmp, sv.rstdV[r], sv.XV[r], h, 0, sv.A[r + 1], B);
+      PMVAE_LAUNCH_CHECK();
+    }
+  }
+  tc::TcGemmArgs eh{};
+  eh.bias = params + head.b; eh.out_f32 = head_out; eh.ld_out_f32 = ld_head;
+  return tc::gemm_nt(sv.A[n.R], 256, himg.wt, himg.ldt, B, head_cols_pad, 256, eh, s);
+}
+
+// weight + bias gradients of one hidden/head Linear: gW += act^T @ dY (tensor), gb += colsum(dY)
+static int lin_bwd_params_b(float* grads, const Leaf& lf, const bf16* act, const bf16* dY, int64_t ld_dy, int n_cols,
+                            int64_t B, float* wtmp, cudaStream_t s) {
+  if (n_cols == lf.cols) {
+    PMVAE_TRY(tc::gemm_tn(act, 256, dY, ld_dy, lf.rows, lf.cols, B, grads + lf.w, lf.cols, 1, 0, nullptr, s));
+  } else {
+    // padded pitch (decoder head): accumulate into a [rows, n_cols] scratch, then add the valid columns
+    PMVAE_CUDA(cudaMemsetAsync(wtmp, 0, (size_t)lf.rows * n_cols * sizeof(float), s));
+    PMVAE_TRY(tc::gemm_tn(act, 256, dY, ld_dy, lf.rows, n_cols, B, wtmp, n_cols, 1, 0, nullptr, s));
+    add_pitched_kernel<<<grid1d((int64_t)lf.rows * lf.cols, 256), 256, 0, s>>>(wtmp, n_cols, grads + lf.w, lf.cols,
+                                                                              lf.rows, lf.cols);
+    PMVAE_LAUNCH_CHECK();
+  }
+  return colsum_bf16(dY, ld_dy, grads + lf.b, B, lf.cols, s);
+}
+
+static int net_bwd_b(const float* params, float* grads, const Net& n, const LeafImg* img, const Leaf& head,
+                     const LeafImg& himg, const bf16* dHead, int64_t ld_dhead, int head_cols_pad, const float* in,
+                     const float* msk, int D_in, int64_t B, const NetSavedB& sv, bf16* dH, bf16* dU, bf16* dG,
+                     float* wtmp, float* dIn, cudaStream_t s) {
+  using tc::TcGemmArgs;
+  // head
+  PMVAE_TRY(lin_bwd_params_b(grads, head, sv.A[n.R], dHead, ld_dhead, head_cols_pad, B, wtmp, s));
+  {
+    TcGemmArgs e{};
+    e.mask_bf16 = sv.A[n.R]; e.ld_mask = 256; e.out_bf16 = dH; e.ld_out_bf16 = 256;
+    PMVAE_TRY(tc::gemm_nt(dHead, ld_dhead, himg.wn, himg.ldn, B, 256, head_cols_pad, e, s));
+  }
+  for (int r = n.R - 1; r >= 0; --r) {
+    const Leaf& l1 = n.lin[2 * r + 1];
+    const Leaf& l2 = n.lin[2 * r + 2];
+    const bf16* dV = dH;
+    if (n.ln) {
+      ln_bwd_bf16_kernel<<<grid1d(B * 32, 256), 256, 0, s>>>(dH, sv.XV[r], sv.rstdV[r], dG, B);
+      PMVAE_LAUNCH_CHECK();
+      dV = dG;
+    }
+    PMVAE_TRY(lin_bwd_params_b(grads, l2, sv.T[r], dV, 256, 256, B, wtmp, s));
+    {
+      TcGemmArgs e{};
+      e.mask_bf16 = sv.T[r]; e.ld_mask = 256; e.out_bf16 = dU; e.ld_out_bf16 = 256;
+      PMVAE_TRY(tc::gemm_nt(dV, 256, img[2 * r + 2].wn, img[2 * r + 2].ldn, B, 256, 256, e, s));
+    }
+    if (n.ln) {
+      ln_bwd_bf16_kernel<<<grid1d(B * 32, 256), 256, 0, s>>>(dU, sv.XU[r], sv.rstdU[r], dU, B);
+      PMVAE_LAUNCH_CHECK();
+    }
+    PMVAE_TRY(lin_bwd_params_b(grads, l1, sv.A[r], dU, 256, 256, B, wtmp, s));
+    {
+      TcGemmArgs e{};
+      e.mask_bf16 = sv.A[r]; e.ld_mask = 256; e.resid_bf16 = dH; e.ld_resid_bf16 = 256; e.out_bf16 = dH; e.ld_out_bf16 = 256;
+      PMVAE_TRY(tc::gemm_nt(dU, 256, img[2 * r + 1].wn, img[2 * r + 1].ldn, B, 256, 256, e, s));
+    }
+  }
+  // first Linear: dH now holds d(loss)/d(h_0) (the relu masks were applied by the epilogues above)
+  if (n.ln) {
+    ln_bwd_bf16_kernel<<<grid1d(B * 32, 256), 256, 0, s>>>(dH, sv.X0, sv.rstd0, dH, B);
+    PMVAE_LAUNCH_CHECK();
+  }
+  const Leaf& l0 = n.lin[0];
+  {
+    int64_t g = ceil_div(B, kInRows);
+    if (g > 148 * 2) g = 148 * 2;
+    in_layer_bwd_kernel<<<(int)g, 256, kInRows * kKC * sizeof(float), s>>>(in, msk, D_in, l0.rows, dH, B,
+                                                                           grads + l0.w, grads + l0.b);
+    PMVAE_LAUNCH_CHECK();
+  }
+  if (dIn) {
+    in_layer_dinput_kernel<<<grid1d(B * 32, 256), 256, 0, s>>>(dH, params + l0.w, l0.rows, B, dIn);
+    PMVAE_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------- public sequences
+#define CHECK_WS(plan)                                                                              \
+  PMVAE_CHECK((plan).bytes <= ws_bytes, "workspace too small (see pmvae_workspace_bytes)");          \
+  PMVAE_CHECK((reinterpret_cast<uintptr_t>(ws) & 1023u) == 0, "workspace must be 1024-byte aligned")
+
+int forward_bf16(const pmvae_config* c, const Layout& L, const float* params, const float* x, const float* b,
+                 const float* eps, int64_t B, float* out_rec, float* out_kl, float* out_match, void* ws,
+                 uint64_t ws_bytes, cudaStream_t s) {
+  PMVAE_CHECK(c->H == 256, "the tensor path is specialised for hidden_units = 256");
+  TrainPlanB p = plan_train_b(c, L, B, ws);
+  CHECK_WS(p);
+  PMVAE_TRY(net_fwd_b(params, L.enc, p.img.enc, L.post, p.img.post, L.P, x, nullptr, c->D, B, p.enc, p.h, p.ytmp,
+                      p.par_e, L.P, s));
+  PMVAE_TRY(latent_fwd(p.par_e, eps, p.z, out_kl, B, c->d, s));
+  PMVAE_TRY(net_fwd_b(params, L.dec, p.img.dec, L.ddist, p.img.ddist, p.Dp, p.z, nullptr, c->d, B, p.dec, p.h, p.ytmp,
+                      p.loc, p.Dp, s));
+  PMVAE_TRY(rec_ll(x, p.loc, p.Dp, params + L.log_scale, nullptr, out_rec, B, c->D, s));
+  PMVAE_TRY(net_fwd_b(params, L.part, p.img.part, L.ppost, p.img.ppost, L.P, x, b, c->D, B, p.part, p.h, p.ytmp,
+                      p.par_p, L.P, s));
+  PMVAE_TRY(match_fwd(p.par_p, p.z, out_match, B, c->d, s));
+  return 0;
+}
+
+int backward_bf16(const pmvae_config* c, const Layout& L, const float* params, const float* x, const float* b,
+                  const float* eps, int64_t B, const float* g_rec, const float* g_kl, const float* g_match,
+                  float* grads, void* ws, uint64_t ws_bytes, cudaStream_t s) {
+  TrainPlanB p = plan_train_b(c, L, B, ws);
+  CHECK_WS(p);
+  PMVAE_TRY(rec_ll_bwd(x, p.loc, p.Dp, params + L.log_scale, g_rec, nullptr, p.dloc_b, p.Dp, grads + L.log_scale, B,
+                       c->D, s));
+  PMVAE_TRY(net_bwd_b(params, grads, L.dec, p.img.dec, L.ddist, p.img.ddist, p.dloc_b, p.Dp, p.Dp, p.z, nullptr, c->d,
+                      B, p.dec, p.dH, p.dU, p.dG, p.wtmp, p.dz, s));
+  PMVAE_TRY(latent_bwd(p.par_e, p.par_p, eps, p.z, p.dz, g_kl, g_match, c->stop_grad, p.dpar_e, p.dpar_p, B, c->d, s));
+  PMVAE_TRY(cast_bf16(p.dpar_e, p.dpar_e_b, B * L.P, 0, s));
+  PMVAE_TRY(cast_bf16(p.dpar_p, p.dpar_p_b, B * L.P, 0, s));
+  PMVAE_TRY(net_bwd_b(params, grads, L.enc, p.img.enc, L.post, p.img.post, p.dpar_e_b, L.P, L.P, x, nullptr, c->D, B,
+                      p.enc, p.dH, p.dU, p.dG, p.wtmp, nullptr, s));
+  PMVAE_TRY(net_bwd_b(params, grads, L.part, p.img.part, L.ppost, p.img.ppost, p.dpar_p_b, L.P, L.P, x, b, c->D, B,
+                      p.part, p.dH, p.dU, p.dG, p.wtmp, nullptr, s));
+  return 0;
+}
+
+int is_log_prob_bf16(const pmvae_config* c, const Layout& L, const float* params, const float* x, const float* b,
+                     int64_t B, int64_t K, const uint32_t key_z[2], const uint32_t key_zxo[2], int64_t B_total,
+                     int64_t row_start, float* out_log_p_x, float* out_cond, void* ws, uint64_t ws_bytes,
+                     cudaStream_t s) {
+  PMVAE_CHECK(c->H == 256, "the tensor path is specialised for hidden_units = 256");
+  EvalPlanB p = plan_eval_b(c, L, B, K, ws);
+  CHECK_WS(p);
+  PMVAE_TRY(net_fwd_b(params, L.enc, p.img.enc, L.post, p.img.post, L.P, x, nullptr, c->D, B, p.enc, p.h, p.ytmp,
+                      p.par_e, L.P, s));
+  PMVAE_TRY(net_fwd_b(params, L.part, p.img.part, L.ppost, p.img.ppost, L.P, x, b, c->D, B, p.part, p.h, p.ytmp,
+                      p.par_p, L.P, s));
+  const float* ls = params + L.log_scale;
+  for (int64_t r0 = 0; r0 < B; r0 += p.rows_per_chunk) {
+    const int64_t nb = (B - r0 < p.rows_per_chunk) ? (B - r0) : p.rows_per_chunk;
+    const int64_t M = nb * K;
+    PMVAE_TRY(sample_latents(p.par_e + r0 * L.P, Key2{key_z[0], key_z[1]}, nb, K, B_total, row_start + r0, c->d, p.z, p.base, s));
+    PMVAE_TRY(net_fwd_b(params, L.dec, p.img.dec, L.ddist, p.img.ddist, p.Dp, p.z, nullptr, c->d, M, p.dec, p.h, p.ytmp,
+                        p.loc, p.Dp, s));
+    PMVAE_TRY(eval_rows_ll(x + r0 * c->D, nullptr, p.loc, p.Dp, ls, p.base, p.llA, nb, K, c->D, s));
+    if (out_log_p_x) PMVAE_TRY(logmeanexp_rows(p.llA, nullptr, out_log_p_x + r0, nb, K, s));
+    if (out_cond) {
+      PMVAE_TRY(sample_latents(p.par_p + r0 * L.P, Key2{key_zxo[0], key_zxo[1]}, nb, K, B_total, row_start + r0, c->d, p.z, p.base, s));
+      PMVAE_TRY(net_fwd_b(params, L.dec, p.img.dec, L.ddist, p.img.ddist, p.Dp, p.z, nullptr, c->d, M, p.dec, p.h,
+                          p.ytmp, p.loc, p.Dp, s));
+      PMVAE_TRY(eval_rows_ll(x + r0 * c->D, b + r0 * c->D, p.loc, p.Dp, ls, p.base, p.llC, nb, K, c->D, s));
+      PMVAE_TRY(logmeanexp_rows(p.llA, p.llC, out_cond + r0, nb, K, s));
+    }
+  }
+  return 0;
+}
+
+int impute_mean_bf16(const pmvae_config* c, const Layout& L, const float* params, const float* x, const float* b,
+                     int64_t B, int64_t K, const uint32_t key[2], int64_t B_total, int64_t row_start, float* out,
+                     void* ws, uint64_t ws_bytes, cudaStream_t s) {
+  PMVAE_CHECK(c->H == 256, "the tensor path is specialised for hidden_units = 256");
+  EvalPlanB p = plan_eval_b(c, L, B, K, ws);
+  CHECK_WS(p);
+  PMVAE_TRY(net_fwd_b(params, L.part, p.img.part, L.ppost, p.img.ppost, L.P, x, b, c->D, B, p.part, p.h, p.ytmp,
+                      p.par_p, L.P, s));
+  for (int64_t r0 = 0; r0 < B; r0 += p.rows_per_chunk) {
+    const int64_t nb = (B - r0 < p.rows_per_chunk) ? (B - r0) : p.rows_per_chunk;
+    PMVAE_TRY(sample_latents(p.par_p + r0 * L.P, Key2{key[0], key[1]}, nb, K, B_total, row_start + r0, c->d, p.z, p.base, s));
+    PMVAE_TRY(net_fwd_b(params, L.dec, p.img.dec, L.ddist, p.img.ddist, p.Dp, p.z, nullptr, c->d, nb * K, p.dec, p.h,
+                        p.ytmp, p.loc, p.Dp, s));
+    PMVAE_TRY(impute_mean(x + r0 * c->D, b + r0 * c->D, p.loc, p.Dp, out + r0 * c->D, nb, K, c->D, s));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------- single Linear (tests / roofline leg)
+// ws: [x bf16 B*Kp][W^T bf16 Np*Kp]
+int linear_bf16(const float* x, const float* w, const float* bias, int64_t B, int K, int N, int relu_in, float* y,
+                void* ws, uint64_t ws_bytes, cudaStream_t s) {
+  PMVAE_CHECK(ws != nullptr, "pmvae_linear(bf16) needs scratch");
+  PMVAE_CHECK(K % 8 == 0 && N % 8 == 0, "pmvae_linear(bf16) needs K % 8 == 0 and N % 8 == 0");
+  PMVAE_CHECK((reinterpret_cast<uintptr_t>(ws) & 1023u) == 0, "workspace must be 1024-byte aligned");
+  const uint64_t xb_bytes = align_up((uint64_t)B * K * 2, 1024);
+  const uint64_t wt_bytes = align_up((uint64_t)N * K * 2, 1024);
+  PMVAE_CHECK(xb_bytes + wt_bytes <= ws_bytes, "workspace too small for pmvae_linear(bf16)");
+  bf16* xb = reinterpret_cast<bf16*>(ws);
+  bf16* wt = reinterpret_cast<bf16*>(reinterpret_cast<char*>(ws) + xb_bytes);
+  PMVAE_TRY(cast_bf16(x, xb, B * K, relu_in, s));
+  PackTable tb{};
+  tb.n = 1;
+  PackLeaf& pl = tb.leaf[0];
+  pl.w_off = 0; pl.rows = K; pl.cols = N; pl.ldn = N; pl.ldt = K; pl.tile0 = 0;
+  pl.wn_off = ~0ull; pl.wt_off = 0;
+  // only the transposed image is needed: reuse the pack kernel with the Wn writes landing in y? no -- use a
+  // dedicated launch where Wn aliases a throw-away region after W^T.
+  PMVAE_CHECK(xb_bytes + 2 * wt_bytes <= ws_bytes, "workspace too small for pmvae_linear(bf16)");
+  pl.wn_off = (uint64_t)(wt_bytes / 2);
+  tb.total_tiles = ((K + 31) / 32) * ((N + 31) / 32);
+  pack_weights_kernel<<<tb.total_tiles, 256, 0, s>>>(w, wt, tb);
+  PMVAE_LAUNCH_CHECK();
+  tc::TcGemmArgs e{};
+  e.bias = bias; e.out_f32 = y; e.ld_out_f32 = N;
+  return tc::gemm_nt(xb, K, wt, K, B, N, K, e, s);
+}
+
 }  // namespace pmvae
