@@ -1,5 +1,9 @@
-// Per-row TriL-Gaussian algebra of the PM-VAE latent: one warp per row, the raw head
-// output (P = d + d(d+1)/2 floats) staged in shared memory, all fp32.
+// Per-row TriL-Gaussian algebra of the PM-VAE latent, all fp32.
+//
+// A row is handled by a group of G lanes (G = 16 for d <= 16, so a warp works on two rows;
+// G = 32 otherwise, with two elements per lane for d in (32, 64]).  The raw head output
+// (P = d + d(d+1)/2 floats) is staged in shared memory with coalesced loads; diagonals
+// (softplus + 1e-5), their reciprocals and logs are computed once per row.
 //
 // Reference sites:
 //   distributions.py:101-113  TriLGaussian: loc = p[:d], L = FillScaleTriL(p[d:])
@@ -12,10 +16,10 @@
 
 namespace pmvae {
 
-constexpr int kWarpsPerBlock = 4;
+constexpr int kThreadsL = 128;
 
-// index into the raw head vector of L[i][j] (j <= i): tfp fill_triangular (lower) after
-// the d loc entries: c = concat(v[d:], reverse(v)), L[i][j] = c[i*d + j].
+// index into the raw head vector of L[i][j] (j <= i): tfp fill_triangular (lower) after the d
+// loc entries: c = concat(v[d:], reverse(v)), L[i][j] = c[i*d + j].
 __device__ __forceinline__ int tril_src(int i, int j, int d, int m) {
   const int k = i * d + j;
   return d + ((k < m - d) ? (d + k) : (m - 1 - (k - (m - d))));
@@ -30,154 +34,207 @@ __device__ __forceinline__ void tril_ij(int s, int d, int m, int& i, int& j) {
   const int k = (m - d) + (m - 1 - s);
   i = k / d; j = k - i * d;
 }
-__device__ __forceinline__ float tril_diag(const float* sp, int i, int d, int m) {
-  return softplus_f(sp[tril_src(i, i, d, m)]) + 1e-5f;
+
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
 
-__device__ __forceinline__ void stage_row(float* sp, const float* __restrict__ src, int P, int lane) {
-  for (int q = lane; q < P; q += 32) sp[q] = src[q];
-  __syncwarp();
+// Work distribution shared by the kernels: every group of a warp runs the same number of
+// iterations (shuffles use the full mask); rows past the end are clamped and not stored.
+template <int G>
+struct RowIter {
+  int gl, grp;
+  int64_t rows_per_iter, first, iters;
+  __device__ RowIter(int64_t B) {
+    gl = threadIdx.x % G;
+    grp = threadIdx.x / G;
+    const int gpb = blockDim.x / G;
+    rows_per_iter = (int64_t)gridDim.x * gpb;
+    first = (int64_t)blockIdx.x * gpb + grp;
+    iters = (B + rows_per_iter - 1) / rows_per_iter;
+  }
+};
+
+// diagonal terms of one row: sd = softplus(raw)+1e-5, si = 1/sd; returns this lane's sum of log(sd)
+template <int G, int E>
+__device__ __forceinline__ float stage_diag(const float* sp, float* sd, float* si, int d, int m, int gl) {
+  float logd = 0.f;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = gl + G * e;
+    if (i < d) {
+      const float dg = softplus_f(sp[tril_src(i, i, d, m)]) + 1e-5f;
+      sd[i] = dg;
+      si[i] = 1.0f / dg;
+      logd += logf(dg);
+    }
+  }
+  return logd;
 }
 
 // ---------------------------------------------------------------- z, KL
-__global__ void __launch_bounds__(32 * kWarpsPerBlock) latent_fwd_kernel(const float* __restrict__ par,
-                                                                         const float* __restrict__ eps,
-                                                                         float* __restrict__ z, float* __restrict__ kl,
-                                                                         int64_t B, int d) {
+template <int G, int E, int DCT>
+__global__ void __launch_bounds__(kThreadsL) latent_fwd_kernel(const float* __restrict__ par,
+                                                               const float* __restrict__ eps, float* __restrict__ z,
+                                                               float* __restrict__ kl, int64_t B, int d_rt) {
   extern __shared__ float smem[];
-  const int P = d + d * (d + 1) / 2, m = d * (d + 1) / 2;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float* sp = smem + (size_t)w * (P + d);
+  const int d = DCT ? DCT : d_rt;
+  const int m = d * (d + 1) / 2, P = d + m;
+  RowIter<G> it(B);
+  float* sp = smem + (size_t)it.grp * (P + 3 * d);
   float* se = sp + P;
-  for (int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + w; r < B; r += (int64_t)gridDim.x * kWarpsPerBlock) {
+  float* sd = se + d;
+  float* si = sd + d;
+  const int gl = it.gl;
+  for (int64_t t = 0; t < it.iters; ++t) {
+    const int64_t r_raw = it.first + t * it.rows_per_iter;
+    const bool valid = r_raw < B;
+    const int64_t r = valid ? r_raw : B - 1;
     __syncwarp();
-    stage_row(sp, par + r * P, P, lane);
-    for (int q = lane; q < d; q += 32) se[q] = eps[r * d + q];
+    for (int q = gl; q < P; q += G) sp[q] = par[r * P + q];
+    for (int q = gl; q < d; q += G) se[q] = eps[r * d + q];
     __syncwarp();
-    float fro = 0.f, logd = 0.f, mu2 = 0.f;
-    for (int i = lane; i < d; i += 32) {
-      const float mu = sp[i];
-      float acc = mu;
-      for (int j = 0; j < i; ++j) {
-        const float l = sp[tril_src(i, j, d, m)];
-        acc = fmaf(l, se[j], acc);
-        fro = fmaf(l, l, fro);
+    float logd = stage_diag<G, E>(sp, sd, si, d, m, gl);
+    __syncwarp();
+    float fro = 0.f, mu2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = gl + G * e;
+      if (i < d) {
+        const float mu = sp[i];
+        float acc = mu;
+        for (int j = 0; j < i; ++j) {
+          const float l = sp[tril_src(i, j, d, m)];
+          acc = fmaf(l, se[j], acc);
+          fro = fmaf(l, l, fro);
+        }
+        const float dg = sd[i];
+        acc = fmaf(dg, se[i], acc);
+        fro = fmaf(dg, dg, fro);
+        mu2 = fmaf(mu, mu, mu2);
+        if (valid) z[r * d + i] = acc;
       }
-      const float dg = tril_diag(sp, i, d, m);
-      acc = fmaf(dg, se[i], acc);
-      fro = fmaf(dg, dg, fro);
-      logd += logf(dg);
-      mu2 = fmaf(mu, mu, mu2);
-      z[r * d + i] = acc;
     }
-    fro = warp_sum(fro); logd = warp_sum(logd); mu2 = warp_sum(mu2);
-    if (lane == 0) kl[r] = -logd + 0.5f * (-(float)d + fro + mu2);
+    fro = group_sum<G>(fro); logd = group_sum<G>(logd); mu2 = group_sum<G>(mu2);
+    if (valid && gl == 0) kl[r] = -logd + 0.5f * (-(float)d + fro + mu2);
   }
-}
-
-int latent_fwd(const float* par, const float* eps, float* z, float* kl, int64_t B, int d, cudaStream_t s) {
-  PMVAE_CHECK(d >= 1 && d <= 64, "latent_dim must be in [1, 64]");
-  if (B == 0) return 0;
-  const int P = d + d * (d + 1) / 2;
-  const size_t smem = (size_t)kWarpsPerBlock * (P + d) * sizeof(float);
-  int64_t g = ceil_div(B, kWarpsPerBlock);
-  if (g > 148 * 16) g = 148 * 16;
-  latent_fwd_kernel<<<(int)g, 32 * kWarpsPerBlock, smem, s>>>(par, eps, z, kl, B, d);
-  PMVAE_LAUNCH_CHECK();
-  return 0;
 }
 
 // ---------------------------------------------------------------- forward substitution (column oriented)
-// lanes hold s[k] for k = lane (s0) and k = lane + 32 (s1); returns r in sr[] (smem),
-// and sum r^2 / sum log L_ii in all lanes.
-__device__ __forceinline__ void solve_lower(const float* sp, float* sr, const float* sz, int d, int m, int lane,
-                                            float& sumsq, float& logd) {
-  float s0 = (lane < d) ? sz[lane] - sp[lane] : 0.f;
-  float s1 = (lane + 32 < d) ? sz[lane + 32] - sp[lane + 32] : 0.f;
-  sumsq = 0.f; logd = 0.f;
+// On entry sz = z (or z - mu is formed here), si = 1/diag.  Lanes hold s[k] for k = gl + G*e.
+// Writes r = L^-1 (z - mu) to sr[] and returns sum r^2 (same value in every lane of the group).
+template <int G, int E>
+__device__ __forceinline__ float solve_lower(const float* sp, const float* sz, const float* si, float* sr, int d, int m,
+                                             int gl) {
+  float s[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int k = gl + G * e;
+    s[e] = (k < d) ? sz[k] - sp[k] : 0.f;
+  }
+  float sumsq = 0.f;
   for (int i = 0; i < d; ++i) {
-    const float lii = tril_diag(sp, i, d, m);
-    const float si = __shfl_sync(0xffffffffu, (i < 32) ? s0 : s1, i & 31);
-    const float ri = si / lii;
+    float src = s[0];
+#pragma unroll
+    for (int e = 1; e < E; ++e) if (i >= G * e) src = s[e];
+    const float ri = __shfl_sync(0xffffffffu, src, i % G, G) * si[i];
     sumsq = fmaf(ri, ri, sumsq);
-    logd += logf(lii);
-    if (lane == 0) sr[i] = ri;
-    if (lane > i && lane < d) s0 = fmaf(-sp[tril_src(lane, i, d, m)], ri, s0);
-    if (lane + 32 > i && lane + 32 < d) s1 = fmaf(-sp[tril_src(lane + 32, i, d, m)], ri, s1);
+    if (gl == 0) sr[i] = ri;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int k = gl + G * e;
+      if (k > i && k < d) s[e] = fmaf(-sp[tril_src(k, i, d, m)], ri, s[e]);
+    }
   }
   __syncwarp();
+  return sumsq;
 }
 
-__global__ void __launch_bounds__(32 * kWarpsPerBlock) match_fwd_kernel(const float* __restrict__ par_p,
-                                                                        const float* __restrict__ z,
-                                                                        float* __restrict__ match, int64_t B, int d) {
+template <int G, int E, int DCT>
+__global__ void __launch_bounds__(kThreadsL) match_fwd_kernel(const float* __restrict__ par_p,
+                                                              const float* __restrict__ z, float* __restrict__ match,
+                                                              int64_t B, int d_rt) {
   extern __shared__ float smem[];
-  const int P = d + d * (d + 1) / 2, m = d * (d + 1) / 2;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float* sp = smem + (size_t)w * (P + 2 * d);
+  const int d = DCT ? DCT : d_rt;
+  const int m = d * (d + 1) / 2, P = d + m;
+  RowIter<G> it(B);
+  float* sp = smem + (size_t)it.grp * (P + 4 * d);
   float* sz = sp + P;
   float* sr = sz + d;
-  for (int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + w; r < B; r += (int64_t)gridDim.x * kWarpsPerBlock) {
+  float* sd = sr + d;
+  float* si = sd + d;
+  const int gl = it.gl;
+  for (int64_t t = 0; t < it.iters; ++t) {
+    const int64_t r_raw = it.first + t * it.rows_per_iter;
+    const bool valid = r_raw < B;
+    const int64_t r = valid ? r_raw : B - 1;
     __syncwarp();
-    stage_row(sp, par_p + r * P, P, lane);
-    for (int q = lane; q < d; q += 32) sz[q] = z[r * d + q];
+    for (int q = gl; q < P; q += G) sp[q] = par_p[r * P + q];
+    for (int q = gl; q < d; q += G) sz[q] = z[r * d + q];
     __syncwarp();
-    float sumsq, logd;
-    solve_lower(sp, sr, sz, d, m, lane, sumsq, logd);
-    if (lane == 0) match[r] = -0.5f * sumsq - logd - 0.5f * (float)d * kLog2Pi;
+    float logd = stage_diag<G, E>(sp, sd, si, d, m, gl);
+    __syncwarp();
+    const float sumsq = solve_lower<G, E>(sp, sz, si, sr, d, m, gl);
+    logd = group_sum<G>(logd);
+    if (valid && gl == 0) match[r] = -0.5f * sumsq - logd - 0.5f * (float)d * kLog2Pi;
   }
-}
-
-int match_fwd(const float* par_p, const float* z, float* match, int64_t B, int d, cudaStream_t s) {
-  PMVAE_CHECK(d >= 1 && d <= 64, "latent_dim must be in [1, 64]");
-  if (B == 0) return 0;
-  const int P = d + d * (d + 1) / 2;
-  const size_t smem = (size_t)kWarpsPerBlock * (P + 2 * d) * sizeof(float);
-  int64_t g = ceil_div(B, kWarpsPerBlock);
-  if (g > 148 * 16) g = 148 * 16;
-  match_fwd_kernel<<<(int)g, 32 * kWarpsPerBlock, smem, s>>>(par_p, z, match, B, d);
-  PMVAE_LAUNCH_CHECK();
-  return 0;
 }
 
 // ---------------------------------------------------------------- backward of both heads
-__global__ void __launch_bounds__(32 * kWarpsPerBlock) latent_bwd_kernel(
+template <int G, int E, int DCT>
+__global__ void __launch_bounds__(kThreadsL) latent_bwd_kernel(
     const float* __restrict__ par_e, const float* __restrict__ par_p, const float* __restrict__ eps,
     const float* __restrict__ z, const float* __restrict__ dz_dec, const float* __restrict__ g_kl,
-    const float* __restrict__ g_match, int stop_grad, float* __restrict__ dpar_e, float* __restrict__ dpar_p, int64_t B,
-    int d) {
+    const float* __restrict__ g_match, int stop_grad, float* __restrict__ dpar_e, float* __restrict__ dpar_p,
+    __nv_bfloat16* __restrict__ dpar_e_b, __nv_bfloat16* __restrict__ dpar_p_b, int64_t B, int d_rt) {
   extern __shared__ float smem[];
-  const int P = d + d * (d + 1) / 2, m = d * (d + 1) / 2;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float* sp = smem + (size_t)w * (P + 4 * d);
+  const int d = DCT ? DCT : d_rt;
+  const int m = d * (d + 1) / 2, P = d + m;
+  RowIter<G> it(B);
+  float* sp = smem + (size_t)it.grp * (P + 6 * d);
   float* sz = sp + P;      // z, later dz_total
   float* sr = sz + d;      // r = L_p^-1 (z - mu_p)
   float* sg = sr + d;      // g = L_p^-T r
   float* se = sg + d;      // eps
-  for (int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + w; r < B; r += (int64_t)gridDim.x * kWarpsPerBlock) {
+  float* sd = se + d;      // diag
+  float* si = sd + d;      // 1 / diag
+  const int gl = it.gl;
+  for (int64_t t = 0; t < it.iters; ++t) {
+    const int64_t r_raw = it.first + t * it.rows_per_iter;
+    const bool valid = r_raw < B;
+    const int64_t r = valid ? r_raw : B - 1;
     __syncwarp();
     // ---- partial posterior: d match / d par_p
-    stage_row(sp, par_p + r * P, P, lane);
-    for (int q = lane; q < d; q += 32) { sz[q] = z[r * d + q]; se[q] = eps[r * d + q]; }
+    for (int q = gl; q < P; q += G) sp[q] = par_p[r * P + q];
+    for (int q = gl; q < d; q += G) { sz[q] = z[r * d + q]; se[q] = eps[r * d + q]; }
     __syncwarp();
-    float sumsq, logd;
-    solve_lower(sp, sr, sz, d, m, lane, sumsq, logd);
-    // backward substitution g = L^-T r: t_j = r_j; for i = d-1..0: g_i = t_i / L_ii; t_j -= L_ij g_i (j < i)
+    stage_diag<G, E>(sp, sd, si, d, m, gl);
+    __syncwarp();
+    solve_lower<G, E>(sp, sz, si, sr, d, m, gl);
+    // backward substitution g = L^-T r: t = r; for i = d-1..0: g_i = t_i / L_ii; t_j -= L_ij g_i (j < i)
     {
-      float t0 = (lane < d) ? sr[lane] : 0.f;
-      float t1 = (lane + 32 < d) ? sr[lane + 32] : 0.f;
+      float tt[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) { const int k = gl + G * e; tt[e] = (k < d) ? sr[k] : 0.f; }
       for (int i = d - 1; i >= 0; --i) {
-        const float lii = tril_diag(sp, i, d, m);
-        const float ti = __shfl_sync(0xffffffffu, (i < 32) ? t0 : t1, i & 31);
-        const float gi = ti / lii;
-        if (lane == 0) sg[i] = gi;
-        if (lane < i) t0 = fmaf(-sp[tril_src(i, lane, d, m)], gi, t0);
-        if (lane + 32 < i) t1 = fmaf(-sp[tril_src(i, lane + 32, d, m)], gi, t1);
+        float src = tt[0];
+#pragma unroll
+        for (int e = 1; e < E; ++e) if (i >= G * e) src = tt[e];
+        const float gi = __shfl_sync(0xffffffffu, src, i % G, G) * si[i];
+        if (gl == 0) sg[i] = gi;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int k = gl + G * e;
+          if (k < i) tt[e] = fmaf(-sp[tril_src(i, k, d, m)], gi, tt[e]);
+        }
       }
       __syncwarp();
     }
     const float mw = g_match[r];
-    for (int q = lane; q < P; q += 32) {
+    for (int q = gl; q < P; q += G) {
       float val;
       if (q < d) {
         val = mw * sg[q];
@@ -185,27 +242,27 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) latent_bwd_kernel(
         int i, j;
         tril_ij(q - d, d, m, i, j);
         val = sg[i] * sr[j];
-        if (i == j) {
-          const float raw = sp[q];
-          val -= 1.0f / (softplus_f(raw) + 1e-5f);
-          val *= sigmoid_f(raw);
-        }
+        if (i == j) { val -= si[i]; val *= sigmoid_f(sp[q]); }
         val *= mw;
       }
-      dpar_p[r * P + q] = val;
+      if (valid) {
+        if (dpar_p) dpar_p[r * P + q] = val;
+        if (dpar_p_b) dpar_p_b[r * P + q] = __float2bfloat16(val);
+      }
     }
     __syncwarp();
     // ---- dz_total = dz_dec - (stop_grad ? 0 : mw * g)
-    for (int q = lane; q < d; q += 32) {
+    for (int q = gl; q < d; q += G) {
       float v = dz_dec ? dz_dec[r * d + q] : 0.f;
       if (!stop_grad) v -= mw * sg[q];
       sz[q] = v;
     }
     __syncwarp();
     // ---- posterior: z = mu + L eps and kw * KL
-    stage_row(sp, par_e + r * P, P, lane);
+    for (int q = gl; q < P; q += G) sp[q] = par_e[r * P + q];
+    __syncwarp();
     const float kw = g_kl[r];
-    for (int q = lane; q < P; q += 32) {
+    for (int q = gl; q < P; q += G) {
       float val;
       if (q < d) {
         val = sz[q] + kw * sp[q];
@@ -215,77 +272,131 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) latent_bwd_kernel(
         const float raw = sp[q];
         if (i == j) {
           const float dg = softplus_f(raw) + 1e-5f;
-          val = sz[i] * se[j] + kw * (dg - 1.0f / dg);
-          val *= sigmoid_f(raw);
+          val = (sz[i] * se[j] + kw * (dg - 1.0f / dg)) * sigmoid_f(raw);
         } else {
           val = sz[i] * se[j] + kw * raw;
         }
       }
-      dpar_e[r * P + q] = val;
+      if (valid) {
+        if (dpar_e) dpar_e[r * P + q] = val;
+        if (dpar_e_b) dpar_e_b[r * P + q] = __float2bfloat16(val);
+      }
     }
   }
 }
 
-int latent_bwd(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
-               const float* g_kl, const float* g_match, int stop_grad, float* dpar_e, float* dpar_p, int64_t B, int d,
-               cudaStream_t s) {
+// ---------------------------------------------------------------- K importance samples per row
+template <int G, int E, int DCT>
+__global__ void __launch_bounds__(kThreadsL) sample_latents_kernel(const float* __restrict__ par, Key2 key, int64_t B,
+                                                                   int64_t K, int64_t B_total, int64_t row_start,
+                                                                   int d_rt, float* __restrict__ z,
+                                                                   float* __restrict__ base) {
+  extern __shared__ float smem[];
+  const int d = DCT ? DCT : d_rt;
+  const int m = d * (d + 1) / 2, P = d + m;
+  constexpr int kChunk = 16;                       // samples per work item
+  const int64_t chunks = (K + kChunk - 1) / kChunk;
+  RowIter<G> it(B * chunks);
+  float* sp = smem + (size_t)it.grp * (P + 3 * d);
+  float* se = sp + P;
+  float* sd = se + d;
+  float* si = sd + d;
+  const int gl = it.gl;
+  const uint64_t n_total = (uint64_t)K * (uint64_t)B_total * (uint64_t)d;
+  for (int64_t t = 0; t < it.iters; ++t) {
+    const int64_t item_raw = it.first + t * it.rows_per_iter;
+    const bool valid = item_raw < B * chunks;
+    const int64_t item = valid ? item_raw : B * chunks - 1;
+    const int64_t r = item / chunks, ck = item - r * chunks;
+    __syncwarp();
+    for (int q = gl; q < P; q += G) sp[q] = par[r * P + q];
+    __syncwarp();
+    float logd = stage_diag<G, E>(sp, sd, si, d, m, gl);
+    logd = group_sum<G>(logd);
+    const int64_t kend = min(K, (ck + 1) * kChunk);
+    for (int64_t k = ck * kChunk; k < kend; ++k) {
+      __syncwarp();
+      float e2 = 0.f;
+      for (int q = gl; q < d; q += G) {
+        const uint64_t idx = ((uint64_t)k * B_total + (uint64_t)(row_start + r)) * d + q;
+        const float ev = bits_to_normal(jax_random_word(key, n_total, idx));
+        se[q] = ev;
+        e2 = fmaf(ev, ev, e2);
+      }
+      __syncwarp();
+      float z2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int i = gl + G * e;
+        if (i < d) {
+          float acc = sp[i];
+          for (int j = 0; j < i; ++j) acc = fmaf(sp[tril_src(i, j, d, m)], se[j], acc);
+          acc = fmaf(sd[i], se[i], acc);
+          if (valid) z[(k * B + r) * d + i] = acc;
+          z2 = fmaf(acc, acc, z2);
+        }
+      }
+      e2 = group_sum<G>(e2); z2 = group_sum<G>(z2);
+      if (valid && gl == 0) base[k * B + r] = -0.5f * z2 + 0.5f * e2 + logd;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- launchers
+static int grid_for_rows(int64_t rows, int G) {
+  const int gpb = kThreadsL / G;
+  int64_t g = (rows + gpb - 1) / gpb;
+  if (g > 148 * 8) g = 148 * 8;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+#define DISPATCH_D(KERNEL, d, rows, smem_per_group, stream, ...)                                         \
+  do {                                                                                                   \
+    if ((d) == 16) {                                                                                     \
+      KERNEL<16, 1, 16><<<grid_for_rows(rows, 16), kThreadsL, (kThreadsL / 16) * (smem_per_group), stream>>>(__VA_ARGS__); \
+    } else if ((d) <= 16) {                                                                              \
+      KERNEL<16, 1, 0><<<grid_for_rows(rows, 16), kThreadsL, (kThreadsL / 16) * (smem_per_group), stream>>>(__VA_ARGS__); \
+    } else if ((d) <= 32) {                                                                              \
+      KERNEL<32, 1, 0><<<grid_for_rows(rows, 32), kThreadsL, (kThreadsL / 32) * (smem_per_group), stream>>>(__VA_ARGS__); \
+    } else if ((d) == 64) {                                                                              \
+      KERNEL<32, 2, 64><<<grid_for_rows(rows, 32), kThreadsL, (kThreadsL / 32) * (smem_per_group), stream>>>(__VA_ARGS__); \
+    } else {                                                                                             \
+      KERNEL<32, 2, 0><<<grid_for_rows(rows, 32), kThreadsL, (kThreadsL / 32) * (smem_per_group), stream>>>(__VA_ARGS__); \
+    }                                                                                                    \
+  } while (0)
+
+int latent_fwd(const float* par, const float* eps, float* z, float* kl, int64_t B, int d, cudaStream_t s) {
   PMVAE_CHECK(d >= 1 && d <= 64, "latent_dim must be in [1, 64]");
   if (B == 0) return 0;
   const int P = d + d * (d + 1) / 2;
-  const size_t smem = (size_t)kWarpsPerBlock * (P + 4 * d) * sizeof(float);
-  int64_t g = ceil_div(B, kWarpsPerBlock);
-  if (g > 148 * 16) g = 148 * 16;
-  latent_bwd_kernel<<<(int)g, 32 * kWarpsPerBlock, smem, s>>>(par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad,
-                                                             dpar_e, dpar_p, B, d);
+  const size_t spg = (size_t)(P + 3 * d) * sizeof(float);
+  DISPATCH_D(latent_fwd_kernel, d, B, spg, s, par, eps, z, kl, B, d);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }
 
-// ---------------------------------------------------------------- K importance samples per row
-__global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_latents_kernel(const float* __restrict__ par, Key2 key,
-                                                                             int64_t B, int64_t K, int64_t B_total,
-                                                                             int64_t row_start, int d,
-                                                                             float* __restrict__ z,
-                                                                             float* __restrict__ base) {
-  extern __shared__ float smem[];
-  const int P = d + d * (d + 1) / 2, m = d * (d + 1) / 2;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float* sp = smem + (size_t)w * (P + d);
-  float* se = sp + P;
-  const uint64_t n_total = (uint64_t)K * (uint64_t)B_total * (uint64_t)d;
-  // work item = (row r, sample chunk): chunks of 32 samples keep small batches parallel
-  const int64_t chunks = ceil_div(K, 32);
-  for (int64_t item = (int64_t)blockIdx.x * kWarpsPerBlock + w; item < B * chunks;
-       item += (int64_t)gridDim.x * kWarpsPerBlock) {
-    const int64_t r = item / chunks, ck = item - r * chunks;
-    __syncwarp();
-    stage_row(sp, par + r * P, P, lane);
-    float logd = 0.f;
-    for (int i = lane; i < d; i += 32) logd += logf(tril_diag(sp, i, d, m));
-    logd = warp_sum(logd);
-    const int64_t kend = min(K, (ck + 1) * 32);
-    for (int64_t k = ck * 32; k < kend; ++k) {
-      __syncwarp();
-      float e2 = 0.f;
-      for (int q = lane; q < d; q += 32) {
-        const uint64_t idx = ((uint64_t)k * B_total + (uint64_t)(row_start + r)) * d + q;
-        const float e = bits_to_normal(jax_random_word(key, n_total, idx));
-        se[q] = e;
-        e2 = fmaf(e, e, e2);
-      }
-      __syncwarp();
-      float z2 = 0.f;
-      for (int i = lane; i < d; i += 32) {
-        float acc = sp[i];
-        for (int j = 0; j < i; ++j) acc = fmaf(sp[tril_src(i, j, d, m)], se[j], acc);
-        acc = fmaf(tril_diag(sp, i, d, m), se[i], acc);
-        z[(k * B + r) * d + i] = acc;
-        z2 = fmaf(acc, acc, z2);
-      }
-      e2 = warp_sum(e2); z2 = warp_sum(z2);
-      if (lane == 0) base[k * B + r] = -0.5f * z2 + 0.5f * e2 + logd;
-    }
-  }
+int match_fwd(const float* par_p, const float* z, float* match, int64_t B, int d, cudaStream_t s) {
+  PMVAE_CHECK(d >= 1 && d <= 64, "latent_dim must be in [1, 64]");
+  if (B == 0) return 0;
+  const int P = d + d * (d + 1) / 2;
+  const size_t spg = (size_t)(P + 4 * d) * sizeof(float);
+  DISPATCH_D(match_fwd_kernel, d, B, spg, s, par_p, z, match, B, d);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int latent_bwd(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
+               const float* g_kl, const float* g_match, int stop_grad, float* dpar_e, float* dpar_p,
+               __nv_bfloat16* dpar_e_b, __nv_bfloat16* dpar_p_b, int64_t B, int d, cudaStream_t s) {
+  PMVAE_CHECK(d >= 1 && d <= 64, "latent_dim must be in [1, 64]");
+  if (B == 0) return 0;
+  const int P = d + d * (d + 1) / 2;
+  const size_t spg = (size_t)(P + 6 * d) * sizeof(float);
+  DISPATCH_D(latent_bwd_kernel, d, B, spg, s, par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad, dpar_e, dpar_p,
+             dpar_e_b, dpar_p_b, B, d);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
 }
 
 int sample_latents(const float* par, Key2 key, int64_t B, int64_t K, int64_t B_total, int64_t row_start, int d,
@@ -295,10 +406,9 @@ int sample_latents(const float* par, Key2 key, int64_t B, int64_t K, int64_t B_t
               "K*B_total*d exceeds one 2^32-1 element draw");
   if (B * K == 0) return 0;
   const int P = d + d * (d + 1) / 2;
-  const size_t smem = (size_t)kWarpsPerBlock * (P + d) * sizeof(float);
-  int64_t g = ceil_div(B * ceil_div(K, 32), kWarpsPerBlock);
-  if (g > 148 * 16) g = 148 * 16;
-  sample_latents_kernel<<<(int)g, 32 * kWarpsPerBlock, smem, s>>>(par, key, B, K, B_total, row_start, d, z, base);
+  const size_t spg = (size_t)(P + 3 * d) * sizeof(float);
+  const int64_t items = B * ((K + 15) / 16);
+  DISPATCH_D(sample_latents_kernel, d, items, spg, s, par, key, B, K, B_total, row_start, d, z, base);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }

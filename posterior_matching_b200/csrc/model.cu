@@ -310,7 +310,7 @@ int backward(const pmvae_config* c, const float* params, const float* x, const f
   PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_workspace_bytes)");
   PMVAE_TRY(rec_ll_bwd(x, p.loc, c->D, params + L.log_scale, g_rec, p.dloc, nullptr, c->D, grads + L.log_scale, B, c->D, s));
   PMVAE_TRY(net_bwd_f32(params, grads, L.dec, L.ddist, c->H, p.z, B, p.dec, p.dloc, p.dH, p.tmp1, p.tmp2, p.dz, s));
-  PMVAE_TRY(latent_bwd(p.par_e, p.par_p, eps, p.z, p.dz, g_kl, g_match, c->stop_grad, p.dpar_e, p.dpar_p, B, c->d, s));
+  PMVAE_TRY(latent_bwd(p.par_e, p.par_p, eps, p.z, p.dz, g_kl, g_match, c->stop_grad, p.dpar_e, p.dpar_p, nullptr, nullptr, B, c->d, s));
   PMVAE_TRY(net_bwd_f32(params, grads, L.enc, L.post, c->H, x, B, p.enc, p.dpar_e, p.dH, p.tmp1, p.tmp2, nullptr, s));
   PMVAE_TRY(net_bwd_f32(params, grads, L.part, L.ppost, c->H, p.xob, B, p.part, p.dpar_p, p.dH, p.tmp1, p.tmp2, nullptr, s));
   return 0;

@@ -8,9 +8,10 @@
 //        contraction runs over the batch rows and is split across CTAs.
 //
 // Structure (one CTA per SM, persistent over tiles):
-//   warp 0      : TMA producer  (cp.async.bulk.tensor 2D, SWIZZLE_128B, 4-stage mbarrier ring)
+//   warp 0      : TMA producer  (cp.async.bulk.tensor 2D, SWIZZLE_128B, 3-stage mbarrier ring)
 //   warp 1      : MMA issuer    (one lane: tcgen05.mma kind::f16, M=128, N<=256, K=16, fp32 accum in TMEM)
-//   warps 2..5  : epilogue      (tcgen05.ld 32x32b.x32 -> bias / mask / residual / relu -> global)
+//   warps 2..9  : epilogue      (tcgen05.ld 32x32b.x32 -> smem transpose -> bias / mask / residual / relu
+//                                -> coalesced global rows; optional fused column sums for bias gradients)
 // Two 256-column TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -24,13 +25,15 @@ namespace tc {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // 64 bf16 = 128 bytes = one swizzle row
 constexpr int kMaxN = 256;
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kAccStages = 2;
-constexpr int kThreads = 192;          // 6 warps
+constexpr int kThreads = 320;          // 10 warps: TMA, MMA, 8 epilogue
+constexpr int kEpiWarps = 8;
+constexpr int kStagePitch = 68;        // floats per staged row: 64 columns + 4 pad (conflict-free both ways)
 constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KB
 constexpr int kBBytes = kMaxN * kBlockK * 2;        // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kSmemBytes = kStages * kStageBytes + 256 /*barriers*/ + kEpiWarps * 32 * kStagePitch * 4 + 1024 /*align slack*/;
 constexpr uint32_t kSpinLimit = 1u << 28;
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -161,7 +164,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -249,8 +252,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue (4 warps, one accumulator row per thread) =====================
-    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    // ===================== epilogue (8 warps) =====================
+    // Warp w may touch TMEM lanes 32*(w%4)..+31 (accumulator rows); the two warps of a quadrant
+    // take alternate 64-column chunks.  A chunk goes TMEM -> registers (thread = row) -> padded
+    // shared-memory stage -> registers (lane = column pair), so every global access below is a
+    // contiguous row segment (256 B fp32 / 128 B bf16 per warp instruction).
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float* stage = reinterpret_cast<float*>(smem_gen + kStages * kStageBytes + 256) + (warp - 2) * (32 * kStagePitch);
+    float2 csum[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile % p.num_m_tiles;
@@ -259,87 +269,86 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int sp = rest / p.num_n_tiles;
       mbar_wait(tfull_bar(acc), acc_phase, 4);
       tc_fence_after();
-      const int64_t row = (int64_t)mt * kBlockM + q * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int64_t row0 = (int64_t)mt * kBlockM + q * 32;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kMaxN);
-      for (int c0 = 0; c0 < n_tile; c0 += 32) {
-        uint32_t r[32];
-        __syncwarp();                             // tcgen05.ld is .sync.aligned: reconverge after the guards below
-        tmem_ld32(t_row + (uint32_t)c0, r);
-        tmem_ld_wait();
-        const int n0 = nt * n_tile + c0;
-        if (!row_ok || n0 >= p.N) continue;
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const int c0 = half * 64 + ci * 128;
+        if (c0 >= n_tile) break;
+        // ---- TMEM -> stage (thread = row)
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          uint32_t r[32];
+          tmem_ld32(t_row + (uint32_t)(c0 + hb * 32), r);
+          tmem_ld_wait();
+          float4* dst = reinterpret_cast<float4*>(stage + lane * kStagePitch + hb * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                 __uint_as_float(r[4 * j + 3]));
+        }
+        __syncwarp();
+        // ---- stage -> global (lane = column pair)
+        const int n = nt * n_tile + c0 + 2 * lane;
+        const bool col_ok = n < p.N;
         if (KIND == 1) {
-          // split-K partial: fp32 tile into the partial buffer (plain stores) or atomics into C
-          float* dst = p.out_f32 + (p.atomic ? 0 : (int64_t)sp * p.M * p.ld_out_f32) + row * p.ld_out_f32 + n0;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (n0 + g * 4 >= p.N) break;
-            if (p.atomic) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) atomicAdd(dst + g * 4 + j, __uint_as_float(r[g * 4 + j]));
-            } else {
-              *reinterpret_cast<float4*>(dst + g * 4) = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]),
-                                                                    __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+          float* base = p.out_f32 + (p.atomic ? 0 : (int64_t)sp * p.M * p.ld_out_f32);
+          for (int rr = 0; rr < 32; ++rr) {
+            const int64_t row = row0 + rr;
+            if (row >= p.M) break;
+            const float2 v = *reinterpret_cast<const float2*>(stage + rr * kStagePitch + 2 * lane);
+            if (col_ok) {
+              float2* dst = reinterpret_cast<float2*>(base + row * p.ld_out_f32 + n);
+              if (p.atomic) atomicAdd(dst, v);
+              else *dst = v;
             }
           }
-          continue;
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {             // 4 groups of 8 columns
-          const int n = n0 + g * 8;
-          if (n >= p.N) break;
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-          if (p.bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-          }
-          if (p.mask_bf16) {
-            const uint4 m = *reinterpret_cast<const uint4*>(p.mask_bf16 + row * p.ld_mask + n);
-            const uint32_t mm[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (!(bf16_lo(mm[j]) > 0.f)) v[2 * j] = 0.f;
-              if (!(bf16_hi(mm[j]) > 0.f)) v[2 * j + 1] = 0.f;
+        } else {
+          float2 bias2 = make_float2(0.f, 0.f);
+          if (p.bias && col_ok) bias2 = __ldg(reinterpret_cast<const float2*>(p.bias + n));
+#pragma unroll 4
+          for (int rr = 0; rr < 32; ++rr) {
+            const int64_t row = row0 + rr;
+            if (row >= p.M) break;
+            float2 v = *reinterpret_cast<const float2*>(stage + rr * kStagePitch + 2 * lane);
+            if (!col_ok) continue;
+            v.x += bias2.x; v.y += bias2.y;
+            if (p.mask_bf16) {
+              const uint32_t m = *reinterpret_cast<const uint32_t*>(p.mask_bf16 + row * p.ld_mask + n);
+              if (!(bf16_lo(m) > 0.f)) v.x = 0.f;
+              if (!(bf16_hi(m) > 0.f)) v.y = 0.f;
             }
-          }
-          if (p.resid_f32) {
-            const float4 a0 = *reinterpret_cast<const float4*>(p.resid_f32 + row * p.ld_resid_f32 + n);
-            const float4 a1 = *reinterpret_cast<const float4*>(p.resid_f32 + row * p.ld_resid_f32 + n + 4);
-            v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
-            v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
-          }
-          if (p.resid_bf16) {
-            const uint4 m = *reinterpret_cast<const uint4*>(p.resid_bf16 + row * p.ld_resid_bf16 + n);
-            const uint32_t mm[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { v[2 * j] += bf16_lo(mm[j]); v[2 * j + 1] += bf16_hi(mm[j]); }
-          }
-          if (p.out_f32) {
-            float* dst = p.out_f32 + row * p.ld_out_f32 + n;
-            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-          }
-          if (p.out_bf16) {
-            if (p.relu_out) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+            if (p.resid_f32) {
+              const float2 a = *reinterpret_cast<const float2*>(p.resid_f32 + row * p.ld_resid_f32 + n);
+              v.x += a.x; v.y += a.y;
             }
-            uint4 o;
-            o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
-            o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-            *reinterpret_cast<uint4*>(p.out_bf16 + row * p.ld_out_bf16 + n) = o;
+            if (p.resid_bf16) {
+              const uint32_t m = *reinterpret_cast<const uint32_t*>(p.resid_bf16 + row * p.ld_resid_bf16 + n);
+              v.x += bf16_lo(m); v.y += bf16_hi(m);
+            }
+            if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + row * p.ld_out_f32 + n) = v;
+            if (p.out_bf16) {
+              if (p.relu_out) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+              const uint32_t o = pack_bf16(v.x, v.y);
+              *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ld_out_bf16 + n) = o;
+              if (p.colsum_out) { csum[ci].x += bf16_lo(o); csum[ci].y += bf16_hi(o); }   // sums what dW will read
+            }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (KIND == 0 && p.colsum_out) {
+      // bias gradient: column sums of the bf16 output over every tile this CTA produced
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const int n = half * 64 + ci * 128 + 2 * lane;
+        if (n < n_tile && n < p.N) { atomicAdd(p.colsum_out + n, csum[ci].x); atomicAdd(p.colsum_out + n + 1, csum[ci].y); }
+      }
     }
   }
 
@@ -430,6 +439,8 @@ int gemm_nt(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Bt, int64_
   ep.num_n_tiles = (int)ceil_div(N, ep.n_tile);
   ep.num_k_blocks = (int)ceil_div(K, kBlockK);
   ep.split_k = 1; ep.kb_per_split = ep.num_k_blocks; ep.atomic = 0;
+  PMVAE_CHECK(ep.colsum_out == nullptr || (ep.num_n_tiles == 1 && ep.out_bf16 != nullptr),
+              "fused column sums need a single N tile and a bf16 output");
   CUtensorMap ma, mb;
   PMVAE_TRY(make_map(&ma, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBlockK, kBlockM));
   PMVAE_TRY(make_map(&mb, Bt, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, kBlockK, (uint32_t)ep.n_tile));

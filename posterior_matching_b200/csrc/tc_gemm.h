@@ -23,6 +23,7 @@ struct TcGemmArgs {
   float* out_f32 = nullptr; int64_t ld_out_f32 = 0;
   __nv_bfloat16* out_bf16 = nullptr; int64_t ld_out_bf16 = 0;
   int relu_out = 0;
+  float* colsum_out = nullptr;   // += column sums of the bf16 output (needs a single N tile)
 };
 
 int gemm_nt(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Bt, int64_t ldb, int64_t M, int N, int K,

@@ -387,7 +387,7 @@ static void plan_net_b(Bump& bp, const Net& n, int64_t B, NetSavedB& s) {
 struct TrainPlanB {
   Images img;
   NetSavedB enc, dec, part;
-  float *h, *ytmp, *par_e, *par_p, *z, *loc, *dpar_e, *dpar_p, *dz, *wtmp;
+  float *h, *ytmp, *par_e, *par_p, *z, *loc, *dz, *wtmp;
   bf16 *dH, *dU, *dG, *dpar_e_b, *dpar_p_b, *dloc_b;
   int Dp;
   uint64_t bytes;
@@ -408,8 +408,6 @@ static TrainPlanB plan_train_b(const pmvae_config* c, const Layout& L, int64_t B
   p.par_p = bp.take<float>((uint64_t)B * L.P);
   p.z = bp.take<float>((uint64_t)B * c->d);
   p.loc = bp.take<float>((uint64_t)B * p.Dp);
-  p.dpar_e = bp.take<float>((uint64_t)B * L.P);
-  p.dpar_p = bp.take<float>((uint64_t)B * L.P);
   p.dz = bp.take<float>((uint64_t)B * c->d);
   p.wtmp = bp.take<float>((uint64_t)256 * p.Dp);         // padded-pitch dW of the decoder head
   p.dH = bp.take<bf16>((uint64_t)B * 256);
@@ -538,9 +536,10 @@ static int net_fwd_b(const float* params, const Net& n, const LeafImg* img, cons
   return tc::gemm_nt(sv.A[n.R], 256, himg.wt, himg.ldt, B, head_cols_pad, 256, eh, s);
 }
 
-// weight + bias gradients of one hidden/head Linear: gW += act^T @ dY (tensor), gb += colsum(dY)
+// weight (+ optionally bias) gradients of one hidden/head Linear: gW += act^T @ dY on the tensor
+// cores; gb += colsum(dY) unless the kernel that produced dY already accumulated it.
 static int lin_bwd_params_b(float* grads, const Leaf& lf, const bf16* act, const bf16* dY, int64_t ld_dy, int n_cols,
-                            int64_t B, float* wtmp, cudaStream_t s) {
+                            int64_t B, float* wtmp, bool do_colsum, cudaStream_t s) {
   if (n_cols == lf.cols) {
     PMVAE_TRY(tc::gemm_tn(act, 256, dY, ld_dy, lf.rows, lf.cols, B, grads + lf.w, lf.cols, 1, 0, nullptr, s));
   } else {
@@ -551,7 +550,8 @@ static int lin_bwd_params_b(float* grads, const Leaf& lf, const bf16* act, const
                                                                               lf.rows, lf.cols);
     PMVAE_LAUNCH_CHECK();
   }
-  return colsum_bf16(dY, ld_dy, grads + lf.b, B, lf.cols, s);
+  if (do_colsum) PMVAE_TRY(colsum_bf16(dY, ld_dy, grads + lf.b, B, lf.cols, s));
+  return 0;
 }
 
 static int net_bwd_b(const float* params, float* grads, const Net& n, const LeafImg* img, const Leaf& head,
@@ -559,11 +559,13 @@ static int net_bwd_b(const float* params, float* grads, const Net& n, const Leaf
                      const float* msk, int D_in, int64_t B, const NetSavedB& sv, bf16* dH, bf16* dU, bf16* dG,
                      float* wtmp, float* dIn, cudaStream_t s) {
   using tc::TcGemmArgs;
+  const bool fuse = !n.ln;   // non-LN nets: the epilogue that writes a gradient tensor also sums its columns
   // head
-  PMVAE_TRY(lin_bwd_params_b(grads, head, sv.A[n.R], dHead, ld_dhead, head_cols_pad, B, wtmp, s));
+  PMVAE_TRY(lin_bwd_params_b(grads, head, sv.A[n.R], dHead, ld_dhead, head_cols_pad, B, wtmp, true, s));
   {
     TcGemmArgs e{};
     e.mask_bf16 = sv.A[n.R]; e.ld_mask = 256; e.out_bf16 = dH; e.ld_out_bf16 = 256;
+    if (fuse && n.R > 0) e.colsum_out = grads + n.lin[2 * n.R].b;        // dH = dY of block R-1's second Linear
     PMVAE_TRY(tc::gemm_nt(dHead, ld_dhead, himg.wn, himg.ldn, B, 256, head_cols_pad, e, s));
   }
   for (int r = n.R - 1; r >= 0; --r) {
@@ -575,20 +577,22 @@ static int net_bwd_b(const float* params, float* grads, const Net& n, const Leaf
       PMVAE_LAUNCH_CHECK();
       dV = dG;
     }
-    PMVAE_TRY(lin_bwd_params_b(grads, l2, sv.T[r], dV, 256, 256, B, wtmp, s));
+    PMVAE_TRY(lin_bwd_params_b(grads, l2, sv.T[r], dV, 256, 256, B, wtmp, !fuse, s));
     {
       TcGemmArgs e{};
       e.mask_bf16 = sv.T[r]; e.ld_mask = 256; e.out_bf16 = dU; e.ld_out_bf16 = 256;
+      if (fuse) e.colsum_out = grads + l1.b;
       PMVAE_TRY(tc::gemm_nt(dV, 256, img[2 * r + 2].wn, img[2 * r + 2].ldn, B, 256, 256, e, s));
     }
     if (n.ln) {
       ln_bwd_bf16_kernel<<<grid1d(B * 32, 256), 256, 0, s>>>(dU, sv.XU[r], sv.rstdU[r], dU, B);
       PMVAE_LAUNCH_CHECK();
     }
-    PMVAE_TRY(lin_bwd_params_b(grads, l1, sv.A[r], dU, 256, 256, B, wtmp, s));
+    PMVAE_TRY(lin_bwd_params_b(grads, l1, sv.A[r], dU, 256, 256, B, wtmp, !fuse, s));
     {
       TcGemmArgs e{};
       e.mask_bf16 = sv.A[r]; e.ld_mask = 256; e.resid_bf16 = dH; e.ld_resid_bf16 = 256; e.out_bf16 = dH; e.ld_out_bf16 = 256;
+      if (fuse && r > 0) e.colsum_out = grads + n.lin[2 * r].b;          // dH = dY of block r-1's second Linear
       PMVAE_TRY(tc::gemm_nt(dU, 256, img[2 * r + 1].wn, img[2 * r + 1].ldn, B, 256, 256, e, s));
     }
   }
@@ -644,9 +648,8 @@ int backward_bf16(const pmvae_config* c, const Layout& L, const float* params, c
                        c->D, s));
   PMVAE_TRY(net_bwd_b(params, grads, L.dec, p.img.dec, L.ddist, p.img.ddist, p.dloc_b, p.Dp, p.Dp, p.z, nullptr, c->d,
                       B, p.dec, p.dH, p.dU, p.dG, p.wtmp, p.dz, s));
-  PMVAE_TRY(latent_bwd(p.par_e, p.par_p, eps, p.z, p.dz, g_kl, g_match, c->stop_grad, p.dpar_e, p.dpar_p, B, c->d, s));
-  PMVAE_TRY(cast_bf16(p.dpar_e, p.dpar_e_b, B * L.P, 0, s));
-  PMVAE_TRY(cast_bf16(p.dpar_p, p.dpar_p_b, B * L.P, 0, s));
+  PMVAE_TRY(latent_bwd(p.par_e, p.par_p, eps, p.z, p.dz, g_kl, g_match, c->stop_grad, nullptr, nullptr, p.dpar_e_b,
+                       p.dpar_p_b, B, c->d, s));
   PMVAE_TRY(net_bwd_b(params, grads, L.enc, p.img.enc, L.post, p.img.post, p.dpar_e_b, L.P, L.P, x, nullptr, c->D, B,
                       p.enc, p.dH, p.dU, p.dG, p.wtmp, nullptr, s));
   PMVAE_TRY(net_bwd_b(params, grads, L.part, p.img.part, L.ppost, p.img.ppost, p.dpar_p_b, L.P, L.P, x, b, c->D, B,
