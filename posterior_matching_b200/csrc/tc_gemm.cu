@@ -15,6 +15,7 @@
 // Two 256-column TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 #include "tc_gemm.h"
@@ -29,6 +30,7 @@ constexpr int kStages = 3;
 constexpr int kAccStages = 2;
 constexpr int kThreads = 320;          // 10 warps: TMA, MMA, 8 epilogue
 constexpr int kEpiWarps = 8;
+constexpr int kRowBatch = 16;          // rows whose epilogue loads are in flight together
 constexpr int kStagePitch = 68;        // floats per staged row: 64 columns + 4 pad (conflict-free both ways)
 constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KB
 constexpr int kBBytes = kMaxN * kBlockK * 2;        // 32 KB
@@ -143,7 +145,9 @@ __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v 
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
 // ---------------------------------------------------------------- kernel
-template <int KIND>
+// EPI selects the auxiliary input streams of the NT epilogue: 0 none, 1 fp32 residual,
+// 2 bf16 relu mask (+ optional bf16 residual).
+template <int KIND, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcGemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -274,23 +278,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci) {
         const int c0 = half * 64 + ci * 128;
-        if (c0 >= n_tile) break;
+        if (c0 >= n_tile || (p.debug & 2)) break;
         // ---- TMEM -> stage (thread = row)
-#pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {
-          uint32_t r[32];
-          tmem_ld32(t_row + (uint32_t)(c0 + hb * 32), r);
+        {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(t_row + (uint32_t)c0, r0);            // both halves in flight before the wait
+          tmem_ld32(t_row + (uint32_t)(c0 + 32), r1);
           tmem_ld_wait();
-          float4* dst = reinterpret_cast<float4*>(stage + lane * kStagePitch + hb * 32);
+          float4* dst = reinterpret_cast<float4*>(stage + lane * kStagePitch);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                 __uint_as_float(r[4 * j + 3]));
+            dst[j] = make_float4(__uint_as_float(r0[4 * j]), __uint_as_float(r0[4 * j + 1]), __uint_as_float(r0[4 * j + 2]),
+                                 __uint_as_float(r0[4 * j + 3]));
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[8 + j] = make_float4(__uint_as_float(r1[4 * j]), __uint_as_float(r1[4 * j + 1]), __uint_as_float(r1[4 * j + 2]),
+                                     __uint_as_float(r1[4 * j + 3]));
         }
         __syncwarp();
         // ---- stage -> global (lane = column pair)
         const int n = nt * n_tile + c0 + 2 * lane;
-        const bool col_ok = n < p.N;
+        const bool col_ok = n < p.N && !(p.debug & 1);
         if (KIND == 1) {
           float* base = p.out_f32 + (p.atomic ? 0 : (int64_t)sp * p.M * p.ld_out_f32);
           for (int rr = 0; rr < 32; ++rr) {
@@ -306,32 +314,41 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         } else {
           float2 bias2 = make_float2(0.f, 0.f);
           if (p.bias && col_ok) bias2 = __ldg(reinterpret_cast<const float2*>(p.bias + n));
-#pragma unroll 4
-          for (int rr = 0; rr < 32; ++rr) {
-            const int64_t row = row0 + rr;
-            if (row >= p.M) break;
-            float2 v = *reinterpret_cast<const float2*>(stage + rr * kStagePitch + 2 * lane);
-            if (!col_ok) continue;
-            v.x += bias2.x; v.y += bias2.y;
-            if (p.mask_bf16) {
-              const uint32_t m = *reinterpret_cast<const uint32_t*>(p.mask_bf16 + row * p.ld_mask + n);
-              if (!(bf16_lo(m) > 0.f)) v.x = 0.f;
-              if (!(bf16_hi(m) > 0.f)) v.y = 0.f;
+          // Rows go in batches of kRowBatch: all global loads of a batch are issued before any is
+          // consumed, so a warp keeps kRowBatch row segments in flight instead of one.
+#pragma unroll 1
+          for (int rb = 0; rb < 32; rb += kRowBatch) {
+            uint32_t mk[kRowBatch], rbv[kRowBatch];
+            float2 rf[kRowBatch];
+#pragma unroll
+            for (int i = 0; i < kRowBatch; ++i) {
+              const int64_t row = row0 + rb + i;
+              const bool ok = col_ok && row < p.M;
+              if (EPI == 2) {
+                mk[i] = ok ? __ldg(reinterpret_cast<const uint32_t*>(p.mask_bf16 + row * p.ld_mask + n)) : 0u;
+                rbv[i] = (ok && p.resid_bf16) ? *reinterpret_cast<const uint32_t*>(p.resid_bf16 + row * p.ld_resid_bf16 + n) : 0u;
+              }
+              if (EPI == 1) rf[i] = ok ? *reinterpret_cast<const float2*>(p.resid_f32 + row * p.ld_resid_f32 + n) : make_float2(0.f, 0.f);
             }
-            if (p.resid_f32) {
-              const float2 a = *reinterpret_cast<const float2*>(p.resid_f32 + row * p.ld_resid_f32 + n);
-              v.x += a.x; v.y += a.y;
-            }
-            if (p.resid_bf16) {
-              const uint32_t m = *reinterpret_cast<const uint32_t*>(p.resid_bf16 + row * p.ld_resid_bf16 + n);
-              v.x += bf16_lo(m); v.y += bf16_hi(m);
-            }
-            if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + row * p.ld_out_f32 + n) = v;
-            if (p.out_bf16) {
-              if (p.relu_out) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
-              const uint32_t o = pack_bf16(v.x, v.y);
-              *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ld_out_bf16 + n) = o;
-              if (p.colsum_out) { csum[ci].x += bf16_lo(o); csum[ci].y += bf16_hi(o); }   // sums what dW will read
+#pragma unroll
+            for (int i = 0; i < kRowBatch; ++i) {
+              const int64_t row = row0 + rb + i;
+              if (!(col_ok && row < p.M)) continue;
+              float2 v = *reinterpret_cast<const float2*>(stage + (rb + i) * kStagePitch + 2 * lane);
+              v.x += bias2.x; v.y += bias2.y;
+              if (EPI == 2) {
+                if (!(bf16_lo(mk[i]) > 0.f)) v.x = 0.f;
+                if (!(bf16_hi(mk[i]) > 0.f)) v.y = 0.f;
+                v.x += bf16_lo(rbv[i]); v.y += bf16_hi(rbv[i]);
+              }
+              if (EPI == 1) { v.x += rf[i].x; v.y += rf[i].y; }
+              if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + row * p.ld_out_f32 + n) = v;
+              if (p.out_bf16) {
+                if (p.relu_out) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+                const uint32_t o = pack_bf16(v.x, v.y);
+                *reinterpret_cast<uint32_t*>(p.out_bf16 + row * p.ld_out_bf16 + n) = o;
+                if (p.colsum_out) { csum[ci].x += bf16_lo(o); csum[ci].y += bf16_hi(o); }   // sums what dW will read
+              }
             }
           }
         }
@@ -396,6 +413,12 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
   return 0;
 }
 
+static int debug_bits() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PMVAE_TC_DEBUG"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 static int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -407,16 +430,16 @@ static int num_sms() {
   return n;
 }
 
-template <int KIND>
+template <int KIND, int EPI>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcGemmArgs& a, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    PMVAE_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    PMVAE_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<KIND, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
   const int tiles = a.num_m_tiles * a.num_n_tiles * a.split_k;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  tc_gemm_kernel<KIND><<<grid, kThreads, kSmemBytes, s>>>(ma, mb, a);
+  tc_gemm_kernel<KIND, EPI><<<grid, kThreads, kSmemBytes, s>>>(ma, mb, a);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -438,13 +461,17 @@ int gemm_nt(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Bt, int64_
   ep.num_m_tiles = (int)ceil_div(M, kBlockM);
   ep.num_n_tiles = (int)ceil_div(N, ep.n_tile);
   ep.num_k_blocks = (int)ceil_div(K, kBlockK);
-  ep.split_k = 1; ep.kb_per_split = ep.num_k_blocks; ep.atomic = 0;
+  ep.split_k = 1; ep.kb_per_split = ep.num_k_blocks; ep.atomic = 0; ep.debug = debug_bits();
   PMVAE_CHECK(ep.colsum_out == nullptr || (ep.num_n_tiles == 1 && ep.out_bf16 != nullptr),
               "fused column sums need a single N tile and a bf16 output");
   CUtensorMap ma, mb;
   PMVAE_TRY(make_map(&ma, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBlockK, kBlockM));
   PMVAE_TRY(make_map(&mb, Bt, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, kBlockK, (uint32_t)ep.n_tile));
-  return launch<0>(ma, mb, ep, s);
+  PMVAE_CHECK(!(ep.resid_f32 && (ep.mask_bf16 || ep.resid_bf16)), "unsupported epilogue combination");
+  PMVAE_CHECK(!(ep.resid_bf16 && !ep.mask_bf16), "bf16 residual needs a mask");
+  if (ep.resid_f32) return launch<0, 1>(ma, mb, ep, s);
+  if (ep.mask_bf16) return launch<0, 2>(ma, mb, ep, s);
+  return launch<0, 0>(ma, mb, ep, s);
 }
 
 // C[M,N] (fp32) = A[rows,M]^T . B[rows,N], contraction over rows split across CTAs.
@@ -475,7 +502,7 @@ int gemm_tn(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t
   CUtensorMap ma, mb;
   PMVAE_TRY(make_map(&ma, A, (uint64_t)rows, (uint64_t)M, (uint64_t)lda, 64, kBlockK));
   PMVAE_TRY(make_map(&mb, B, (uint64_t)rows, (uint64_t)N, (uint64_t)ldb, 64, kBlockK));
-  return launch<1>(ma, mb, ep, s);
+  return launch<1, 0>(ma, mb, ep, s);
 }
 
 }  // namespace tc

@@ -24,6 +24,7 @@ struct TcGemmArgs {
   __nv_bfloat16* out_bf16 = nullptr; int64_t ld_out_bf16 = 0;
   int relu_out = 0;
   float* colsum_out = nullptr;   // += column sums of the bf16 output (needs a single N tile)
+  int debug = 0;                 // PMVAE_TC_DEBUG bits (profiling only): 1 = no epilogue global I/O, 2 = no epilogue work
 };
 
 int gemm_nt(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Bt, int64_t ldb, int64_t M, int N, int K,

@@ -384,6 +384,24 @@ static void plan_net_b(Bump& bp, const Net& n, int64_t B, NetSavedB& s) {
   }
 }
 
+static NetSavedB shift_saved(const NetSavedB& s, const Net& n, int64_t r0) {
+  NetSavedB o = s;
+  for (int r = 0; r <= n.R; ++r) o.A[r] = s.A[r] + r0 * 256;
+  for (int r = 0; r < n.R; ++r) o.T[r] = s.T[r] + r0 * 256;
+  if (n.ln) {
+    o.X0 = s.X0 + r0 * 256; o.rstd0 = s.rstd0 + r0;
+    for (int r = 0; r < n.R; ++r) {
+      o.XU[r] = s.XU[r] + r0 * 256; o.XV[r] = s.XV[r] + r0 * 256;
+      o.rstdU[r] = s.rstdU[r] + r0; o.rstdV[r] = s.rstdV[r] + r0;
+    }
+  }
+  return o;
+}
+
+// Rows are processed in micro-batches so that the tensors one kernel writes and the next reads
+// (h, T, dH, dU: 8 MB each at 16 Ki rows) are still in the 126 MB L2 when they are re-read.
+constexpr int64_t kMicroRows = 16384;
+
 struct TrainPlanB {
   Images img;
   NetSavedB enc, dec, part;
@@ -627,15 +645,20 @@ int forward_bf16(const pmvae_config* c, const Layout& L, const float* params, co
   PMVAE_CHECK(c->H == 256, "the tensor path is specialised for hidden_units = 256");
   TrainPlanB p = plan_train_b(c, L, B, ws);
   CHECK_WS(p);
-  PMVAE_TRY(net_fwd_b(params, L.enc, p.img.enc, L.post, p.img.post, L.P, x, nullptr, c->D, B, p.enc, p.h, p.ytmp,
-                      p.par_e, L.P, s));
-  PMVAE_TRY(latent_fwd(p.par_e, eps, p.z, out_kl, B, c->d, s));
-  PMVAE_TRY(net_fwd_b(params, L.dec, p.img.dec, L.ddist, p.img.ddist, p.Dp, p.z, nullptr, c->d, B, p.dec, p.h, p.ytmp,
-                      p.loc, p.Dp, s));
-  PMVAE_TRY(rec_ll(x, p.loc, p.Dp, params + L.log_scale, nullptr, out_rec, B, c->D, s));
-  PMVAE_TRY(net_fwd_b(params, L.part, p.img.part, L.ppost, p.img.ppost, L.P, x, b, c->D, B, p.part, p.h, p.ytmp,
-                      p.par_p, L.P, s));
-  PMVAE_TRY(match_fwd(p.par_p, p.z, out_match, B, c->d, s));
+  const int D = c->D, d = c->d;
+  for (int64_t r0 = 0; r0 < B; r0 += kMicroRows) {
+    const int64_t nb = (B - r0 < kMicroRows) ? (B - r0) : kMicroRows;
+    const float* xc = x + r0 * D;
+    PMVAE_TRY(net_fwd_b(params, L.enc, p.img.enc, L.post, p.img.post, L.P, xc, nullptr, D, nb,
+                        shift_saved(p.enc, L.enc, r0), p.h, p.ytmp, p.par_e + r0 * L.P, L.P, s));
+    PMVAE_TRY(latent_fwd(p.par_e + r0 * L.P, eps + r0 * d, p.z + r0 * d, out_kl + r0, nb, d, s));
+    PMVAE_TRY(net_fwd_b(params, L.dec, p.img.dec, L.ddist, p.img.ddist, p.Dp, p.z + r0 * d, nullptr, d, nb,
+                        shift_saved(p.dec, L.dec, r0), p.h, p.ytmp, p.loc + r0 * p.Dp, p.Dp, s));
+    PMVAE_TRY(rec_ll(xc, p.loc + r0 * p.Dp, p.Dp, params + L.log_scale, nullptr, out_rec + r0, nb, D, s));
+    PMVAE_TRY(net_fwd_b(params, L.part, p.img.part, L.ppost, p.img.ppost, L.P, xc, b + r0 * D, D, nb,
+                        shift_saved(p.part, L.part, r0), p.h, p.ytmp, p.par_p + r0 * L.P, L.P, s));
+    PMVAE_TRY(match_fwd(p.par_p + r0 * L.P, p.z + r0 * d, out_match + r0, nb, d, s));
+  }
   return 0;
 }
 
@@ -644,16 +667,22 @@ int backward_bf16(const pmvae_config* c, const Layout& L, const float* params, c
                   float* grads, void* ws, uint64_t ws_bytes, cudaStream_t s) {
   TrainPlanB p = plan_train_b(c, L, B, ws);
   CHECK_WS(p);
-  PMVAE_TRY(rec_ll_bwd(x, p.loc, p.Dp, params + L.log_scale, g_rec, nullptr, p.dloc_b, p.Dp, grads + L.log_scale, B,
-                       c->D, s));
-  PMVAE_TRY(net_bwd_b(params, grads, L.dec, p.img.dec, L.ddist, p.img.ddist, p.dloc_b, p.Dp, p.Dp, p.z, nullptr, c->d,
-                      B, p.dec, p.dH, p.dU, p.dG, p.wtmp, p.dz, s));
-  PMVAE_TRY(latent_bwd(p.par_e, p.par_p, eps, p.z, p.dz, g_kl, g_match, c->stop_grad, nullptr, nullptr, p.dpar_e_b,
-                       p.dpar_p_b, B, c->d, s));
-  PMVAE_TRY(net_bwd_b(params, grads, L.enc, p.img.enc, L.post, p.img.post, p.dpar_e_b, L.P, L.P, x, nullptr, c->D, B,
-                      p.enc, p.dH, p.dU, p.dG, p.wtmp, nullptr, s));
-  PMVAE_TRY(net_bwd_b(params, grads, L.part, p.img.part, L.ppost, p.img.ppost, p.dpar_p_b, L.P, L.P, x, b, c->D, B,
-                      p.part, p.dH, p.dU, p.dG, p.wtmp, nullptr, s));
+  const int D = c->D, d = c->d;
+  for (int64_t r0 = 0; r0 < B; r0 += kMicroRows) {
+    const int64_t nb = (B - r0 < kMicroRows) ? (B - r0) : kMicroRows;
+    const float* xc = x + r0 * D;
+    // gradient temporaries (dloc, dH, dU, dG, dz, dpar) are reused by every micro-batch
+    PMVAE_TRY(rec_ll_bwd(xc, p.loc + r0 * p.Dp, p.Dp, params + L.log_scale, g_rec + r0, nullptr, p.dloc_b, p.Dp,
+                         grads + L.log_scale, nb, D, s));
+    PMVAE_TRY(net_bwd_b(params, grads, L.dec, p.img.dec, L.ddist, p.img.ddist, p.dloc_b, p.Dp, p.Dp, p.z + r0 * d,
+                        nullptr, d, nb, shift_saved(p.dec, L.dec, r0), p.dH, p.dU, p.dG, p.wtmp, p.dz, s));
+    PMVAE_TRY(latent_bwd(p.par_e + r0 * L.P, p.par_p + r0 * L.P, eps + r0 * d, p.z + r0 * d, p.dz, g_kl + r0,
+                         g_match + r0, c->stop_grad, nullptr, nullptr, p.dpar_e_b, p.dpar_p_b, nb, d, s));
+    PMVAE_TRY(net_bwd_b(params, grads, L.enc, p.img.enc, L.post, p.img.post, p.dpar_e_b, L.P, L.P, xc, nullptr, D, nb,
+                        shift_saved(p.enc, L.enc, r0), p.dH, p.dU, p.dG, p.wtmp, nullptr, s));
+    PMVAE_TRY(net_bwd_b(params, grads, L.part, p.img.part, L.ppost, p.img.ppost, p.dpar_p_b, L.P, L.P, xc, b + r0 * D,
+                        D, nb, shift_saved(p.part, L.part, r0), p.dH, p.dU, p.dG, p.wtmp, nullptr, s));
+  }
   return 0;
 }
 
