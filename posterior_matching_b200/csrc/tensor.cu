@@ -11,6 +11,7 @@
 // Linear of each net (K = D, 2D or d <= 126) and its gradients are fp32 SIMT kernels that
 // also build [x*b, b] on the fly (vae.py:132-133).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 #include "model.h"
@@ -399,8 +400,17 @@ static NetSavedB shift_saved(const NetSavedB& s, const Net& n, int64_t r0) {
 }
 
 // Rows are processed in micro-batches so that the tensors one kernel writes and the next reads
-// (h, T, dH, dU: 8 MB each at 16 Ki rows) are still in the 126 MB L2 when they are re-read.
-constexpr int64_t kMicroRows = 16384;
+// (h, T, dH, dU: 64 MB each at 128 Ki rows) can still be partly L2-resident when they are re-read;
+// smaller micro-batches lose more to per-launch overhead than they gain (measured, profiles/).
+static int64_t micro_rows() {
+  static int64_t v = 0;
+  if (v == 0) {
+    const char* e = getenv("PMVAE_MICRO_ROWS");
+    v = e ? atoll(e) : (1ll << 17);
+    if (v < 1024) v = 1024;
+  }
+  return v;
+}
 
 struct TrainPlanB {
   Images img;
@@ -646,6 +656,7 @@ int forward_bf16(const pmvae_config* c, const Layout& L, const float* params, co
   TrainPlanB p = plan_train_b(c, L, B, ws);
   CHECK_WS(p);
   const int D = c->D, d = c->d;
+  const int64_t kMicroRows = micro_rows();
   for (int64_t r0 = 0; r0 < B; r0 += kMicroRows) {
     const int64_t nb = (B - r0 < kMicroRows) ? (B - r0) : kMicroRows;
     const float* xc = x + r0 * D;
@@ -668,6 +679,7 @@ int backward_bf16(const pmvae_config* c, const Layout& L, const float* params, c
   TrainPlanB p = plan_train_b(c, L, B, ws);
   CHECK_WS(p);
   const int D = c->D, d = c->d;
+  const int64_t kMicroRows = micro_rows();
   for (int64_t r0 = 0; r0 < B; r0 += kMicroRows) {
     const int64_t nb = (B - r0 < kMicroRows) ? (B - r0) : kMicroRows;
     const float* xc = x + r0 * D;
