@@ -13,6 +13,7 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
+#include "fused_mlp.cuh"
 #include "kernels.h"
 #include "model.h"
 #include "tc_gemm.h"
@@ -65,8 +66,17 @@ struct LeafImg { const bf16* wn; const bf16* wt; int ldn, ldt; };   // wn: [rows
 
 struct Images {
   LeafImg enc[2 * kMaxBlocks + 1], dec[2 * kMaxBlocks + 1], part[2 * kMaxBlocks + 1], post, ddist, ppost;
+  // operand images of the fused ResidualMLP kernels (fused_mlp.cu), for the nets they cover
+  bool f_enc_ok, f_dec_ok, f_part_ok;
+  fused::NetImages f_enc, f_dec, f_part;
   uint64_t bytes;
 };
+
+static bool fused_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PMVAE_FUSED"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
 
 static void plan_images(const Layout& L, void* ws, Images* im, PackTable* tb) {
   uint64_t off = 0;  // in bf16 elements
@@ -90,6 +100,16 @@ static void plan_images(const Layout& L, void* ws, Images* im, PackTable* tb) {
   net(L.enc, im->enc); one(L.post, im->post);
   net(L.dec, im->dec); one(L.ddist, im->ddist);
   net(L.part, im->part); one(L.ppost, im->ppost);
+  off = align_up(off, 512);
+  auto fnet = [&](const Net& n, const Leaf& head, int in_kind, bool& ok, fused::NetImages& out) {
+    ok = fused_enabled() && fused::supported(n, 256, in_kind);
+    if (!ok) return;
+    out = fused::plan_images(n, head, in_kind, ws ? reinterpret_cast<bf16*>(ws) + off : nullptr);
+    off += out.elems;
+  };
+  fnet(L.enc, L.post, 0, im->f_enc_ok, im->f_enc);
+  fnet(L.dec, L.ddist, 0, im->f_dec_ok, im->f_dec);
+  fnet(L.part, L.ppost, 1, im->f_part_ok, im->f_part);
   im->bytes = align_up(off * 2, 1024);
   if (tb) tb->total_tiles = tiles;
 }
@@ -364,6 +384,8 @@ struct Bump {
 };
 
 struct NetSavedB {
+  // one stack [(2R+1), Bpad, 256]: slab 2r = A[r], slab 2r+1 = T[r]; relu bits of every slab after it
+  bf16* stack; uint32_t* masks; int64_t Bpad;
   bf16* A[kMaxBlocks + 1];
   bf16* T[kMaxBlocks];
   // LN nets: normalised pre-activations and 1/sigma
@@ -373,8 +395,11 @@ struct NetSavedB {
 
 static void plan_net_b(Bump& bp, const Net& n, int64_t B, NetSavedB& s) {
   const uint64_t e = (uint64_t)B * 256;
-  for (int r = 0; r <= n.R; ++r) s.A[r] = bp.take<bf16>(e);
-  for (int r = 0; r < n.R; ++r) s.T[r] = bp.take<bf16>(e);
+  s.Bpad = (B + 127) / 128 * 128;
+  s.stack = bp.take<bf16>((uint64_t)(2 * n.R + 1) * s.Bpad * 256);
+  s.masks = bp.take<uint32_t>((uint64_t)(2 * n.R + 1) * s.Bpad * 8);
+  for (int r = 0; r <= n.R; ++r) s.A[r] = s.stack + (uint64_t)(2 * r) * s.Bpad * 256;
+  for (int r = 0; r < n.R; ++r) s.T[r] = s.stack + (uint64_t)(2 * r + 1) * s.Bpad * 256;
   if (n.ln) {
     s.X0 = bp.take<bf16>(e);
     s.rstd0 = bp.take<float>(B);
@@ -387,6 +412,8 @@ static void plan_net_b(Bump& bp, const Net& n, int64_t B, NetSavedB& s) {
 
 static NetSavedB shift_saved(const NetSavedB& s, const Net& n, int64_t r0) {
   NetSavedB o = s;
+  o.stack = s.stack + r0 * 256;
+  o.masks = s.masks + r0 * 8;
   for (int r = 0; r <= n.R; ++r) o.A[r] = s.A[r] + r0 * 256;
   for (int r = 0; r < n.R; ++r) o.T[r] = s.T[r] + r0 * 256;
   if (n.ln) {
@@ -408,6 +435,7 @@ static int64_t micro_rows() {
     const char* e = getenv("PMVAE_MICRO_ROWS");
     v = e ? atoll(e) : (1ll << 17);
     if (v < 1024) v = 1024;
+    v = v / 128 * 128;          // the fused kernels store whole 128-row tiles
   }
   return v;
 }
@@ -508,6 +536,9 @@ int prepare_params_bf16(const pmvae_config* c, const float* params, void* ws, ui
   PMVAE_CHECK((reinterpret_cast<uintptr_t>(ws) & 1023u) == 0, "workspace must be 1024-byte aligned");
   pack_weights_kernel<<<tb.total_tiles, 256, 0, s>>>(params, reinterpret_cast<bf16*>(ws), tb);
   PMVAE_LAUNCH_CHECK();
+  if (im.f_enc_ok) PMVAE_TRY(fused::pack_images(params, L.enc, L.post, im.f_enc, s));
+  if (im.f_dec_ok) PMVAE_TRY(fused::pack_images(params, L.dec, L.ddist, im.f_dec, s));
+  if (im.f_part_ok) PMVAE_TRY(fused::pack_images(params, L.part, L.ppost, im.f_part, s));
   return 0;
 }
 
@@ -526,8 +557,12 @@ static int in_layer_fwd(const float* params, const Leaf& lf, const float* in, co
 
 static int net_fwd_b(const float* params, const Net& n, const LeafImg* img, const Leaf& head, const LeafImg& himg,
                      int head_cols_pad, const float* in, const float* msk, int D_in, int64_t B, const NetSavedB& sv,
-                     float* h, float* ytmp, float* head_out, int64_t ld_head, cudaStream_t s) {
+                     float* h, float* ytmp, float* head_out, int64_t ld_head, const fused::NetImages* fim, bool save,
+                     cudaStream_t s) {
   using tc::TcGemmArgs;
+  if (fim)   // one persistent kernel for the whole net + head, activations stay on chip
+    return fused::net_forward(params, n, head, *fim, in, msk, B, save ? sv.stack : nullptr, save ? sv.masks : nullptr,
+                              sv.Bpad, head_out, ld_head, s);
   if (!n.ln) {
     PMVAE_TRY(in_layer_fwd(params, n.lin[0], in, msk, D_in, B, h, sv.A[0], s));
   } else {
@@ -661,13 +696,16 @@ int forward_bf16(const pmvae_config* c, const Layout& L, const float* params, co
     const int64_t nb = (B - r0 < kMicroRows) ? (B - r0) : kMicroRows;
     const float* xc = x + r0 * D;
     PMVAE_TRY(net_fwd_b(params, L.enc, p.img.enc, L.post, p.img.post, L.P, xc, nullptr, D, nb,
-                        shift_saved(p.enc, L.enc, r0), p.h, p.ytmp, p.par_e + r0 * L.P, L.P, s));
+                        shift_saved(p.enc, L.enc, r0), p.h, p.ytmp, p.par_e + r0 * L.P, L.P,
+                        p.img.f_enc_ok ? &p.img.f_enc : nullptr, true, s));
     PMVAE_TRY(latent_fwd(p.par_e + r0 * L.P, eps + r0 * d, p.z + r0 * d, out_kl + r0, nb, d, s));
     PMVAE_TRY(net_fwd_b(params, L.dec, p.img.dec, L.ddist, p.img.ddist, p.Dp, p.z + r0 * d, nullptr, d, nb,
-                        shift_saved(p.dec, L.dec, r0), p.h, p.ytmp, p.loc + r0 * p.Dp, p.Dp, s));
+                        shift_saved(p.dec, L.dec, r0), p.h, p.ytmp, p.loc + r0 * p.Dp, p.Dp,
+                        p.img.f_dec_ok ? &p.img.f_dec : nullptr, true, s));
     PMVAE_TRY(rec_ll(xc, p.loc + r0 * p.Dp, p.Dp, params + L.log_scale, nullptr, out_rec + r0, nb, D, s));
     PMVAE_TRY(net_fwd_b(params, L.part, p.img.part, L.ppost, p.img.ppost, L.P, xc, b + r0 * D, D, nb,
-                        shift_saved(p.part, L.part, r0), p.h, p.ytmp, p.par_p + r0 * L.P, L.P, s));
+                        shift_saved(p.part, L.part, r0), p.h, p.ytmp, p.par_p + r0 * L.P, L.P,
+                        p.img.f_part_ok ? &p.img.f_part : nullptr, true, s));
     PMVAE_TRY(match_fwd(p.par_p + r0 * L.P, p.z + r0 * d, out_match + r0, nb, d, s));
   }
   return 0;
@@ -706,22 +744,22 @@ int is_log_prob_bf16(const pmvae_config* c, const Layout& L, const float* params
   EvalPlanB p = plan_eval_b(c, L, B, K, ws);
   CHECK_WS(p);
   PMVAE_TRY(net_fwd_b(params, L.enc, p.img.enc, L.post, p.img.post, L.P, x, nullptr, c->D, B, p.enc, p.h, p.ytmp,
-                      p.par_e, L.P, s));
+                      p.par_e, L.P, p.img.f_enc_ok ? &p.img.f_enc : nullptr, false, s));
   PMVAE_TRY(net_fwd_b(params, L.part, p.img.part, L.ppost, p.img.ppost, L.P, x, b, c->D, B, p.part, p.h, p.ytmp,
-                      p.par_p, L.P, s));
+                      p.par_p, L.P, p.img.f_part_ok ? &p.img.f_part : nullptr, false, s));
   const float* ls = params + L.log_scale;
   for (int64_t r0 = 0; r0 < B; r0 += p.rows_per_chunk) {
     const int64_t nb = (B - r0 < p.rows_per_chunk) ? (B - r0) : p.rows_per_chunk;
     const int64_t M = nb * K;
     PMVAE_TRY(sample_latents(p.par_e + r0 * L.P, Key2{key_z[0], key_z[1]}, nb, K, B_total, row_start + r0, c->d, p.z, p.base, s));
     PMVAE_TRY(net_fwd_b(params, L.dec, p.img.dec, L.ddist, p.img.ddist, p.Dp, p.z, nullptr, c->d, M, p.dec, p.h, p.ytmp,
-                        p.loc, p.Dp, s));
+                        p.loc, p.Dp, p.img.f_dec_ok ? &p.img.f_dec : nullptr, false, s));
     PMVAE_TRY(eval_rows_ll(x + r0 * c->D, nullptr, p.loc, p.Dp, ls, p.base, p.llA, nb, K, c->D, s));
     if (out_log_p_x) PMVAE_TRY(logmeanexp_rows(p.llA, nullptr, out_log_p_x + r0, nb, K, s));
     if (out_cond) {
       PMVAE_TRY(sample_latents(p.par_p + r0 * L.P, Key2{key_zxo[0], key_zxo[1]}, nb, K, B_total, row_start + r0, c->d, p.z, p.base, s));
       PMVAE_TRY(net_fwd_b(params, L.dec, p.img.dec, L.ddist, p.img.ddist, p.Dp, p.z, nullptr, c->d, M, p.dec, p.h,
-                          p.ytmp, p.loc, p.Dp, s));
+                          p.ytmp, p.loc, p.Dp, p.img.f_dec_ok ? &p.img.f_dec : nullptr, false, s));
       PMVAE_TRY(eval_rows_ll(x + r0 * c->D, b + r0 * c->D, p.loc, p.Dp, ls, p.base, p.llC, nb, K, c->D, s));
       PMVAE_TRY(logmeanexp_rows(p.llA, p.llC, out_cond + r0, nb, K, s));
     }
@@ -736,12 +774,12 @@ int impute_mean_bf16(const pmvae_config* c, const Layout& L, const float* params
   EvalPlanB p = plan_eval_b(c, L, B, K, ws);
   CHECK_WS(p);
   PMVAE_TRY(net_fwd_b(params, L.part, p.img.part, L.ppost, p.img.ppost, L.P, x, b, c->D, B, p.part, p.h, p.ytmp,
-                      p.par_p, L.P, s));
+                      p.par_p, L.P, p.img.f_part_ok ? &p.img.f_part : nullptr, false, s));
   for (int64_t r0 = 0; r0 < B; r0 += p.rows_per_chunk) {
     const int64_t nb = (B - r0 < p.rows_per_chunk) ? (B - r0) : p.rows_per_chunk;
     PMVAE_TRY(sample_latents(p.par_p + r0 * L.P, Key2{key[0], key[1]}, nb, K, B_total, row_start + r0, c->d, p.z, p.base, s));
     PMVAE_TRY(net_fwd_b(params, L.dec, p.img.dec, L.ddist, p.img.ddist, p.Dp, p.z, nullptr, c->d, nb * K, p.dec, p.h,
-                        p.ytmp, p.loc, p.Dp, s));
+                        p.ytmp, p.loc, p.Dp, p.img.f_dec_ok ? &p.img.f_dec : nullptr, false, s));
     PMVAE_TRY(impute_mean(x + r0 * c->D, b + r0 * c->D, p.loc, p.Dp, out + r0 * c->D, nb, K, c->D, s));
   }
   return 0;
