@@ -147,6 +147,17 @@ int pmvae_adamw(const pmvae_config* cfg, float* params, const float* grads, floa
                 int64_t count, float lr, float wd, float b1, float b2, float eps,
                 pmvae_stream_t stream);
 
+/* One network + its distribution head on its own: the module attributes .encoder, .decoder and
+ * .partial_encoder (vae.py:47-53; used by lookahead.py:77,126,133,219 and the MNIST notebook).
+ *   which = 0: encoder(x[B,D])             -> out[B,P]  raw TriL parameters (loc | FillScaleTriL input)
+ *   which = 1: decoder(z[B,d])             -> out[B,D]  IdentityGaussian loc
+ *   which = 2: partial_encoder([x*b, b])   -> out[B,P]  (in = x, msk = b, both [B,D])
+ * P = d + d(d+1)/2. */
+enum { PMVAE_NET_ENCODER = 0, PMVAE_NET_DECODER = 1, PMVAE_NET_PARTIAL_ENCODER = 2 };
+int pmvae_net_apply(const pmvae_config* cfg, const float* params, int32_t which, const float* in,
+                    const float* msk, int64_t B, float* out, void* ws, uint64_t ws_bytes,
+                    pmvae_stream_t stream);
+
 /* PosteriorMatchingVAE.is_log_prob (vae.py:171-226) with K samples per row; eps drawn
  * on device from key_z / key_zxo as normal(key, [K, B_total, d]) restricted to rows
  * [row_start, row_start+B).  Either output may be NULL. */

@@ -67,6 +67,7 @@ _SIGS = {
     "pmvae_loss_cotangents": (_i32, [_i64, _i64, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pmvae_adamw": (_i32, [_cfgp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _vp]),
     "pmvae_is_log_prob": (_i32, [_cfgp, _vp, _vp, _vp, _i64, _i64, _u32p, _u32p, _i64, _i64, _vp, _vp, _vp, _u64, _vp]),
+    "pmvae_net_apply": (_i32, [_cfgp, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _u64, _vp]),
     "pmvae_impute_mean": (_i32, [_cfgp, _vp, _vp, _vp, _i64, _i64, _u32p, _i64, _i64, _vp, _vp, _u64, _vp]),
 }
 EXPORTS = tuple(_SIGS)

@@ -17,6 +17,8 @@
 // weight-gradient operands) together with one relu bit per element.
 #include "fused_mlp.cuh"
 
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "tc_ptx.cuh"
 
@@ -47,6 +49,8 @@ struct FwdArgs {
   const float* bias[kMaxLayers];
   const float* head_bias; int head_N, head_NT, head_tiles;
   int64_t Bpad; uint32_t* masks;
+  long long* trace;   // PMVAE_FUSED_TRACE: per-phase clock64 stamps of block 0 (profiling only)
+  int debug;   // PMVAE_FUSED_DEBUG bits (profiling only): 1 no epilogue math/stores, 2 no weight loads, 4 no MMAs
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -54,6 +58,12 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16(v)); }
+// relu on a packed bf16 pair (rounding is monotonic, so relu(bf16(v)) == bf16(relu(v)))
+__device__ __forceinline__ uint32_t relu2(uint32_t v) {
+  uint32_t o;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(o) : "r"(v), "r"(0u));
+  return o;
+}
 
 template <bool SAVE>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -103,6 +113,14 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // trace: role 0 = MMA thread, role 1 = epilogue warp 0 lane 0; entries (tag, clock) from slot 1, count in slot 0
+  int tr_n = 0;
+  auto stamp = [&](int role, int tag) {
+    if (p.trace && blockIdx.x == 0 && tr_n < 1000) {
+      long long* t = p.trace + role * 2048;
+      t[1 + 2 * tr_n] = tag; t[2 + 2 * tr_n] = clock64(); ++tr_n; t[0] = tr_n;
+    }
+  };
 
   if (warp == 0) {
     // ===================== weight producer =====================
@@ -110,8 +128,11 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       int stage = 0; uint32_t ph = 0;
       auto load = [&](const CUtensorMap* m, int c0, int c1, uint32_t bytes) {
         mbar_wait(w_empty(stage), ph ^ 1u, 1);
-        mbar_arrive_expect_tx(w_full(stage), bytes);
-        tma_load_2d(wring + stage * kWStageBytes, m, w_full(stage), c0, c1);
+        if (p.debug & 2) { mbar_arrive(w_full(stage)); }
+        else {
+          mbar_arrive_expect_tx(w_full(stage), bytes);
+          tma_load_2d(wring + stage * kWStageBytes, m, w_full(stage), c0, c1);
+        }
         if (++stage == kWStages) { stage = 0; ph ^= 1u; }
       };
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -130,9 +151,11 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       auto step = [&](int s_idx, int nk16, int N, bool accum, bool wait_opnd) {
         const int region = (s_idx & 1) ? 0 : 1;
         uint32_t& uc = region ? use_cnt1 : use_cnt0;
+        stamp(0, 100 + s_idx);
         mbar_wait(acc_empty(region), (uc & 1u) ^ 1u, 2);
         ++uc;
         tc_fence_after();
+        stamp(0, 200 + s_idx);
         const uint32_t d_tmem = tmem_base + (uint32_t)(region * 256);
         const uint32_t idesc = instr_desc(128, N, 0, 0);
         const int nkb = (nk16 + 3) >> 2;
@@ -141,18 +164,21 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             mbar_wait(opnd_ready(kb), (ready_par >> kb) & 1u, 3);
             ready_par ^= 1u << kb;
           }
+          stamp(0, 300 + kb);
           mbar_wait(w_full(stage), ph, 4);
           tc_fence_after();
+          stamp(0, 400 + kb);
           const uint32_t sa = opnd + kb * kChunkBytes;
           const uint32_t sb = wring + stage * kWStageBytes;
           const int ks = min(4, nk16 - 4 * kb);
-          for (int k = 0; k < ks; ++k)
+          for (int k = 0; k < ks && !(p.debug & 4); ++k)
             umma_f16(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sb + k * 32, 16, 1024), idesc,
                      (accum || kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(w_empty(stage));
           if (++stage == kWStages) { stage = 0; ph ^= 1u; }
         }
         umma_commit(acc_full(region));
+        stamp(0, 500 + s_idx);
       };
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         step(0, p.k16_0, 256, false, true);
@@ -180,6 +206,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int64_t g = (int64_t)tile * 128 + row;
       const bool row_ok = g < p.B;
+      if (ew == 0 && lane == 0) stamp(1, 1000);
       // ---- first-layer operand: hi/lo bf16 split of the fp32 input, [x*b, b] built here (vae.py:132-133)
       if (SAVE) drain_sync();
       {
@@ -219,30 +246,44 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       // ---- hidden Linears: accumulator -> bf16 operand of the next Linear
       for (int l = 0; l < n_hidden; ++l) {
         const int region = (l & 1) ? 0 : 1;
+        if (ew == 0 && lane == 0) stamp(1, 1100 + l);
         mbar_wait(acc_full(region), (full_par >> region) & 1u, 5);
+        if (ew == 0 && lane == 0) stamp(1, 1200 + l);
         full_par ^= 1u << region;
         tc_fence_after();
-        if (SAVE) drain_sync();
+        const uint32_t t_acc = t_lane + (uint32_t)(region * 256 + 32 * half);
         uint32_t mw[4];
+        uint32_t ra[32], rb[32];
+        tmem_ld32(t_acc, ra);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint32_t r[32];
-          tmem_ld32(t_lane + (uint32_t)(region * 256 + 64 * j + 32 * half), r);
+          // the accumulator columns of chunk j+1 are fetched while chunk j is converted
+          uint32_t (&r)[32] = (j & 1) ? rb : ra;
           tmem_ld_wait();
+          if (j < 3) tmem_ld32(t_acc + 64 * (j + 1), (j & 1) ? ra : rb);
+          if (p.debug & 1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(opnd_ready(j));
+            continue;
+          }
           const float4* bp = reinterpret_cast<const float4*>(bias_tbl + l * 256 + 64 * j + 32 * half);
           uint32_t pk[16];
-          uint32_t bits = 0;
+          uint32_t neg = 0;          // sign bits of the pre-activations, element 0 ends up in bit 31
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 bv = bp[i];
             const float v0 = __uint_as_float(r[4 * i]) + bv.x, v1 = __uint_as_float(r[4 * i + 1]) + bv.y;
             const float v2 = __uint_as_float(r[4 * i + 2]) + bv.z, v3 = __uint_as_float(r[4 * i + 3]) + bv.w;
-            bits |= (v0 > 0.f ? 1u : 0u) << (4 * i) | (v1 > 0.f ? 1u : 0u) << (4 * i + 1) |
-                    (v2 > 0.f ? 1u : 0u) << (4 * i + 2) | (v3 > 0.f ? 1u : 0u) << (4 * i + 3);
-            pk[2 * i] = pack2(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
-            pk[2 * i + 1] = pack2(fmaxf(v2, 0.f), fmaxf(v3, 0.f));
+            if (SAVE) {
+              neg = __funnelshift_l(__float_as_uint(v0), neg, 1);
+              neg = __funnelshift_l(__float_as_uint(v1), neg, 1);
+              neg = __funnelshift_l(__float_as_uint(v2), neg, 1);
+              neg = __funnelshift_l(__float_as_uint(v3), neg, 1);
+            }
+            pk[2 * i] = relu2(pack2(v0, v1));
+            pk[2 * i + 1] = relu2(pack2(v2, v3));
           }
-          mw[j] = bits;
+          mw[j] = ~neg;
           const uint32_t rowaddr = opnd + j * kChunkBytes + row * 128;
 #pragma unroll
           for (int i4 = 0; i4 < 4; ++i4) {
@@ -252,7 +293,11 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(opnd_ready(j));
+          if (ew == 0 && lane == 0) stamp(1, 1300 + j);
           if (SAVE) {
+            // Before chunk j+1 (or chunk 0 of the next Linear) is overwritten its previous TMA store must
+            // have finished reading: that store is the oldest of the three groups still in flight.
+            if (half == 0 && lane == 0) tma_store_wait_read<2>();
             named_bar_sync(1 + q, 64);
             if (half == 0 && lane == 0) {
               tma_store_2d(&map_s, opnd + j * kChunkBytes + q * 4096, 64 * j,
@@ -270,7 +315,9 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       // ---- head Linear: accumulator + bias -> fp32 rows, staged per warp and stored by TMA
       for (int t = 0; t < p.head_tiles; ++t) {
         const int region = ((n_hidden + t) & 1) ? 0 : 1;
+        if (ew == 0 && lane == 0) stamp(1, 1400 + t);
         mbar_wait(acc_full(region), (full_par >> region) & 1u, 6);
+        if (ew == 0 && lane == 0) stamp(1, 1500 + t);
         full_par ^= 1u << region;
         tc_fence_after();
         for (int pc = half; pc * 32 < p.head_NT; pc += 2) {
@@ -299,6 +346,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             tma_store_2d(&map_o, my_stag, nb, (int)((int64_t)tile * 128 + q * 32));
             tma_store_commit();
           }
+          if (ew == 0 && lane == 0) stamp(1, 1600 + pc);
         }
         tc_fence_before();
         __syncwarp();
@@ -306,6 +354,278 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       }
     }
     if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------- backward chain
+// Input-gradient chain of one ResidualMLP + head over 128-row tiles (the VJP of net_fwd_kernel with respect
+// to the activations).  Per tile, with s = dL/dh (the gradient of the residual stream) and M_l the relu bits
+// the forward saved for Linear l:
+//   s    = M_2R . (dHead @ W_head^T)
+//   for r = R-1 .. 0:   dU = M_{2r+1} . (s @ W_{2r+2}^T);   s += M_{2r} . (dU @ W_{2r+1}^T)
+//   dIn  = s @ W_0^T                                         (decoder only: dL/dz)
+// s and dU live in two bf16 operand buffers in shared memory (each is the A operand of the next
+// contraction, handed over 64 columns at a time exactly like the forward); every version of them is also
+// streamed to HBM by TMA as dY_l, the operand of the weight-gradient GEMM of Linear l, and their column sums
+// (the bias gradients) are accumulated in registers and flushed once per CTA.
+constexpr int kBwdOffU = kOpndBytes;
+constexpr int kBwdOffW = 2 * kOpndBytes;
+constexpr int kBwdOffBar = kBwdOffW + kWStages * kWStageBytes;
+constexpr int kBwdSmemBytes = kBwdOffBar + 256;
+
+struct BwdArgs {
+  int64_t B; int num_tiles;
+  int k16_h;                  // K = 16 steps of the head contraction (ceil(head_N / 16))
+  int din_N, din_cols;        // dIn: MMA N (multiple of 16, 0 = none) and valid columns
+  float* dIn;                 // [B, din_cols] fp32
+  const uint32_t* masks; int64_t Bpad;
+  float* db[kMaxLayers];      // bias-gradient destinations (atomicAdd), Linear 0..2R
+};
+
+template <int R, bool DIN>
+__global__ void __launch_bounds__(kThreads, 1)
+net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant__ CUtensorMap map_wh,
+               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w0,
+               const __grid_constant__ CUtensorMap map_dy, BwdArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if ((sbase & 1023u) != 0) { if (threadIdx.x == 0) printf("pmvae net_bwd_kernel: shared memory base is not 1024-byte aligned\n"); __trap(); }
+  const uint32_t sbuf = sbase, ubuf = sbase + kBwdOffU, wring = sbase + kBwdOffW, bar = sbase + kBwdOffBar;
+  auto w_full = [&](int s) { return bar + 8u * s; };
+  auto w_empty = [&](int s) { return bar + 8u * (kWStages + s); };
+  auto opnd_ready = [&](int c) { return bar + 8u * (2 * kWStages + c); };
+  auto acc_full = [&](int r) { return bar + 8u * (2 * kWStages + 4 + r); };
+  auto acc_empty = [&](int r) { return bar + 8u * (2 * kWStages + 6 + r); };
+  const uint32_t dh_full = bar + 8u * (2 * kWStages + 8);
+  const uint32_t ubuf_free = bar + 8u * (2 * kWStages + 9);
+  const uint32_t tmem_slot = bar + 8u * (2 * kWStages + 10);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + kBwdOffBar + 8 * (2 * kWStages + 10));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int n_hidden = 2 * R + 1;
+  const int nkb_h = (p.k16_h + 3) >> 2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_dh); tma_prefetch_desc(&map_wh); tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_dy);
+    if (DIN) tma_prefetch_desc(&map_w0);
+    for (int s = 0; s < kWStages; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    for (int c = 0; c < 4; ++c) mbar_init(opnd_ready(c), kEpiWarps);
+    for (int r = 0; r < 2; ++r) { mbar_init(acc_full(r), 1); mbar_init(acc_empty(r), kEpiWarps); }
+    mbar_init(dh_full, 1);
+    mbar_init(ubuf_free, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ===================== producer: dHead tiles and weight K-blocks =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t ph = 0; uint32_t uf_cnt = 0;
+      auto load = [&](const CUtensorMap* m, int c0, int c1, uint32_t bytes) {
+        mbar_wait(w_empty(stage), ph ^ 1u, 1);
+        mbar_arrive_expect_tx(w_full(stage), bytes);
+        tma_load_2d(wring + stage * kWStageBytes, m, w_full(stage), c0, c1);
+        if (++stage == kWStages) { stage = 0; ph ^= 1u; }
+      };
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        // dHead rows of this tile go into the dU buffer once the previous tile no longer needs it
+        mbar_wait(ubuf_free, (uf_cnt & 1u) ^ 1u, 7);
+        ++uf_cnt;
+        mbar_arrive_expect_tx(dh_full, (uint32_t)nkb_h * kChunkBytes);
+        for (int kb = 0; kb < nkb_h; ++kb) tma_load_2d(ubuf + kb * kChunkBytes, &map_dh, dh_full, kb * 64, tile * 128);
+        for (int kb = 0; kb < nkb_h; ++kb) load(&map_wh, kb * 64, 0, kWStageBytes);
+        for (int l = 2 * R; l >= 1; --l)
+          for (int kb = 0; kb < 4; ++kb) load(&map_w, kb * 64, (l - 1) * 256, kWStageBytes);
+        if (DIN)
+          for (int kb = 0; kb < 4; ++kb) load(&map_w0, kb * 64, 0, (uint32_t)p.din_N * 128u);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t ph = 0;
+      uint32_t ready_par = 0, use_cnt0 = 0, use_cnt1 = 0, dh_par = 0;
+      auto step = [&](int s_idx, uint32_t abuf, int nk16, int N, bool wait_opnd) {
+        const int region = s_idx & 1;
+        uint32_t& uc = region ? use_cnt1 : use_cnt0;
+        mbar_wait(acc_empty(region), (uc & 1u) ^ 1u, 2);
+        ++uc;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(region * 256);
+        const uint32_t idesc = instr_desc(128, N, 0, 0);
+        const int nkb = (nk16 + 3) >> 2;
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (wait_opnd) {
+            mbar_wait(opnd_ready(kb), (ready_par >> kb) & 1u, 3);
+            ready_par ^= 1u << kb;
+          }
+          mbar_wait(w_full(stage), ph, 4);
+          tc_fence_after();
+          const uint32_t sa = abuf + kb * kChunkBytes;
+          const uint32_t sb = wring + stage * kWStageBytes;
+          const int ks = min(4, nk16 - 4 * kb);
+          for (int k = 0; k < ks; ++k)
+            umma_f16(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sb + k * 32, 16, 1024), idesc,
+                     (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(w_empty(stage));
+          if (++stage == kWStages) { stage = 0; ph ^= 1u; }
+        }
+        umma_commit(acc_full(region));
+      };
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(dh_full, dh_par, 8);
+        dh_par ^= 1u;
+        tc_fence_after();
+        int t = 0;
+        step(t++, ubuf, p.k16_h, 256, false);
+        for (int r = R - 1; r >= 0; --r) {
+          step(t++, sbuf, 16, 256, true);
+          step(t++, ubuf, 16, 256, true);
+        }
+        if (DIN) step(t++, sbuf, 16, p.din_N, true);
+      }
+    }
+  } else {
+    // ===================== epilogue (8 warps) =====================
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t full_par = 0;
+    float csum[n_hidden][4];
+#pragma unroll
+    for (int l = 0; l < n_hidden; ++l)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) csum[l][j] = 0.f;
+
+    // One epilogue step: accumulator (region) . mask_l [+ old s] -> bf16 chunk of `dst` (+ TMA store as dY_l,
+    // + column sums).  ADD: dst is the s buffer and the new value is old s + masked accumulator.
+    auto epi_step = [&](int s_idx, int l, uint32_t dst, bool add, int tile, int64_t g, float (&cs)[4], bool free_ubuf,
+                        bool has_consumer) {
+      const int region = s_idx & 1;
+      const uint4 mq = *reinterpret_cast<const uint4*>(p.masks + (((int64_t)l * p.Bpad + g) * 8 + half * 4));
+      const uint32_t mw[4] = {mq.x, mq.y, mq.z, mq.w};
+      mbar_wait(acc_full(region), (full_par >> region) & 1u, 5);
+      full_par ^= 1u << region;
+      tc_fence_after();
+      if (free_ubuf) {
+        // every MMA that read the dU buffer has retired; once its TMA stores have been read out the
+        // producer may overwrite it with the next tile's dHead rows
+        if (half == 0 && lane == 0) { tma_store_wait_read<0>(); mbar_arrive(ubuf_free); }
+      }
+      const uint32_t t_acc = t_lane + (uint32_t)(region * 256 + 32 * half);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t r[32];
+        tmem_ld32(t_acc + 64 * j, r);
+        const uint32_t rowaddr = dst + j * kChunkBytes + row * 128;
+        uint32_t old[16];
+        if (add) {
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const int slot = (half * 4 + i4) ^ (row & 7);
+            ld_shared_v4(rowaddr + slot * 16, old[4 * i4], old[4 * i4 + 1], old[4 * i4 + 2], old[4 * i4 + 3]);
+          }
+        }
+        tmem_ld_wait();
+        float v[32];
+        const uint32_t m = mw[j];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float a = ((int32_t)(m << i) < 0) ? __uint_as_float(r[i]) : 0.f;
+          if (add) a += (i & 1) ? bf16_hi(old[i >> 1]) : bf16_lo(old[i >> 1]);
+          v[i] = a;
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack2(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int slot = (half * 4 + i4) ^ (row & 7);
+          st_shared_v4(rowaddr + slot * 16, pk[4 * i4], pk[4 * i4 + 1], pk[4 * i4 + 2], pk[4 * i4 + 3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (has_consumer && lane == 0) mbar_arrive(opnd_ready(j));     // a chunk nobody multiplies is not announced
+        if (half == 0 && lane == 0) tma_store_wait_read<2>();
+        named_bar_sync(1 + q, 64);
+        if (half == 0 && lane == 0) {
+          tma_store_2d(&map_dy, dst + j * kChunkBytes + q * 4096, 64 * j,
+                       (int)((int64_t)l * p.Bpad + (int64_t)tile * 128 + q * 32));
+          tma_store_commit();
+        }
+        // column sums over this warp's 32 rows: butterfly transpose-reduce, lane c ends up with column c
+#pragma unroll
+        for (int sft = 16, n = 32; sft >= 1; sft >>= 1, n >>= 1) {
+          const bool up = (lane & sft) != 0;
+#pragma unroll
+          for (int i = 0; i < n / 2; ++i) {
+            const float send = up ? v[i] : v[i + n / 2];
+            const float keep = up ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+          }
+        }
+        cs[j] += v[0];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(region));
+    };
+
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int64_t g = (int64_t)tile * 128 + row;
+      // all TMA stores of the previous tile that read the s buffer must be done before it is rewritten
+      if (half == 0 && lane == 0) tma_store_wait_read<0>();
+      named_bar_sync(1 + q, 64);
+      int t = 0;
+      epi_step(t++, 2 * R, sbuf, false, tile, g, csum[2 * R], false, true);
+#pragma unroll
+      for (int r = R - 1; r >= 0; --r) {
+        epi_step(t++, 2 * r + 1, ubuf, false, tile, g, csum[2 * r + 1], false, true);
+        epi_step(t++, 2 * r, sbuf, true, tile, g, csum[2 * r], r == 0, DIN || r > 0);
+      }
+      if (DIN) {
+        const int region = t & 1;
+        mbar_wait(acc_full(region), (full_par >> region) & 1u, 6);
+        full_par ^= 1u << region;
+        tc_fence_after();
+        for (int pc = half; pc * 32 < p.din_N; pc += 2) {
+          uint32_t r[32];
+          tmem_ld32(t_lane + (uint32_t)(region * 256 + pc * 32), r);
+          tmem_ld_wait();
+          if (g < p.B) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (pc * 32 + i < p.din_cols) p.dIn[g * p.din_cols + pc * 32 + i] = __uint_as_float(r[i]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(region));
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+    // bias gradients: lane c of warp (q, half) holds columns 64 j + 32 half + c summed over its rows
+#pragma unroll
+    for (int l = 0; l < n_hidden; ++l)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (p.db[l]) atomicAdd(p.db[l] + 64 * j + 32 * half + lane, csum[l][j]);
   }
 
   tc_fence_before();
@@ -381,6 +701,10 @@ NetImages plan_images(const Net& n, const Leaf& head, int in_kind, bf16* base) {
   im.head_t = take((uint64_t)im.head_tiles * im.head_NT * 256);
   im.stack_n = take((uint64_t)(2 * n.R > 0 ? 2 * n.R : 1) * 256 * 256);
   im.head_n = take((uint64_t)256 * im.head_Kp);
+  im.din_N = (n.in_dim + 15) / 16 * 16;
+  im.w0_n = (in_kind == 0 && im.din_N <= 256) ? take((uint64_t)im.din_N * 256) : nullptr;
+  if (!base && in_kind == 0 && im.din_N <= 256) im.w0_n = nullptr;
+  im.has_w0_n = (in_kind == 0 && im.din_N <= 256);
   im.elems = off;
   return im;
 }
@@ -400,6 +724,7 @@ int pack_images(const float* params, const Net& n, const Leaf& head, const NetIm
   add(im.head_t, head.w, im.head_tiles * im.head_NT, 256, 0, 256, head.cols);
   for (int l = 1; l <= 2 * n.R; ++l) add(im.stack_n + (uint64_t)(l - 1) * 65536, n.lin[l].w, 256, 256, 3, 256, 256);
   add(im.head_n, head.w, 256, im.head_Kp, 3, 256, head.cols);
+  if (im.has_w0_n) add(im.w0_n, n.lin[0].w, im.din_N, 256, 3, n.lin[0].rows, 256);
   pack_fused_kernel<<<tiles, 256, 0, s>>>(params, const_cast<bf16*>(base), tb);
   PMVAE_LAUNCH_CHECK();
   return 0;
@@ -419,6 +744,7 @@ int net_forward(const float* params, const Net& n, const Leaf& head, const NetIm
   a.head_bias = params + head.b; a.head_N = im.head_N; a.head_NT = im.head_NT; a.head_tiles = im.head_tiles;
   a.Bpad = Bpad;
   a.masks = nullptr;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PMVAE_FUSED_DEBUG"); dbg = e ? atoi(e) : 0; } a.debug = dbg; }
   CUtensorMap mw, mh, ms, mo;
   PMVAE_TRY(make_map_2d(&mw, im.stack_t, 2, (uint64_t)(1 + 2 * n.R) * 256, 256, 256, 64, 256));
   PMVAE_TRY(make_map_2d(&mh, im.head_t, 2, (uint64_t)im.head_tiles * im.head_NT, 256, 256, 64, (uint32_t)im.head_NT));
@@ -432,6 +758,14 @@ int net_forward(const float* params, const Net& n, const Leaf& head, const NetIm
     ms = mw;
   }
   const int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
+  static long long* trace_buf = nullptr;
+  static int trace_on = -1;
+  if (trace_on < 0) { const char* e = getenv("PMVAE_FUSED_TRACE"); trace_on = e ? atoi(e) : 0; }
+  if (trace_on) {
+    if (!trace_buf) cudaMalloc(&trace_buf, 2 * 2048 * sizeof(long long));
+    cudaMemsetAsync(trace_buf, 0, 2 * 2048 * sizeof(long long), s);
+    a.trace = trace_buf;
+  }
   static bool attr_set[2] = {false, false};
   if (saved) {
     if (!attr_set[1]) {
@@ -447,7 +781,69 @@ int net_forward(const float* params, const Net& n, const Leaf& head, const NetIm
     net_fwd_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(mw, mh, ms, mo, a);
   }
   PMVAE_LAUNCH_CHECK();
+  if (trace_on) {
+    static long long host[2 * 2048];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(host, trace_buf, sizeof(host), cudaMemcpyDeviceToHost);
+    if (trace_on == 1) {   // print once
+      trace_on = 2;
+      const long long t0 = host[2048 + 2];
+      for (int role = 0; role < 2; ++role) {
+        const long long* t = host + role * 2048;
+        printf("trace role %d (%lld stamps)\n", role, t[0]);
+        for (int i = 0; i < t[0] && i < 400; ++i) printf("  %4lld @ %8lld\n", t[1 + 2 * i], t[2 + 2 * i] - t0);
+      }
+    }
+  }
   return 0;
+}
+
+template <int R, bool DIN>
+static int launch_bwd(const CUtensorMap& mdh, const CUtensorMap& mwh, const CUtensorMap& mw, const CUtensorMap& mw0,
+                      const CUtensorMap& mdy, const BwdArgs& a, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PMVAE_CUDA(cudaFuncSetAttribute(net_bwd_kernel<R, DIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes));
+    attr_set = true;
+  }
+  const int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
+  net_bwd_kernel<R, DIN><<<grid, kThreads, kBwdSmemBytes, s>>>(mdh, mwh, mw, mw0, mdy, a);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+bool backward_supported(const Net& n, int H, int in_kind) { return supported(n, H, in_kind) && n.R >= 1 && n.R <= 4; }
+
+int net_backward(const Net& n, const Leaf& head, const NetImages& im, const bf16* dHead, int64_t ld_dhead, int64_t B,
+                 const uint32_t* masks, int64_t Bpad, bf16* dY, float* grads, float* dIn, cudaStream_t s) {
+  if (B <= 0) return 0;
+  PMVAE_CHECK(backward_supported(n, 256, im.in_kind), "net not covered by the fused backward kernel");
+  PMVAE_CHECK(dIn == nullptr || im.has_w0_n, "no first-layer image for the input gradient");
+  PMVAE_CHECK(Bpad % 128 == 0 && Bpad >= B && (int64_t)(2 * n.R + 1) * Bpad < (1ll << 31), "bad slab pitch");
+  BwdArgs a{};
+  a.B = B; a.num_tiles = (int)ceil_div(B, 128);
+  a.k16_h = (im.head_N + 15) / 16;
+  a.din_N = dIn ? im.din_N : 0; a.din_cols = n.in_dim; a.dIn = dIn;
+  a.masks = masks; a.Bpad = Bpad;
+  for (int l = 0; l <= 2 * n.R; ++l) a.db[l] = grads + n.lin[l].b;
+  CUtensorMap mdh, mwh, mw, mw0, mdy;
+  PMVAE_TRY(make_map_2d(&mdh, dHead, 2, (uint64_t)B, (uint64_t)im.head_N, (uint64_t)ld_dhead, 64, 128));
+  PMVAE_TRY(make_map_2d(&mwh, im.head_n, 2, 256, (uint64_t)im.head_Kp, (uint64_t)im.head_Kp, 64, 256));
+  PMVAE_TRY(make_map_2d(&mw, im.stack_n, 2, (uint64_t)(2 * n.R) * 256, 256, 256, 64, 256));
+  PMVAE_TRY(make_map_2d(&mdy, dY, 2, (uint64_t)(2 * n.R + 1) * Bpad, 256, 256, 64, 32));
+  if (dIn) PMVAE_TRY(make_map_2d(&mw0, im.w0_n, 2, (uint64_t)im.din_N, 256, 256, 64, (uint32_t)im.din_N));
+  else mw0 = mw;
+#define PMVAE_BWD_CASE(RR)                                                             \
+  case RR: return dIn ? launch_bwd<RR, true>(mdh, mwh, mw, mw0, mdy, a, s) : launch_bwd<RR, false>(mdh, mwh, mw, mw0, mdy, a, s)
+  switch (n.R) {
+    PMVAE_BWD_CASE(1);
+    PMVAE_BWD_CASE(2);
+    PMVAE_BWD_CASE(3);
+    PMVAE_BWD_CASE(4);
+  }
+#undef PMVAE_BWD_CASE
+  PMVAE_CHECK(false, "unsupported number of residual blocks");
+  return 1;
 }
 
 }  // namespace fused

@@ -20,6 +20,8 @@ namespace fused {
 struct NetImages {
   const __nv_bfloat16* stack_t; const __nv_bfloat16* head_t;
   const __nv_bfloat16* stack_n; const __nv_bfloat16* head_n;
+  const __nv_bfloat16* w0_n;            // [din_N, 256] first Linear (natural), in_kind 0 only: dL/d(input)
+  bool has_w0_n; int din_N;
   int R, D_in, in_kind, k16_0;          // k16_0 = ceil(K_ext / 16)
   int head_N, head_NT, head_tiles, head_Kp;
   uint64_t elems;                       // bf16 elements used by the four images
@@ -43,6 +45,15 @@ int pack_images(const float* params, const Net& n, const Leaf& head, const NetIm
 int net_forward(const float* params, const Net& n, const Leaf& head, const NetImages& im, const float* in,
                 const float* msk, int64_t B, __nv_bfloat16* saved, uint32_t* masks, int64_t Bpad, float* out,
                 int64_t ld_out, cudaStream_t s);
+
+// Input-gradient chain of the same net (the activations' VJP): reads dHead [B, ld_dhead] (bf16, columns >=
+// head_N zero) and the relu bits of the forward, writes dY_l (bf16, slab l of [(2R+1), Bpad, 256]) = the
+// gradient with respect to the output of Linear l (operand of its weight-gradient GEMM), adds the bias
+// gradients of Linear 0..2R into `grads`, and optionally dL/d(input) [B, in_dim] (fp32).
+bool backward_supported(const Net& n, int H, int in_kind);
+int net_backward(const Net& n, const Leaf& head, const NetImages& im, const __nv_bfloat16* dHead, int64_t ld_dhead,
+                 int64_t B, const uint32_t* masks, int64_t Bpad, __nv_bfloat16* dY, float* grads, float* dIn,
+                 cudaStream_t s);
 
 }  // namespace fused
 }  // namespace pmvae

@@ -394,6 +394,22 @@ int impute_mean_seq(const pmvae_config* c, const float* params, const float* x, 
   return 0;
 }
 
+int net_apply(const pmvae_config* c, const float* params, int which, const float* in, const float* msk, int64_t B,
+              float* out, void* ws, uint64_t ws_bytes, cudaStream_t s) {
+  Layout L;
+  PMVAE_TRY(build_layout(c, &L));
+  PMVAE_CHECK(which >= 0 && which <= 2, "net id must be 0 (encoder), 1 (decoder) or 2 (partial encoder)");
+  PMVAE_CHECK(params && in && out && ws && B >= 0 && (which != 2 || msk), "null pointer");
+  if (B == 0) return 0;
+  if (c->precision == PMVAE_PREC_BF16) return net_apply_bf16(c, L, params, which, in, msk, B, out, ws, ws_bytes, s);
+  TrainPlan p = plan_train(c, L, B, ws);
+  PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_workspace_bytes)");
+  if (which == 0) return net_fwd_f32(params, L.enc, L.post, c->H, in, B, p.enc, out, s);
+  if (which == 1) return net_fwd_f32(params, L.dec, L.ddist, c->H, in, B, p.dec, out, s);
+  PMVAE_TRY(concat_masked(in, msk, p.xob, B, c->D, s));
+  return net_fwd_f32(params, L.part, L.ppost, c->H, p.xob, B, p.part, out, s);
+}
+
 }  // namespace pmvae
 
 using namespace pmvae;
@@ -479,6 +495,12 @@ int pmvae_is_log_prob(const pmvae_config* cfg, const float* params, const float*
                       pmvae_stream_t stream) {
   return is_log_prob(cfg, params, x, b, B, K, key_z, key_zxo, B_total, row_start, out_log_p_x, out_log_p_xu_given_xo,
                      ws, ws_bytes, as_stream(stream));
+}
+
+int pmvae_net_apply(const pmvae_config* cfg, const float* params, int32_t which, const float* in, const float* msk,
+                    int64_t B, float* out, void* ws, uint64_t ws_bytes, pmvae_stream_t stream) {
+  PMVAE_CHECK(cfg != nullptr, "null config");
+  return net_apply(cfg, params, which, in, msk, B, out, ws, ws_bytes, as_stream(stream));
 }
 
 int pmvae_impute_mean(const pmvae_config* cfg, const float* params, const float* x, const float* b, int64_t B,

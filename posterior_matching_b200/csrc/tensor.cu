@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) in_layer_bwd_kernel(const float* __restri
 #pragma unroll
     for (int k = 0; k < kKC; ++k)
       if (k < kn) atomicAdd(dW + (kc + k) * 256 + c, acc[k]);
-    if (kc == 0) atomicAdd(db + c, accb);
+    if (kc == 0 && db) atomicAdd(db + c, accb);
   }
 }
 
@@ -445,6 +445,7 @@ struct TrainPlanB {
   NetSavedB enc, dec, part;
   float *h, *ytmp, *par_e, *par_p, *z, *loc, *dz, *wtmp;
   bf16 *dH, *dU, *dG, *dpar_e_b, *dpar_p_b, *dloc_b;
+  bf16* dY;   // [(2 Rmax + 1), Bpad, 256] gradient operands of the fused backward (shared by the three nets)
   int Dp;
   uint64_t bytes;
 };
@@ -472,6 +473,11 @@ static TrainPlanB plan_train_b(const pmvae_config* c, const Layout& L, int64_t B
   p.dpar_e_b = bp.take<bf16>((uint64_t)B * L.P);
   p.dpar_p_b = bp.take<bf16>((uint64_t)B * L.P);
   p.dloc_b = bp.take<bf16>((uint64_t)B * p.Dp);
+  {
+    int Rm = L.enc.R > L.dec.R ? L.enc.R : L.dec.R;
+    if (L.part.R > Rm) Rm = L.part.R;
+    p.dY = bp.take<bf16>((uint64_t)(2 * Rm + 1) * p.enc.Bpad * 256);
+  }
   p.bytes = bp.off;
   return p;
 }
@@ -620,8 +626,24 @@ static int lin_bwd_params_b(float* grads, const Leaf& lf, const bf16* act, const
 static int net_bwd_b(const float* params, float* grads, const Net& n, const LeafImg* img, const Leaf& head,
                      const LeafImg& himg, const bf16* dHead, int64_t ld_dhead, int head_cols_pad, const float* in,
                      const float* msk, int D_in, int64_t B, const NetSavedB& sv, bf16* dH, bf16* dU, bf16* dG,
-                     float* wtmp, float* dIn, cudaStream_t s) {
+                     float* wtmp, float* dIn, const fused::NetImages* fim, bf16* dY, cudaStream_t s) {
   using tc::TcGemmArgs;
+  if (fim && fused::backward_supported(n, 256, fim->in_kind) && (dIn == nullptr || fim->has_w0_n)) {
+    // head Linear parameters, then the fused input-gradient chain (dY_l of every Linear + bias gradients),
+    // then one tensor-core weight-gradient GEMM per Linear: gW_l += act_{l-1}^T @ dY_l
+    PMVAE_TRY(lin_bwd_params_b(grads, head, sv.A[n.R], dHead, ld_dhead, head_cols_pad, B, wtmp, true, s));
+    PMVAE_TRY(fused::net_backward(n, head, *fim, dHead, ld_dhead, B, sv.masks, sv.Bpad, dY, grads, dIn, s));
+    for (int l = 1; l <= 2 * n.R; ++l)
+      PMVAE_TRY(tc::gemm_tn(sv.stack + (uint64_t)(l - 1) * sv.Bpad * 256, 256, dY + (uint64_t)l * sv.Bpad * 256, 256,
+                            256, 256, B, grads + n.lin[l].w, 256, 1, 0, nullptr, s));
+    const Leaf& l0 = n.lin[0];
+    int64_t g = ceil_div(B, kInRows);
+    if (g > 148 * 2) g = 148 * 2;
+    in_layer_bwd_kernel<<<(int)g, 256, kInRows * kKC * sizeof(float), s>>>(in, msk, D_in, l0.rows, dY, B, grads + l0.w,
+                                                                           nullptr);
+    PMVAE_LAUNCH_CHECK();
+    return 0;
+  }
   const bool fuse = !n.ln;   // non-LN nets: the epilogue that writes a gradient tensor also sums its columns
   // head
   PMVAE_TRY(lin_bwd_params_b(grads, head, sv.A[n.R], dHead, ld_dhead, head_cols_pad, B, wtmp, true, s));
@@ -725,13 +747,16 @@ int backward_bf16(const pmvae_config* c, const Layout& L, const float* params, c
     PMVAE_TRY(rec_ll_bwd(xc, p.loc + r0 * p.Dp, p.Dp, params + L.log_scale, g_rec + r0, nullptr, p.dloc_b, p.Dp,
                          grads + L.log_scale, nb, D, s));
     PMVAE_TRY(net_bwd_b(params, grads, L.dec, p.img.dec, L.ddist, p.img.ddist, p.dloc_b, p.Dp, p.Dp, p.z + r0 * d,
-                        nullptr, d, nb, shift_saved(p.dec, L.dec, r0), p.dH, p.dU, p.dG, p.wtmp, p.dz, s));
+                        nullptr, d, nb, shift_saved(p.dec, L.dec, r0), p.dH, p.dU, p.dG, p.wtmp, p.dz,
+                        p.img.f_dec_ok ? &p.img.f_dec : nullptr, p.dY, s));
     PMVAE_TRY(latent_bwd(p.par_e + r0 * L.P, p.par_p + r0 * L.P, eps + r0 * d, p.z + r0 * d, p.dz, g_kl + r0,
                          g_match + r0, c->stop_grad, nullptr, nullptr, p.dpar_e_b, p.dpar_p_b, nb, d, s));
     PMVAE_TRY(net_bwd_b(params, grads, L.enc, p.img.enc, L.post, p.img.post, p.dpar_e_b, L.P, L.P, xc, nullptr, D, nb,
-                        shift_saved(p.enc, L.enc, r0), p.dH, p.dU, p.dG, p.wtmp, nullptr, s));
+                        shift_saved(p.enc, L.enc, r0), p.dH, p.dU, p.dG, p.wtmp, nullptr,
+                        p.img.f_enc_ok ? &p.img.f_enc : nullptr, p.dY, s));
     PMVAE_TRY(net_bwd_b(params, grads, L.part, p.img.part, L.ppost, p.img.ppost, p.dpar_p_b, L.P, L.P, xc, b + r0 * D,
-                        D, nb, shift_saved(p.part, L.part, r0), p.dH, p.dU, p.dG, p.wtmp, nullptr, s));
+                        D, nb, shift_saved(p.part, L.part, r0), p.dH, p.dU, p.dG, p.wtmp, nullptr,
+                        p.img.f_part_ok ? &p.img.f_part : nullptr, p.dY, s));
   }
   return 0;
 }
@@ -782,6 +807,26 @@ int impute_mean_bf16(const pmvae_config* c, const Layout& L, const float* params
                         p.ytmp, p.loc, p.Dp, p.img.f_dec_ok ? &p.img.f_dec : nullptr, false, s));
     PMVAE_TRY(impute_mean(x + r0 * c->D, b + r0 * c->D, p.loc, p.Dp, out + r0 * c->D, nb, K, c->D, s));
   }
+  return 0;
+}
+
+// One net + its distribution head on its own (the module's .encoder / .decoder / .partial_encoder):
+// which = 0 encoder(x) -> [B, P], 1 decoder(z) -> [B, D], 2 partial_encoder([x*b, b]) -> [B, P].
+int net_apply_bf16(const pmvae_config* c, const Layout& L, const float* params, int which, const float* in,
+                   const float* msk, int64_t B, float* out, void* ws, uint64_t ws_bytes, cudaStream_t s) {
+  PMVAE_CHECK(c->H == 256, "the tensor path is specialised for hidden_units = 256");
+  TrainPlanB p = plan_train_b(c, L, B, ws);
+  CHECK_WS(p);
+  if (which == 0)
+    return net_fwd_b(params, L.enc, p.img.enc, L.post, p.img.post, L.P, in, nullptr, c->D, B, p.enc, p.h, p.ytmp, out,
+                     L.P, p.img.f_enc_ok ? &p.img.f_enc : nullptr, false, s);
+  if (which == 2)
+    return net_fwd_b(params, L.part, p.img.part, L.ppost, p.img.ppost, L.P, in, msk, c->D, B, p.part, p.h, p.ytmp, out,
+                     L.P, p.img.f_part_ok ? &p.img.f_part : nullptr, false, s);
+  PMVAE_TRY(net_fwd_b(params, L.dec, p.img.dec, L.ddist, p.img.ddist, p.Dp, in, nullptr, c->d, B, p.dec, p.h, p.ytmp,
+                      p.loc, p.Dp, p.img.f_dec_ok ? &p.img.f_dec : nullptr, false, s));
+  PMVAE_CUDA(cudaMemcpy2DAsync(out, (size_t)c->D * 4, p.loc, (size_t)p.Dp * 4, (size_t)c->D * 4, (size_t)B,
+                               cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 

@@ -258,6 +258,38 @@ class PosteriorMatchingVAE:
                    "pmvae_backward")
         return self.grads
 
+    def net_apply(self, which: int, inp: torch.Tensor, msk: Optional[torch.Tensor] = None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Raw distribution parameters of one network + head (pmvae_net_apply): which = 0
+        encoder(x) -> [B, P], 1 decoder(z) -> [B, D], 2 partial_encoder([x*b, b]) -> [B, P]."""
+        inp = _f32c(inp, self.device)
+        msk = _f32c(msk, self.device) if msk is not None else None
+        B = inp.shape[0]
+        d = self.latent_dim
+        cols = self.num_features if which == 1 else d + d * (d + 1) // 2
+        if out is None:
+            out = torch.empty((B, cols), dtype=torch.float32, device=self.device)
+        ws = self.workspace(B)
+        self._prepare(ws)
+        _lib.check(_lib.lib.pmvae_net_apply(self._cfgp, self.arena.data_ptr(), int(which), inp.data_ptr(),
+                                            msk.data_ptr() if msk is not None else None, B, out.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), _stream()), "pmvae_net_apply")
+        return out
+
+    def encoder(self, x: torch.Tensor) -> torch.Tensor:
+        """`self.encoder(x)` of vae.py:47-49 as raw TriLGaussian parameters [B, d + d(d+1)/2]."""
+        return self.net_apply(0, x)
+
+    def decoder(self, z: torch.Tensor) -> torch.Tensor:
+        """`self.decoder(z).mean()` of vae.py:50-51: the IdentityGaussian loc [B, D]."""
+        return self.net_apply(1, z)
+
+    def partial_encoder(self, x_o_b: torch.Tensor) -> torch.Tensor:
+        """`self.partial_encoder(concat([x_o, b]))` of vae.py:52-53,132-134: takes the
+        concatenated [B, 2D] input like the reference and returns raw TriL parameters."""
+        D = self.num_features
+        return self.net_apply(2, x_o_b[:, :D], x_o_b[:, D:])
+
     def impute_mean(self, x_o: torch.Tensor, b: torch.Tensor, num_samples: int = 100, *, key,
                     row_start: int = 0, total_rows: Optional[int] = None) -> torch.Tensor:
         """mean over samples of `impute` (vae.py:146-169; eval_pm_vae_uci.py:88-89)."""
