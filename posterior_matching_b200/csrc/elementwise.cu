@@ -276,26 +276,44 @@ int eval_rows_ll(const float* x, const float* w, const float* loc, int64_t ld_lo
   return 0;
 }
 
-__global__ void __launch_bounds__(256) logmeanexp_kernel(const float* __restrict__ a, const float* __restrict__ c,
-                                                         float* __restrict__ out, int64_t B, int64_t K) {
+// block = 32 rows x 32 slices of K: thread (row, slice) covers k = slice, slice + 32, ...
+__global__ void __launch_bounds__(1024) logmeanexp_kernel(const float* __restrict__ a, const float* __restrict__ c,
+                                                          float* __restrict__ out, int64_t B, int64_t K) {
+  __shared__ float red[32][33];
   const float logK = logf((float)K);
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < B; r += (int64_t)gridDim.x * blockDim.x) {
+  const int rl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  for (int64_t r0 = (int64_t)blockIdx.x * 32; r0 < B; r0 += (int64_t)gridDim.x * 32) {
+    const int64_t r = r0 + rl;
+    const bool ok = r < B;
     float res[2] = {0.f, 0.f};
     for (int t = 0; t < (c ? 2 : 1); ++t) {
       const float* src = t ? c : a;
       float mx = -INFINITY;
-      for (int64_t k = 0; k < K; ++k) mx = fmaxf(mx, src[k * B + r]);
+      if (ok) for (int64_t k = sl; k < K; k += 32) mx = fmaxf(mx, src[k * B + r]);
+      __syncthreads();
+      red[sl][rl] = mx;
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, red[i][rl]);
+      const bool fin = mx > -INFINITY && mx < INFINITY;
       float sum = 0.f;
-      if (mx > -INFINITY && mx < INFINITY)
-        for (int64_t k = 0; k < K; ++k) sum += expf(src[k * B + r] - mx);
-      res[t] = (mx > -INFINITY && mx < INFINITY) ? (mx + logf(sum) - logK) : mx;
+      if (ok && fin) for (int64_t k = sl; k < K; k += 32) sum += expf(src[k * B + r] - mx);
+      __syncthreads();
+      red[sl][rl] = sum;
+      __syncthreads();
+      sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sum += red[i][rl];
+      res[t] = fin ? (mx + logf(sum) - logK) : mx;
     }
-    out[r] = res[0] - res[1];
+    if (ok && sl == 0) out[r] = res[0] - res[1];
   }
 }
 int logmeanexp_rows(const float* a, const float* c, float* out, int64_t B, int64_t K, cudaStream_t s) {
   if (B == 0) return 0;
-  logmeanexp_kernel<<<grid1d(B, 128), 128, 0, s>>>(a, c, out, B, K);
+  int64_t g = ceil_div(B, 32);
+  if (g > 148 * 2) g = 148 * 2;
+  logmeanexp_kernel<<<(int)g, 1024, 0, s>>>(a, c, out, B, K);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }

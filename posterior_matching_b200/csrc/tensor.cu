@@ -223,6 +223,23 @@ __global__ void __launch_bounds__(256) in_layer_dinput_kernel(const bf16* __rest
   }
 }
 
+// bf16 image of a net's input, [B, ld] with ld = pad8(K0): in (K0 = D_in) or [in*msk, msk] (K0 = 2 D_in);
+// it is the A operand of the first Linear's weight-gradient GEMM (gW_0 += in^T @ dY_0).
+__global__ void __launch_bounds__(256) cast_input_kernel(const float* __restrict__ in, const float* __restrict__ msk,
+                                                         int D_in, int K0, int ld, int64_t B, bf16* __restrict__ out) {
+  const int64_t n = B * ld;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ld;
+    const int k = (int)(i - r * ld);
+    float v = 0.f;
+    if (k < K0) {
+      if (msk) v = (k < D_in) ? in[r * D_in + k] * msk[r * D_in + k] : msk[r * D_in + (k - D_in)];
+      else v = in[r * D_in + k];
+    }
+    out[i] = __float2bfloat16(v);
+  }
+}
+
 // ---------------------------------------------------------------- small bf16 helpers
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n,
                                                         int relu) {
@@ -445,6 +462,7 @@ struct TrainPlanB {
   NetSavedB enc, dec, part;
   float *h, *ytmp, *par_e, *par_p, *z, *loc, *dz, *wtmp;
   bf16 *dH, *dU, *dG, *dpar_e_b, *dpar_p_b, *dloc_b;
+  bf16* in_b; // [B, pad8(2 D)] bf16 image of a net's input (first-Linear weight gradient)
   bf16* dY;   // [(2 Rmax + 1), Bpad, 256] gradient operands of the fused backward (shared by the three nets)
   int Dp;
   uint64_t bytes;
@@ -477,6 +495,8 @@ static TrainPlanB plan_train_b(const pmvae_config* c, const Layout& L, int64_t B
     int Rm = L.enc.R > L.dec.R ? L.enc.R : L.dec.R;
     if (L.part.R > Rm) Rm = L.part.R;
     p.dY = bp.take<bf16>((uint64_t)(2 * Rm + 1) * p.enc.Bpad * 256);
+    const int kin = 2 * c->D > c->d ? 2 * c->D : c->d;
+    p.in_b = bp.take<bf16>((uint64_t)B * pad8(kin));
   }
   p.bytes = bp.off;
   return p;
@@ -626,7 +646,7 @@ static int lin_bwd_params_b(float* grads, const Leaf& lf, const bf16* act, const
 static int net_bwd_b(const float* params, float* grads, const Net& n, const LeafImg* img, const Leaf& head,
                      const LeafImg& himg, const bf16* dHead, int64_t ld_dhead, int head_cols_pad, const float* in,
                      const float* msk, int D_in, int64_t B, const NetSavedB& sv, bf16* dH, bf16* dU, bf16* dG,
-                     float* wtmp, float* dIn, const fused::NetImages* fim, bf16* dY, cudaStream_t s) {
+                     float* wtmp, float* dIn, const fused::NetImages* fim, bf16* dY, bf16* in_b, cudaStream_t s) {
   using tc::TcGemmArgs;
   if (fim && fused::backward_supported(n, 256, fim->in_kind) && (dIn == nullptr || fim->has_w0_n)) {
     // head Linear parameters, then the fused input-gradient chain (dY_l of every Linear + bias gradients),
@@ -637,12 +657,10 @@ static int net_bwd_b(const float* params, float* grads, const Net& n, const Leaf
       PMVAE_TRY(tc::gemm_tn(sv.stack + (uint64_t)(l - 1) * sv.Bpad * 256, 256, dY + (uint64_t)l * sv.Bpad * 256, 256,
                             256, 256, B, grads + n.lin[l].w, 256, 1, 0, nullptr, s));
     const Leaf& l0 = n.lin[0];
-    int64_t g = ceil_div(B, kInRows);
-    if (g > 148 * 2) g = 148 * 2;
-    in_layer_bwd_kernel<<<(int)g, 256, kInRows * kKC * sizeof(float), s>>>(in, msk, D_in, l0.rows, dY, B, grads + l0.w,
-                                                                           nullptr);
+    const int ld0 = pad8(l0.rows);
+    cast_input_kernel<<<grid1d(B * ld0, 256), 256, 0, s>>>(in, msk, D_in, l0.rows, ld0, B, in_b);
     PMVAE_LAUNCH_CHECK();
-    return 0;
+    return tc::gemm_tn(in_b, ld0, dY, 256, l0.rows, 256, B, grads + l0.w, 256, 1, 0, nullptr, s);
   }
   const bool fuse = !n.ln;   // non-LN nets: the epilogue that writes a gradient tensor also sums its columns
   // head
@@ -748,15 +766,15 @@ int backward_bf16(const pmvae_config* c, const Layout& L, const float* params, c
                          grads + L.log_scale, nb, D, s));
     PMVAE_TRY(net_bwd_b(params, grads, L.dec, p.img.dec, L.ddist, p.img.ddist, p.dloc_b, p.Dp, p.Dp, p.z + r0 * d,
                         nullptr, d, nb, shift_saved(p.dec, L.dec, r0), p.dH, p.dU, p.dG, p.wtmp, p.dz,
-                        p.img.f_dec_ok ? &p.img.f_dec : nullptr, p.dY, s));
+                        p.img.f_dec_ok ? &p.img.f_dec : nullptr, p.dY, p.in_b, s));
     PMVAE_TRY(latent_bwd(p.par_e + r0 * L.P, p.par_p + r0 * L.P, eps + r0 * d, p.z + r0 * d, p.dz, g_kl + r0,
                          g_match + r0, c->stop_grad, nullptr, nullptr, p.dpar_e_b, p.dpar_p_b, nb, d, s));
     PMVAE_TRY(net_bwd_b(params, grads, L.enc, p.img.enc, L.post, p.img.post, p.dpar_e_b, L.P, L.P, xc, nullptr, D, nb,
                         shift_saved(p.enc, L.enc, r0), p.dH, p.dU, p.dG, p.wtmp, nullptr,
-                        p.img.f_enc_ok ? &p.img.f_enc : nullptr, p.dY, s));
+                        p.img.f_enc_ok ? &p.img.f_enc : nullptr, p.dY, p.in_b, s));
     PMVAE_TRY(net_bwd_b(params, grads, L.part, p.img.part, L.ppost, p.img.ppost, p.dpar_p_b, L.P, L.P, xc, b + r0 * D,
                         D, nb, shift_saved(p.part, L.part, r0), p.dH, p.dU, p.dG, p.wtmp, nullptr,
-                        p.img.f_part_ok ? &p.img.f_part : nullptr, p.dY, s));
+                        p.img.f_part_ok ? &p.img.f_part : nullptr, p.dY, p.in_b, s));
   }
   return 0;
 }
