@@ -65,7 +65,9 @@ __device__ __forceinline__ uint32_t relu2(uint32_t v) {
   return o;
 }
 
-template <bool SAVE>
+// CTA2: two CTAs of a cluster run as one tcgen05 pair (cta_group::2, M = 256): each owns a 128-row tile and
+// half of every weight K-block, so the weight traffic from L2 is halved and the ring covers twice the latency.
+template <bool SAVE, bool CTA2>
 __global__ void __launch_bounds__(kThreads, 1)
 net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_h,
                const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_o, FwdArgs p) {
@@ -74,13 +76,26 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const uint32_t opnd = sbase, wring = sbase + kOffW, stag = sbase + kOffStag, bar = sbase + kOffBar;
   float* bias_tbl = reinterpret_cast<float*>(sgen + kOffBias);
+  constexpr int kStg = CTA2 ? 2 * kWStages : kWStages;             // ring stages
+  constexpr int kStgBytes = CTA2 ? kWStageBytes / 2 : kWStageBytes;  // [128 or 256 n] x [64 k]
+  constexpr int kArrive = CTA2 ? 2 * kEpiWarps : kEpiWarps;         // epilogue warps feeding one MMA issuer
   auto w_full = [&](int s) { return bar + 8u * s; };
-  auto w_empty = [&](int s) { return bar + 8u * (kWStages + s); };
-  auto opnd_ready = [&](int c) { return bar + 8u * (2 * kWStages + c); };
-  auto acc_full = [&](int r) { return bar + 8u * (2 * kWStages + 4 + r); };
-  auto acc_empty = [&](int r) { return bar + 8u * (2 * kWStages + 6 + r); };
-  const uint32_t tmem_slot = bar + 8u * (2 * kWStages + 8);
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sgen + kOffBar + 8 * (2 * kWStages + 8));
+  auto w_empty = [&](int s) { return bar + 8u * (kStg + s); };
+  auto opnd_ready = [&](int c) { return bar + 8u * (2 * kStg + c); };
+  auto acc_full = [&](int r) { return bar + 8u * (2 * kStg + 4 + r); };
+  auto acc_empty = [&](int r) { return bar + 8u * (2 * kStg + 6 + r); };
+  const uint32_t tmem_slot = bar + 8u * (2 * kStg + 8);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sgen + kOffBar + 8 * (2 * kStg + 8));
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;               // 0 = the CTA that issues the pair's MMAs
+  // barriers the MMA issuer waits on live in the leader CTA; the peer's warps arrive there remotely
+  auto arrive_leader = [&](uint32_t b) {
+    if (CTA2) mbar_arrive_cluster(mapa_shared(b, 0));
+    else mbar_arrive(b);
+  };
+  // persistent schedule: a CTA (or CTA pair) takes every stride-th tile (pair of tiles)
+  const int it_first = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int it_stride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int it_count = CTA2 ? (p.num_tiles + 1) / 2 : p.num_tiles;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int R = p.R;
@@ -90,14 +105,14 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_h); tma_prefetch_desc(&map_o);
     if (SAVE) tma_prefetch_desc(&map_s);
-    for (int s = 0; s < kWStages; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
-    for (int c = 0; c < 4; ++c) mbar_init(opnd_ready(c), kEpiWarps);
-    for (int r = 0; r < 2; ++r) { mbar_init(acc_full(r), 1); mbar_init(acc_empty(r), kEpiWarps); }
+    for (int s = 0; s < kStg; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    for (int c = 0; c < 4; ++c) mbar_init(opnd_ready(c), kArrive);
+    for (int r = 0; r < 2; ++r) { mbar_init(acc_full(r), 1); mbar_init(acc_empty(r), kArrive); }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (CTA2) { tmem_alloc_cta2(tmem_slot, 512); tmem_relinquish_cta2(); }
+    else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   }
   // bias table: row l = what the epilogue of Linear l adds (running sum for the residual stream)
   for (int c = threadIdx.x; c < 256; c += kThreads) {
@@ -111,6 +126,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();          // both CTAs' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   // trace: role 0 = MMA thread, role 1 = epilogue warp 0 lane 0; entries (tag, clock) from slot 1, count in slot 0
@@ -126,61 +142,71 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     // ===================== weight producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t ph = 0;
-      auto load = [&](const CUtensorMap* m, int c0, int c1, uint32_t bytes) {
-        mbar_wait(w_empty(stage), ph ^ 1u, 1);
-        if (p.debug & 2) { mbar_arrive(w_full(stage)); }
-        else {
-          mbar_arrive_expect_tx(w_full(stage), bytes);
-          tma_load_2d(wring + stage * kWStageBytes, m, w_full(stage), c0, c1);
+      // one K-block of `rows` weight rows starting at row c1 (CTA2: this CTA's half of them)
+      auto load = [&](const CUtensorMap* m, int c0, int c1, int rows) {
+        mbar_wait_x<CTA2>(w_empty(stage), ph ^ 1u, 1);
+        const uint32_t dst = wring + stage * kStgBytes;
+        if (CTA2) {
+          const int half_rows = rows >> 1;
+          if (rank == 0) mbar_arrive_expect_tx(w_full(stage), (uint32_t)rows * 128u);
+          tma_load_2d_cta2(dst, m, mapa_shared(w_full(stage), 0), c0, c1 + (int)rank * half_rows);
+        } else if (p.debug & 2) {
+          mbar_arrive(w_full(stage));
+        } else {
+          mbar_arrive_expect_tx(w_full(stage), (uint32_t)rows * 128u);
+          tma_load_2d(dst, m, w_full(stage), c0, c1);
         }
-        if (++stage == kWStages) { stage = 0; ph ^= 1u; }
+        if (++stage == kStg) { stage = 0; ph ^= 1u; }
       };
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int kb = 0; kb < nkb0; ++kb) load(&map_w, kb * 64, 0, kWStageBytes);
+      for (int it = it_first; it < it_count; it += it_stride) {
+        for (int kb = 0; kb < nkb0; ++kb) load(&map_w, kb * 64, 0, 256);
         for (int l = 1; l < n_hidden; ++l)
-          for (int kb = 0; kb < 4; ++kb) load(&map_w, kb * 64, l * 256, kWStageBytes);
+          for (int kb = 0; kb < 4; ++kb) load(&map_w, kb * 64, l * 256, 256);
         for (int t = 0; t < p.head_tiles; ++t)
-          for (int kb = 0; kb < 4; ++kb) load(&map_h, kb * 64, t * p.head_NT, (uint32_t)p.head_NT * 128u);
+          for (int kb = 0; kb < 4; ++kb) load(&map_h, kb * 64, t * p.head_NT, p.head_NT);
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (CTA2: the leader CTA issues for the pair) =====================
+    if (lane == 0 && rank == 0) {
       int stage = 0; uint32_t ph = 0;
       uint32_t ready_par = 0, use_cnt0 = 0, use_cnt1 = 0;
       auto step = [&](int s_idx, int nk16, int N, bool accum, bool wait_opnd) {
         const int region = (s_idx & 1) ? 0 : 1;
         uint32_t& uc = region ? use_cnt1 : use_cnt0;
         stamp(0, 100 + s_idx);
-        mbar_wait(acc_empty(region), (uc & 1u) ^ 1u, 2);
+        mbar_wait_x<CTA2>(acc_empty(region), (uc & 1u) ^ 1u, 2);
         ++uc;
         tc_fence_after();
         stamp(0, 200 + s_idx);
         const uint32_t d_tmem = tmem_base + (uint32_t)(region * 256);
-        const uint32_t idesc = instr_desc(128, N, 0, 0);
+        const uint32_t idesc = instr_desc(CTA2 ? 256 : 128, N, 0, 0);
         const int nkb = (nk16 + 3) >> 2;
         for (int kb = 0; kb < nkb; ++kb) {
           if (wait_opnd) {
-            mbar_wait(opnd_ready(kb), (ready_par >> kb) & 1u, 3);
+            mbar_wait_x<CTA2>(opnd_ready(kb), (ready_par >> kb) & 1u, 3);
             ready_par ^= 1u << kb;
           }
           stamp(0, 300 + kb);
-          mbar_wait(w_full(stage), ph, 4);
+          mbar_wait_x<CTA2>(w_full(stage), ph, 4);
           tc_fence_after();
           stamp(0, 400 + kb);
           const uint32_t sa = opnd + kb * kChunkBytes;
-          const uint32_t sb = wring + stage * kWStageBytes;
+          const uint32_t sb = wring + stage * kStgBytes;
           const int ks = min(4, nk16 - 4 * kb);
-          for (int k = 0; k < ks && !(p.debug & 4); ++k)
-            umma_f16(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sb + k * 32, 16, 1024), idesc,
-                     (accum || kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(w_empty(stage));
-          if (++stage == kWStages) { stage = 0; ph ^= 1u; }
+          for (int k = 0; k < ks && !(p.debug & 4); ++k) {
+            const uint64_t da = smem_desc(sa + k * 32, 16, 1024), db = smem_desc(sb + k * 32, 16, 1024);
+            const uint32_t acc = (accum || kb > 0 || k > 0) ? 1u : 0u;
+            if (CTA2) umma_f16_cta2(d_tmem, da, db, idesc, acc);
+            else umma_f16(d_tmem, da, db, idesc, acc);
+          }
+          if (CTA2) umma_commit_cta2(w_empty(stage), 3); else umma_commit(w_empty(stage));
+          if (++stage == kStg) { stage = 0; ph ^= 1u; }
         }
-        umma_commit(acc_full(region));
+        if (CTA2) umma_commit_cta2(acc_full(region), 3); else umma_commit(acc_full(region));
         stamp(0, 500 + s_idx);
       };
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int it = it_first; it < it_count; it += it_stride) {
         step(0, p.k16_0, 256, false, true);
         for (int l = 1; l < n_hidden; ++l) step(l, 16, 256, (l & 1) == 0, true);
         for (int t = 0; t < p.head_tiles; ++t) step(n_hidden + t, 16, p.head_NT, false, t == 0);
@@ -203,7 +229,8 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       named_bar_sync(1 + q, 64);
     };
 
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int it = it_first; it < it_count; it += it_stride) {
+      const int tile = CTA2 ? 2 * it + (int)rank : it;
       const int64_t g = (int64_t)tile * 128 + row;
       const bool row_ok = g < p.B;
       if (ew == 0 && lane == 0) stamp(1, 1000);
@@ -240,14 +267,14 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(opnd_ready(c));
+          if (lane == 0) arrive_leader(opnd_ready(c));
         }
       }
       // ---- hidden Linears: accumulator -> bf16 operand of the next Linear
       for (int l = 0; l < n_hidden; ++l) {
         const int region = (l & 1) ? 0 : 1;
         if (ew == 0 && lane == 0) stamp(1, 1100 + l);
-        mbar_wait(acc_full(region), (full_par >> region) & 1u, 5);
+        mbar_wait_x<CTA2>(acc_full(region), (full_par >> region) & 1u, 5);
         if (ew == 0 && lane == 0) stamp(1, 1200 + l);
         full_par ^= 1u << region;
         tc_fence_after();
@@ -263,7 +290,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           if (j < 3) tmem_ld32(t_acc + 64 * (j + 1), (j & 1) ? ra : rb);
           if (p.debug & 1) {
             __syncwarp();
-            if (lane == 0) mbar_arrive(opnd_ready(j));
+            if (lane == 0) arrive_leader(opnd_ready(j));
             continue;
           }
           const float4* bp = reinterpret_cast<const float4*>(bias_tbl + l * 256 + 64 * j + 32 * half);
@@ -292,7 +319,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(opnd_ready(j));
+          if (lane == 0) arrive_leader(opnd_ready(j));
           if (ew == 0 && lane == 0) stamp(1, 1300 + j);
           if (SAVE) {
             // Before chunk j+1 (or chunk 0 of the next Linear) is overwritten its previous TMA store must
@@ -310,13 +337,13 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           *reinterpret_cast<uint4*>(p.masks + (((int64_t)l * p.Bpad + g) * 8 + half * 4)) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty(region));
+        if (lane == 0) arrive_leader(acc_empty(region));
       }
       // ---- head Linear: accumulator + bias -> fp32 rows, staged per warp and stored by TMA
       for (int t = 0; t < p.head_tiles; ++t) {
         const int region = ((n_hidden + t) & 1) ? 0 : 1;
         if (ew == 0 && lane == 0) stamp(1, 1400 + t);
-        mbar_wait(acc_full(region), (full_par >> region) & 1u, 6);
+        mbar_wait_x<CTA2>(acc_full(region), (full_par >> region) & 1u, 6);
         if (ew == 0 && lane == 0) stamp(1, 1500 + t);
         full_par ^= 1u << region;
         tc_fence_after();
@@ -350,7 +377,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty(region));
+        if (lane == 0) arrive_leader(acc_empty(region));
       }
     }
     if (lane == 0) tma_store_wait_all();
@@ -358,9 +385,11 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();          // the peer may still be signalling this CTA's barriers / reading its TMEM
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (CTA2) tmem_dealloc_cta2(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -730,6 +759,35 @@ int pack_images(const float* params, const Net& n, const Leaf& head, const NetIm
   return 0;
 }
 
+static bool cta2_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PMVAE_FUSED_CTA2"); v = e ? atoi(e) : 0;   // measured: no gain yet (the MMA issuer, not L2, paces the chain) }
+  return v != 0;
+}
+
+template <bool SAVE, bool CTA2>
+static int launch_fwd_t(int grid, const CUtensorMap& mw, const CUtensorMap& mh, const CUtensorMap& ms,
+                        const CUtensorMap& mo, const FwdArgs& a, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PMVAE_CUDA(cudaFuncSetAttribute(net_fwd_kernel<SAVE, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CTA2 ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  PMVAE_CUDA(cudaLaunchKernelEx(&cfg, net_fwd_kernel<SAVE, CTA2>, mw, mh, ms, mo, a));
+  return 0;
+}
+static int launch_fwd(bool save, bool cta2, int grid, const CUtensorMap& mw, const CUtensorMap& mh, const CUtensorMap& ms,
+                      const CUtensorMap& mo, const FwdArgs& a, cudaStream_t s) {
+  if (save) return cta2 ? launch_fwd_t<true, true>(grid, mw, mh, ms, mo, a, s) : launch_fwd_t<true, false>(grid, mw, mh, ms, mo, a, s);
+  return cta2 ? launch_fwd_t<false, true>(grid, mw, mh, ms, mo, a, s) : launch_fwd_t<false, false>(grid, mw, mh, ms, mo, a, s);
+}
+
 int net_forward(const float* params, const Net& n, const Leaf& head, const NetImages& im, const float* in,
                 const float* msk, int64_t B, bf16* saved, uint32_t* masks, int64_t Bpad, float* out, int64_t ld_out,
                 cudaStream_t s) {
@@ -746,8 +804,10 @@ int net_forward(const float* params, const Net& n, const Leaf& head, const NetIm
   a.masks = nullptr;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PMVAE_FUSED_DEBUG"); dbg = e ? atoi(e) : 0; } a.debug = dbg; }
   CUtensorMap mw, mh, ms, mo;
-  PMVAE_TRY(make_map_2d(&mw, im.stack_t, 2, (uint64_t)(1 + 2 * n.R) * 256, 256, 256, 64, 256));
-  PMVAE_TRY(make_map_2d(&mh, im.head_t, 2, (uint64_t)im.head_tiles * im.head_NT, 256, 256, 64, (uint32_t)im.head_NT));
+  const bool cta2 = cta2_enabled();
+  PMVAE_TRY(make_map_2d(&mw, im.stack_t, 2, (uint64_t)(1 + 2 * n.R) * 256, 256, 256, 64, cta2 ? 128 : 256));
+  PMVAE_TRY(make_map_2d(&mh, im.head_t, 2, (uint64_t)im.head_tiles * im.head_NT, 256, 256, 64,
+                        (uint32_t)(cta2 ? im.head_NT / 2 : im.head_NT)));
   PMVAE_TRY(make_map_2d(&mo, out, 4, (uint64_t)B, (uint64_t)im.head_N, (uint64_t)ld_out, 32, 32));
   if (saved) {
     PMVAE_CHECK(Bpad % 128 == 0 && Bpad >= B, "saved activations need a 128-row padded slab pitch");
@@ -757,7 +817,12 @@ int net_forward(const float* params, const Net& n, const Leaf& head, const NetIm
   } else {
     ms = mw;
   }
-  const int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
+  int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
+  if (cta2) {
+    const int pairs = (a.num_tiles + 1) / 2;
+    grid = 2 * (pairs < num_sms() / 2 ? pairs : num_sms() / 2);
+    PMVAE_CHECK(saved == nullptr || Bpad % 256 == 0, "CTA pairs need a 256-row padded slab pitch");
+  }
   static long long* trace_buf = nullptr;
   static int trace_on = -1;
   if (trace_on < 0) { const char* e = getenv("PMVAE_FUSED_TRACE"); trace_on = e ? atoi(e) : 0; }
@@ -766,20 +831,7 @@ int net_forward(const float* params, const Net& n, const Leaf& head, const NetIm
     cudaMemsetAsync(trace_buf, 0, 2 * 2048 * sizeof(long long), s);
     a.trace = trace_buf;
   }
-  static bool attr_set[2] = {false, false};
-  if (saved) {
-    if (!attr_set[1]) {
-      PMVAE_CUDA(cudaFuncSetAttribute(net_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      attr_set[1] = true;
-    }
-    net_fwd_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(mw, mh, ms, mo, a);
-  } else {
-    if (!attr_set[0]) {
-      PMVAE_CUDA(cudaFuncSetAttribute(net_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-      attr_set[0] = true;
-    }
-    net_fwd_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(mw, mh, ms, mo, a);
-  }
+  PMVAE_TRY(launch_fwd(saved != nullptr, cta2, grid, mw, mh, ms, mo, a, s));
   PMVAE_LAUNCH_CHECK();
   if (trace_on) {
     static long long host[2 * 2048];

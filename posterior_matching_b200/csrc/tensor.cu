@@ -412,7 +412,7 @@ struct NetSavedB {
 
 static void plan_net_b(Bump& bp, const Net& n, int64_t B, NetSavedB& s) {
   const uint64_t e = (uint64_t)B * 256;
-  s.Bpad = (B + 127) / 128 * 128;
+  s.Bpad = (B + 255) / 256 * 256;        // whole tiles for a CTA pair (2 x 128 rows)
   s.stack = bp.take<bf16>((uint64_t)(2 * n.R + 1) * s.Bpad * 256);
   s.masks = bp.take<uint32_t>((uint64_t)(2 * n.R + 1) * s.Bpad * 8);
   for (int r = 0; r <= n.R; ++r) s.A[r] = s.stack + (uint64_t)(2 * r) * s.Bpad * 256;
