@@ -761,7 +761,8 @@ int pack_images(const float* params, const Net& n, const Leaf& head, const NetIm
 
 static bool cta2_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("PMVAE_FUSED_CTA2"); v = e ? atoi(e) : 0;   // measured: no gain yet (the MMA issuer, not L2, paces the chain) }
+  // default off: measured no gain yet (the per-layer hand-offs, not weight streaming from L2, pace the chain)
+  if (v < 0) { const char* e = getenv("PMVAE_FUSED_CTA2"); v = e ? atoi(e) : 0; }
   return v != 0;
 }
 
