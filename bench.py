@@ -223,6 +223,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     name = args.config
@@ -254,12 +256,20 @@ def main():
         return float(t.item())
 
     # ---- device-resident timing
-    for _ in range(W):
-        tr.train_step(x_dev)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(W):
+        tr.train_step(x_dev)
+    barrier()
+    # nvidia-smi samples every 100 ms and a step is a few ms: keep the same load running (untimed) long enough
+    # for the clock record to describe the state the timed steps run in
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 0.6:
+        for _ in range(10):
+            tr.train_step(x_dev)
+        torch.cuda.synchronize()
+    barrier()
     l0 = int(_lib.lib.pmvae_launch_count())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -287,40 +297,67 @@ def main():
     e2e = {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": 12,
            "ms_per_step": e2e_s / K * 1e3}
 
-    # ---- dominant kernel alone: one hidden hk.Linear [B,256] x [256,256] (90% of the MACs)
+    # ---- dominant kernel alone: the fused ResidualMLP forward (encoder net + TriL head) over B rows
     peaks = measured_peaks()
     H = 256
     stream = torch.cuda.current_stream().cuda_stream
-    bias = torch.zeros(H, device="cuda")
-    y = torch.empty(B, H, device="cuda")
+    d_lat = model.latent_dim
+    P = d_lat + d_lat * (d_lat + 1) // 2
+    R_enc = int(model.cfg.R_enc)
+    enc_macs = D * H + 2 * R_enc * H * H + H * P            # Linear MACs per row (SURVEY §8 convention)
+    extra = []
     if precision == "bf16":
-        xin = torch.randn(B, H, device="cuda").to(torch.bfloat16)
-        wt = (torch.randn(H, H, device="cuda") / 16).to(torch.bfloat16)
+        out_par = torch.empty(B, P, device="cuda")
 
-        def lin():
-            _lib.check(_lib.lib.pmvae_tc_gemm_nt(xin.data_ptr(), H, wt.data_ptr(), H, bias.data_ptr(), B, H, H,
-                                                 y.data_ptr(), stream), "pmvae_tc_gemm_nt")
-        kname = f"tc_gemm_kernel<0> (tcgen05, bf16 -> fp32 out) {B}x{H}x{H} via pmvae_tc_gemm_nt"
+        def kern():
+            model.net_apply(0, x_dev, None, out_par)
+        kname = (f"fused::net_fwd_kernel (tcgen05 chain: {1 + 2 * R_enc} hidden Linears + TriL head, activations on chip) "
+                 f"{B} rows via pmvae_net_apply(encoder)")
+        k_flop = 2.0 * enc_macs * B
     else:
         xin = torch.randn(B, H, device="cuda")
         wt = torch.randn(H, H, device="cuda") / 16
+        bias = torch.zeros(H, device="cuda")
+        y = torch.empty(B, H, device="cuda")
 
-        def lin():
+        def kern():
             _lib.check(_lib.lib.pmvae_linear(_lib.PREC_F32, xin.data_ptr(), wt.data_ptr(), bias.data_ptr(), B, H, H, 1,
                                              y.data_ptr(), None, 0, stream), "pmvae_linear")
         kname = f"gemm_f32_kernel {B}x{H}x{H} via pmvae_linear"
-    for _ in range(3):
-        lin()
-    torch.cuda.synchronize()
+        k_flop = 2.0 * B * H * H
+
+    def time_alone(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(reps):
+            fn()
+        k1.record()
+        torch.cuda.synchronize()
+        return k0.elapsed_time(k1) / reps
+
     reps = 20
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for _ in range(reps):
-        lin()
-    k1.record()
-    torch.cuda.synchronize()
-    k_ms = k0.elapsed_time(k1) / reps
-    k_tflops = 2.0 * B * H * H / (k_ms * 1e-3) / 1e12
+    k_ms = time_alone(kern, reps)
+    k_tflops = k_flop / (k_ms * 1e-3) / 1e12
+    if precision == "bf16":
+        # the two stand-alone tcgen05 GEMM shapes of the step, for reference
+        xin = torch.randn(B, H, device="cuda").to(torch.bfloat16)
+        wt = (torch.randn(H, H, device="cuda") / 16).to(torch.bfloat16)
+        gy = torch.randn(B, H, device="cuda").to(torch.bfloat16)
+        bias = torch.zeros(H, device="cuda")
+        y = torch.empty(B, H, device="cuda")
+        gw = torch.zeros(H, H, device="cuda")
+        t_nt = time_alone(lambda: _lib.check(_lib.lib.pmvae_tc_gemm_nt(xin.data_ptr(), H, wt.data_ptr(), H, bias.data_ptr(),
+                                                                       B, H, H, y.data_ptr(), stream), "nt"))
+        t_tn = time_alone(lambda: _lib.check(_lib.lib.pmvae_tc_gemm_tn(xin.data_ptr(), H, gy.data_ptr(), H, H, H, B,
+                                                                       gw.data_ptr(), stream), "tn"))
+        for nm, t, byts in (("tc_gemm_kernel<NT> one hidden Linear, fp32 out", t_nt, B * H * 6.0),
+                            ("tc_gemm_kernel<TN> one weight gradient (act^T @ dY, split over rows)", t_tn, B * H * 4.0)):
+            extra.append({"kernel": nm, "ms": t, "tflops": 2.0 * B * H * H / (t * 1e-3) / 1e12,
+                          "hbm_gbs": byts / (t * 1e-3) / 1e9, "hbm_frac": byts / (t * 1e-3) / 1e9 / peaks["hbm_gbs"]})
+        del xin, y, gy
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
@@ -334,9 +371,10 @@ def main():
                 "frac": k_tflops / peaks["bf16_tflops"], "traffic": traffic,
                 "kernel": kname + f", timed alone ({reps} launches)",
                 "kernel_ms": k_ms, "peak_source": peaks["source"] + " (bf16 burst)",
+                "algorithmic_flop_per_launch": k_flop,
                 "step_tflops_per_gpu": step_tflops / world,
-                "step_frac_of_sustained_peak": step_tflops / world / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"])}
-    del xin, y
+                "step_frac_of_sustained_peak": step_tflops / world / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]),
+                "other_kernels": extra}
 
     # ---- cond-LL evaluation throughput (eval_pm_vae_uci.py eval_fn's is_log_prob, K = 512)
     cond = None

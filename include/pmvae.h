@@ -174,6 +174,40 @@ int pmvae_impute_mean(const pmvae_config* cfg, const float* params, const float*
                       int64_t row_start, float* out /* [B,D] */, void* ws, uint64_t ws_bytes,
                       pmvae_stream_t stream);
 
+/* ---- XLA custom-call targets (jax.ffi / xla_client registration, api_version 1) --------------
+ * The reference is driven by jax.jit / jax.value_and_grad (bax.Trainer, train_pm_vae.py:85,96;
+ * eval_pm_vae_uci.py:96), so the binding a maintainer adds is an XLA custom call per entry
+ * point.  Each target has the status-returning legacy signature
+ *     void target(cudaStream_t stream, void** buffers, const char* opaque, size_t opaque_len,
+ *                 XlaCustomCallStatus* status)
+ * with `buffers` = the operands followed by the results (all device pointers owned by XLA) and
+ * `opaque` = one pmvae_xla_opaque.  Scratch (`ws`) is a result buffer XLA allocates; the forward's
+ * `ws` is a residual of the custom_vjp and is passed to the backward as an operand aliased to a
+ * result.  posterior_matching_b200/jax_ffi.py registers them; INTEGRATION.md shows the wiring.
+ *
+ *   pmvae_xla_forward      operands [params, x, b, eps]                        results [rec, kl, match, ws]
+ *   pmvae_xla_backward     operands [params, x, b, eps, g_rec, g_kl, g_match, ws]  results [grads, ws (aliased)]
+ *   pmvae_xla_is_log_prob  operands [params, x, b]                             results [log_p_x, log_p_xu_given_xo, ws]
+ *   pmvae_xla_impute_mean  operands [params, x_o, b]                           results [mean, ws]
+ *   pmvae_xla_mask_bernoulli  operands []                                      results [mask]
+ */
+typedef struct pmvae_xla_opaque {
+  pmvae_config cfg;
+  int64_t B, K, B_total, row_start;
+  uint64_t ws_bytes;
+  uint32_t key0[2], key1[2];
+  float p;           /* Bernoulli rate (mask target)                                   */
+  int32_t prepare;   /* != 0: refresh the bf16 operand images first (params changed)   */
+  int32_t D;         /* mask width                                                     */
+  int32_t reserved;
+} pmvae_xla_opaque;
+uint64_t pmvae_xla_opaque_size(void);
+void pmvae_xla_forward(pmvae_stream_t stream, void** buffers, const char* opaque, size_t opaque_len, void* status);
+void pmvae_xla_backward(pmvae_stream_t stream, void** buffers, const char* opaque, size_t opaque_len, void* status);
+void pmvae_xla_is_log_prob(pmvae_stream_t stream, void** buffers, const char* opaque, size_t opaque_len, void* status);
+void pmvae_xla_impute_mean(pmvae_stream_t stream, void** buffers, const char* opaque, size_t opaque_len, void* status);
+void pmvae_xla_mask_bernoulli(pmvae_stream_t stream, void** buffers, const char* opaque, size_t opaque_len, void* status);
+
 #ifdef __cplusplus
 }
 #endif

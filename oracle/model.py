@@ -199,6 +199,14 @@ def tril_kl_std_normal(mu, L):
             + 0.5 * (-d + (L ** 2).sum((-2, -1)) + (mu ** 2).sum(-1)))
 
 
+def net_head(p: Params, spec: ModelSpec, net: str, head: str, x):
+    """One ResidualMLP followed by its distribution head's hk.Linear: the raw parameters behind
+    `model.encoder(x)`, `model.decoder(z)`, `model.partial_encoder(x_o_b)` (vae.py:47-53)."""
+    R, ln = {"encoder_net": (spec.R_enc, spec.ln_enc), "decoder_net": (spec.R_dec, spec.ln_dec),
+             "partial_encoder_net": (spec.R_part, spec.ln_part)}[net]
+    return linear(p, head, residual_mlp(p, net, x, R, ln))
+
+
 def std_normal_log_prob(z):
     return -0.5 * (z ** 2).sum(-1) - 0.5 * z.shape[-1] * LOG2PI
 

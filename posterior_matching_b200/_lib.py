@@ -25,6 +25,13 @@ class Leaf(C.Structure):
                 ("w_off", C.c_uint64), ("b_off", C.c_uint64)]
 
 
+class XlaOpaque(C.Structure):
+    """pmvae_xla_opaque (include/pmvae.h): the `opaque` descriptor of the XLA custom-call targets."""
+    _fields_ = [("cfg", Config), ("B", C.c_int64), ("K", C.c_int64), ("B_total", C.c_int64), ("row_start", C.c_int64),
+                ("ws_bytes", C.c_uint64), ("key0", C.c_uint32 * 2), ("key1", C.c_uint32 * 2), ("p", C.c_float),
+                ("prepare", C.c_int32), ("D", C.c_int32), ("reserved", C.c_int32)]
+
+
 class PmvaeError(RuntimeError):
     pass
 
@@ -68,6 +75,12 @@ _SIGS = {
     "pmvae_adamw": (_i32, [_cfgp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _vp]),
     "pmvae_is_log_prob": (_i32, [_cfgp, _vp, _vp, _vp, _i64, _i64, _u32p, _u32p, _i64, _i64, _vp, _vp, _vp, _u64, _vp]),
     "pmvae_net_apply": (_i32, [_cfgp, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _u64, _vp]),
+    "pmvae_xla_opaque_size": (_u64, []),
+    "pmvae_xla_forward": (None, [_vp, C.POINTER(_vp), C.c_char_p, C.c_size_t, _vp]),
+    "pmvae_xla_backward": (None, [_vp, C.POINTER(_vp), C.c_char_p, C.c_size_t, _vp]),
+    "pmvae_xla_is_log_prob": (None, [_vp, C.POINTER(_vp), C.c_char_p, C.c_size_t, _vp]),
+    "pmvae_xla_impute_mean": (None, [_vp, C.POINTER(_vp), C.c_char_p, C.c_size_t, _vp]),
+    "pmvae_xla_mask_bernoulli": (None, [_vp, C.POINTER(_vp), C.c_char_p, C.c_size_t, _vp]),
     "pmvae_impute_mean": (_i32, [_cfgp, _vp, _vp, _vp, _i64, _i64, _u32p, _i64, _i64, _vp, _vp, _u64, _vp]),
 }
 EXPORTS = tuple(_SIGS)

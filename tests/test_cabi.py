@@ -105,3 +105,20 @@ def test_device_entry_points_fail_loudly_without_gpu():
     from posterior_matching_b200 import PosteriorMatchingVAE
     with pytest.raises(RuntimeError):
         PosteriorMatchingVAE.from_config(pm_vae_config("gas").model)
+
+
+def test_xla_opaque_layout_and_guarded_jax_module():
+    """The ctypes mirror of pmvae_xla_opaque matches the C struct; the JAX registration module imports
+    without JAX and only fails (ImportError) when asked to register."""
+    assert _lib.lib.pmvae_xla_opaque_size() == C.sizeof(_lib.XlaOpaque)
+    from posterior_matching_b200 import jax_ffi
+    cfg = _lib.make_config(8, 16, 256, 2, 2, 2, 0, 0, 0, 1, _lib.PREC_BF16)
+    blob = jax_ffi.opaque(cfg, B=5, K=7, key0=(1, 2), ws_bytes=99)
+    assert len(blob) == C.sizeof(_lib.XlaOpaque)
+    back = _lib.XlaOpaque.from_buffer_copy(blob)
+    assert (back.B, back.K, back.B_total, back.ws_bytes, back.key0[1], back.cfg.d) == (5, 7, 5, 99, 2, 16)
+    try:
+        import jax  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            jax_ffi.register()
