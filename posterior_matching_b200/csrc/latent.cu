@@ -12,9 +12,18 @@
 //   vae.py:136-138            log q(stop_grad(z) | x_o)           (match_fwd)
 //   vae.py:192-195,203-212    K samples + prior/posterior log-probs (sample_latents)
 // Closed forms and backward formulas: SURVEY.md §8a-E/F and Appendix A.3/A.6.
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace pmvae {
+
+// d = 16 takes the thread-per-row kernels of latent16.cu (PMVAE_LATENT16=0 keeps the group-per-row ones)
+static bool fast16() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PMVAE_LATENT16"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
 
 constexpr int kThreadsL = 128;
 
@@ -369,6 +378,7 @@ static int grid_for_rows(int64_t rows, int G) {
 int latent_fwd(const float* par, const float* eps, float* z, float* kl, int64_t B, int d, cudaStream_t s) {
   PMVAE_CHECK(d >= 1 && d <= 64, "latent_dim must be in [1, 64]");
   if (B == 0) return 0;
+  if (d == 16 && fast16()) return latent_fwd16(par, eps, z, kl, B, s);
   const int P = d + d * (d + 1) / 2;
   const size_t spg = (size_t)(P + 3 * d) * sizeof(float);
   DISPATCH_D(latent_fwd_kernel, d, B, spg, s, par, eps, z, kl, B, d);
@@ -379,6 +389,7 @@ int latent_fwd(const float* par, const float* eps, float* z, float* kl, int64_t 
 int match_fwd(const float* par_p, const float* z, float* match, int64_t B, int d, cudaStream_t s) {
   PMVAE_CHECK(d >= 1 && d <= 64, "latent_dim must be in [1, 64]");
   if (B == 0) return 0;
+  if (d == 16 && fast16()) return match_fwd16(par_p, z, match, B, s);
   const int P = d + d * (d + 1) / 2;
   const size_t spg = (size_t)(P + 4 * d) * sizeof(float);
   DISPATCH_D(match_fwd_kernel, d, B, spg, s, par_p, z, match, B, d);
@@ -391,6 +402,8 @@ int latent_bwd(const float* par_e, const float* par_p, const float* eps, const f
                __nv_bfloat16* dpar_e_b, __nv_bfloat16* dpar_p_b, int64_t B, int d, cudaStream_t s) {
   PMVAE_CHECK(d >= 1 && d <= 64, "latent_dim must be in [1, 64]");
   if (B == 0) return 0;
+  if (d == 16 && fast16() && dpar_e == nullptr && dpar_p == nullptr && dpar_e_b && dpar_p_b)
+    return latent_bwd16(par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad, dpar_e_b, dpar_p_b, B, s);
   const int P = d + d * (d + 1) / 2;
   const size_t spg = (size_t)(P + 6 * d) * sizeof(float);
   DISPATCH_D(latent_bwd_kernel, d, B, spg, s, par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad, dpar_e, dpar_p,
