@@ -174,6 +174,41 @@ int pmvae_impute_mean(const pmvae_config* cfg, const float* params, const float*
                       int64_t row_start, float* out /* [B,D] */, void* ws, uint64_t ws_bytes,
                       pmvae_stream_t stream);
 
+/* ---- distribution heads of configs/pm_vae_mnist.py (float32 arithmetic) -------------------------
+ * Bernoulli decoder (distributions.py:20-25; summed over the event at vae.py:127-128):
+ *   out[r] = sum_j w[r,j] * Bernoulli(logits[r,j]).log_prob(x[r,j]),  x a float in [0,1], w optional (NULL = 1)
+ * and its VJP dlogits[r,j] = g[r] * w[r,j] * (x - sigmoid(logits)). */
+int pmvae_bernoulli_ll(const float* logits, const float* x, const float* w, int64_t B, int32_t D,
+                       float* out, pmvae_stream_t stream);
+int pmvae_bernoulli_ll_backward(const float* logits, const float* x, const float* w, const float* g,
+                                int64_t B, int32_t D, float* dlogits, pmvae_stream_t stream);
+
+/* AutoregressiveGMM (distributions.py:192-223) = ResidualMLP(R, H) + OneDimensionalGMM(d, n_comp)
+ * (:116-134) over [z * (arange(d) < i), (arange(d) < i), context]; log_prob follows
+ * _AutoregressiveDistribution.log_prob (:152-166) with the d steps batched as d*B rows.
+ * Parameters: one flat float32 arena, leaves `partial_posterior_dist/residual_mlp/linear{,_1..}` and
+ * `partial_posterior_dist/one_dimensional_gmm/linear` (pmvae_argmm_layout). */
+typedef struct pmvae_argmm_config {
+  int32_t d;       /* event_size (latent_dim)            */
+  int32_t n_comp;  /* num_components                      */
+  int32_t R;       /* residual_blocks                     */
+  int32_t H;       /* hidden_units                        */
+  int32_t C;       /* flattened context features          */
+  int32_t reserved[3];
+} pmvae_argmm_config;
+uint64_t pmvae_argmm_param_count(const pmvae_argmm_config* cfg);
+int pmvae_argmm_layout(const pmvae_argmm_config* cfg, pmvae_leaf* out, int cap);
+uint64_t pmvae_argmm_workspace_bytes(const pmvae_argmm_config* cfg, int64_t B);
+/* out[b] = log q(z[b] | context[b]) */
+int pmvae_argmm_log_prob(const pmvae_argmm_config* cfg, const float* params, const float* z,
+                         const float* context, int64_t B, float* out, void* ws, uint64_t ws_bytes,
+                         pmvae_stream_t stream);
+/* VJP of the preceding pmvae_argmm_log_prob on the same `ws`: g[B] -> grads (arena, overwritten),
+ * dz[B,d] and dcontext[B,C] (either may be NULL). */
+int pmvae_argmm_backward(const pmvae_argmm_config* cfg, const float* params, const float* z,
+                         const float* context, int64_t B, const float* g, float* grads, float* dz,
+                         float* dcontext, void* ws, uint64_t ws_bytes, pmvae_stream_t stream);
+
 /* ---- XLA custom-call targets (jax.ffi / xla_client registration, api_version 1) --------------
  * The reference is driven by jax.jit / jax.value_and_grad (bax.Trainer, train_pm_vae.py:85,96;
  * eval_pm_vae_uci.py:96), so the binding a maintainer adds is an XLA custom call per entry

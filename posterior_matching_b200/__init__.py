@@ -10,3 +10,4 @@ from .vae import PosteriorMatchingVAE, get_distribution, get_network  # noqa: F4
 from .masking import BernoulliMaskGenerator, MNISTMaskGenerator, get_mask_generator  # noqa: F401
 from .train import Trainer, get_beta_schedule, cyclical_annealing_schedule  # noqa: F401
 from .evaluate import eval_fn, nrmse_score  # noqa: F401
+from .distributions import AutoregressiveGMM, Bernoulli  # noqa: F401

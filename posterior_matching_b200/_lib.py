@@ -25,6 +25,10 @@ class Leaf(C.Structure):
                 ("w_off", C.c_uint64), ("b_off", C.c_uint64)]
 
 
+class ArgmmConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("d", "n_comp", "R", "H", "C")] + [("reserved", C.c_int32 * 3)]
+
+
 class XlaOpaque(C.Structure):
     """pmvae_xla_opaque (include/pmvae.h): the `opaque` descriptor of the XLA custom-call targets."""
     _fields_ = [("cfg", Config), ("B", C.c_int64), ("K", C.c_int64), ("B_total", C.c_int64), ("row_start", C.c_int64),
@@ -75,6 +79,13 @@ _SIGS = {
     "pmvae_adamw": (_i32, [_cfgp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _vp]),
     "pmvae_is_log_prob": (_i32, [_cfgp, _vp, _vp, _vp, _i64, _i64, _u32p, _u32p, _i64, _i64, _vp, _vp, _vp, _u64, _vp]),
     "pmvae_net_apply": (_i32, [_cfgp, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _u64, _vp]),
+    "pmvae_bernoulli_ll": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "pmvae_bernoulli_ll_backward": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "pmvae_argmm_param_count": (_u64, [C.POINTER(ArgmmConfig)]),
+    "pmvae_argmm_layout": (_i32, [C.POINTER(ArgmmConfig), C.POINTER(Leaf), _i32]),
+    "pmvae_argmm_workspace_bytes": (_u64, [C.POINTER(ArgmmConfig), _i64]),
+    "pmvae_argmm_log_prob": (_i32, [C.POINTER(ArgmmConfig), _vp, _vp, _vp, _i64, _vp, _vp, _u64, _vp]),
+    "pmvae_argmm_backward": (_i32, [C.POINTER(ArgmmConfig), _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
     "pmvae_xla_opaque_size": (_u64, []),
     "pmvae_xla_forward": (None, [_vp, C.POINTER(_vp), C.c_char_p, C.c_size_t, _vp]),
     "pmvae_xla_backward": (None, [_vp, C.POINTER(_vp), C.c_char_p, C.c_size_t, _vp]),

@@ -68,4 +68,15 @@ int latent_bwd16(const float* par_e, const float* par_p, const float* eps, const
 int sample_latents(const float* par, Key2 key, int64_t B, int64_t K, int64_t B_total, int64_t row_start, int d,
                    float* z, float* base, cudaStream_t s);
 
+// ---- dists_mnist.cu (MNIST-config heads: Bernoulli decoder, autoregressive GMM partial posterior)
+int bernoulli_ll(const float* logits, const float* x, const float* w, int64_t B, int D, float* out, cudaStream_t s);
+int bernoulli_ll_bwd(const float* logits, const float* x, const float* w, const float* g, int64_t B, int D,
+                     float* dlogits, cudaStream_t s);
+int argmm_input(const float* z, const float* ctx, int64_t B, int d, int C, float* X, cudaStream_t s);
+int argmm_lp(const float* head_out, const float* z, int64_t B, int d, int K, float* out, cudaStream_t s);
+int argmm_lp_bwd(const float* head_out, const float* z, const float* g, int64_t B, int d, int K, float* d_head,
+                 float* dz_direct, cudaStream_t s);
+int argmm_reduce_dx(const float* dX, const float* dz_direct, int64_t B, int d, int C, float* dz, float* dctx,
+                    cudaStream_t s);
+
 }  // namespace pmvae

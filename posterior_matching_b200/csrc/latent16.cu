@@ -45,10 +45,22 @@ __device__ __forceinline__ void load_rows(const float* __restrict__ src, int64_t
   const int nvec = (int)nrows * (P / 4);
   const float4* s4 = reinterpret_cast<const float4*>(src + row0 * P);
   __syncwarp();
-#pragma unroll 2
-  for (int f = lane; f < nvec; f += 32) {
-    const int r = f / (P / 4), q = f - r * (P / 4);
-    *reinterpret_cast<float4*>(tile + r * kPitch + q * 4) = __ldg(s4 + f);
+  if (nrows == 32) {
+    // full tile: all 38 loads of a lane are issued before the first one is consumed
+    float4 buf[P / 4];
+#pragma unroll
+    for (int it = 0; it < P / 4; ++it) buf[it] = __ldg(s4 + it * 32 + lane);
+#pragma unroll
+    for (int it = 0; it < P / 4; ++it) {
+      const int f = it * 32 + lane;
+      const int r = f / (P / 4), q = f - r * (P / 4);
+      *reinterpret_cast<float4*>(tile + r * kPitch + q * 4) = buf[it];
+    }
+  } else {
+    for (int f = lane; f < nvec; f += 32) {
+      const int r = f / (P / 4), q = f - r * (P / 4);
+      *reinterpret_cast<float4*>(tile + r * kPitch + q * 4) = __ldg(s4 + f);
+    }
   }
   __syncwarp();
   const float4* t4 = reinterpret_cast<const float4*>(tile + lane * kPitch);

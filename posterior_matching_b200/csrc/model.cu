@@ -394,6 +394,85 @@ int impute_mean_seq(const pmvae_config* c, const float* params, const float* x, 
   return 0;
 }
 
+// ---------------------------------------------------------------- AutoregressiveGMM (MNIST partial posterior)
+struct ArgmmLayout { Net net; Leaf head; uint64_t total; int F, cols; };
+
+static int build_argmm_layout(const pmvae_argmm_config* c, ArgmmLayout* L) {
+  PMVAE_CHECK(c != nullptr, "null config");
+  PMVAE_CHECK(c->d >= 1 && c->d <= 64 && c->n_comp >= 1 && c->n_comp <= 32 && c->C >= 0 && c->C <= 4096,
+              "AutoregressiveGMM: event_size in [1, 64], num_components in [1, 32], context in [0, 4096]");
+  PMVAE_CHECK(c->H >= 4 && c->H % 4 == 0 && c->H <= 1024 && c->R >= 0 && c->R <= kMaxBlocks, "bad hidden_units / residual_blocks");
+  uint64_t off = 0;
+  auto leaf = [&](Leaf& lf, int rows, int cols) {
+    lf.rows = rows; lf.cols = cols;
+    lf.w = off; off += pad64((uint64_t)rows * cols);
+    lf.b = off; off += pad64((uint64_t)cols);
+  };
+  L->F = 2 * c->d + c->C;
+  L->cols = 3 * c->n_comp * c->d;
+  L->net.in_dim = L->F; L->net.R = c->R; L->net.ln = 0;
+  leaf(L->net.lin[0], L->F, c->H);
+  for (int i = 1; i <= 2 * c->R; ++i) leaf(L->net.lin[i], c->H, c->H);
+  leaf(L->head, c->H, L->cols);
+  L->total = off;
+  return 0;
+}
+
+struct ArgmmPlan {
+  NetSaved sv;
+  float *X, *out, *dout, *dH, *tmp1, *tmp2, *dX, *dzd;
+  uint64_t bytes;
+};
+
+static ArgmmPlan plan_argmm(const pmvae_argmm_config* c, const ArgmmLayout& L, int64_t B, void* ws) {
+  ArgmmPlan p{};
+  Bump bp(ws);
+  const int64_t M = (int64_t)c->d * B;
+  plan_net(bp, L.net, M, c->H, p.sv, true);
+  p.X = bp.take<float>((uint64_t)M * L.F);
+  p.out = bp.take<float>((uint64_t)M * L.cols);
+  p.dout = bp.take<float>((uint64_t)M * L.cols);
+  p.dH = bp.take<float>((uint64_t)M * c->H);
+  p.tmp1 = bp.take<float>((uint64_t)M * c->H);
+  p.tmp2 = bp.take<float>((uint64_t)M * c->H);
+  p.dX = bp.take<float>((uint64_t)M * L.F);
+  p.dzd = bp.take<float>((uint64_t)B * c->d);
+  p.bytes = bp.off;
+  return p;
+}
+
+int argmm_log_prob(const pmvae_argmm_config* c, const float* params, const float* z, const float* ctx, int64_t B,
+                   float* out, void* ws, uint64_t ws_bytes, cudaStream_t s) {
+  ArgmmLayout L;
+  PMVAE_TRY(build_argmm_layout(c, &L));
+  PMVAE_CHECK(params && z && (ctx || c->C == 0) && out && ws && B >= 0, "null pointer");
+  if (B == 0) return 0;
+  ArgmmPlan p = plan_argmm(c, L, B, ws);
+  PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_argmm_workspace_bytes)");
+  PMVAE_TRY(argmm_input(z, ctx, B, c->d, c->C, p.X, s));
+  PMVAE_TRY(net_fwd_f32(params, L.net, L.head, c->H, p.X, (int64_t)c->d * B, p.sv, p.out, s));
+  return argmm_lp(p.out, z, B, c->d, c->n_comp, out, s);
+}
+
+// VJP of argmm_log_prob (whose intermediates are still in `ws`): cotangent g[B] -> parameter gradients
+// (overwritten) and, optionally, d/dz [B, d] and d/dcontext [B, C].
+int argmm_backward(const pmvae_argmm_config* c, const float* params, const float* z, const float* ctx, int64_t B,
+                   const float* g, float* grads, float* dz, float* dctx, void* ws, uint64_t ws_bytes, cudaStream_t s) {
+  ArgmmLayout L;
+  PMVAE_TRY(build_argmm_layout(c, &L));
+  PMVAE_CHECK(params && z && g && grads && ws && B >= 0, "null pointer");
+  PMVAE_CUDA(cudaMemsetAsync(grads, 0, L.total * sizeof(float), s));
+  if (B == 0) return 0;
+  ArgmmPlan p = plan_argmm(c, L, B, ws);
+  PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_argmm_workspace_bytes)");
+  const int64_t M = (int64_t)c->d * B;
+  PMVAE_CUDA(cudaMemsetAsync(p.dout, 0, (size_t)M * L.cols * sizeof(float), s));
+  PMVAE_TRY(argmm_lp_bwd(p.out, z, g, B, c->d, c->n_comp, p.dout, p.dzd, s));
+  PMVAE_TRY(net_bwd_f32(params, grads, L.net, L.head, c->H, p.X, M, p.sv, p.dout, p.dH, p.tmp1, p.tmp2, p.dX, s));
+  if (dz || dctx) PMVAE_TRY(argmm_reduce_dx(p.dX, p.dzd, B, c->d, c->C, dz, dctx, s));
+  return 0;
+}
+
 int net_apply(const pmvae_config* c, const float* params, int which, const float* in, const float* msk, int64_t B,
               float* out, void* ws, uint64_t ws_bytes, cudaStream_t s) {
   Layout L;
@@ -495,6 +574,47 @@ int pmvae_is_log_prob(const pmvae_config* cfg, const float* params, const float*
                       pmvae_stream_t stream) {
   return is_log_prob(cfg, params, x, b, B, K, key_z, key_zxo, B_total, row_start, out_log_p_x, out_log_p_xu_given_xo,
                      ws, ws_bytes, as_stream(stream));
+}
+
+uint64_t pmvae_argmm_param_count(const pmvae_argmm_config* cfg) {
+  ArgmmLayout L;
+  return build_argmm_layout(cfg, &L) == 0 ? L.total : 0;
+}
+int pmvae_argmm_layout(const pmvae_argmm_config* cfg, pmvae_leaf* out, int cap) {
+  ArgmmLayout L;
+  if (build_argmm_layout(cfg, &L) != 0) return -1;
+  const int n = 2 * L.net.R + 2;
+  for (int i = 0; i < n && i < cap; ++i) {
+    pmvae_leaf l{};
+    if (i <= 2 * L.net.R) name_leaf(&l, "partial_posterior_dist/residual_mlp", i, L.net.lin[i]);
+    else name_leaf(&l, "partial_posterior_dist/one_dimensional_gmm", 0, L.head);
+    out[i] = l;
+  }
+  return n;
+}
+uint64_t pmvae_argmm_workspace_bytes(const pmvae_argmm_config* cfg, int64_t B) {
+  ArgmmLayout L;
+  if (build_argmm_layout(cfg, &L) != 0) return 0;
+  return plan_argmm(cfg, L, B < 1 ? 1 : B, nullptr).bytes + 256;
+}
+int pmvae_argmm_log_prob(const pmvae_argmm_config* cfg, const float* params, const float* z, const float* context,
+                         int64_t B, float* out, void* ws, uint64_t ws_bytes, pmvae_stream_t stream) {
+  return argmm_log_prob(cfg, params, z, context, B, out, ws, ws_bytes, as_stream(stream));
+}
+int pmvae_argmm_backward(const pmvae_argmm_config* cfg, const float* params, const float* z, const float* context,
+                         int64_t B, const float* g, float* grads, float* dz, float* dcontext, void* ws,
+                         uint64_t ws_bytes, pmvae_stream_t stream) {
+  return argmm_backward(cfg, params, z, context, B, g, grads, dz, dcontext, ws, ws_bytes, as_stream(stream));
+}
+int pmvae_bernoulli_ll(const float* logits, const float* x, const float* w, int64_t B, int32_t D, float* out,
+                       pmvae_stream_t stream) {
+  PMVAE_CHECK(B >= 0 && D >= 1 && (B == 0 || (logits && x && out)), "bad arguments");
+  return bernoulli_ll(logits, x, w, B, D, out, as_stream(stream));
+}
+int pmvae_bernoulli_ll_backward(const float* logits, const float* x, const float* w, const float* g, int64_t B,
+                                int32_t D, float* dlogits, pmvae_stream_t stream) {
+  PMVAE_CHECK(B >= 0 && D >= 1 && (B == 0 || (logits && x && g && dlogits)), "bad arguments");
+  return bernoulli_ll_bwd(logits, x, w, g, B, D, dlogits, as_stream(stream));
 }
 
 int pmvae_net_apply(const pmvae_config* cfg, const float* params, int32_t which, const float* in, const float* msk,

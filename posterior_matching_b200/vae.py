@@ -56,6 +56,8 @@ class IdentityGaussian(_Dist):
 
 _NETWORKS = {"ResidualMLP": ResidualMLP}
 _DISTRIBUTIONS = {"TriLGaussian": TriLGaussian, "IdentityGaussian": IdentityGaussian}
+# Bernoulli and AutoregressiveGMM exist as stand-alone device operators (distributions.py in this package); the
+# module itself still needs the convolutional networks of the MNIST config to use them.
 _NEXT_ROWS = {"ConvEncoder", "ConvDecoder", "Bernoulli", "AutoregressiveGMM", "DiagonalGaussian", "Independent"}
 
 

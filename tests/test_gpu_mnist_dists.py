@@ -1,0 +1,73 @@
+"""GPU parity of the MNIST-config distribution heads (float32 kernels) against the float64 oracle,
+including gradients (torch autograd of the oracle)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dists_mnist as DM
+from tests.util import rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,D,weighted", [(37, 784, False), (5, 63, True), (1, 1, False)])
+def test_bernoulli_log_prob_and_gradient(B, D, weighted):
+    from posterior_matching_b200.distributions import Bernoulli
+    torch.manual_seed(B + D)
+    logits = (torch.randn(B, D, dtype=torch.float64) * 3).requires_grad_(True)
+    x = (torch.rand(B, D, dtype=torch.float64) < 0.13).double()
+    w = (torch.rand(B, D, dtype=torch.float64) < 0.5).double() if weighted else None
+    ll = DM.bernoulli_log_prob(logits, x)
+    want = (ll * w).sum(-1) if weighted else ll.sum(-1)
+    g = torch.randn(B, dtype=torch.float64)
+    (want * g).sum().backward()
+    dist = Bernoulli()
+    got = dist.log_prob(logits.detach().float().cuda(), x.float().cuda(), w.float().cuda() if weighted else None)
+    dl = dist.backward(g.float().cuda())
+    torch.cuda.synchronize()
+    assert rel_err(got.cpu().numpy(), want.detach().numpy()) < 2e-6
+    assert rel_err(dl.cpu().numpy(), logits.grad.numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("d,K,R,H,Cx,B", [(32, 10, 2, 256, 128, 64), (5, 3, 1, 64, 7, 33), (1, 1, 0, 32, 0, 4)])
+def test_argmm_log_prob_and_gradients(d, K, R, H, Cx, B):
+    from posterior_matching_b200.distributions import AutoregressiveGMM
+    spec = DM.ArgmmSpec(d=d, n_comp=K, R=R, H=H, C=Cx)
+    p = DM.argmm_init(spec)
+    for leaf in p.values():
+        for t in leaf.values():
+            t.requires_grad_(True)
+    torch.manual_seed(d)
+    z = torch.randn(B, d, dtype=torch.float64, requires_grad=True)
+    ctx = torch.randn(B, Cx, dtype=torch.float64, requires_grad=True)
+    want = DM.argmm_log_prob(p, spec, z, ctx)
+    g = torch.randn(B, dtype=torch.float64)
+    (want * g).sum().backward()
+
+    dist = AutoregressiveGMM(d, K, R, H, context_size=Cx)
+    assert [(n, r, c) for n, r, c, _, _ in dist.leaves] == DM.argmm_leaf_shapes(spec)
+    dist.load_params({n: {k: t.detach() for k, t in leaf.items()} for n, leaf in p.items()})
+    got = dist.log_prob(z.detach().float().cuda(), ctx.detach().float().cuda())
+    grads, dz, dctx = dist.backward(g.float().cuda())
+    torch.cuda.synchronize()
+    assert np.isfinite(got.cpu().numpy()).all()
+    assert rel_err(got.cpu().numpy(), want.detach().numpy()) < 2e-5
+    assert rel_l2(dz.cpu().numpy(), z.grad.numpy()) < 2e-4
+    if Cx:
+        assert rel_l2(dctx.cpu().numpy(), ctx.grad.numpy()) < 2e-4
+    for n, leaf in p.items():
+        for k, t in leaf.items():
+            w = t.grad.numpy()
+            gg = grads[n][k].cpu().numpy()
+            e = rel_l2(gg, w) if np.linalg.norm(w) > 0 else float(np.abs(gg).max())
+            assert e < 5e-4, (n, k, e)
+
+
+def test_argmm_rejects_bad_shapes_and_configs():
+    from posterior_matching_b200 import _lib
+    from posterior_matching_b200.distributions import AutoregressiveGMM
+    with pytest.raises(_lib.PmvaeError):
+        AutoregressiveGMM(65, 10, 2, 256, context_size=8)
+    dist = AutoregressiveGMM(4, 2, 1, 32, context_size=3)
+    with pytest.raises(ValueError):
+        dist.log_prob(torch.zeros(2, 5), torch.zeros(2, 3))
