@@ -34,11 +34,13 @@ constexpr int kChunkBytes = 16384;             // [128 rows] x [64 k] bf16
 constexpr int kOpndBytes = 4 * kChunkBytes;
 constexpr int kWStageBytes = 32768;            // [256 n] x [64 k] bf16
 constexpr int kWStages = 3;
-constexpr int kStagBytes = kEpiWarps * 4096;   // per-warp [32 rows] x [32 cols] fp32 head staging
+constexpr int kInPitch = 33;                   // floats per staged input row (odd: conflict-free row access)
+constexpr int kInBytes = 128 * kInPitch * 4;   // fp32 input rows of the NEXT tile (x | mask), filled by cp.async
 constexpr int kMaxLayers = 2 * kMaxBlocks + 1;
 constexpr int kOffW = kOpndBytes;
-constexpr int kOffStag = kOffW + kWStages * kWStageBytes;
-constexpr int kOffBias = kOffStag + kStagBytes;
+constexpr int kOffL0 = kOffW + kWStages * kWStageBytes;   // A operand of the first Linear (one 64-wide K-block)
+constexpr int kOffIn = kOffL0 + kChunkBytes;
+constexpr int kOffBias = kOffIn + kInBytes;
 constexpr int kOffBar = kOffBias + kMaxLayers * 1024;
 constexpr int kSmemBytes = kOffBar + 256 + 1024;
 
@@ -48,6 +50,8 @@ struct FwdArgs {
   int64_t B; int num_tiles;
   const float* bias[kMaxLayers];
   const float* head_bias; int head_N, head_NT, head_tiles;
+  float* out; int64_t ld_out;     // head output [B, ld_out] fp32
+  int head_tma;                   // 1: head rows staged in the (idle) operand buffer and stored by TMA
   int64_t Bpad; uint32_t* masks;
   long long* trace;   // PMVAE_FUSED_TRACE: per-phase clock64 stamps of block 0 (profiling only)
   int debug;   // PMVAE_FUSED_DEBUG bits (profiling only): 1 no epilogue math/stores, 2 no weight loads, 4 no MMAs
@@ -74,7 +78,8 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const uint32_t opnd = sbase, wring = sbase + kOffW, stag = sbase + kOffStag, bar = sbase + kOffBar;
+  const uint32_t opnd = sbase, wring = sbase + kOffW, l0buf = sbase + kOffL0, inbuf = sbase + kOffIn, bar = sbase + kOffBar;
+  const float* inbuf_gen = reinterpret_cast<const float*>(sgen + kOffIn);
   float* bias_tbl = reinterpret_cast<float*>(sgen + kOffBias);
   constexpr int kStg = CTA2 ? 2 * kWStages : kWStages;             // ring stages
   constexpr int kStgBytes = CTA2 ? kWStageBytes / 2 : kWStageBytes;  // [128 or 256 n] x [64 k]
@@ -86,6 +91,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   auto acc_empty = [&](int r) { return bar + 8u * (2 * kStg + 6 + r); };
   const uint32_t tmem_slot = bar + 8u * (2 * kStg + 8);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sgen + kOffBar + 8 * (2 * kStg + 8));
+  const uint32_t in_ready = bar + 8u * (2 * kStg + 9);      // first-Linear operand of the next tile is in l0buf
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;               // 0 = the CTA that issues the pair's MMAs
   // barriers the MMA issuer waits on live in the leader CTA; the peer's warps arrive there remotely
   auto arrive_leader = [&](uint32_t b) {
@@ -108,6 +114,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     for (int s = 0; s < kStg; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
     for (int c = 0; c < 4; ++c) mbar_init(opnd_ready(c), kArrive);
     for (int r = 0; r < 2; ++r) { mbar_init(acc_full(r), 1); mbar_init(acc_empty(r), kArrive); }
+    mbar_init(in_ready, kArrive);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -170,8 +177,9 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     // ===================== MMA issuer (CTA2: the leader CTA issues for the pair) =====================
     if (lane == 0 && rank == 0) {
       int stage = 0; uint32_t ph = 0;
-      uint32_t ready_par = 0, use_cnt0 = 0, use_cnt1 = 0;
-      auto step = [&](int s_idx, int nk16, int N, bool accum, bool wait_opnd) {
+      uint32_t ready_par = 0, use_cnt0 = 0, use_cnt1 = 0, in_par = 0;
+      // wait_mode: 0 = operand already announced, 1 = chunk by chunk (opnd_ready), 2 = first-Linear buffer (in_ready)
+      auto step = [&](int s_idx, uint32_t abuf, int nk16, int N, bool accum, int wait_mode) {
         const int region = (s_idx & 1) ? 0 : 1;
         uint32_t& uc = region ? use_cnt1 : use_cnt0;
         stamp(0, 100 + s_idx);
@@ -183,15 +191,18 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         const uint32_t idesc = instr_desc(CTA2 ? 256 : 128, N, 0, 0);
         const int nkb = (nk16 + 3) >> 2;
         for (int kb = 0; kb < nkb; ++kb) {
-          if (wait_opnd) {
+          if (wait_mode == 1) {
             mbar_wait_x<CTA2>(opnd_ready(kb), (ready_par >> kb) & 1u, 3);
             ready_par ^= 1u << kb;
+          } else if (wait_mode == 2) {
+            mbar_wait_x<CTA2>(in_ready, in_par, 9);
+            in_par ^= 1u;
           }
           stamp(0, 300 + kb);
           mbar_wait_x<CTA2>(w_full(stage), ph, 4);
           tc_fence_after();
           stamp(0, 400 + kb);
-          const uint32_t sa = opnd + kb * kChunkBytes;
+          const uint32_t sa = abuf + kb * kChunkBytes;
           const uint32_t sb = wring + stage * kStgBytes;
           const int ks = min(4, nk16 - 4 * kb);
           for (int k = 0; k < ks && !(p.debug & 4); ++k) {
@@ -207,9 +218,9 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         stamp(0, 500 + s_idx);
       };
       for (int it = it_first; it < it_count; it += it_stride) {
-        step(0, p.k16_0, 256, false, true);
-        for (int l = 1; l < n_hidden; ++l) step(l, 16, 256, (l & 1) == 0, true);
-        for (int t = 0; t < p.head_tiles; ++t) step(n_hidden + t, 16, p.head_NT, false, t == 0);
+        step(0, l0buf, p.k16_0, 256, false, 2);
+        for (int l = 1; l < n_hidden; ++l) step(l, opnd, 16, 256, (l & 1) == 0, 1);
+        for (int t = 0; t < p.head_tiles; ++t) step(n_hidden + t, opnd, 16, p.head_NT, false, t == 0 ? 1 : 0);
       }
     }
   } else {
@@ -219,60 +230,78 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     const int half = ew >> 2;          // which 32 of the 64 columns of a chunk
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t my_stag = stag + ew * 4096;
     uint32_t full_par = 0;
     const int D = p.D_in;
+    const int n_in = p.msk ? 2 * D : D;              // fp32 values a row contributes (x [, mask])
+    const bool can_stage = n_in <= kInPitch - 1;     // they fit the per-row staging slot
+    bool staged = false;
 
-    auto drain_sync = [&]() {
-      // the TMA stores of the previous operand tile must have finished reading shared memory
-      if (half == 0 && lane == 0) tma_store_wait_read0();
-      named_bar_sync(1 + q, 64);
+    // cp.async of the next tile's input row into this thread's private staging slot (half 0 only)
+    auto prefetch_input = [&](int tile_n) {
+      staged = false;
+      if (!can_stage) return;
+      staged = true;
+      if (half != 0) return;
+      const int64_t gn = (int64_t)tile_n * 128 + row;
+      if (gn < p.B) {
+        const uint32_t dst = inbuf + (uint32_t)(row * kInPitch) * 4u;
+        for (int k = 0; k < D; ++k) cp_async4(dst + 4u * k, p.in + gn * D + k);
+        if (p.msk) for (int k = 0; k < D; ++k) cp_async4(dst + 4u * (D + k), p.msk + gn * D + k);
+      }
+      cp_async_commit();
+    };
+    // first-Linear operand of tile_n: hi/lo bf16 split of the fp32 input, [x*b, b] built here (vae.py:132-133)
+    auto prologue = [&](int tile_n) {
+      const int64_t gn = (int64_t)tile_n * 128 + row;
+      const bool ok = gn < p.B;
+      if (staged) {
+        if (half == 0) cp_async_wait_all();
+        named_bar_sync(5 + q, 64);                   // the half-1 warp of this quadrant reads the same rows
+      }
+      const float* srow = inbuf_gen + row * kInPitch;
+      const float* xin = p.in + gn * D;
+      const float* xm = p.msk ? p.msk + gn * D : nullptr;
+      auto val = [&](int k) -> float { return staged ? srow[k] : __ldg(xin + k); };
+      auto mval = [&](int k) -> float { return staged ? srow[D + k] : __ldg(xm + k); };
+      auto ext = [&](int kk) -> float {
+        if (!ok) return 0.f;
+        if (kk < D) { float v = val(kk); if (xm) v *= mval(kk); return v; }
+        if (kk < 2 * D) { float v = val(kk - D); if (xm) v *= mval(kk - D); return v - bf16_round(v); }
+        if (xm && kk < 3 * D) return mval(kk - 2 * D);
+        return 0.f;
+      };
+      const int kk0 = 32 * half;
+      const uint32_t rowaddr = l0buf + row * 128;
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = pack2(ext(kk0 + 8 * i4 + 2 * i), ext(kk0 + 8 * i4 + 2 * i + 1));
+        const int slot = (half * 4 + i4) ^ (row & 7);
+        st_shared_v4(rowaddr + slot * 16, w[0], w[1], w[2], w[3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) arrive_leader(in_ready);
     };
 
+    if (it_first < it_count) prologue(CTA2 ? 2 * it_first + (int)rank : it_first);
     for (int it = it_first; it < it_count; it += it_stride) {
       const int tile = CTA2 ? 2 * it + (int)rank : it;
+      const bool has_next = it + it_stride < it_count;
+      const int tile_next = CTA2 ? 2 * (it + it_stride) + (int)rank : it + it_stride;
       const int64_t g = (int64_t)tile * 128 + row;
       const bool row_ok = g < p.B;
       if (ew == 0 && lane == 0) stamp(1, 1000);
-      // ---- first-layer operand: hi/lo bf16 split of the fp32 input, [x*b, b] built here (vae.py:132-133)
-      if (SAVE) drain_sync();
-      {
-        const float* xin = p.in + g * D;
-        const float* xm = p.msk ? p.msk + g * D : nullptr;
-        auto ext = [&](int kk) -> float {
-          if (!row_ok) return 0.f;
-          if (kk < D) {
-            float v = __ldg(xin + kk);
-            if (xm) v *= __ldg(xm + kk);
-            return v;
-          }
-          if (kk < 2 * D) {
-            float v = __ldg(xin + kk - D);
-            if (xm) v *= __ldg(xm + kk - D);
-            return v - bf16_round(v);
-          }
-          if (xm && kk < 3 * D) return __ldg(xm + kk - 2 * D);
-          return 0.f;
-        };
-        for (int c = 0; c < nkb0; ++c) {
-          const int kk0 = 64 * c + 32 * half;
-          const uint32_t rowaddr = opnd + c * kChunkBytes + row * 128;
-#pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            uint32_t w[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) w[i] = pack2(ext(kk0 + 8 * i4 + 2 * i), ext(kk0 + 8 * i4 + 2 * i + 1));
-            const int slot = (half * 4 + i4) ^ (row & 7);
-            st_shared_v4(rowaddr + slot * 16, w[0], w[1], w[2], w[3]);
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) arrive_leader(opnd_ready(c));
-        }
-      }
       // ---- hidden Linears: accumulator -> bf16 operand of the next Linear
       for (int l = 0; l < n_hidden; ++l) {
         const int region = (l & 1) ? 0 : 1;
+        if (l == n_hidden - 1 && has_next) prefetch_input(tile_next);     // lands while this Linear is drained
+        if (l == 0 && p.head_tma) {
+          // the previous tile's head rows were staged in the operand buffer: their TMA stores must have been read out
+          if (lane == 0) tma_store_wait_read<0>();
+          named_bar_sync(1 + q, 64);
+        }
         if (ew == 0 && lane == 0) stamp(1, 1100 + l);
         mbar_wait_x<CTA2>(acc_full(region), (full_par >> region) & 1u, 5);
         if (ew == 0 && lane == 0) stamp(1, 1200 + l);
@@ -339,7 +368,9 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         __syncwarp();
         if (lane == 0) arrive_leader(acc_empty(region));
       }
-      // ---- head Linear: accumulator + bias -> fp32 rows, staged per warp and stored by TMA
+      // ---- the next tile's first Linear can run while this tile's head is stored
+      if (has_next) prologue(tile_next);
+      // ---- head Linear: accumulator + bias -> fp32 rows (thread = row, 128 contiguous bytes per 32 columns)
       for (int t = 0; t < p.head_tiles; ++t) {
         const int region = ((n_hidden + t) & 1) ? 0 : 1;
         if (ew == 0 && lane == 0) stamp(1, 1400 + t);
@@ -347,31 +378,55 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         if (ew == 0 && lane == 0) stamp(1, 1500 + t);
         full_par ^= 1u << region;
         tc_fence_after();
-        for (int pc = half; pc * 32 < p.head_NT; pc += 2) {
+        if (p.head_tma && t == 0) {
+          // the operand buffer is idle now (every MMA that read it has retired); in training mode its own TMA
+          // stores (the last activation tile) must have been read out before it is reused as staging
+          if (SAVE) {
+            if (half == 0 && lane == 0) tma_store_wait_read<0>();
+            named_bar_sync(1 + q, 64);
+          }
+        }
+        int kpiece = 0;
+        for (int pc = half; pc * 32 < p.head_NT; pc += 2, ++kpiece) {
           const int nb = t * p.head_NT + pc * 32;
           if (nb >= p.head_N) break;
           uint32_t r[32];
           tmem_ld32(t_lane + (uint32_t)(region * 256 + pc * 32), r);
           tmem_ld_wait();
-          if (lane == 0) tma_store_wait_read0();      // the staging tile is free again
-          __syncwarp();
-#pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            float v[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int n = nb + 4 * i4 + i;
-              v[i] = __uint_as_float(r[4 * i4 + i]) + (n < p.head_N ? __ldg(p.head_bias + n) : 0.f);
+          if (p.head_tma) {
+            // two 4 KB staging tiles per warp inside its quadrant's rows of the operand buffer
+            const uint32_t st = opnd + (uint32_t)((2 * half + (kpiece & 1)) * kChunkBytes + q * 4096);
+            if (kpiece >= 2) {
+              if (lane == 0) tma_store_wait_read<1>();
+              __syncwarp();
             }
-            const int slot = i4 ^ (lane & 7);
-            st_shared_v4(my_stag + lane * 128 + slot * 16, __float_as_uint(v[0]), __float_as_uint(v[1]),
-                         __float_as_uint(v[2]), __float_as_uint(v[3]));
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&map_o, my_stag, nb, (int)((int64_t)tile * 128 + q * 32));
-            tma_store_commit();
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+              float v[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int n = nb + 4 * i4 + i;
+                v[i] = __uint_as_float(r[4 * i4 + i]) + (n < p.head_N ? __ldg(p.head_bias + n) : 0.f);
+              }
+              const int slot = i4 ^ (lane & 7);
+              st_shared_v4(st + lane * 128 + slot * 16, __float_as_uint(v[0]), __float_as_uint(v[1]),
+                           __float_as_uint(v[2]), __float_as_uint(v[3]));
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_o, st, nb, (int)((int64_t)tile * 128 + q * 32));
+              tma_store_commit();
+            }
+          } else if (row_ok) {
+            float* orow = p.out + g * p.ld_out;
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+              const int n0 = nb + 4 * i4;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (n0 + i < p.head_N) orow[n0 + i] = __uint_as_float(r[4 * i4 + i]) + __ldg(p.head_bias + n0 + i);
+            }
           }
           if (ew == 0 && lane == 0) stamp(1, 1600 + pc);
         }
@@ -515,11 +570,13 @@ net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant
         }
         umma_commit(acc_full(region));
       };
+      int t = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(dh_full, dh_par, 8);
         dh_par ^= 1u;
         tc_fence_after();
-        int t = 0;
+        // t runs on across tiles: consecutive steps alternate TMEM regions, so the first contraction of a tile
+        // overlaps the last epilogue of the previous one
         step(t++, ubuf, p.k16_h, 256, false);
         for (int r = R - 1; r >= 0; --r) {
           step(t++, sbuf, 16, 256, true);
@@ -616,12 +673,12 @@ net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant
       if (lane == 0) mbar_arrive(acc_empty(region));
     };
 
+    int t = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int64_t g = (int64_t)tile * 128 + row;
       // all TMA stores of the previous tile that read the s buffer must be done before it is rewritten
       if (half == 0 && lane == 0) tma_store_wait_read<0>();
       named_bar_sync(1 + q, 64);
-      int t = 0;
       epi_step(t++, 2 * R, sbuf, false, tile, g, csum[2 * R], false, true);
 #pragma unroll
       for (int r = R - 1; r >= 0; --r) {
@@ -630,6 +687,7 @@ net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant
       }
       if (DIN) {
         const int region = t & 1;
+        ++t;
         mbar_wait(acc_full(region), (full_par >> region) & 1u, 6);
         full_par ^= 1u << region;
         tc_fence_after();
@@ -710,7 +768,7 @@ __global__ void __launch_bounds__(256) pack_fused_kernel(const float* __restrict
 bool supported(const Net& n, int H, int in_kind) {
   if (n.ln || H != 256) return false;
   const int kext = (in_kind == 1) ? 3 * (n.in_dim / 2) : 2 * n.in_dim;
-  return kext <= 256;
+  return kext <= 64;       // the expanded first-Linear operand is one 64-wide K-block
 }
 
 NetImages plan_images(const Net& n, const Leaf& head, int in_kind, bf16* base) {
@@ -801,6 +859,7 @@ int net_forward(const float* params, const Net& n, const Leaf& head, const NetIm
   a.B = B; a.num_tiles = (int)ceil_div(B, 128);
   for (int l = 0; l <= 2 * n.R; ++l) a.bias[l] = params + n.lin[l].b;
   a.head_bias = params + head.b; a.head_N = im.head_N; a.head_NT = im.head_NT; a.head_tiles = im.head_tiles;
+  a.out = out; a.ld_out = ld_out;
   a.Bpad = Bpad;
   a.masks = nullptr;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PMVAE_FUSED_DEBUG"); dbg = e ? atoi(e) : 0; } a.debug = dbg; }
@@ -809,7 +868,7 @@ int net_forward(const float* params, const Net& n, const Leaf& head, const NetIm
   PMVAE_TRY(make_map_2d(&mw, im.stack_t, 2, (uint64_t)(1 + 2 * n.R) * 256, 256, 256, 64, cta2 ? 128 : 256));
   PMVAE_TRY(make_map_2d(&mh, im.head_t, 2, (uint64_t)im.head_tiles * im.head_NT, 256, 256, 64,
                         (uint32_t)(cta2 ? im.head_NT / 2 : im.head_NT)));
-  PMVAE_TRY(make_map_2d(&mo, out, 4, (uint64_t)B, (uint64_t)im.head_N, (uint64_t)ld_out, 32, 32));
+  PMVAE_CHECK(im.k16_0 <= 4 && ld_out >= im.head_N, "first-Linear operand must fit one K-block");
   if (saved) {
     PMVAE_CHECK(Bpad % 128 == 0 && Bpad >= B, "saved activations need a 128-row padded slab pitch");
     PMVAE_CHECK((int64_t)(2 * n.R + 1) * Bpad < (1ll << 31), "saved activation stack too large");
@@ -818,6 +877,9 @@ int net_forward(const float* params, const Net& n, const Leaf& head, const NetIm
   } else {
     ms = mw;
   }
+  a.head_tma = ((ld_out * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) ? 1 : 0;
+  if (a.head_tma) PMVAE_TRY(make_map_2d(&mo, out, 4, (uint64_t)B, (uint64_t)im.head_N, (uint64_t)ld_out, 32, 32));
+  else mo = mw;
   int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
   if (cta2) {
     const int pairs = (a.num_tiles + 1) / 2;

@@ -196,7 +196,9 @@ class PosteriorMatchingVAE:
             nbytes = int(_lib.lib.pmvae_workspace_bytes(self._cfgp, Bk, Kk))
             if nbytes == 0:
                 _lib.check(1, "pmvae_workspace_bytes")
-            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+            off = (-raw.data_ptr()) % 1024          # libpmvae wants a 1024-byte aligned workspace
+            self._ws_raw, self._ws = raw, raw[off:off + nbytes]
             self._ws_key = (Bk, Kk)
             self._params_dirty = True
         return self._ws

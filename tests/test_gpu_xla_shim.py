@@ -13,6 +13,12 @@ from tests.util import conditioned_params, make_inputs, spec_of
 pytestmark = pytest.mark.gpu
 
 
+def _aligned_ws(nbytes):
+    raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device="cuda")
+    off = (-raw.data_ptr()) % 1024
+    return raw[off:off + nbytes]
+
+
 def _buffers(*tensors):
     arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
     return arr
@@ -36,7 +42,7 @@ def test_forward_backward_targets_match_direct_calls(precision):
 
     S = torch.cuda.current_stream().cuda_stream
     ws_bytes = int(_lib.lib.pmvae_workspace_bytes(C.byref(m.cfg), B, 0))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    ws = _aligned_ws(ws_bytes)
     out = torch.empty(3, B, device="cuda")
     op = opaque(m.cfg, B=B, ws_bytes=ws_bytes, prepare=True)
     _lib.lib.pmvae_xla_forward(S, _buffers(m.arena, x, b, eps, out[0], out[1], out[2], ws), op, len(op), None)
@@ -68,7 +74,7 @@ def test_eval_and_mask_targets_match_direct_calls():
     imp = m.impute_mean(x, b, K, key=(5, 6)).clone()
     S = torch.cuda.current_stream().cuda_stream
     ws_bytes = int(_lib.lib.pmvae_workspace_bytes(C.byref(m.cfg), B, K))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    ws = _aligned_ws(ws_bytes)
     o1, o2 = torch.empty(B, device="cuda"), torch.empty(B, device="cuda")
     op = opaque(m.cfg, B=B, K=K, ws_bytes=ws_bytes, key0=keys[0], key1=keys[1], prepare=True)
     _lib.lib.pmvae_xla_is_log_prob(S, _buffers(m.arena, x, b, o1, o2, ws), op, len(op), None)
