@@ -34,7 +34,7 @@ constexpr int kChunkBytes = 16384;             // [128 rows] x [64 k] bf16
 constexpr int kOpndBytes = 4 * kChunkBytes;
 constexpr int kWStageBytes = 32768;            // [256 n] x [64 k] bf16
 constexpr int kWStages = 3;
-constexpr int kInPitch = 33;                   // floats per staged input row (odd: conflict-free row access)
+constexpr int kInPitch = 49;                   // floats per staged input row (up to 48 values: x | mask)
 constexpr int kInBytes = 128 * kInPitch * 4;   // fp32 input rows of the NEXT tile (x | mask), filled by cp.async
 constexpr int kMaxLayers = 2 * kMaxBlocks + 1;
 constexpr int kOffW = kOpndBytes;
@@ -130,6 +130,8 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       run += p.bias[2 * r + 2][c];
       bias_tbl[(2 * r + 2) * 256 + c] = run;
     }
+    // head bias (single head tile): row 2R+1, zero beyond the valid columns
+    if (p.head_tiles == 1) bias_tbl[n_hidden * 256 + c] = c < p.head_N ? p.head_bias[c] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -232,59 +234,50 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t full_par = 0;
     const int D = p.D_in;
-    const int n_in = p.msk ? 2 * D : D;              // fp32 values a row contributes (x [, mask])
-    const bool can_stage = n_in <= kInPitch - 1;     // they fit the per-row staging slot
-    bool staged = false;
 
-    // cp.async of the next tile's input row into this thread's private staging slot (half 0 only)
+    // cp.async of a tile's fp32 input rows (x | mask) into the staging slots: thread (q, half 0, lane) copies row 32q+lane
     auto prefetch_input = [&](int tile_n) {
-      staged = false;
-      if (!can_stage) return;
-      staged = true;
       if (half != 0) return;
       const int64_t gn = (int64_t)tile_n * 128 + row;
+      const uint32_t dst = inbuf + (uint32_t)(row * kInPitch) * 4u;
       if (gn < p.B) {
-        const uint32_t dst = inbuf + (uint32_t)(row * kInPitch) * 4u;
         for (int k = 0; k < D; ++k) cp_async4(dst + 4u * k, p.in + gn * D + k);
         if (p.msk) for (int k = 0; k < D; ++k) cp_async4(dst + 4u * (D + k), p.msk + gn * D + k);
       }
       cp_async_commit();
     };
-    // first-Linear operand of tile_n: hi/lo bf16 split of the fp32 input, [x*b, b] built here (vae.py:132-133)
+    // First-Linear operand of tile_n from the staged rows: hi/lo bf16 split of the fp32 input, [x*b, b] built
+    // here (vae.py:132-133).  Lane = operand column (its source element and kind are fixed per lane), loop over the
+    // warp's 32 rows: conflict-free LDS / STS and no per-element branching.
     auto prologue = [&](int tile_n) {
-      const int64_t gn = (int64_t)tile_n * 128 + row;
-      const bool ok = gn < p.B;
-      if (staged) {
-        if (half == 0) cp_async_wait_all();
-        named_bar_sync(5 + q, 64);                   // the half-1 warp of this quadrant reads the same rows
-      }
-      const float* srow = inbuf_gen + row * kInPitch;
-      const float* xin = p.in + gn * D;
-      const float* xm = p.msk ? p.msk + gn * D : nullptr;
-      auto val = [&](int k) -> float { return staged ? srow[k] : __ldg(xin + k); };
-      auto mval = [&](int k) -> float { return staged ? srow[D + k] : __ldg(xm + k); };
-      auto ext = [&](int kk) -> float {
-        if (!ok) return 0.f;
-        if (kk < D) { float v = val(kk); if (xm) v *= mval(kk); return v; }
-        if (kk < 2 * D) { float v = val(kk - D); if (xm) v *= mval(kk - D); return v - bf16_round(v); }
-        if (xm && kk < 3 * D) return mval(kk - 2 * D);
-        return 0.f;
-      };
-      const int kk0 = 32 * half;
-      const uint32_t rowaddr = l0buf + row * 128;
-#pragma unroll
-      for (int i4 = 0; i4 < 4; ++i4) {
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) w[i] = pack2(ext(kk0 + 8 * i4 + 2 * i), ext(kk0 + 8 * i4 + 2 * i + 1));
-        const int slot = (half * 4 + i4) ^ (row & 7);
-        st_shared_v4(rowaddr + slot * 16, w[0], w[1], w[2], w[3]);
+      if (half == 0) cp_async_wait_all();
+      named_bar_sync(5 + q, 64);                     // the half-1 warp of this quadrant reads the same rows
+      const int kk = 32 * half + lane;               // operand column 0..63
+      int src = 0, kind = 3;                         // kind 0: hi(v), 1: lo(v), 2: mask, 3: zero
+      if (kk < D) { src = kk; kind = 0; }
+      else if (kk < 2 * D) { src = kk - D; kind = 1; }
+      else if (p.msk && kk < 3 * D) { src = kk - 2 * D; kind = 2; }
+      const bool has_m = p.msk != nullptr;
+      const int64_t g0 = (int64_t)tile_n * 128 + q * 32;
+#pragma unroll 8
+      for (int rr = 0; rr < 32; ++rr) {
+        const float* srow = inbuf_gen + (q * 32 + rr) * kInPitch;
+        float v = 0.f;
+        if (kind != 3 && g0 + rr < p.B) {
+          const float m = has_m ? srow[D + src] : 1.f;
+          v = (kind == 2) ? m : srow[src] * m;
+          if (kind == 1) v -= bf16_round(v);
+        }
+        const int r = q * 32 + rr;
+        const uint32_t addr = l0buf + r * 128 + (((kk >> 3) ^ (r & 7)) << 4) + ((kk & 7) << 1);
+        st_shared_u16(addr, __bfloat16_as_ushort(__float2bfloat16(v)));
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) arrive_leader(in_ready);
     };
 
+    if (it_first < it_count) prefetch_input(CTA2 ? 2 * it_first + (int)rank : it_first);
     if (it_first < it_count) prologue(CTA2 ? 2 * it_first + (int)rank : it_first);
     for (int it = it_first; it < it_count; it += it_stride) {
       const int tile = CTA2 ? 2 * it + (int)rank : it;
@@ -404,9 +397,16 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             for (int i4 = 0; i4 < 8; ++i4) {
               float v[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int n = nb + 4 * i4 + i;
-                v[i] = __uint_as_float(r[4 * i4 + i]) + (n < p.head_N ? __ldg(p.head_bias + n) : 0.f);
+              if (p.head_tiles == 1) {
+                const float4 bv = *reinterpret_cast<const float4*>(bias_tbl + n_hidden * 256 + nb + 4 * i4);
+                v[0] = __uint_as_float(r[4 * i4]) + bv.x; v[1] = __uint_as_float(r[4 * i4 + 1]) + bv.y;
+                v[2] = __uint_as_float(r[4 * i4 + 2]) + bv.z; v[3] = __uint_as_float(r[4 * i4 + 3]) + bv.w;
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int n = nb + 4 * i4 + i;
+                  v[i] = __uint_as_float(r[4 * i4 + i]) + (n < p.head_N ? __ldg(p.head_bias + n) : 0.f);
+                }
               }
               const int slot = i4 ^ (lane & 7);
               st_shared_v4(st + lane * 128 + slot * 16, __float_as_uint(v[0]), __float_as_uint(v[1]),
@@ -768,7 +768,8 @@ __global__ void __launch_bounds__(256) pack_fused_kernel(const float* __restrict
 bool supported(const Net& n, int H, int in_kind) {
   if (n.ln || H != 256) return false;
   const int kext = (in_kind == 1) ? 3 * (n.in_dim / 2) : 2 * n.in_dim;
-  return kext <= 64;       // the expanded first-Linear operand is one 64-wide K-block
+  // the expanded first-Linear operand is one 64-wide K-block; a row's fp32 inputs (x | mask) fit its staging slot
+  return kext <= 64 && n.in_dim <= kInPitch - 1 && n.R < kMaxBlocks;
 }
 
 NetImages plan_images(const Net& n, const Leaf& head, int in_kind, bf16* base) {
