@@ -463,6 +463,7 @@ constexpr int kBwdOffU = kOpndBytes;
 constexpr int kBwdOffW = 2 * kOpndBytes;
 constexpr int kBwdOffBar = kBwdOffW + kWStages * kWStageBytes;
 constexpr int kBwdSmemBytes = kBwdOffBar + 256;
+constexpr int kBwdThreads = kThreads + 4 * 32;   // + 4 helper warps (TMA stores of dY, bias-gradient sums)
 
 struct BwdArgs {
   int64_t B; int num_tiles;
@@ -471,10 +472,11 @@ struct BwdArgs {
   float* dIn;                 // [B, din_cols] fp32
   const uint32_t* masks; int64_t Bpad;
   float* db[kMaxLayers];      // bias-gradient destinations (atomicAdd), Linear 0..2R
+  int debug;                  // PMVAE_FUSED_DEBUG bits (profiling only): 16 no column sums, 32 no dY stores
 };
 
 template <int R, bool DIN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant__ CUtensorMap map_wh,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w0,
                const __grid_constant__ CUtensorMap map_dy, BwdArgs p) {
@@ -489,8 +491,12 @@ net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant
   auto acc_empty = [&](int r) { return bar + 8u * (2 * kWStages + 6 + r); };
   const uint32_t dh_full = bar + 8u * (2 * kWStages + 8);
   const uint32_t ubuf_free = bar + 8u * (2 * kWStages + 9);
-  const uint32_t tmem_slot = bar + 8u * (2 * kWStages + 10);
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + kBwdOffBar + 8 * (2 * kWStages + 10));
+  // chunk hand-offs to the helper warps: written[j] = chunk j of the buffer being filled is complete (8 epilogue
+  // warps); chunk_free(buf, j) = its TMA store has been read out and its column sums taken (helper j)
+  auto written = [&](int c) { return bar + 8u * (2 * kWStages + 10 + c); };
+  auto chunk_free = [&](int buf, int c) { return bar + 8u * (2 * kWStages + 14 + 4 * buf + c); };
+  const uint32_t tmem_slot = bar + 8u * (2 * kWStages + 22);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + kBwdOffBar + 8 * (2 * kWStages + 22));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int n_hidden = 2 * R + 1;
@@ -504,6 +510,7 @@ net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant
     for (int r = 0; r < 2; ++r) { mbar_init(acc_full(r), 1); mbar_init(acc_empty(r), kEpiWarps); }
     mbar_init(dh_full, 1);
     mbar_init(ubuf_free, 4);
+    for (int c = 0; c < 4; ++c) { mbar_init(written(c), kEpiWarps); mbar_init(chunk_free(0, c), 1); mbar_init(chunk_free(1, c), 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -585,7 +592,7 @@ net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant
         if (DIN) step(t++, sbuf, 16, p.din_N, true);
       }
     }
-  } else {
+  } else if (warp < 2 + kEpiWarps) {
     // ===================== epilogue (8 warps) =====================
     const int ew = warp - 2;
     const int q = warp & 3;
@@ -593,33 +600,27 @@ net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t full_par = 0;
-    float csum[n_hidden][4];
-#pragma unroll
-    for (int l = 0; l < n_hidden; ++l)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) csum[l][j] = 0.f;
+    uint32_t nwr[2] = {0, 0};          // writes so far into each operand buffer (all four chunks move together)
 
-    // One epilogue step: accumulator (region) . mask_l [+ old s] -> bf16 chunk of `dst` (+ TMA store as dY_l,
-    // + column sums).  ADD: dst is the s buffer and the new value is old s + masked accumulator.
-    auto epi_step = [&](int s_idx, int l, uint32_t dst, bool add, int tile, int64_t g, float (&cs)[4], bool free_ubuf,
-                        bool has_consumer) {
+    // One epilogue step: accumulator (region) . mask_l [+ old s] -> bf16 chunk of buffer `buf` (0 = s, 1 = dU).
+    // The helper warps store the chunk as dY_l and take its column sums.
+    auto epi_step = [&](int s_idx, int l, int buf, bool add, int64_t g, bool has_consumer) {
       const int region = s_idx & 1;
+      const uint32_t dst = buf ? ubuf : sbuf;
       const uint4 mq = *reinterpret_cast<const uint4*>(p.masks + (((int64_t)l * p.Bpad + g) * 8 + half * 4));
       const uint32_t mw[4] = {mq.x, mq.y, mq.z, mq.w};
       mbar_wait(acc_full(region), (full_par >> region) & 1u, 5);
       full_par ^= 1u << region;
       tc_fence_after();
-      if (free_ubuf) {
-        // every MMA that read the dU buffer has retired; once its TMA stores have been read out the
-        // producer may overwrite it with the next tile's dHead rows
-        if (half == 0 && lane == 0) { tma_store_wait_read<0>(); mbar_arrive(ubuf_free); }
-      }
       const uint32_t t_acc = t_lane + (uint32_t)(region * 256 + 32 * half);
+      const uint32_t fpar = (nwr[buf] & 1u) ^ 1u;      // previous contents of this buffer have been stored and summed
+      ++nwr[buf];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint32_t r[32];
         tmem_ld32(t_acc + 64 * j, r);
         const uint32_t rowaddr = dst + j * kChunkBytes + row * 128;
+        mbar_wait(chunk_free(buf, j), fpar, 10);
         uint32_t old[16];
         if (add) {
 #pragma unroll
@@ -629,17 +630,15 @@ net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant
           }
         }
         tmem_ld_wait();
-        float v[32];
         const uint32_t m = mw[j];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float a = ((int32_t)(m << i) < 0) ? __uint_as_float(r[i]) : 0.f;
-          if (add) a += (i & 1) ? bf16_hi(old[i >> 1]) : bf16_lo(old[i >> 1]);
-          v[i] = a;
-        }
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = pack2(v[2 * i], v[2 * i + 1]);
+        for (int i = 0; i < 16; ++i) {
+          float a0 = ((int32_t)(m << (2 * i)) < 0) ? __uint_as_float(r[2 * i]) : 0.f;
+          float a1 = ((int32_t)(m << (2 * i + 1)) < 0) ? __uint_as_float(r[2 * i + 1]) : 0.f;
+          if (add) { a0 += bf16_lo(old[i]); a1 += bf16_hi(old[i]); }
+          pk[i] = pack2(a0, a1);
+        }
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
           const int slot = (half * 4 + i4) ^ (row & 7);
@@ -647,26 +646,10 @@ net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant
         }
         fence_proxy_async();
         __syncwarp();
-        if (has_consumer && lane == 0) mbar_arrive(opnd_ready(j));     // a chunk nobody multiplies is not announced
-        if (half == 0 && lane == 0) tma_store_wait_read<2>();
-        named_bar_sync(1 + q, 64);
-        if (half == 0 && lane == 0) {
-          tma_store_2d(&map_dy, dst + j * kChunkBytes + q * 4096, 64 * j,
-                       (int)((int64_t)l * p.Bpad + (int64_t)tile * 128 + q * 32));
-          tma_store_commit();
+        if (lane == 0) {
+          if (has_consumer) mbar_arrive(opnd_ready(j));       // a chunk nobody multiplies is not announced to the MMA warp
+          mbar_arrive(written(j));
         }
-        // column sums over this warp's 32 rows: butterfly transpose-reduce, lane c ends up with column c
-#pragma unroll
-        for (int sft = 16, n = 32; sft >= 1; sft >>= 1, n >>= 1) {
-          const bool up = (lane & sft) != 0;
-#pragma unroll
-          for (int i = 0; i < n / 2; ++i) {
-            const float send = up ? v[i] : v[i + n / 2];
-            const float keep = up ? v[i + n / 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
-          }
-        }
-        cs[j] += v[0];
       }
       tc_fence_before();
       __syncwarp();
@@ -676,14 +659,11 @@ net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant
     int t = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int64_t g = (int64_t)tile * 128 + row;
-      // all TMA stores of the previous tile that read the s buffer must be done before it is rewritten
-      if (half == 0 && lane == 0) tma_store_wait_read<0>();
-      named_bar_sync(1 + q, 64);
-      epi_step(t++, 2 * R, sbuf, false, tile, g, csum[2 * R], false, true);
+      epi_step(t++, 2 * R, 0, false, g, true);
 #pragma unroll
       for (int r = R - 1; r >= 0; --r) {
-        epi_step(t++, 2 * r + 1, ubuf, false, tile, g, csum[2 * r + 1], false, true);
-        epi_step(t++, 2 * r, sbuf, true, tile, g, csum[2 * r], r == 0, DIN || r > 0);
+        epi_step(t++, 2 * r + 1, 1, false, g, true);
+        epi_step(t++, 2 * r, 0, true, g, DIN || r > 0);
       }
       if (DIN) {
         const int region = t & 1;
@@ -706,13 +686,66 @@ net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant
         if (lane == 0) mbar_arrive(acc_empty(region));
       }
     }
+  } else {
+    // ===================== helpers (4 warps): warp j owns chunk j of every operand tile =====================
+    // As soon as the epilogue has written chunk j: one TMA store of the [128 rows x 64 cols] chunk as dY_l, and the
+    // bias gradient (column sums of the bf16 values the weight-gradient GEMM will read) from shared memory, two
+    // columns per lane; then the chunk is handed back.  This keeps stores and reductions off the epilogue's path.
+    const int j = warp - (2 + kEpiWarps);
+    float cs[n_hidden][2];
+#pragma unroll
+    for (int l = 0; l < n_hidden; ++l) { cs[l][0] = 0.f; cs[l][1] = 0.f; }
+    uint32_t wr_cnt = 0, reg_uses[2] = {0, 0};
+    auto help = [&](int l, int buf, int tile, float (&c2)[2]) {
+      const uint32_t src = (buf ? ubuf : sbuf) + j * kChunkBytes;
+      mbar_wait(written(j), wr_cnt & 1u, 11);
+      ++wr_cnt;
+      if (lane == 0 && !(p.debug & 32)) {
+        tma_store_2d(&map_dy, src, 64 * j, (int)((int64_t)l * p.Bpad + (int64_t)tile * 128));
+        tma_store_commit();
+      }
+      if (!(p.debug & 16)) {
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 128; r += 2) {
+          const uint32_t w0 = ld_shared_u32(src + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+          const uint32_t w1 = ld_shared_u32(src + (r + 1) * 128 + ((((lane >> 2) ^ ((r + 1) & 7)) << 4) | ((lane & 3) << 2)));
+          a0 += bf16_lo(w0); a1 += bf16_hi(w0);
+          b0 += bf16_lo(w1); b1 += bf16_hi(w1);
+        }
+        c2[0] += a0 + b0; c2[1] += a1 + b1;
+      }
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(chunk_free(buf, j));
+    };
+    int t = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      ++reg_uses[t & 1]; ++t;                         // s0
+      help(2 * R, 0, tile, cs[2 * R]);
+#pragma unroll
+      for (int r = R - 1; r >= 0; --r) {
+        ++reg_uses[t & 1]; ++t;                       // dU step
+        help(2 * r + 1, 1, tile, cs[2 * r + 1]);
+        const int region = t & 1;                     // s step: its accumulator being full means every MMA that read
+        const uint32_t n_before = reg_uses[region];   // the dU buffer has retired
+        ++reg_uses[region]; ++t;
+        if (r == 0) {
+          mbar_wait(acc_full(region), n_before & 1u, 12);
+          if (lane == 0) mbar_arrive(ubuf_free);      // the producer may load the next tile's dHead rows into it
+        }
+        help(2 * r, 0, tile, cs[2 * r]);
+      }
+      if (DIN) { ++reg_uses[t & 1]; ++t; }
+    }
     if (lane == 0) tma_store_wait_all();
-    // bias gradients: lane c of warp (q, half) holds columns 64 j + 32 half + c summed over its rows
+    // bias gradients: lane c of helper j holds columns 64 j + 2 c, + 1 summed over every tile of this CTA
 #pragma unroll
     for (int l = 0; l < n_hidden; ++l)
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (p.db[l]) atomicAdd(p.db[l] + 64 * j + 32 * half + lane, csum[l][j]);
+      if (p.db[l] && !(p.debug & 16)) {
+        atomicAdd(p.db[l] + 64 * j + 2 * lane, cs[l][0]);
+        atomicAdd(p.db[l] + 64 * j + 2 * lane + 1, cs[l][1]);
+      }
   }
 
   tc_fence_before();
@@ -923,7 +956,7 @@ static int launch_bwd(const CUtensorMap& mdh, const CUtensorMap& mwh, const CUte
     attr_set = true;
   }
   const int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
-  net_bwd_kernel<R, DIN><<<grid, kThreads, kBwdSmemBytes, s>>>(mdh, mwh, mw, mw0, mdy, a);
+  net_bwd_kernel<R, DIN><<<grid, kBwdThreads, kBwdSmemBytes, s>>>(mdh, mwh, mw, mw0, mdy, a);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -942,11 +975,12 @@ int net_backward(const Net& n, const Leaf& head, const NetImages& im, const bf16
   a.din_N = dIn ? im.din_N : 0; a.din_cols = n.in_dim; a.dIn = dIn;
   a.masks = masks; a.Bpad = Bpad;
   for (int l = 0; l <= 2 * n.R; ++l) a.db[l] = grads + n.lin[l].b;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PMVAE_FUSED_DEBUG"); dbg = e ? atoi(e) : 0; } a.debug = dbg; }
   CUtensorMap mdh, mwh, mw, mw0, mdy;
   PMVAE_TRY(make_map_2d(&mdh, dHead, 2, (uint64_t)B, (uint64_t)im.head_N, (uint64_t)ld_dhead, 64, 128));
   PMVAE_TRY(make_map_2d(&mwh, im.head_n, 2, 256, (uint64_t)im.head_Kp, (uint64_t)im.head_Kp, 64, 256));
   PMVAE_TRY(make_map_2d(&mw, im.stack_n, 2, (uint64_t)(2 * n.R) * 256, 256, 256, 64, 256));
-  PMVAE_TRY(make_map_2d(&mdy, dY, 2, (uint64_t)(2 * n.R + 1) * Bpad, 256, 256, 64, 32));
+  PMVAE_TRY(make_map_2d(&mdy, dY, 2, (uint64_t)(2 * n.R + 1) * Bpad, 256, 256, 64, 128));
   if (dIn) PMVAE_TRY(make_map_2d(&mw0, im.w0_n, 2, (uint64_t)im.din_N, 256, 256, 64, (uint32_t)im.din_N));
   else mw0 = mw;
 #define PMVAE_BWD_CASE(RR)                                                             \

@@ -86,7 +86,7 @@ class Trainer:
                                                  seed=seed + 1, device=self.device)
         self._rng = prng.PRNGSequence(prng.PRNGKey(seed + 2))
         self._cot = None
-        self._sums = torch.zeros(3, dtype=torch.float32, device=self.device)
+        self._sums = self.model.grad_tail[:3]       # batch sums ride along with the gradient all-reduce
         self.last_beta = 1.0
 
     def _buffers(self, B):
@@ -115,8 +115,7 @@ class Trainer:
         mdl.backward(cot[0, :B], cot[1, :B], cot[2, :B])
         if self.world > 1:
             # mean of per-rank mean-gradients == sum of the 1/B_global-scaled shard gradients
-            torch.distributed.all_reduce(mdl.grad_arena, group=self.pg)
-            torch.distributed.all_reduce(self._sums, group=self.pg)
+            torch.distributed.all_reduce(mdl._grad_store, group=self.pg)    # gradients + the three batch sums
         lr = float(self.lr_schedule(self.step))
         _lib.check(_lib.lib.pmvae_adamw(mdl._cfgp, mdl.arena.data_ptr(), mdl.grad_arena.data_ptr(),
                                         self.m.data_ptr(), self.v.data_ptr(), self.step, lr, self.weight_decay,

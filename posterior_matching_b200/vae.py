@@ -121,7 +121,10 @@ class PosteriorMatchingVAE:
             _lib.check(1, "pmvae_param_count")
         self.leaves = _lib.layout(self.cfg)
         self.arena = torch.zeros(self.n_arena, dtype=torch.float32, device=self.device)
-        self.grad_arena = torch.zeros_like(self.arena)
+        # gradient arena + 64 trailing floats for per-step batch statistics, so that one all-reduce carries both
+        self._grad_store = torch.zeros(self.n_arena + 64, dtype=torch.float32, device=self.device)
+        self.grad_arena = self._grad_store[:self.n_arena]
+        self.grad_tail = self._grad_store[self.n_arena:]
         self.params = self._views(self.arena)
         self.grads = self._views(self.grad_arena)
         self._ws = None
