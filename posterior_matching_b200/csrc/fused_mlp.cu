@@ -29,6 +29,7 @@ using namespace tc;
 typedef __nv_bfloat16 bf16;
 
 constexpr int kThreads = 320;
+constexpr int kFwdThreads = kThreads + 32;      // + 1 helper warp (training mode: TMA stores of the saved activations)
 constexpr int kEpiWarps = 8;
 constexpr int kChunkBytes = 16384;             // [128 rows] x [64 k] bf16
 constexpr int kOpndBytes = 4 * kChunkBytes;
@@ -72,7 +73,7 @@ __device__ __forceinline__ uint32_t relu2(uint32_t v) {
 // CTA2: two CTAs of a cluster run as one tcgen05 pair (cta_group::2, M = 256): each owns a 128-row tile and
 // half of every weight K-block, so the weight traffic from L2 is halved and the ring covers twice the latency.
 template <bool SAVE, bool CTA2>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_h,
                const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_o, FwdArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -92,6 +93,10 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   const uint32_t tmem_slot = bar + 8u * (2 * kStg + 8);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sgen + kOffBar + 8 * (2 * kStg + 8));
   const uint32_t in_ready = bar + 8u * (2 * kStg + 9);      // first-Linear operand of the next tile is in l0buf
+  // training mode: written(j) = operand chunk j is complete (this CTA's 8 epilogue warps), chunk_free(j) = the
+  // helper warp's TMA store of it (the saved activation tile) has been read out
+  auto written = [&](int c) { return bar + 8u * (2 * kStg + 10 + c); };
+  auto chunk_free = [&](int c) { return bar + 8u * (2 * kStg + 14 + c); };
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;               // 0 = the CTA that issues the pair's MMAs
   // barriers the MMA issuer waits on live in the leader CTA; the peer's warps arrive there remotely
   auto arrive_leader = [&](uint32_t b) {
@@ -115,6 +120,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     for (int c = 0; c < 4; ++c) mbar_init(opnd_ready(c), kArrive);
     for (int r = 0; r < 2; ++r) { mbar_init(acc_full(r), 1); mbar_init(acc_empty(r), kArrive); }
     mbar_init(in_ready, kArrive);
+    for (int c = 0; c < 4; ++c) { mbar_init(written(c), kEpiWarps); mbar_init(chunk_free(c), 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -225,7 +231,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         for (int t = 0; t < p.head_tiles; ++t) step(n_hidden + t, opnd, 16, p.head_NT, false, t == 0 ? 1 : 0);
       }
     }
-  } else {
+  } else if (warp < 2 + kEpiWarps) {
     // ===================== epilogue (8 warps) =====================
     const int ew = warp - 2;
     const int q = warp & 3;            // TMEM lane quadrant this warp may read
@@ -233,6 +239,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t full_par = 0;
+    uint32_t n_writes = 0;             // operand tiles written so far (training mode: chunk_free phase tracking)
     const int D = p.D_in;
 
     // cp.async of a tile's fp32 input rows (x | mask) into the staging slots: thread (q, half 0, lane) copies row 32q+lane
@@ -333,6 +340,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             pk[2 * i + 1] = relu2(pack2(v2, v3));
           }
           mw[j] = ~neg;
+          if (SAVE) mbar_wait(chunk_free(j), (n_writes & 1u) ^ 1u, 13);   // the previous tile in this chunk has been stored
           const uint32_t rowaddr = opnd + j * kChunkBytes + row * 128;
 #pragma unroll
           for (int i4 = 0; i4 < 4; ++i4) {
@@ -343,18 +351,9 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           __syncwarp();
           if (lane == 0) arrive_leader(opnd_ready(j));
           if (ew == 0 && lane == 0) stamp(1, 1300 + j);
-          if (SAVE) {
-            // Before chunk j+1 (or chunk 0 of the next Linear) is overwritten its previous TMA store must
-            // have finished reading: that store is the oldest of the three groups still in flight.
-            if (half == 0 && lane == 0) tma_store_wait_read<2>();
-            named_bar_sync(1 + q, 64);
-            if (half == 0 && lane == 0) {
-              tma_store_2d(&map_s, opnd + j * kChunkBytes + q * 4096, 64 * j,
-                           (int)((int64_t)l * p.Bpad + (int64_t)tile * 128 + q * 32));
-              tma_store_commit();
-            }
-          }
+          if (SAVE && lane == 0) mbar_arrive(written(j));
         }
+        ++n_writes;
         if (SAVE && p.masks)
           *reinterpret_cast<uint4*>(p.masks + (((int64_t)l * p.Bpad + g) * 8 + half * 4)) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
         tc_fence_before();
@@ -375,8 +374,8 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           // the operand buffer is idle now (every MMA that read it has retired); in training mode its own TMA
           // stores (the last activation tile) must have been read out before it is reused as staging
           if (SAVE) {
-            if (half == 0 && lane == 0) tma_store_wait_read<0>();
-            named_bar_sync(1 + q, 64);
+            mbar_wait(chunk_free(2 * half), (n_writes & 1u) ^ 1u, 14);
+            mbar_wait(chunk_free(2 * half + 1), (n_writes & 1u) ^ 1u, 14);
           }
         }
         int kpiece = 0;
@@ -433,6 +432,25 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_leader(acc_empty(region));
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  } else if (SAVE) {
+    // ===================== helper warp (training mode): streams every finished operand chunk to HBM =====================
+    uint32_t cnt = 0;
+    for (int it = it_first; it < it_count; it += it_stride) {
+      const int tile = CTA2 ? 2 * it + (int)rank : it;
+      for (int l = 0; l < n_hidden; ++l, ++cnt) {
+        for (int j = 0; j < 4; ++j) {
+          mbar_wait(written(j), cnt & 1u, 15);
+          if (lane == 0) {
+            tma_store_2d(&map_s, opnd + j * kChunkBytes, 64 * j, (int)((int64_t)l * p.Bpad + (int64_t)tile * 128));
+            tma_store_commit();
+            tma_store_wait_read<0>();
+            mbar_arrive(chunk_free(j));
+          }
+          __syncwarp();
+        }
       }
     }
     if (lane == 0) tma_store_wait_all();
@@ -867,7 +885,7 @@ static int launch_fwd_t(int grid, const CUtensorMap& mw, const CUtensorMap& mh, 
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = s;
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kFwdThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CTA2 ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -906,7 +924,7 @@ int net_forward(const float* params, const Net& n, const Leaf& head, const NetIm
   if (saved) {
     PMVAE_CHECK(Bpad % 128 == 0 && Bpad >= B, "saved activations need a 128-row padded slab pitch");
     PMVAE_CHECK((int64_t)(2 * n.R + 1) * Bpad < (1ll << 31), "saved activation stack too large");
-    PMVAE_TRY(make_map_2d(&ms, saved, 2, (uint64_t)(2 * n.R + 1) * Bpad, 256, 256, 64, 32));
+    PMVAE_TRY(make_map_2d(&ms, saved, 2, (uint64_t)(2 * n.R + 1) * Bpad, 256, 256, 64, 128));
     a.masks = masks;
   } else {
     ms = mw;
