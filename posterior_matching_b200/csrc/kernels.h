@@ -60,6 +60,8 @@ int latent_bwd(const float* par_e, const float* par_p, const float* eps, const f
 // latent16.cu: thread-per-row versions for d = 16 (bf16 gradient outputs only)
 int latent_fwd16(const float* par, const float* eps, float* z, float* kl, int64_t B, cudaStream_t s);
 int match_fwd16(const float* par_p, const float* z, float* match, int64_t B, cudaStream_t s);
+int sample_latents16(const float* par, Key2 key, int64_t B, int64_t K, int64_t B_total, int64_t row_start, float* z,
+                     float* base, cudaStream_t s);
 int latent_bwd16(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
                  const float* g_kl, const float* g_match, int stop_grad, __nv_bfloat16* dpar_e_b,
                  __nv_bfloat16* dpar_p_b, int64_t B, cudaStream_t s);

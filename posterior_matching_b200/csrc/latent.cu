@@ -418,6 +418,7 @@ int sample_latents(const float* par, Key2 key, int64_t B, int64_t K, int64_t B_t
   PMVAE_CHECK((uint64_t)K * (uint64_t)B_total * (uint64_t)d <= 0xFFFFFFFFull,
               "K*B_total*d exceeds one 2^32-1 element draw");
   if (B * K == 0) return 0;
+  if (d == 16 && fast16()) return sample_latents16(par, key, B, K, B_total, row_start, z, base, s);
   const int P = d + d * (d + 1) / 2;
   const size_t spg = (size_t)(P + 3 * d) * sizeof(float);
   const int64_t items = B * ((K + 15) / 16);

@@ -273,6 +273,55 @@ __global__ void __launch_bounds__(kThreads) latent_bwd16_kernel(
   }
 }
 
+// ---------------------------------------------------------------- K importance samples per row (evaluators)
+// z[k, r, :] = mu_r + L_r eps[k, r, :] with eps = jax.random.normal(key, [K, B_total, 16]) restricted to rows
+// row_start + r (vae.py:192-195), base[k, r] = log N(z; 0, I) - log q(z) = -|z|^2/2 + |eps|^2/2 + sum log L_ii
+// (vae.py:203-212 at the posterior's own samples).  A warp takes 32 rows x kS samples: the rows' head vectors sit in
+// registers, consecutive lanes write consecutive rows of z (coalesced).
+constexpr int kS = 4;
+__global__ void __launch_bounds__(kThreads) sample_latents16_kernel(const float* __restrict__ par, Key2 key, int64_t B,
+                                                                    int64_t K, int64_t B_total, int64_t row_start,
+                                                                    float* __restrict__ z, float* __restrict__ base) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* tile = smem + warp * kTileFloats;
+  const int64_t nwt = (B + 31) / 32, nks = (K + kS - 1) / kS;
+  const uint64_t n_total = (uint64_t)K * (uint64_t)B_total * (uint64_t)D;
+  for (int64_t item = (int64_t)blockIdx.x * kWarps + warp; item < nwt * nks; item += (int64_t)gridDim.x * kWarps) {
+    const int64_t wt = item % nwt, ks = item / nwt;
+    const int64_t row0 = wt * 32, row = row0 + lane;
+    const bool ok = row < B;
+    float v[P], dg[D];
+    load_rows(par, row0, B, tile, lane, v);
+    const float logd = diagonals(v, dg);
+    for (int kk = 0; kk < kS; ++kk) {
+      const int64_t k = ks * kS + kk;
+      if (k >= K) break;
+      const uint64_t idx0 = ((uint64_t)k * (uint64_t)B_total + (uint64_t)(row_start + (ok ? row : 0))) * D;
+      float e[D], zz[D];
+      float e2 = 0.f, z2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        e[i] = bits_to_normal(jax_random_word(key, n_total, idx0 + i));
+        e2 = fmaf(e[i], e[i], e2);
+        zz[i] = v[i];
+      }
+#pragma unroll
+      for (int t = 0; t < M; ++t) {
+        const IJ ij = tril_ij(t);
+        const float l = (ij.i == ij.j) ? dg[ij.i] : v[D + t];
+        zz[ij.i] = fmaf(l, e[ij.j], zz[ij.i]);
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) z2 = fmaf(zz[i], zz[i], z2);
+      if (ok) {
+        store16(z, k * B + row, zz);
+        base[k * B + row] = -0.5f * z2 + 0.5f * e2 + logd;
+      }
+    }
+  }
+}
+
 static int grid_for(int64_t B) {
   int64_t g = ((B + 31) / 32 + kWarps - 1) / kWarps;
   if (g > 148 * 2) g = 148 * 2;
@@ -300,6 +349,18 @@ int match_fwd16(const float* par_p, const float* z, float* match, int64_t B, cud
   static bool once = false;
   if (!once) { PMVAE_TRY(l16::set_smem(l16::match_fwd16_kernel)); once = true; }
   l16::match_fwd16_kernel<<<l16::grid_for(B), l16::kThreads, l16::kSmem, s>>>(par_p, z, match, B);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+int sample_latents16(const float* par, Key2 key, int64_t B, int64_t K, int64_t B_total, int64_t row_start, float* z,
+                     float* base, cudaStream_t s) {
+  static bool once = false;
+  if (!once) { PMVAE_TRY(l16::set_smem(l16::sample_latents16_kernel)); once = true; }
+  const int64_t items = ((B + 31) / 32) * ((K + l16::kS - 1) / l16::kS);
+  int64_t g = (items + l16::kWarps - 1) / l16::kWarps;
+  if (g > 148 * 4) g = 148 * 4;
+  if (g < 1) g = 1;
+  l16::sample_latents16_kernel<<<(int)g, l16::kThreads, l16::kSmem, s>>>(par, key, B, K, B_total, row_start, z, base);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }
