@@ -153,7 +153,10 @@ __global__ void __launch_bounds__(256) rec_ll_bwd_kernel(const float* __restrict
                                                          int64_t ld_loc, const float* __restrict__ log_scale,
                                                          const float* __restrict__ g, float* __restrict__ dloc,
                                                          __nv_bfloat16* __restrict__ dloc_bf16, int64_t ld_dloc,
-                                                         float* __restrict__ dls, int64_t B, int D) {
+                                                         float* __restrict__ dls, int64_t B, int D, float* __restrict__ db) {
+  __shared__ float dbs[64];
+  if (db) { if (threadIdx.x < 64) dbs[threadIdx.x] = 0.f; __syncthreads(); }
+  const bool do_db = db != nullptr && D <= 64;
   const float ls = *log_scale;
   const float inv2 = expf(-2.0f * ls);
   float part = 0.f;
@@ -164,7 +167,11 @@ __global__ void __launch_bounds__(256) rec_ll_bwd_kernel(const float* __restrict
       const float df = x[r * D + j] - loc[r * ld_loc + j];
       const float dv = gr * df * inv2;
       if (dloc) dloc[r * ld_dloc + j] = dv;
-      if (dloc_bf16) dloc_bf16[r * ld_dloc + j] = __float2bfloat16(dv);
+      if (dloc_bf16) {
+        const __nv_bfloat16 hb = __float2bfloat16(dv);
+        dloc_bf16[r * ld_dloc + j] = hb;
+        if (do_db) atomicAdd(&dbs[j], __bfloat162float(hb));     // spread over D addresses; flushed once per block
+      }
       acc += df * df * inv2 - 1.0f;
     }
     if (dloc_bf16)
@@ -180,11 +187,13 @@ __global__ void __launch_bounds__(256) rec_ll_bwd_kernel(const float* __restrict
     for (int i = 0; i < 8; ++i) t += sm[i];
     atomicAdd(dls, t);
   }
+  if (do_db && (int)threadIdx.x < D) atomicAdd(db + threadIdx.x, dbs[threadIdx.x]);   // (after the __syncthreads above)
 }
 int rec_ll_bwd(const float* x, const float* loc, int64_t ld_loc, const float* log_scale, const float* g, float* dloc,
-               __nv_bfloat16* dloc_bf16, int64_t ld_dloc, float* dls, int64_t B, int D, cudaStream_t s) {
+               __nv_bfloat16* dloc_bf16, int64_t ld_dloc, float* dls, int64_t B, int D, cudaStream_t s, float* db) {
   if (B == 0) return 0;
-  rec_ll_bwd_kernel<<<grid1d(B, 256, 4), 256, 0, s>>>(x, loc, ld_loc, log_scale, g, dloc, dloc_bf16, ld_dloc, dls, B, D);
+  PMVAE_CHECK(db == nullptr || (D <= 64 && dloc_bf16 != nullptr), "fused decoder-head bias gradient needs D <= 64");
+  rec_ll_bwd_kernel<<<grid1d(B, 256, 4), 256, 0, s>>>(x, loc, ld_loc, log_scale, g, dloc, dloc_bf16, ld_dloc, dls, B, D, db);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -35,8 +35,10 @@ int rec_ll(const float* x, const float* loc, int64_t ld_loc, const float* log_sc
            int64_t B, int D, cudaStream_t s);
 // dloc[r,j] = g[r] * (x - loc) * exp(-2 ls);  *dls += sum_r g[r] * sum_j ((x-loc)^2 exp(-2 ls) - 1)
 // (either dloc output may be null; the bf16 one is zero-padded to its pitch)
+// db (optional): += column sums of the bf16 dloc (the decoder head's bias gradient)
 int rec_ll_bwd(const float* x, const float* loc, int64_t ld_loc, const float* log_scale, const float* g, float* dloc,
-               __nv_bfloat16* dloc_bf16, int64_t ld_dloc, float* dls, int64_t B, int D, cudaStream_t s);
+               __nv_bfloat16* dloc_bf16, int64_t ld_dloc, float* dls, int64_t B, int D, cudaStream_t s,
+               float* db = nullptr);
 int loss_cotangents(int64_t B, int64_t B_global, float beta, float coef, const float* rec, const float* kl,
                     const float* match, float* g_rec, float* g_kl, float* g_match, float* out_sums, cudaStream_t s);
 struct AdamSegs { int n; uint32_t beg[48]; uint32_t end[48]; };  // no-decay (bias) ranges
@@ -56,7 +58,8 @@ int latent_fwd(const float* par, const float* eps, float* z, float* kl, int64_t 
 int match_fwd(const float* par_p, const float* z, float* match, int64_t B, int d, cudaStream_t s);
 int latent_bwd(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
                const float* g_kl, const float* g_match, int stop_grad, float* dpar_e, float* dpar_p,
-               __nv_bfloat16* dpar_e_b, __nv_bfloat16* dpar_p_b, int64_t B, int d, cudaStream_t s);
+               __nv_bfloat16* dpar_e_b, __nv_bfloat16* dpar_p_b, int64_t B, int d, cudaStream_t s,
+               float* db_e = nullptr, float* db_p = nullptr, bool* db_done = nullptr);
 // latent16.cu: thread-per-row versions for d = 16 (bf16 gradient outputs only)
 int latent_fwd16(const float* par, const float* eps, float* z, float* kl, int64_t B, cudaStream_t s);
 int match_fwd16(const float* par_p, const float* z, float* match, int64_t B, cudaStream_t s);
@@ -64,7 +67,7 @@ int sample_latents16(const float* par, Key2 key, int64_t B, int64_t K, int64_t B
                      float* base, cudaStream_t s);
 int latent_bwd16(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
                  const float* g_kl, const float* g_match, int stop_grad, __nv_bfloat16* dpar_e_b,
-                 __nv_bfloat16* dpar_p_b, int64_t B, cudaStream_t s);
+                 __nv_bfloat16* dpar_p_b, float* db_e, float* db_p, int64_t B, cudaStream_t s);
 // z[k,r,:] = mu_r + L_r eps[k,r,:], eps = normal(key, [K, B_total, d]) rows row_start..;
 // base[k,r] = log N(z;0,I) - log q(z) = -0.5|z|^2 + 0.5|eps|^2 + sum log L_ii
 int sample_latents(const float* par, Key2 key, int64_t B, int64_t K, int64_t B_total, int64_t row_start, int d,

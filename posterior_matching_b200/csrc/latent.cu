@@ -399,11 +399,15 @@ int match_fwd(const float* par_p, const float* z, float* match, int64_t B, int d
 
 int latent_bwd(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
                const float* g_kl, const float* g_match, int stop_grad, float* dpar_e, float* dpar_p,
-               __nv_bfloat16* dpar_e_b, __nv_bfloat16* dpar_p_b, int64_t B, int d, cudaStream_t s) {
+               __nv_bfloat16* dpar_e_b, __nv_bfloat16* dpar_p_b, int64_t B, int d, cudaStream_t s, float* db_e,
+               float* db_p, bool* db_done) {
+  if (db_done) *db_done = false;
   PMVAE_CHECK(d >= 1 && d <= 64, "latent_dim must be in [1, 64]");
   if (B == 0) return 0;
-  if (d == 16 && fast16() && dpar_e == nullptr && dpar_p == nullptr && dpar_e_b && dpar_p_b)
-    return latent_bwd16(par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad, dpar_e_b, dpar_p_b, B, s);
+  if (d == 16 && fast16() && dpar_e == nullptr && dpar_p == nullptr && dpar_e_b && dpar_p_b) {
+    if (db_done) *db_done = (db_e != nullptr && db_p != nullptr);     // head bias gradients are taken here as well
+    return latent_bwd16(par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad, dpar_e_b, dpar_p_b, db_e, db_p, B, s);
+  }
   const int P = d + d * (d + 1) / 2;
   const size_t spg = (size_t)(P + 6 * d) * sizeof(float);
   DISPATCH_D(latent_bwd_kernel, d, B, spg, s, par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad, dpar_e, dpar_p,

@@ -72,8 +72,9 @@ __device__ __forceinline__ void load_rows(const float* __restrict__ src, int64_t
 }
 
 // registers (bf16-rounded) -> global [rows, P] bf16, through the same tile (pitch kPitch/2 words per row)
+// csum (optional): per-lane partial column sums of the staged bf16 values, words lane, lane + 32, lane + 64
 __device__ __forceinline__ void store_rows_bf16(const float (&v)[P], __nv_bfloat16* __restrict__ dst, int64_t row0, int64_t B,
-                                                float* tile, int lane) {
+                                                float* tile, int lane, float (*csum)[2] = nullptr) {
   uint32_t* tw = reinterpret_cast<uint32_t*>(tile);
   constexpr int kPitchW = 84;            // words per staged bf16 row (76 used): 84 = 20 mod 32 keeps uint4 stores by row conflict free
   __syncwarp();
@@ -89,6 +90,21 @@ __device__ __forceinline__ void store_rows_bf16(const float (&v)[P], __nv_bfloat
   }
   __syncwarp();
   const int64_t nrows = (B - row0 < 32) ? (B - row0) : 32;
+  if (csum) {
+    // bias gradient of the head Linear = column sums of these rows (the values the weight-gradient GEMM reads)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int w = lane + 32 * c;
+      if (w < P / 2) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int r = 0; r < (int)nrows; ++r) {
+          const uint32_t x = tw[r * kPitchW + w];
+          a0 += __uint_as_float(x << 16); a1 += __uint_as_float(x & 0xFFFF0000u);
+        }
+        csum[c][0] += a0; csum[c][1] += a1;
+      }
+    }
+  }
   const int nvec = (int)nrows * (P / 8);                 // uint4 = 8 bf16; 19 per row
   uint4* d4 = reinterpret_cast<uint4*>(dst + row0 * P);
 #pragma unroll 2
@@ -202,11 +218,12 @@ __global__ void __launch_bounds__(kThreads) latent_bwd16_kernel(
     const float* __restrict__ par_e, const float* __restrict__ par_p, const float* __restrict__ eps,
     const float* __restrict__ z, const float* __restrict__ dz_dec, const float* __restrict__ g_kl,
     const float* __restrict__ g_match, int stop_grad, __nv_bfloat16* __restrict__ dpar_e_b,
-    __nv_bfloat16* __restrict__ dpar_p_b, int64_t B) {
+    __nv_bfloat16* __restrict__ dpar_p_b, float* __restrict__ db_e, float* __restrict__ db_p, int64_t B) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* tile = smem + warp * kTileFloats;
   const int64_t nwt = (B + 31) / 32;
+  float cse[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}}, csp[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
   for (int64_t wt = (int64_t)blockIdx.x * kWarps + warp; wt < nwt; wt += (int64_t)gridDim.x * kWarps) {
     const int64_t row0 = wt * 32, row = row0 + lane;
     const bool ok = row < B;
@@ -246,7 +263,7 @@ __global__ void __launch_bounds__(kThreads) latent_bwd16_kernel(
         for (int i = 0; i < D; ++i) dz[i] -= mw * g[i];
       }
     }
-    store_rows_bf16(v, dpar_p_b, row0, B, tile, lane);
+    store_rows_bf16(v, dpar_p_b, row0, B, tile, lane, db_p ? csp : nullptr);
     // ---- posterior: z = mu + L eps (cotangent dz) and kw * KL
     load_rows(par_e, row0, B, tile, lane, v);
     {
@@ -269,7 +286,16 @@ __global__ void __launch_bounds__(kThreads) latent_bwd16_kernel(
 #pragma unroll
       for (int i = 0; i < D; ++i) v[i] = dz[i] + kw * v[i];
     }
-    store_rows_bf16(v, dpar_e_b, row0, B, tile, lane);
+    store_rows_bf16(v, dpar_e_b, row0, B, tile, lane, db_e ? cse : nullptr);
+  }
+  // head bias gradients: one atomic per column per warp
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int w = lane + 32 * c;
+    if (w < P / 2) {
+      if (db_e) { atomicAdd(db_e + 2 * w, cse[c][0]); atomicAdd(db_e + 2 * w + 1, cse[c][1]); }
+      if (db_p) { atomicAdd(db_p + 2 * w, csp[c][0]); atomicAdd(db_p + 2 * w + 1, csp[c][1]); }
+    }
   }
 }
 
@@ -366,11 +392,11 @@ int sample_latents16(const float* par, Key2 key, int64_t B, int64_t K, int64_t B
 }
 int latent_bwd16(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
                  const float* g_kl, const float* g_match, int stop_grad, __nv_bfloat16* dpar_e_b,
-                 __nv_bfloat16* dpar_p_b, int64_t B, cudaStream_t s) {
+                 __nv_bfloat16* dpar_p_b, float* db_e, float* db_p, int64_t B, cudaStream_t s) {
   static bool once = false;
   if (!once) { PMVAE_TRY(l16::set_smem(l16::latent_bwd16_kernel)); once = true; }
   l16::latent_bwd16_kernel<<<l16::grid_for(B), l16::kThreads, l16::kSmem, s>>>(par_e, par_p, eps, z, dz_dec, g_kl, g_match,
-                                                                              stop_grad, dpar_e_b, dpar_p_b, B);
+                                                                              stop_grad, dpar_e_b, dpar_p_b, db_e, db_p, B);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -646,12 +646,12 @@ static int lin_bwd_params_b(float* grads, const Leaf& lf, const bf16* act, const
 static int net_bwd_b(const float* params, float* grads, const Net& n, const LeafImg* img, const Leaf& head,
                      const LeafImg& himg, const bf16* dHead, int64_t ld_dhead, int head_cols_pad, const float* in,
                      const float* msk, int D_in, int64_t B, const NetSavedB& sv, bf16* dH, bf16* dU, bf16* dG,
-                     float* wtmp, float* dIn, const fused::NetImages* fim, bf16* dY, bf16* in_b, cudaStream_t s) {
+                     float* wtmp, float* dIn, const fused::NetImages* fim, bf16* dY, bf16* in_b, bool head_db_done, cudaStream_t s) {
   using tc::TcGemmArgs;
   if (fim && fused::backward_supported(n, 256, fim->in_kind) && (dIn == nullptr || fim->has_w0_n)) {
     // head Linear parameters, then the fused input-gradient chain (dY_l of every Linear + bias gradients),
     // then one tensor-core weight-gradient GEMM per Linear: gW_l += act_{l-1}^T @ dY_l
-    PMVAE_TRY(lin_bwd_params_b(grads, head, sv.A[n.R], dHead, ld_dhead, head_cols_pad, B, wtmp, true, s));
+    PMVAE_TRY(lin_bwd_params_b(grads, head, sv.A[n.R], dHead, ld_dhead, head_cols_pad, B, wtmp, !head_db_done, s));
     PMVAE_TRY(fused::net_backward(n, head, *fim, dHead, ld_dhead, B, sv.masks, sv.Bpad, dY, grads, dIn, s));
     for (int l = 1; l <= 2 * n.R; ++l)
       PMVAE_TRY(tc::gemm_tn(sv.stack + (uint64_t)(l - 1) * sv.Bpad * 256, 256, dY + (uint64_t)l * sv.Bpad * 256, 256,
@@ -664,7 +664,7 @@ static int net_bwd_b(const float* params, float* grads, const Net& n, const Leaf
   }
   const bool fuse = !n.ln;   // non-LN nets: the epilogue that writes a gradient tensor also sums its columns
   // head
-  PMVAE_TRY(lin_bwd_params_b(grads, head, sv.A[n.R], dHead, ld_dhead, head_cols_pad, B, wtmp, true, s));
+  PMVAE_TRY(lin_bwd_params_b(grads, head, sv.A[n.R], dHead, ld_dhead, head_cols_pad, B, wtmp, !head_db_done, s));
   {
     TcGemmArgs e{};
     e.mask_bf16 = sv.A[n.R]; e.ld_mask = 256; e.out_bf16 = dH; e.ld_out_bf16 = 256;
@@ -762,19 +762,22 @@ int backward_bf16(const pmvae_config* c, const Layout& L, const float* params, c
     const int64_t nb = (B - r0 < kMicroRows) ? (B - r0) : kMicroRows;
     const float* xc = x + r0 * D;
     // gradient temporaries (dloc, dH, dU, dG, dz, dpar) are reused by every micro-batch
+    const bool dec_db = D <= 64;
     PMVAE_TRY(rec_ll_bwd(xc, p.loc + r0 * p.Dp, p.Dp, params + L.log_scale, g_rec + r0, nullptr, p.dloc_b, p.Dp,
-                         grads + L.log_scale, nb, D, s));
+                         grads + L.log_scale, nb, D, s, dec_db ? grads + L.ddist.b : nullptr));
     PMVAE_TRY(net_bwd_b(params, grads, L.dec, p.img.dec, L.ddist, p.img.ddist, p.dloc_b, p.Dp, p.Dp, p.z + r0 * d,
                         nullptr, d, nb, shift_saved(p.dec, L.dec, r0), p.dH, p.dU, p.dG, p.wtmp, p.dz,
-                        p.img.f_dec_ok ? &p.img.f_dec : nullptr, p.dY, p.in_b, s));
+                        p.img.f_dec_ok ? &p.img.f_dec : nullptr, p.dY, p.in_b, dec_db, s));
+    bool lat_db = false;
     PMVAE_TRY(latent_bwd(p.par_e + r0 * L.P, p.par_p + r0 * L.P, eps + r0 * d, p.z + r0 * d, p.dz, g_kl + r0,
-                         g_match + r0, c->stop_grad, nullptr, nullptr, p.dpar_e_b, p.dpar_p_b, nb, d, s));
+                         g_match + r0, c->stop_grad, nullptr, nullptr, p.dpar_e_b, p.dpar_p_b, nb, d, s, grads + L.post.b,
+                         grads + L.ppost.b, &lat_db));
     PMVAE_TRY(net_bwd_b(params, grads, L.enc, p.img.enc, L.post, p.img.post, p.dpar_e_b, L.P, L.P, xc, nullptr, D, nb,
                         shift_saved(p.enc, L.enc, r0), p.dH, p.dU, p.dG, p.wtmp, nullptr,
-                        p.img.f_enc_ok ? &p.img.f_enc : nullptr, p.dY, p.in_b, s));
+                        p.img.f_enc_ok ? &p.img.f_enc : nullptr, p.dY, p.in_b, lat_db, s));
     PMVAE_TRY(net_bwd_b(params, grads, L.part, p.img.part, L.ppost, p.img.ppost, p.dpar_p_b, L.P, L.P, xc, b + r0 * D,
                         D, nb, shift_saved(p.part, L.part, r0), p.dH, p.dU, p.dG, p.wtmp, nullptr,
-                        p.img.f_part_ok ? &p.img.f_part : nullptr, p.dY, p.in_b, s));
+                        p.img.f_part_ok ? &p.img.f_part : nullptr, p.dY, p.in_b, lat_db, s));
   }
   return 0;
 }
