@@ -281,9 +281,9 @@ int forward(const pmvae_config* c, const float* params, const float* x, const fl
             float* out_rec, float* out_kl, float* out_match, void* ws, uint64_t ws_bytes, cudaStream_t s) {
   Layout L;
   PMVAE_TRY(build_layout(c, &L));
-  PMVAE_CHECK(params && x && b && eps && out_rec && out_kl && out_match && ws, "null pointer");
   PMVAE_CHECK(B >= 0, "negative batch");
-  if (B == 0) return 0;
+  if (B == 0) return 0;            // an empty batch has no rows to point at
+  PMVAE_CHECK(params && x && b && eps && out_rec && out_kl && out_match && ws, "null pointer");
   if (c->precision == PMVAE_PREC_BF16) return forward_bf16(c, L, params, x, b, eps, B, out_rec, out_kl, out_match, ws, ws_bytes, s);
   TrainPlan p = plan_train(c, L, B, ws);
   PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_workspace_bytes)");
@@ -302,9 +302,10 @@ int backward(const pmvae_config* c, const float* params, const float* x, const f
              cudaStream_t s) {
   Layout L;
   PMVAE_TRY(build_layout(c, &L));
-  PMVAE_CHECK(params && x && b && eps && g_rec && g_kl && g_match && grads && ws, "null pointer");
+  PMVAE_CHECK(grads != nullptr && B >= 0, "null gradient arena / negative batch");
   PMVAE_CUDA(cudaMemsetAsync(grads, 0, L.total * sizeof(float), s));
-  if (B <= 0) return 0;
+  if (B == 0) return 0;            // an empty batch contributes zero gradients
+  PMVAE_CHECK(params && x && b && eps && g_rec && g_kl && g_match && ws, "null pointer");
   if (c->precision == PMVAE_PREC_BF16) return backward_bf16(c, L, params, x, b, eps, B, g_rec, g_kl, g_match, grads, ws, ws_bytes, s);
   TrainPlan p = plan_train(c, L, B, ws);
   PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_workspace_bytes)");
@@ -344,6 +345,7 @@ int is_log_prob(const pmvae_config* c, const float* params, const float* x, cons
                 float* out_log_p_x, float* out_cond, void* ws, uint64_t ws_bytes, cudaStream_t s) {
   Layout L;
   PMVAE_TRY(build_layout(c, &L));
+  if (B == 0) return 0;
   PMVAE_CHECK(params && x && b && key_z && key_zxo && ws, "null pointer");
   PMVAE_CHECK(K >= 1 && B >= 0 && row_start >= 0 && row_start + B <= B_total, "bad K / row range");
   if (B == 0) return 0;
@@ -377,6 +379,7 @@ int impute_mean_seq(const pmvae_config* c, const float* params, const float* x, 
                     cudaStream_t s) {
   Layout L;
   PMVAE_TRY(build_layout(c, &L));
+  if (B == 0) return 0;
   PMVAE_CHECK(params && x && b && key && out && ws, "null pointer");
   PMVAE_CHECK(K >= 1 && B >= 0 && row_start >= 0 && row_start + B <= B_total, "bad K / row range");
   if (B == 0) return 0;
@@ -445,8 +448,8 @@ int argmm_log_prob(const pmvae_argmm_config* c, const float* params, const float
                    float* out, void* ws, uint64_t ws_bytes, cudaStream_t s) {
   ArgmmLayout L;
   PMVAE_TRY(build_argmm_layout(c, &L));
-  PMVAE_CHECK(params && z && (ctx || c->C == 0) && out && ws && B >= 0, "null pointer");
   if (B == 0) return 0;
+  PMVAE_CHECK(params && z && (ctx || c->C == 0) && out && ws && B >= 0, "null pointer");
   ArgmmPlan p = plan_argmm(c, L, B, ws);
   PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_argmm_workspace_bytes)");
   PMVAE_TRY(argmm_input(z, ctx, B, c->d, c->C, p.X, s));
@@ -460,9 +463,10 @@ int argmm_backward(const pmvae_argmm_config* c, const float* params, const float
                    const float* g, float* grads, float* dz, float* dctx, void* ws, uint64_t ws_bytes, cudaStream_t s) {
   ArgmmLayout L;
   PMVAE_TRY(build_argmm_layout(c, &L));
-  PMVAE_CHECK(params && z && g && grads && ws && B >= 0, "null pointer");
+  PMVAE_CHECK(grads != nullptr && B >= 0, "null gradient arena / negative batch");
   PMVAE_CUDA(cudaMemsetAsync(grads, 0, L.total * sizeof(float), s));
   if (B == 0) return 0;
+  PMVAE_CHECK(params && z && g && ws, "null pointer");
   ArgmmPlan p = plan_argmm(c, L, B, ws);
   PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_argmm_workspace_bytes)");
   const int64_t M = (int64_t)c->d * B;
@@ -478,8 +482,8 @@ int net_apply(const pmvae_config* c, const float* params, int which, const float
   Layout L;
   PMVAE_TRY(build_layout(c, &L));
   PMVAE_CHECK(which >= 0 && which <= 2, "net id must be 0 (encoder), 1 (decoder) or 2 (partial encoder)");
-  PMVAE_CHECK(params && in && out && ws && B >= 0 && (which != 2 || msk), "null pointer");
   if (B == 0) return 0;
+  PMVAE_CHECK(params && in && out && ws && B >= 0 && (which != 2 || msk), "null pointer");
   if (c->precision == PMVAE_PREC_BF16) return net_apply_bf16(c, L, params, which, in, msk, B, out, ws, ws_bytes, s);
   TrainPlan p = plan_train(c, L, B, ws);
   PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_workspace_bytes)");

@@ -762,7 +762,7 @@ int backward_bf16(const pmvae_config* c, const Layout& L, const float* params, c
     const int64_t nb = (B - r0 < kMicroRows) ? (B - r0) : kMicroRows;
     const float* xc = x + r0 * D;
     // gradient temporaries (dloc, dH, dU, dG, dz, dpar) are reused by every micro-batch
-    const bool dec_db = D <= 64;
+    const bool dec_db = D <= 16;     // wider decoders keep the separate column-sum kernel (shared-memory atomics serialise)
     PMVAE_TRY(rec_ll_bwd(xc, p.loc + r0 * p.Dp, p.Dp, params + L.log_scale, g_rec + r0, nullptr, p.dloc_b, p.Dp,
                          grads + L.log_scale, nb, D, s, dec_db ? grads + L.ddist.b : nullptr));
     PMVAE_TRY(net_bwd_b(params, grads, L.dec, p.img.dec, L.ddist, p.img.ddist, p.dloc_b, p.Dp, p.Dp, p.z + r0 * d,

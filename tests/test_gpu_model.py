@@ -224,3 +224,56 @@ def test_large_batch_properties(precision):
     for k in o1:
         cat = torch.cat([q[k] for q in parts])
         assert rel_err(cat.cpu().numpy(), o1[k].cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_empty_and_ragged_batches(precision):
+    """B = 0 is a no-op everywhere; batches that do not fill a 128-row tile (or a 256-row tile pair) give the
+    same rows as the same data inside a larger batch."""
+    spec = spec_of("gas")
+    p = conditioned_params(spec)
+    m = _model("gas", precision, p)
+    x, b, eps = make_inputs(spec, 385, seed=11)
+    xc, bc, ec = _cuda(x), _cuda(b), _cuda(eps)
+    empty = m(xc[:0], bc[:0], eps=ec[:0])
+    assert all(v.numel() == 0 for v in empty.values())
+    z0 = torch.zeros(0, device="cuda")
+    m.backward(z0, z0, z0)
+    assert float(m.grad_arena.abs().max()) == 0.0
+    lp = m.is_log_prob(xc[:0], bc[:0], 4, keys=((1, 2), (3, 4)))
+    assert lp[0].numel() == 0 and lp[1].numel() == 0
+    full = {k: v.clone() for k, v in m(xc, bc, eps=ec).items()}
+    for n in (1, 127, 128, 129, 255, 257, 384):
+        part = m(xc[:n], bc[:n], eps=ec[:n])
+        for k in full:
+            assert rel_err(part[k].cpu().numpy(), full[k][:n].cpu().numpy()) < 1e-6, (n, k)
+
+
+def test_bench_size_tensor_path_tracks_fp32_path():
+    """At the benchmark's batch the bf16 tensor path and the fp32 path (itself held to 2e-5 of the oracle on
+    small batches) agree on the three batch means to the 1e-3 contract, and on every gradient leaf to the
+    operand-rounding level."""
+    if "bf16" not in PRECISIONS or "fp32" not in PRECISIONS:
+        pytest.skip("needs both precisions")
+    spec = spec_of("power")
+    p = conditioned_params(spec)
+    B = 1 << 17
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(B, spec.D, device="cuda", generator=g)
+    b = (torch.rand(B, spec.D, device="cuda", generator=g) < 0.5).float()
+    cot = [torch.full((B,), 1.0 / B, device="cuda"), torch.full((B,), -0.4 / B, device="cuda"),
+           torch.full((B,), 1.0 / B, device="cuda")]
+    res = {}
+    for precision in ("fp32", "bf16"):
+        m = _model("power", precision, p)
+        out = m(x, b, rng=(0, 7))
+        means = {k: float(v.double().mean()) for k, v in out.items()}
+        m.backward(*cot)
+        res[precision] = (means, m.grad_arena.clone())
+        del m
+        torch.cuda.empty_cache()
+    for k in res["fp32"][0]:
+        a, c = res["bf16"][0][k], res["fp32"][0][k]
+        assert abs(a - c) < 1e-3 * abs(c), (k, a, c)
+    g32, g16 = res["fp32"][1], res["bf16"][1]
+    assert float((g16 - g32).norm() / g32.norm()) < 5e-2
