@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--eval-rows", type=int, default=2048, help="rows per cond-LL eval call (K = 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="drive the step from the host (Trainer.train_step) instead of "
+                    "replaying the CUDA graph of pmvae_train_step")
     return ap.parse_args()
 
 
@@ -243,6 +245,11 @@ def main():
     x_host = torch.from_numpy(synthetic_x(name, B, 100 + rank)).pin_memory()
     x_dev = x_host.cuda()
 
+    if args.no_graph:
+        step_fn = tr.train_step
+    else:
+        step_fn = tr.train_step_fused          # one pmvae_train_step per step, captured in a CUDA graph
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -260,37 +267,39 @@ def main():
     if rank == 0:
         sampler.start()
     for _ in range(W):
-        tr.train_step(x_dev)
+        step_fn(x_dev)
     barrier()
     # nvidia-smi samples every 100 ms and a step is a few ms: keep the same load running (untimed) long enough
     # for the clock record to describe the state the timed steps run in
     t_load = time.perf_counter()
     while time.perf_counter() - t_load < 0.6:
         for _ in range(10):
-            tr.train_step(x_dev)
+            step_fn(x_dev)
         torch.cuda.synchronize()
     barrier()
     l0 = int(_lib.lib.pmvae_launch_count())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):
-        tr.train_step(x_dev)
+        step_fn(x_dev)
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = int(_lib.lib.pmvae_launch_count()) - l0
+    if not args.no_graph and tr.graph_launches_per_step:
+        launches = K * tr.graph_launches_per_step     # replayed graph nodes are not seen by the enqueue-time counter
     clocks = sampler.stop() if rank == 0 else None
     metrics = tr.metrics()
     value = world * B * K / (ms * 1e-3)
 
     # ---- end-to-end: host buffers, H2D of x and D2H of the metrics every step
     for _ in range(2):
-        x_dev.copy_(x_host, non_blocking=True); tr.train_step(x_dev); tr.metrics()
+        x_dev.copy_(x_host, non_blocking=True); step_fn(x_dev); tr.metrics()
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
         x_dev.copy_(x_host, non_blocking=True)
-        tr.train_step(x_dev)
+        step_fn(x_dev)
         tr.metrics()            # D2H of the three batch sums (synchronises the step)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
@@ -412,6 +421,7 @@ def main():
                                    f"{'NCCL grad all-reduce, ' if world > 1 else ''}AdamW)",
                        "rows_per_gpu_per_step": B, "global_batch": world * B, "features": D,
                        "parallelism": f"dp{world}", "accumulate": "fp32",
+                       "launch": "host-driven C-ABI calls" if args.no_graph else "pmvae_train_step replayed as a CUDA graph",
                        "l2": "saved activations of one step exceed the 126 MB L2 (no explicit flush)",
                        "weights": "Haiku-default init, TriL heads x0.1"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,

@@ -174,6 +174,47 @@ int pmvae_impute_mean(const pmvae_config* cfg, const float* params, const float*
                       int64_t row_start, float* out /* [B,D] */, void* ws, uint64_t ws_bytes,
                       pmvae_stream_t stream);
 
+/* ---- the whole training step as one launch sequence ---------------------------------------------
+ * train_pm_vae.py's step (mask draw, eps draw, loss_fn forward, value_and_grad, optax update) enqueued by ONE
+ * call with nothing step-dependent passed from the host: per-step PRNG keys, beta (train_pm_vae.py:28-43,
+ * utils.py:124-136), the learning rate and Adam's bias corrections (train_pm_vae.py:74-83) are derived on the
+ * device from a small state block, so the sequence can be captured once in a CUDA graph and replayed.
+ * Same arithmetic and key chain as pmvae_mask_bernoulli / pmvae_normal / pmvae_forward / pmvae_loss_cotangents /
+ * pmvae_backward / pmvae_adamw driven from the host (Trainer.train_step). */
+enum { PMVAE_BETA_CONST = 0, PMVAE_BETA_CYCLIC = 1, PMVAE_BETA_MONOTONIC = 2 };
+typedef struct pmvae_train_config {
+  int32_t beta_schedule;                       /* PMVAE_BETA_*                                         */
+  float beta_low, beta_high;                   /* low_value / high_value                               */
+  int64_t beta_period, beta_delay;             /* cyclic                                               */
+  int64_t beta_transition_steps, beta_transition_begin; /* monotonic                                  */
+  float matching_coef;                         /* config.get("matching_coef", 1.0)                     */
+  float lr_init, lr_decay_rate;                /* optax.exponential_decay                              */
+  int64_t lr_transition_steps;
+  float weight_decay, adam_b1, adam_b2, adam_eps;
+  float mask_p;                                /* BernoulliMaskGenerator p                             */
+  int32_t reserved[3];
+} pmvae_train_config;
+typedef struct pmvae_train_state_host {        /* host copy of the device state, for checkpoints/tests */
+  uint32_t seq_key[2], mask_key[2], eps_key[2];
+  uint32_t mask_calls, pad;
+  int64_t step;
+  float beta, lr, bc1, bc2;
+} pmvae_train_state_host;
+uint64_t pmvae_train_state_bytes(void);
+uint64_t pmvae_train_scratch_floats(const pmvae_config* cfg, int64_t B);
+/* seq_key: key of the Haiku PRNGSequence handing out the per-step rng; mask_key: the mask generator's key
+ * (call c draws with fold_in(mask_key, c)); step: optimizer updates already applied.  Synchronises `stream`. */
+int pmvae_train_state_init(void* state, const uint32_t seq_key[2], const uint32_t mask_key[2], int64_t step,
+                           uint32_t mask_calls, pmvae_stream_t stream);
+int pmvae_train_state_read(const void* state, pmvae_train_state_host* out, pmvae_stream_t stream);
+/* phase bit 0: advance state, draw mask + eps, forward, loss cotangents (+ batch sums into out_sums[3]), backward
+ * (grads overwritten);  phase bit 1: AdamW, refresh of the operand images, step counter.  With several ranks call
+ * phase 1, all-reduce `grads` and `out_sums`, then phase 2.  `scratch`: pmvae_train_scratch_floats floats. */
+int pmvae_train_step(const pmvae_config* cfg, const pmvae_train_config* tc, float* params, float* m, float* v,
+                     float* grads, void* state, const float* x, int64_t B, int64_t B_global, int64_t row_start,
+                     float* scratch, float* out_sums, void* ws, uint64_t ws_bytes, int32_t phase,
+                     pmvae_stream_t stream);
+
 /* ---- distribution heads of configs/pm_vae_mnist.py (float32 arithmetic) -------------------------
  * Bernoulli decoder (distributions.py:20-25; summed over the event at vae.py:127-128):
  *   out[r] = sum_j w[r,j] * Bernoulli(logits[r,j]).log_prob(x[r,j]),  x a float in [0,1], w optional (NULL = 1)

@@ -29,6 +29,25 @@ class ArgmmConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("d", "n_comp", "R", "H", "C")] + [("reserved", C.c_int32 * 3)]
 
 
+class TrainConfig(C.Structure):
+    """pmvae_train_config (include/pmvae.h)."""
+    _fields_ = [("beta_schedule", C.c_int32), ("beta_low", C.c_float), ("beta_high", C.c_float),
+                ("beta_period", C.c_int64), ("beta_delay", C.c_int64), ("beta_transition_steps", C.c_int64),
+                ("beta_transition_begin", C.c_int64), ("matching_coef", C.c_float), ("lr_init", C.c_float),
+                ("lr_decay_rate", C.c_float), ("lr_transition_steps", C.c_int64), ("weight_decay", C.c_float),
+                ("adam_b1", C.c_float), ("adam_b2", C.c_float), ("adam_eps", C.c_float), ("mask_p", C.c_float),
+                ("reserved", C.c_int32 * 3)]
+
+
+class TrainStateHost(C.Structure):
+    _fields_ = [("seq_key", C.c_uint32 * 2), ("mask_key", C.c_uint32 * 2), ("eps_key", C.c_uint32 * 2),
+                ("mask_calls", C.c_uint32), ("pad", C.c_uint32), ("step", C.c_int64), ("beta", C.c_float),
+                ("lr", C.c_float), ("bc1", C.c_float), ("bc2", C.c_float)]
+
+
+BETA_CONST, BETA_CYCLIC, BETA_MONOTONIC = 0, 1, 2
+
+
 class XlaOpaque(C.Structure):
     """pmvae_xla_opaque (include/pmvae.h): the `opaque` descriptor of the XLA custom-call targets."""
     _fields_ = [("cfg", Config), ("B", C.c_int64), ("K", C.c_int64), ("B_total", C.c_int64), ("row_start", C.c_int64),
@@ -79,6 +98,12 @@ _SIGS = {
     "pmvae_adamw": (_i32, [_cfgp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _vp]),
     "pmvae_is_log_prob": (_i32, [_cfgp, _vp, _vp, _vp, _i64, _i64, _u32p, _u32p, _i64, _i64, _vp, _vp, _vp, _u64, _vp]),
     "pmvae_net_apply": (_i32, [_cfgp, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _u64, _vp]),
+    "pmvae_train_state_bytes": (_u64, []),
+    "pmvae_train_scratch_floats": (_u64, [_cfgp, _i64]),
+    "pmvae_train_state_init": (_i32, [_vp, _u32p, _u32p, _i64, C.c_uint32, _vp]),
+    "pmvae_train_state_read": (_i32, [_vp, C.POINTER(TrainStateHost), _vp]),
+    "pmvae_train_step": (_i32, [_cfgp, C.POINTER(TrainConfig), _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp,
+                                _vp, _u64, _i32, _vp]),
     "pmvae_bernoulli_ll": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "pmvae_bernoulli_ll_backward": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "pmvae_argmm_param_count": (_u64, [C.POINTER(ArgmmConfig)]),

@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(256) loss_cot_kernel(int64_t B, float a, float
                                                        const float* __restrict__ rec, const float* __restrict__ kl,
                                                        const float* __restrict__ match, float* __restrict__ g_rec,
                                                        float* __restrict__ g_kl, float* __restrict__ g_match,
-                                                       float* __restrict__ sums) {
+                                                       float* __restrict__ sums, const StepState* __restrict__ st) {
+  if (st) k = st->beta * (-a);        // a = -1/B_global
   float s0 = 0.f, s1 = 0.f, s2 = 0.f;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < B; r += (int64_t)gridDim.x * blockDim.x) {
     s0 += rec[r]; s1 += kl[r]; s2 += match[r];
@@ -220,13 +221,14 @@ __global__ void __launch_bounds__(256) loss_cot_kernel(int64_t B, float a, float
   }
 }
 int loss_cotangents(int64_t B, int64_t B_global, float beta, float coef, const float* rec, const float* kl,
-                    const float* match, float* g_rec, float* g_kl, float* g_match, float* out_sums, cudaStream_t s) {
+                    const float* match, float* g_rec, float* g_kl, float* g_match, float* out_sums, cudaStream_t s,
+                    const StepState* st) {
   PMVAE_CHECK(B_global > 0, "B_global must be positive");
   PMVAE_CUDA(cudaMemsetAsync(out_sums, 0, 3 * sizeof(float), s));
   if (B == 0) return 0;
   const float inv = 1.0f / (float)B_global;
   loss_cot_kernel<<<grid1d(B, 256, 2), 256, 0, s>>>(B, -inv, beta * inv, -coef * inv, rec, kl, match, g_rec, g_kl,
-                                                    g_match, out_sums);
+                                                    g_match, out_sums, st);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -235,7 +237,8 @@ int loss_cotangents(int64_t B, int64_t B_global, float beta, float coef, const f
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                     float* __restrict__ m, float* __restrict__ v, uint64_t n,
                                                     AdamSegs nd, float lr, float wd, float b1, float b2, float eps,
-                                                    float bc1, float bc2) {
+                                                    float bc1, float bc2, const StepState* __restrict__ st) {
+  if (st) { lr = st->lr; bc1 = st->bc1; bc2 = st->bc2; }
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const float gi = g[i];
     const float mi = b1 * m[i] + (1.0f - b1) * gi;
@@ -250,8 +253,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
   }
 }
 int adamw(float* p, const float* g, float* m, float* v, uint64_t n, const AdamSegs& nodecay, float lr, float wd,
-          float b1, float b2, float eps, float bc1, float bc2, cudaStream_t s) {
-  adamw_kernel<<<grid1d((int64_t)n, 256), 256, 0, s>>>(p, g, m, v, n, nodecay, lr, wd, b1, b2, eps, bc1, bc2);
+          float b1, float b2, float eps, float bc1, float bc2, cudaStream_t s, const StepState* st) {
+  adamw_kernel<<<grid1d((int64_t)n, 256), 256, 0, s>>>(p, g, m, v, n, nodecay, lr, wd, b1, b2, eps, bc1, bc2, st);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }

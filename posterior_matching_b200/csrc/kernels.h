@@ -6,6 +6,19 @@
 
 namespace pmvae {
 
+// Device-resident state of the fused training step (train_step.cu): everything a step needs from the host-side
+// loop of train_pm_vae.py (per-step PRNG keys, beta, learning rate, Adam bias corrections) is derived on the
+// device from this block, so that a whole step is a fixed launch sequence (CUDA-graph replayable).
+struct StepState {
+  uint32_t seq_key[2];    // Haiku PRNGSequence key behind the per-step rng of the transformed loss_fn
+  uint32_t mask_base[2];  // mask generator key; call c draws with fold_in(mask_base, c)
+  uint32_t mask_key[2];   // derived for the current step
+  uint32_t eps_key[2];    // derived for the current step (key of z ~ q(z|x), vae.py:124)
+  uint32_t mask_calls, pad0;
+  int64_t step;           // optimizer updates applied before the current step
+  float beta, lr, bc1, bc2;
+};
+
 // ---- gemm_f32.cu
 struct GemmF32Args {
   int64_t M, N, K;
@@ -39,11 +52,18 @@ int rec_ll(const float* x, const float* loc, int64_t ld_loc, const float* log_sc
 int rec_ll_bwd(const float* x, const float* loc, int64_t ld_loc, const float* log_scale, const float* g, float* dloc,
                __nv_bfloat16* dloc_bf16, int64_t ld_dloc, float* dls, int64_t B, int D, cudaStream_t s,
                float* db = nullptr);
+// st (optional): beta is read from the device step state instead
 int loss_cotangents(int64_t B, int64_t B_global, float beta, float coef, const float* rec, const float* kl,
-                    const float* match, float* g_rec, float* g_kl, float* g_match, float* out_sums, cudaStream_t s);
+                    const float* match, float* g_rec, float* g_kl, float* g_match, float* out_sums, cudaStream_t s,
+                    const StepState* st = nullptr);
 struct AdamSegs { int n; uint32_t beg[48]; uint32_t end[48]; };  // no-decay (bias) ranges
+// st (optional): lr and the bias corrections are read from the device step state instead
 int adamw(float* p, const float* g, float* m, float* v, uint64_t n, const AdamSegs& nodecay, float lr, float wd,
-          float b1, float b2, float eps, float bc1, float bc2, cudaStream_t s);
+          float b1, float b2, float eps, float bc1, float bc2, cudaStream_t s, const StepState* st = nullptr);
+// rng.cu: draws whose key lives in the device step state
+int mask_bernoulli_dev(const StepState* st, float p, uint64_t B_total, uint64_t row_start, uint64_t rows, int D, float* out,
+                       cudaStream_t s);
+int normal_dev(const StepState* st, uint64_t n_total, uint64_t start, uint64_t count, float* out, cudaStream_t s);
 // evaluators
 // ll[k*B + r] = sum_j w * logN(x[r]; loc[k*B + r]) + base[k*B + r]
 int eval_rows_ll(const float* x, const float* w, const float* loc, int64_t ld_loc, const float* log_scale,

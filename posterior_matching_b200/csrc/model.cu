@@ -397,6 +397,17 @@ int impute_mean_seq(const pmvae_config* c, const float* params, const float* x, 
   return 0;
 }
 
+int adamw_step_dev(const pmvae_config* c, float* params, const float* grads, float* m, float* v, float wd, float b1,
+                   float b2, float eps, const StepState* st, cudaStream_t s) {
+  Layout L;
+  PMVAE_TRY(build_layout(c, &L));
+  AdamSegs seg{};
+  auto add = [&](const Leaf& lf) { seg.beg[seg.n] = (uint32_t)lf.b; seg.end[seg.n] = (uint32_t)(lf.b + pad64(lf.cols)); ++seg.n; };
+  auto addnet = [&](const Net& n) { for (int i = 0; i <= 2 * n.R; ++i) add(n.lin[i]); };
+  addnet(L.enc); add(L.post); addnet(L.dec); add(L.ddist); addnet(L.part); add(L.ppost);
+  return adamw(params, grads, m, v, L.total, seg, 0.f, wd, b1, b2, eps, 1.f, 1.f, s, st);
+}
+
 // ---------------------------------------------------------------- AutoregressiveGMM (MNIST partial posterior)
 struct ArgmmLayout { Net net; Leaf head; uint64_t total; int F, cols; };
 

@@ -7,6 +7,7 @@
 // (SURVEY F3); the device contract re-defines them on the JAX threefry stream and is
 // specified by oracle/prng.py + oracle/masks.py, which these kernels match bit for bit.
 #include "common.cuh"
+#include "kernels.h"
 
 namespace pmvae {
 
@@ -88,6 +89,41 @@ __global__ void __launch_bounds__(256) mask_bernoulli_kernel(Key2 key, float p, 
     const float u = bits_to_unit_float(jax_random_word(key, n_total, start + t));
     out[t] = (u < p) ? 1.0f : 0.0f;
   }
+}
+
+// same draws with the key read from the device step state (fused training step)
+__global__ void __launch_bounds__(256) mask_bernoulli_dev_kernel(const StepState* __restrict__ st, float p, uint64_t n_total,
+                                                                 uint64_t start, uint64_t count, float* out) {
+  const Key2 key{st->mask_key[0], st->mask_key[1]};
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+    const float u = bits_to_unit_float(jax_random_word(key, n_total, start + t));
+    out[t] = (u < p) ? 1.0f : 0.0f;
+  }
+}
+__global__ void __launch_bounds__(256) normal_dev_kernel(const StepState* __restrict__ st, uint64_t n_total, uint64_t start,
+                                                         uint64_t count, float* out) {
+  const Key2 key{st->eps_key[0], st->eps_key[1]};
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride)
+    out[t] = bits_to_normal(jax_random_word(key, n_total, start + t));
+}
+int mask_bernoulli_dev(const StepState* st, float p, uint64_t B_total, uint64_t row_start, uint64_t rows, int D, float* out,
+                       cudaStream_t s) {
+  const uint64_t n_total = B_total * (uint64_t)D;
+  PMVAE_CHECK(n_total <= 0xFFFFFFFFull && row_start + rows <= B_total, "bad mask draw");
+  if (rows == 0) return 0;
+  const uint64_t count = rows * (uint64_t)D;
+  mask_bernoulli_dev_kernel<<<grid_for(count, 256), 256, 0, s>>>(st, p, n_total, row_start * (uint64_t)D, count, out);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+int normal_dev(const StepState* st, uint64_t n_total, uint64_t start, uint64_t count, float* out, cudaStream_t s) {
+  PMVAE_CHECK(n_total <= 0xFFFFFFFFull && start + count <= n_total, "bad normal draw");
+  if (count == 0) return 0;
+  normal_dev_kernel<<<grid_for(count, 256), 256, 0, s>>>(st, n_total, start, count, out);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
 }
 
 // ---------------------------------------------------------------- MNIST mixture mask

@@ -88,6 +88,113 @@ class Trainer:
         self._cot = None
         self._sums = self.model.grad_tail[:3]       # batch sums ride along with the gradient all-reduce
         self.last_beta = 1.0
+        self._seed = seed
+        self._fused = None                          # state of train_step_fused (device step state, graphs)
+
+    # ---- the step as one launch sequence / CUDA graph --------------------------------------------
+    def _train_config(self) -> "_lib.TrainConfig":
+        tc = _lib.TrainConfig()
+        beta = dict(self.config.get("beta", {}) or {})
+        kind = beta.get("schedule")
+        tc.beta_schedule = {None: _lib.BETA_CONST, "cyclic": _lib.BETA_CYCLIC, "monotonic": _lib.BETA_MONOTONIC}[kind]
+        tc.beta_low, tc.beta_high = float(beta.get("low_value", 1.0)), float(beta.get("high_value", 1.0))
+        tc.beta_period, tc.beta_delay = int(beta.get("period", 1)), int(beta.get("delay", 0))
+        tc.beta_transition_steps = int(beta.get("transition_steps", 1))
+        tc.beta_transition_begin = int(beta.get("transition_begin", 0))
+        tc.matching_coef = self.matching_coef
+        ls = self.config["lr_schedule"]
+        tc.lr_init, tc.lr_decay_rate = float(ls["init_value"]), float(ls["decay_rate"])
+        tc.lr_transition_steps = int(ls["transition_steps"])
+        tc.weight_decay, tc.adam_b1, tc.adam_b2, tc.adam_eps = self.weight_decay, self.b1, self.b2, self.adam_eps
+        tc.mask_p = float(getattr(self.mask_generator, "p", 0.5))
+        return tc
+
+    def _fused_setup(self, B: int):
+        """Moves the host loop's state (rng sequence, mask-call counter, step) into the device state block."""
+        mdl = self.model
+        f = {"B": B, "tc": self._train_config(), "graphs": None}
+        f["state"] = torch.zeros(int(_lib.lib.pmvae_train_state_bytes()), dtype=torch.uint8, device=self.device)
+        f["scratch"] = torch.empty(int(_lib.lib.pmvae_train_scratch_floats(mdl._cfgp, B)), dtype=torch.float32,
+                                   device=self.device)
+        f["x"] = torch.empty((B, mdl.num_features), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib.pmvae_train_state_init(f["state"].data_ptr(), _lib.key_arg(self._rng.key),
+                                                   _lib.key_arg(self.mask_generator._key), self.step,
+                                                   self.mask_generator._calls, _stream()), "pmvae_train_state_init")
+        self._fused = f
+        return f
+
+    def _fused_call(self, phase: int):
+        f, mdl = self._fused, self.model
+        ws = mdl.workspace(f["B"])
+        _lib.check(_lib.lib.pmvae_train_step(
+            mdl._cfgp, C.byref(f["tc"]), mdl.arena.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+            mdl.grad_arena.data_ptr(), f["state"].data_ptr(), f["x"].data_ptr(), f["B"], f["B"] * self.world,
+            self.rank * f["B"], f["scratch"].data_ptr(), self._sums.data_ptr(), ws.data_ptr(), ws.numel(), phase,
+            _stream()), "pmvae_train_step")
+
+    def train_step_fused(self, x: torch.Tensor, graph: bool = True):
+        """Same step as `train_step(x)` (same keys, schedules and arithmetic) issued through pmvae_train_step:
+        one C call per step, every step-dependent scalar derived on the device.  With `graph=True` the launch
+        sequence is captured once per batch size in a CUDA graph and replayed (the second call onwards)."""
+        mdl = self.model
+        B = x.shape[0]
+        if not isinstance(self.mask_generator, __import__("posterior_matching_b200.masking", fromlist=["x"]).BernoulliMaskGenerator):
+            raise NotImplementedError("the fused step draws Bernoulli masks (the four UCI configs)")
+        f = self._fused if (self._fused is not None and self._fused["B"] == B) else self._fused_setup(B)
+        f["x"].copy_(x, non_blocking=True)
+        ws = mdl.workspace(B)
+        if f.get("ws_ptr") != ws.data_ptr():          # the workspace moved (e.g. an evaluator grew it): re-capture
+            f["ws_ptr"], f["graphs"] = ws.data_ptr(), None
+        mdl._prepare(ws)
+        if not graph:
+            self._fused_call(1)
+            if self.world > 1:
+                torch.distributed.all_reduce(mdl._grad_store, group=self.pg)
+            self._fused_call(2)
+        else:
+            if f["graphs"] is None:
+                if f.get("warm", 0) < 1:             # one eager step first (lazy kernel attributes, workspace)
+                    f["warm"] = 1
+                    return self.train_step_fused(x, graph=False)
+                torch.cuda.synchronize()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                graphs = []
+                n0 = int(_lib.lib.pmvae_launch_count())
+                with torch.cuda.stream(side):
+                    for phase in ((1, 2) if self.world > 1 else (3,)):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, stream=side):
+                            self._fused_call(phase)
+                        graphs.append(g)
+                torch.cuda.current_stream().wait_stream(side)
+                f["launches"] = int(_lib.lib.pmvae_launch_count()) - n0    # kernels one replayed step launches
+                # capturing does not execute: the state block is untouched, so the first replay is this step
+                f["graphs"] = graphs
+            gs = f["graphs"]
+            gs[0].replay()
+            if self.world > 1:
+                torch.distributed.all_reduce(mdl._grad_store, group=self.pg)
+                gs[1].replay()
+        mdl._params_dirty = False                    # phase 2 refreshed the operand images
+        # keep the host-side mirrors in step (so train_step / metrics keep working)
+        self._rng.next()
+        self.mask_generator._calls += 1
+        self.last_beta = float(self.beta_schedule(self.step))
+        self.step += 1
+        self._last_Bg = B * self.world
+        return self._sums
+
+    @property
+    def graph_launches_per_step(self) -> int:
+        """Kernels of this library inside one replayed step (counted while the graph was captured)."""
+        return int(self._fused.get("launches", 0)) if self._fused else 0
+
+    def fused_state(self) -> "_lib.TrainStateHost":
+        out = _lib.TrainStateHost()
+        _lib.check(_lib.lib.pmvae_train_state_read(self._fused["state"].data_ptr(), C.byref(out), _stream()),
+                   "pmvae_train_state_read")
+        return out
 
     def _buffers(self, B):
         if self._cot is None or self._cot.shape[1] < B:
