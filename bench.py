@@ -407,6 +407,25 @@ def main():
                 "ms_per_call": cms, "tflops_per_gpu": CONDLL_GFLOP[name] * 1e9 * cval / world / 1e12,
                 "frac_of_tensor_peak": CONDLL_GFLOP[name] * 1e9 * cval / world / 1e12 / peaks["bf16_tflops"]}
 
+    # ---- latency point: the reference's own batch size (configs/pm_vae_*.py train_batch_size = 512)
+    ref_batch = None
+    if not args.no_graph:
+        Br = int(cfg.data.train_batch_size)
+        xr = x_dev[:Br].contiguous()
+        for _ in range(5):
+            tr.train_step_fused(xr)
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_ref = 100
+        r0.record()
+        for _ in range(n_ref):
+            tr.train_step_fused(xr)
+        r1.record()
+        barrier()
+        rms = max_over_ranks(r0.elapsed_time(r1)) / n_ref
+        ref_batch = {"rows_per_gpu_per_step": Br, "ms_per_step": rms, "value": world * Br / (rms * 1e-3), "unit": UNIT,
+                     "note": "train_batch_size of the reference config; launch-latency bound"}
+
     # ---- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -429,6 +448,8 @@ def main():
         }
         if cond is not None:
             out["cond_ll_eval"] = cond
+        if ref_batch is not None:
+            out["reference_batch"] = ref_batch
         if cpu is not None:
             out["cpu_baseline"] = cpu
         print(json.dumps(out))
