@@ -35,7 +35,7 @@ constexpr int kChunkBytes = 16384;             // [128 rows] x [64 k] bf16
 constexpr int kOpndBytes = 4 * kChunkBytes;
 constexpr int kWStageBytes = 32768;            // [256 n] x [64 k] bf16
 constexpr int kWStages = 3;
-constexpr int kInPitch = 49;                   // floats per staged input row (up to 48 values: x | mask)
+constexpr int kInPitch = 65;                   // floats per staged input row (up to 64 values: x | mask)
 constexpr int kInBytes = 128 * kInPitch * 4;   // fp32 input rows of the NEXT tile (x | mask), filled by cp.async
 constexpr int kMaxLayers = 2 * kMaxBlocks + 1;
 constexpr int kOffW = kOpndBytes;
@@ -47,7 +47,7 @@ constexpr int kSmemBytes = kOffBar + 256 + 1024;
 
 struct FwdArgs {
   const float* in; const float* msk;
-  int D_in, in_kind, k16_0, R;
+  int D_in, in_kind, in_lo, k16_0, R;   // in_lo: the first-Linear operand carries the lo(v) columns too
   int64_t B; int num_tiles;
   const float* bias[kMaxLayers];
   const float* head_bias; int head_N, head_NT, head_tiles;
@@ -72,7 +72,10 @@ __device__ __forceinline__ uint32_t relu2(uint32_t v) {
 
 // CTA2: two CTAs of a cluster run as one tcgen05 pair (cta_group::2, M = 256): each owns a 128-row tile and
 // half of every weight K-block, so the weight traffic from L2 is halved and the ring covers twice the latency.
-template <bool SAVE, bool CTA2>
+// LN: hk.LayerNorm(-1, False, False) after every Linear (networks.py:117-118,123-124,128-129; the bsds config).  The
+// residual stream then cannot be accumulated by the MMA, so the epilogue keeps it in TMEM columns [256, 512) with
+// tcgen05.ld / tcgen05.st and every hidden Linear writes columns [0, 256); forward only (evaluators).
+template <bool SAVE, bool CTA2, bool LN>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_h,
                const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_o, FwdArgs p) {
@@ -112,6 +115,9 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   const int R = p.R;
   const int n_hidden = 2 * R + 1;                 // Linears that feed the operand buffer
   const int nkb0 = (p.k16_0 + 3) >> 2;
+  // accumulator region of step s: hidden Linears alternate (h lives in region 1 and is accumulated in place), except
+  // under LayerNorm where they all land in region 0; head tiles alternate
+  auto region_of = [&](int s_idx) { return (LN && s_idx < n_hidden) ? 0 : ((s_idx & 1) ? 0 : 1); };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_h); tma_prefetch_desc(&map_o);
@@ -133,7 +139,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     bias_tbl[c] = run;
     for (int r = 0; r < R; ++r) {
       bias_tbl[(2 * r + 1) * 256 + c] = p.bias[2 * r + 1][c];
-      run += p.bias[2 * r + 2][c];
+      run = LN ? p.bias[2 * r + 2][c] : run + p.bias[2 * r + 2][c];
       bias_tbl[(2 * r + 2) * 256 + c] = run;
     }
     // head bias (single head tile): row 2R+1, zero beyond the valid columns
@@ -188,7 +194,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       uint32_t ready_par = 0, use_cnt0 = 0, use_cnt1 = 0, in_par = 0;
       // wait_mode: 0 = operand already announced, 1 = chunk by chunk (opnd_ready), 2 = first-Linear buffer (in_ready)
       auto step = [&](int s_idx, uint32_t abuf, int nk16, int N, bool accum, int wait_mode) {
-        const int region = (s_idx & 1) ? 0 : 1;
+        const int region = region_of(s_idx);
         uint32_t& uc = region ? use_cnt1 : use_cnt0;
         stamp(0, 100 + s_idx);
         mbar_wait_x<CTA2>(acc_empty(region), (uc & 1u) ^ 1u, 2);
@@ -227,7 +233,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       };
       for (int it = it_first; it < it_count; it += it_stride) {
         step(0, l0buf, p.k16_0, 256, false, 2);
-        for (int l = 1; l < n_hidden; ++l) step(l, opnd, 16, 256, (l & 1) == 0, 1);
+        for (int l = 1; l < n_hidden; ++l) step(l, opnd, 16, 256, !LN && (l & 1) == 0, 1);
         for (int t = 0; t < p.head_tiles; ++t) step(n_hidden + t, opnd, 16, p.head_NT, false, t == 0 ? 1 : 0);
       }
     }
@@ -262,7 +268,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       const int kk = 32 * half + lane;               // operand column 0..63
       int src = 0, kind = 3;                         // kind 0: hi(v), 1: lo(v), 2: mask, 3: zero
       if (kk < D) { src = kk; kind = 0; }
-      else if (kk < 2 * D) { src = kk - D; kind = 1; }
+      else if (p.in_lo && kk < 2 * D) { src = kk - D; kind = 1; }
       else if (p.msk && kk < 3 * D) { src = kk - 2 * D; kind = 2; }
       const bool has_m = p.msk != nullptr;
       const int64_t g0 = (int64_t)tile_n * 128 + q * 32;
@@ -294,9 +300,83 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       const bool row_ok = g < p.B;
       if (ew == 0 && lane == 0) stamp(1, 1000);
       // ---- hidden Linears: accumulator -> bf16 operand of the next Linear
+      // LayerNorm epilogue of hidden Linear l: y = acc + b_l; xhat = (y - mean) / sqrt(var + 1e-5) over the 256
+      // columns of the row (each of the two warps of a quadrant holds 128 of them; partial sums meet in shared memory);
+      // l even: h (+)= xhat kept in TMEM, operand = relu(h);  l odd: operand = relu(xhat).
+      auto epi_ln = [&](int l) {
+        mbar_wait_x<CTA2>(acc_full(0), full_par & 1u, 5);
+        full_par ^= 1u;
+        tc_fence_after();
+        if (l == 0 && p.head_tma) {
+          if (lane == 0) tma_store_wait_read<0>();
+          named_bar_sync(1 + q, 64);
+        }
+        float* xch = bias_tbl + 14 * 256;                       // [2 passes][128 rows][2 halves]
+        const uint32_t t_u = t_lane + (uint32_t)(32 * half);
+        const uint32_t t_h = t_lane + (uint32_t)(256 + 32 * half);
+        const float* brow = bias_tbl + l * 256 + 32 * half;
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t r[32];
+          tmem_ld32(t_u + 64 * j, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sum += __uint_as_float(r[i]) + brow[64 * j + i];
+        }
+        xch[row * 2 + half] = sum;
+        named_bar_sync(1 + q, 64);
+        const float mean = (xch[row * 2] + xch[row * 2 + 1]) * (1.0f / 256.0f);
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t r[32];
+          tmem_ld32(t_u + 64 * j, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { const float v = __uint_as_float(r[i]) + brow[64 * j + i] - mean; sq = fmaf(v, v, sq); }
+        }
+        xch[256 + row * 2 + half] = sq;
+        named_bar_sync(1 + q, 64);
+        const float rstd = rsqrtf((xch[256 + row * 2] + xch[256 + row * 2 + 1]) * (1.0f / 256.0f) + 1e-5f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t r[32], hreg[32];
+          tmem_ld32(t_u + 64 * j, r);
+          if ((l & 1) == 0 && l > 0) tmem_ld32(t_h + 64 * j, hreg);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float v = (__uint_as_float(r[i]) + brow[64 * j + i] - mean) * rstd;
+            if ((l & 1) == 0) {
+              if (l > 0) v += __uint_as_float(hreg[i]);
+              hreg[i] = __float_as_uint(v);
+            }
+            r[i] = __float_as_uint(v);
+          }
+          if ((l & 1) == 0) tmem_st32(t_h + 64 * j, hreg);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = relu2(pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])));
+          const uint32_t rowaddr = opnd + j * kChunkBytes + row * 128;
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const int slot = (half * 4 + i4) ^ (row & 7);
+            st_shared_v4(rowaddr + slot * 16, pk[4 * i4], pk[4 * i4 + 1], pk[4 * i4 + 2], pk[4 * i4 + 3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) arrive_leader(opnd_ready(j));
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_leader(acc_empty(0));
+      };
       for (int l = 0; l < n_hidden; ++l) {
-        const int region = (l & 1) ? 0 : 1;
+        const int region = region_of(l);
         if (l == n_hidden - 1 && has_next) prefetch_input(tile_next);     // lands while this Linear is drained
+        if (LN) { epi_ln(l); continue; }
         if (l == 0 && p.head_tma) {
           // the previous tile's head rows were staged in the operand buffer: their TMA stores must have been read out
           if (lane == 0) tma_store_wait_read<0>();
@@ -364,7 +444,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       if (has_next) prologue(tile_next);
       // ---- head Linear: accumulator + bias -> fp32 rows (thread = row, 128 contiguous bytes per 32 columns)
       for (int t = 0; t < p.head_tiles; ++t) {
-        const int region = ((n_hidden + t) & 1) ? 0 : 1;
+        const int region = region_of(n_hidden + t);
         if (ew == 0 && lane == 0) stamp(1, 1400 + t);
         mbar_wait_x<CTA2>(acc_full(region), (full_par >> region) & 1u, 6);
         if (ew == 0 && lane == 0) stamp(1, 1500 + t);
@@ -386,11 +466,22 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           tmem_ld32(t_lane + (uint32_t)(region * 256 + pc * 32), r);
           tmem_ld_wait();
           if (p.head_tma) {
-            // two 4 KB staging tiles per warp inside its quadrant's rows of the operand buffer
-            const uint32_t st = opnd + (uint32_t)((2 * half + (kpiece & 1)) * kChunkBytes + q * 4096);
-            if (kpiece >= 2) {
-              if (lane == 0) tma_store_wait_read<1>();
-              __syncwarp();
+            // One head tile: the operand buffer is idle, two 4 KB staging tiles per warp inside its quadrant's rows.
+            // Several head tiles: later tiles still multiply the operand, so the (by now consumed) input staging
+            // area is used instead, one tile per warp.
+            uint32_t st;
+            if (p.head_tiles == 1) {
+              st = opnd + (uint32_t)((2 * half + (kpiece & 1)) * kChunkBytes + q * 4096);
+              if (kpiece >= 2) {
+                if (lane == 0) tma_store_wait_read<1>();
+                __syncwarp();
+              }
+            } else {
+              st = inbuf + (uint32_t)(ew * 4096);
+              if (t > 0 || kpiece > 0) {
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+              }
             }
 #pragma unroll
             for (int i4 = 0; i4 < 8; ++i4) {
@@ -816,18 +907,28 @@ __global__ void __launch_bounds__(256) pack_fused_kernel(const float* __restrict
   }
 }
 
-bool supported(const Net& n, int H, int in_kind) {
-  if (n.ln || H != 256) return false;
-  const int kext = (in_kind == 1) ? 3 * (n.in_dim / 2) : 2 * n.in_dim;
-  // the expanded first-Linear operand is one 64-wide K-block; a row's fp32 inputs (x | mask) fit its staging slot
-  return kext <= 64 && n.in_dim <= kInPitch - 1 && n.R < kMaxBlocks;
+// expanded first-Linear operand: plain input [hi | lo] when both fit one 64-wide K-block, else [hi] only (fan-in up
+// to 64: operand rounding like every other Linear); masked input [hi(x*b) | lo(x*b) | b]
+static int first_kext(const Net& n, int in_kind, int* in_lo) {
+  if (in_kind == 1) { *in_lo = 1; return 3 * (n.in_dim / 2); }
+  *in_lo = 2 * n.in_dim <= 64 ? 1 : 0;
+  return *in_lo ? 2 * n.in_dim : n.in_dim;
 }
+bool forward_supported(const Net& n, int H, int in_kind) {
+  if (H != 256) return false;
+  int lo;
+  const int kext = first_kext(n, in_kind, &lo);
+  // one K-block for the first Linear; a row's fp32 inputs (x | mask) fit its staging slot; LayerNorm nets keep the
+  // exchange buffer in the tail of the bias table
+  return kext <= 64 && n.in_dim <= kInPitch - 1 && n.R < (n.ln ? 6 : kMaxBlocks);
+}
+bool supported(const Net& n, int H, int in_kind) { return !n.ln && forward_supported(n, H, in_kind); }
 
 NetImages plan_images(const Net& n, const Leaf& head, int in_kind, bf16* base) {
   NetImages im{};
   im.R = n.R; im.in_kind = in_kind;
   im.D_in = (in_kind == 1) ? n.in_dim / 2 : n.in_dim;
-  const int kext = (in_kind == 1) ? 3 * im.D_in : 2 * im.D_in;
+  const int kext = first_kext(n, in_kind, &im.in_lo);
   im.k16_0 = (kext + 15) / 16;
   im.head_N = head.cols;
   const int np16 = (head.cols + 15) / 16 * 16;
@@ -858,7 +959,7 @@ int pack_images(const float* params, const Net& n, const Leaf& head, const NetIm
     sl.src_rows = src_rows; sl.src_cols = src_cols; sl.D = im.D_in; sl.tile0 = tiles;
     tiles += ((rows + 31) / 32) * ((cols + 31) / 32);
   };
-  add(im.stack_t, n.lin[0].w, 256, 256, im.in_kind == 1 ? 2 : 1, n.lin[0].rows, 256);
+  add(im.stack_t, n.lin[0].w, 256, 256, im.in_kind == 1 ? 2 : (im.in_lo ? 1 : 0), n.lin[0].rows, 256);
   for (int l = 1; l <= 2 * n.R; ++l) add(im.stack_t + (uint64_t)l * 65536, n.lin[l].w, 256, 256, 0, 256, 256);
   add(im.head_t, head.w, im.head_tiles * im.head_NT, 256, 0, 256, head.cols);
   for (int l = 1; l <= 2 * n.R; ++l) add(im.stack_n + (uint64_t)(l - 1) * 65536, n.lin[l].w, 256, 256, 3, 256, 256);
@@ -876,12 +977,12 @@ static bool cta2_enabled() {
   return v != 0;
 }
 
-template <bool SAVE, bool CTA2>
+template <bool SAVE, bool CTA2, bool LN>
 static int launch_fwd_t(int grid, const CUtensorMap& mw, const CUtensorMap& mh, const CUtensorMap& ms,
                         const CUtensorMap& mo, const FwdArgs& a, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    PMVAE_CUDA(cudaFuncSetAttribute(net_fwd_kernel<SAVE, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    PMVAE_CUDA(cudaFuncSetAttribute(net_fwd_kernel<SAVE, CTA2, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
@@ -890,24 +991,25 @@ static int launch_fwd_t(int grid, const CUtensorMap& mw, const CUtensorMap& mh, 
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CTA2 ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  PMVAE_CUDA(cudaLaunchKernelEx(&cfg, net_fwd_kernel<SAVE, CTA2>, mw, mh, ms, mo, a));
+  PMVAE_CUDA(cudaLaunchKernelEx(&cfg, net_fwd_kernel<SAVE, CTA2, LN>, mw, mh, ms, mo, a));
   return 0;
 }
-static int launch_fwd(bool save, bool cta2, int grid, const CUtensorMap& mw, const CUtensorMap& mh, const CUtensorMap& ms,
-                      const CUtensorMap& mo, const FwdArgs& a, cudaStream_t s) {
-  if (save) return cta2 ? launch_fwd_t<true, true>(grid, mw, mh, ms, mo, a, s) : launch_fwd_t<true, false>(grid, mw, mh, ms, mo, a, s);
-  return cta2 ? launch_fwd_t<false, true>(grid, mw, mh, ms, mo, a, s) : launch_fwd_t<false, false>(grid, mw, mh, ms, mo, a, s);
+static int launch_fwd(bool save, bool cta2, bool ln, int grid, const CUtensorMap& mw, const CUtensorMap& mh,
+                      const CUtensorMap& ms, const CUtensorMap& mo, const FwdArgs& a, cudaStream_t s) {
+  if (ln) return launch_fwd_t<false, false, true>(grid, mw, mh, ms, mo, a, s);
+  if (save) return cta2 ? launch_fwd_t<true, true, false>(grid, mw, mh, ms, mo, a, s) : launch_fwd_t<true, false, false>(grid, mw, mh, ms, mo, a, s);
+  return cta2 ? launch_fwd_t<false, true, false>(grid, mw, mh, ms, mo, a, s) : launch_fwd_t<false, false, false>(grid, mw, mh, ms, mo, a, s);
 }
 
 int net_forward(const float* params, const Net& n, const Leaf& head, const NetImages& im, const float* in,
                 const float* msk, int64_t B, bf16* saved, uint32_t* masks, int64_t Bpad, float* out, int64_t ld_out,
                 cudaStream_t s) {
   if (B <= 0) return 0;
-  PMVAE_CHECK(supported(n, 256, im.in_kind), "net not covered by the fused kernels");
+  PMVAE_CHECK(forward_supported(n, 256, im.in_kind) && (saved == nullptr || !n.ln), "net not covered by the fused kernels");
   PMVAE_CHECK((im.in_kind == 1) == (msk != nullptr), "mask pointer does not match the first-layer layout");
   PMVAE_CHECK(B < (1ll << 30), "too many rows");
   FwdArgs a{};
-  a.in = in; a.msk = msk; a.D_in = im.D_in; a.in_kind = im.in_kind; a.k16_0 = im.k16_0; a.R = n.R;
+  a.in = in; a.msk = msk; a.D_in = im.D_in; a.in_kind = im.in_kind; a.in_lo = im.in_lo; a.k16_0 = im.k16_0; a.R = n.R;
   a.B = B; a.num_tiles = (int)ceil_div(B, 128);
   for (int l = 0; l <= 2 * n.R; ++l) a.bias[l] = params + n.lin[l].b;
   a.head_bias = params + head.b; a.head_N = im.head_N; a.head_NT = im.head_NT; a.head_tiles = im.head_tiles;
@@ -916,7 +1018,7 @@ int net_forward(const float* params, const Net& n, const Leaf& head, const NetIm
   a.masks = nullptr;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PMVAE_FUSED_DEBUG"); dbg = e ? atoi(e) : 0; } a.debug = dbg; }
   CUtensorMap mw, mh, ms, mo;
-  const bool cta2 = cta2_enabled();
+  const bool cta2 = cta2_enabled() && !n.ln;
   PMVAE_TRY(make_map_2d(&mw, im.stack_t, 2, (uint64_t)(1 + 2 * n.R) * 256, 256, 256, 64, cta2 ? 128 : 256));
   PMVAE_TRY(make_map_2d(&mh, im.head_t, 2, (uint64_t)im.head_tiles * im.head_NT, 256, 256, 64,
                         (uint32_t)(cta2 ? im.head_NT / 2 : im.head_NT)));
@@ -946,7 +1048,7 @@ int net_forward(const float* params, const Net& n, const Leaf& head, const NetIm
     cudaMemsetAsync(trace_buf, 0, 2 * 2048 * sizeof(long long), s);
     a.trace = trace_buf;
   }
-  PMVAE_TRY(launch_fwd(saved != nullptr, cta2, grid, mw, mh, ms, mo, a, s));
+  PMVAE_TRY(launch_fwd(saved != nullptr, cta2, n.ln != 0, grid, mw, mh, ms, mo, a, s));
   PMVAE_LAUNCH_CHECK();
   if (trace_on) {
     static long long host[2 * 2048];

@@ -22,12 +22,14 @@ struct NetImages {
   const __nv_bfloat16* stack_n; const __nv_bfloat16* head_n;
   const __nv_bfloat16* w0_n;            // [din_N, 256] first Linear (natural), in_kind 0 only: dL/d(input)
   bool has_w0_n; int din_N;
-  int R, D_in, in_kind, k16_0;          // k16_0 = ceil(K_ext / 16)
+  int R, D_in, in_kind, in_lo, k16_0;   // k16_0 = ceil(K_ext / 16); in_lo: the [lo(v)] columns are present
   int head_N, head_NT, head_tiles, head_Kp;
   uint64_t elems;                       // bf16 elements used by the four images
 };
 
-// true when the fused kernels cover this net (no LayerNorm, H = 256, expanded fan-in <= 256)
+// forward_supported: the fused forward covers this net (H = 256, expanded fan-in <= 64; LayerNorm nets forward only);
+// supported: forward with saved activations + backward (no LayerNorm)
+bool forward_supported(const Net& n, int H, int in_kind);
 bool supported(const Net& n, int H, int in_kind);
 
 // plans the images at `base` (may be null to size only)

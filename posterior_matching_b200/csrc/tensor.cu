@@ -102,7 +102,7 @@ static void plan_images(const Layout& L, void* ws, Images* im, PackTable* tb) {
   net(L.part, im->part); one(L.ppost, im->ppost);
   off = align_up(off, 512);
   auto fnet = [&](const Net& n, const Leaf& head, int in_kind, bool& ok, fused::NetImages& out) {
-    ok = fused_enabled() && fused::supported(n, 256, in_kind);
+    ok = fused_enabled() && fused::forward_supported(n, 256, in_kind);
     if (!ok) return;
     out = fused::plan_images(n, head, in_kind, ws ? reinterpret_cast<bf16*>(ws) + off : nullptr);
     off += out.elems;
@@ -586,7 +586,7 @@ static int net_fwd_b(const float* params, const Net& n, const LeafImg* img, cons
                      float* h, float* ytmp, float* head_out, int64_t ld_head, const fused::NetImages* fim, bool save,
                      cudaStream_t s) {
   using tc::TcGemmArgs;
-  if (fim)   // one persistent kernel for the whole net + head, activations stay on chip
+  if (fim && (!save || !n.ln))   // one persistent kernel for the whole net + head, activations stay on chip
     return fused::net_forward(params, n, head, *fim, in, msk, B, save ? sv.stack : nullptr, save ? sv.masks : nullptr,
                               sv.Bpad, head_out, ld_head, s);
   if (!n.ln) {
