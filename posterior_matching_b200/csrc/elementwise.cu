@@ -160,21 +160,33 @@ __global__ void __launch_bounds__(256) rec_ll_bwd_kernel(const float* __restrict
   const float ls = *log_scale;
   const float inv2 = expf(-2.0f * ls);
   float part = 0.f;
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < B; r += (int64_t)gridDim.x * blockDim.x) {
-    const float gr = g[r];
+  // every warp runs the same number of iterations so that the column sums can be reduced with full-warp shuffles
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t iters = (B + stride - 1) / stride;
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t r = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = r < B;
+    const float gr = ok ? g[r] : 0.f;
     float acc = 0.f;
     for (int j = 0; j < D; ++j) {
-      const float df = x[r * D + j] - loc[r * ld_loc + j];
-      const float dv = gr * df * inv2;
-      if (dloc) dloc[r * ld_dloc + j] = dv;
-      if (dloc_bf16) {
-        const __nv_bfloat16 hb = __float2bfloat16(dv);
-        dloc_bf16[r * ld_dloc + j] = hb;
-        if (do_db) atomicAdd(&dbs[j], __bfloat162float(hb));     // spread over D addresses; flushed once per block
+      float hbv = 0.f;
+      if (ok) {
+        const float df = x[r * D + j] - loc[r * ld_loc + j];
+        const float dv = gr * df * inv2;
+        if (dloc) dloc[r * ld_dloc + j] = dv;
+        if (dloc_bf16) {
+          const __nv_bfloat16 hb = __float2bfloat16(dv);
+          dloc_bf16[r * ld_dloc + j] = hb;
+          hbv = __bfloat162float(hb);
+        }
+        acc += df * df * inv2 - 1.0f;
       }
-      acc += df * df * inv2 - 1.0f;
+      if (do_db) {
+        hbv = warp_sum(hbv);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&dbs[j], hbv);     // one add per warp and column; flushed once per block
+      }
     }
-    if (dloc_bf16)
+    if (ok && dloc_bf16)
       for (int j = D; j < ld_dloc; ++j) dloc_bf16[r * ld_dloc + j] = __float2bfloat16(0.f);
     part += gr * acc;
   }
