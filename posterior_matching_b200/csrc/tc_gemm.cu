@@ -31,6 +31,7 @@ constexpr int kStages = 3;
 constexpr int kAccStages = 2;
 constexpr int kThreads = 320;          // 10 warps: TMA, MMA, 8 epilogue
 constexpr int kEpiWarps = 8;
+constexpr int kMaxGroup = 8;
 constexpr int kRowBatch = 16;          // rows whose epilogue loads are in flight together
 constexpr int kStagePitch = 68;        // floats per staged row: 64 columns + 4 pad (conflict-free both ways)
 constexpr int kABytes = kBlockM * kBlockK * 2;      // 16 KB
@@ -271,6 +272,155 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
+// ---------------------------------------------------------------- grouped weight gradients
+// Up to kMaxGroup independent TN problems C_g[M_g, N_g] += A_g[rows, M_g]^T . B_g[rows, N_g] (all the Linears of one
+// net) in ONE persistent launch: the tile list is the concatenation of every problem's (m-tile, split) pairs, so a
+// net's weight gradients fill the machine once instead of once per Linear (at small batches the per-launch latency of
+// eighteen 5 us GEMMs is most of the step).  Same pipeline as tc_gemm_kernel<1, 0>; fp32 atomics into C.
+struct TnProblem {
+  CUtensorMap ma, mb;
+  float* out; int64_t ld_out;
+  int M, N, n_tile, num_m_tiles, num_k_blocks, split_k, kb_per_split, tile0;
+};
+struct TnGroup { int n; int total_tiles; TnProblem p[kMaxGroup]; };
+
+__global__ void __launch_bounds__(kThreads, 1) tn_grouped_kernel(const __grid_constant__ TnGroup g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + kAccStages + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 2 * kAccStages);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * kStageBytes + 8 * (2 * kStages + 2 * kAccStages));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < g.n; ++i) { tma_prefetch_desc(&g.p[i].ma); tma_prefetch_desc(&g.p[i].mb); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  // tile -> (problem, m-tile, split)
+  auto locate = [&](int tile, int& pi, int& mt, int& sp) {
+    pi = 0;
+    while (pi + 1 < g.n && tile >= g.p[pi + 1].tile0) ++pi;
+    const int t = tile - g.p[pi].tile0;
+    mt = t % g.p[pi].num_m_tiles;
+    sp = t / g.p[pi].num_m_tiles;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        int pi, mt, sp;
+        locate(tile, pi, mt, sp);
+        const TnProblem& P = g.p[pi];
+        const int kb0 = sp * P.kb_per_split, kb1 = min(P.num_k_blocks, kb0 + P.kb_per_split);
+        const uint32_t tx = (uint32_t)(kABytes + P.n_tile * kBlockK * 2);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, 1);
+          mbar_arrive_expect_tx(full_bar(stage), tx);
+          const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+          for (int j = 0; j < kBlockM / 64; ++j) tma_load_2d(sa + j * 8192, &P.ma, full_bar(stage), mt * kBlockM + j * 64, kb * kBlockK);
+          for (int j = 0; j < P.n_tile / 64; ++j) tma_load_2d(sb + j * 8192, &P.mb, full_bar(stage), j * 64, kb * kBlockK);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        int pi, mt, sp;
+        locate(tile, pi, mt, sp);
+        const TnProblem& P = g.p[pi];
+        const int kb0 = sp * P.kb_per_split, kb1 = min(P.num_k_blocks, kb0 + P.kb_per_split);
+        const uint32_t idesc = instr_desc(kBlockM, P.n_tile, 1, 1);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kMaxN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase, 3);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_f16(d_tmem, smem_desc(sa + k * 2048, 8192, 1024), smem_desc(sb + k * 2048, 8192, 1024), idesc,
+                     (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float* stage = reinterpret_cast<float*>(smem_gen + kStages * kStageBytes + 256) + (warp - 2) * (32 * kStagePitch);
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      int pi, mt, sp;
+      locate(tile, pi, mt, sp);
+      const TnProblem& P = g.p[pi];
+      const bool empty_split = sp * P.kb_per_split >= P.num_k_blocks;
+      mbar_wait(tfull_bar(acc), acc_phase, 4);
+      tc_fence_after();
+      const int64_t row0 = (int64_t)mt * kBlockM + q * 32;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kMaxN);
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const int c0 = half * 64 + ci * 128;
+        if (c0 >= P.n_tile || empty_split) break;
+        {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(t_row + (uint32_t)c0, r0);
+          tmem_ld32(t_row + (uint32_t)(c0 + 32), r1);
+          tmem_ld_wait();
+          float4* dst = reinterpret_cast<float4*>(stage + lane * kStagePitch);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(r0[4 * j]), __uint_as_float(r0[4 * j + 1]), __uint_as_float(r0[4 * j + 2]),
+                                 __uint_as_float(r0[4 * j + 3]));
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[8 + j] = make_float4(__uint_as_float(r1[4 * j]), __uint_as_float(r1[4 * j + 1]), __uint_as_float(r1[4 * j + 2]),
+                                     __uint_as_float(r1[4 * j + 3]));
+        }
+        __syncwarp();
+        const int n = c0 + 2 * lane;
+        if (n < P.N) {
+          for (int rr = 0; rr < 32; ++rr) {
+            const int64_t row = row0 + rr;
+            if (row >= P.M) break;
+            const float2 v = *reinterpret_cast<const float2*>(stage + rr * kStagePitch + 2 * lane);
+            atomicAdd(reinterpret_cast<float2*>(P.out + row * P.ld_out + n), v);
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -403,6 +553,46 @@ int gemm_tn(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t
   PMVAE_TRY(make_map(&ma, A, (uint64_t)rows, (uint64_t)M, (uint64_t)lda, 64, kBlockK));
   PMVAE_TRY(make_map(&mb, B, (uint64_t)rows, (uint64_t)N, (uint64_t)ldb, 64, kBlockK));
   return launch<1, 0>(ma, mb, ep, s);
+}
+
+int gemm_tn_grouped(const TnDesc* d, int count, cudaStream_t s) {
+  PMVAE_CHECK(count >= 1 && count <= kMaxGroup, "bad group size");
+  TnGroup g{};
+  int out_tiles = 0;
+  for (int i = 0; i < count; ++i) {
+    PMVAE_CHECK(d[i].M > 0 && d[i].N > 0 && d[i].N % 4 == 0 && d[i].N <= kMaxN && d[i].rows >= 0, "bad grouped gemm shape");
+    out_tiles += (int)ceil_div(d[i].M, kBlockM);
+  }
+  int split = num_sms() / out_tiles;
+  if (split < 1) split = 1;
+  int tiles = 0, n = 0;
+  for (int i = 0; i < count; ++i) {
+    if (d[i].rows == 0) continue;
+    TnProblem& P = g.p[n];
+    P.out = d[i].out; P.ld_out = d[i].ld_out; P.M = d[i].M; P.N = d[i].N;
+    P.n_tile = pick_n_tile(d[i].N, 64);
+    P.num_m_tiles = (int)ceil_div(d[i].M, kBlockM);
+    P.num_k_blocks = (int)ceil_div(d[i].rows, kBlockK);
+    int sp = split > P.num_k_blocks ? P.num_k_blocks : split;
+    P.kb_per_split = (int)ceil_div(P.num_k_blocks, sp);
+    P.split_k = (int)ceil_div(P.num_k_blocks, P.kb_per_split);
+    P.tile0 = tiles;
+    tiles += P.num_m_tiles * P.split_k;
+    PMVAE_TRY(make_map(&P.ma, d[i].A, (uint64_t)d[i].rows, (uint64_t)d[i].M, (uint64_t)d[i].lda, 64, kBlockK));
+    PMVAE_TRY(make_map(&P.mb, d[i].B, (uint64_t)d[i].rows, (uint64_t)d[i].N, (uint64_t)d[i].ldb, 64, kBlockK));
+    ++n;
+  }
+  if (n == 0) return 0;
+  g.n = n; g.total_tiles = tiles;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PMVAE_CUDA(cudaFuncSetAttribute(tn_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  tn_grouped_kernel<<<grid, kThreads, kSmemBytes, s>>>(g);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace tc

@@ -32,5 +32,15 @@ int gemm_nt(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Bt, int64_
 int gemm_tn(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* B, int64_t ldb, int M, int N, int64_t rows,
             float* out, int64_t ld_out, int atomic, int max_split, int* split_out, cudaStream_t s);
 
+// One launch for several weight gradients: out_i[M_i, N_i] (fp32, pitch ld_out, atomically accumulated) +=
+// A_i[rows, M_i]^T . B_i[rows, N_i]; up to 8 problems, N_i <= 256.
+struct TnDesc {
+  const __nv_bfloat16* A; int64_t lda;
+  const __nv_bfloat16* B; int64_t ldb;
+  int M, N; int64_t rows;
+  float* out; int64_t ld_out;
+};
+int gemm_tn_grouped(const TnDesc* d, int count, cudaStream_t s);
+
 }  // namespace tc
 }  // namespace pmvae

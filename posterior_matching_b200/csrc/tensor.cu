@@ -643,6 +643,7 @@ static int lin_bwd_params_b(float* grads, const Leaf& lf, const bf16* act, const
   return 0;
 }
 
+constexpr int tc_group_cap = 8;
 static int net_bwd_b(const float* params, float* grads, const Net& n, const LeafImg* img, const Leaf& head,
                      const LeafImg& himg, const bf16* dHead, int64_t ld_dhead, int head_cols_pad, const float* in,
                      const float* msk, int D_in, int64_t B, const NetSavedB& sv, bf16* dH, bf16* dU, bf16* dG,
@@ -651,16 +652,25 @@ static int net_bwd_b(const float* params, float* grads, const Net& n, const Leaf
   if (fim && fused::backward_supported(n, 256, fim->in_kind) && (dIn == nullptr || fim->has_w0_n)) {
     // head Linear parameters, then the fused input-gradient chain (dY_l of every Linear + bias gradients),
     // then one tensor-core weight-gradient GEMM per Linear: gW_l += act_{l-1}^T @ dY_l
-    PMVAE_TRY(lin_bwd_params_b(grads, head, sv.A[n.R], dHead, ld_dhead, head_cols_pad, B, wtmp, !head_db_done, s));
     PMVAE_TRY(fused::net_backward(n, head, *fim, dHead, ld_dhead, B, sv.masks, sv.Bpad, dY, grads, dIn, s));
-    for (int l = 1; l <= 2 * n.R; ++l)
-      PMVAE_TRY(tc::gemm_tn(sv.stack + (uint64_t)(l - 1) * sv.Bpad * 256, 256, dY + (uint64_t)l * sv.Bpad * 256, 256,
-                            256, 256, B, grads + n.lin[l].w, 256, 1, 0, nullptr, s));
     const Leaf& l0 = n.lin[0];
     const int ld0 = pad8(l0.rows);
     cast_input_kernel<<<grid1d(B * ld0, 256), 256, 0, s>>>(in, msk, D_in, l0.rows, ld0, B, in_b);
     PMVAE_LAUNCH_CHECK();
-    return tc::gemm_tn(in_b, ld0, dY, 256, l0.rows, 256, B, grads + l0.w, 256, 1, 0, nullptr, s);
+    // every weight gradient of the net in one grouped launch
+    tc::TnDesc td[2 * kMaxBlocks + 2];
+    int nt = 0;
+    td[nt++] = tc::TnDesc{in_b, ld0, dY, 256, l0.rows, 256, B, grads + l0.w, 256};
+    for (int l = 1; l <= 2 * n.R; ++l)
+      td[nt++] = tc::TnDesc{sv.stack + (uint64_t)(l - 1) * sv.Bpad * 256, 256, dY + (uint64_t)l * sv.Bpad * 256, 256, 256, 256, B,
+                            grads + n.lin[l].w, 256};
+    const bool head_direct = head_cols_pad == head.cols && head.cols <= 256;
+    if (head_direct) td[nt++] = tc::TnDesc{sv.A[n.R], 256, dHead, ld_dhead, head.rows, head.cols, B, grads + head.w, head.cols};
+    for (int i0 = 0; i0 < nt; i0 += tc_group_cap)
+      PMVAE_TRY(tc::gemm_tn_grouped(td + i0, nt - i0 < tc_group_cap ? nt - i0 : tc_group_cap, s));
+    if (!head_direct) PMVAE_TRY(lin_bwd_params_b(grads, head, sv.A[n.R], dHead, ld_dhead, head_cols_pad, B, wtmp, false, s));
+    if (!head_db_done) PMVAE_TRY(colsum_bf16(dHead, ld_dhead, grads + head.b, B, head.cols, s));
+    return 0;
   }
   const bool fuse = !n.ln;   // non-LN nets: the epilogue that writes a gradient tensor also sums its columns
   // head
