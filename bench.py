@@ -292,19 +292,25 @@ def main():
     metrics = tr.metrics()
     value = world * B * K / (ms * 1e-3)
 
-    # ---- end-to-end: host buffers, H2D of x and D2H of the metrics every step
+    # ---- end-to-end: host buffers; every step's x comes from pinned host memory (H2D inside the timed region,
+    #      double-buffered on a copy stream like the reference's prefetching input pipeline) and every step's
+    #      metrics are read back to the host (D2H, synchronises the step)
+    from posterior_matching_b200 import HostFeeder
+    feeder = HostFeeder((B, D))
+    slot = feeder.put(x_host)
     for _ in range(2):
-        x_dev.copy_(x_host, non_blocking=True); step_fn(x_dev); tr.metrics()
+        xb = feeder.get(slot); slot = feeder.put(x_host); step_fn(xb); tr.metrics()
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
-        x_dev.copy_(x_host, non_blocking=True)
-        step_fn(x_dev)
-        tr.metrics()            # D2H of the three batch sums (synchronises the step)
+        xb = feeder.get(slot)           # this step's batch (its copy was started during the previous step)
+        slot = feeder.put(x_host)       # start the next batch's H2D copy
+        step_fn(xb)
+        tr.metrics()                    # D2H of the three batch sums
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": 12,
-           "ms_per_step": e2e_s / K * 1e3}
+           "ms_per_step": e2e_s / K * 1e3, "feed": "pinned host batches, double-buffered H2D on a copy stream"}
 
     # ---- dominant kernel alone: the fused ResidualMLP forward (encoder net + TriL head) over B rows
     peaks = measured_peaks()

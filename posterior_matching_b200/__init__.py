@@ -8,6 +8,6 @@ from . import _lib  # noqa: F401  (raises if the CUDA library is missing)
 from .config import pm_vae_config  # noqa: F401
 from .vae import PosteriorMatchingVAE, get_distribution, get_network  # noqa: F401
 from .masking import BernoulliMaskGenerator, MNISTMaskGenerator, get_mask_generator  # noqa: F401
-from .train import Trainer, get_beta_schedule, cyclical_annealing_schedule  # noqa: F401
+from .train import HostFeeder, Trainer, get_beta_schedule, cyclical_annealing_schedule  # noqa: F401
 from .evaluate import eval_fn, nrmse_score  # noqa: F401
 from .distributions import AutoregressiveGMM, Bernoulli  # noqa: F401

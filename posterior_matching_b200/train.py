@@ -53,6 +53,33 @@ def get_beta_schedule(config: Mapping[str, Any]) -> Callable:
     raise ValueError(config["schedule"])
 
 
+class HostFeeder:
+    """Double-buffered host -> device feed (what the reference's tf.data prefetch + device_put does for
+    train_pm_vae.py's loop): batch i+1 is copied from pinned host memory on a side stream while step i runs."""
+
+    def __init__(self, shape, device=None):
+        self.device = torch.device("cuda" if device is None else device)
+        self.bufs = [torch.empty(shape, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.events = [torch.cuda.Event(), torch.cuda.Event()]
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.i = 0
+
+    def put(self, x_host: torch.Tensor) -> int:
+        """Starts the copy of `x_host` (pinned) into the next buffer; returns its slot."""
+        slot = self.i & 1
+        self.i += 1
+        self.stream.wait_stream(torch.cuda.current_stream())     # the step that last read this buffer has been issued
+        with torch.cuda.stream(self.stream):
+            self.bufs[slot].copy_(x_host, non_blocking=True)
+            self.events[slot].record(self.stream)
+        return slot
+
+    def get(self, slot: int) -> torch.Tensor:
+        """The device batch of `slot`, ordered after its copy on the current stream."""
+        torch.cuda.current_stream().wait_event(self.events[slot])
+        return self.bufs[slot]
+
+
 class Trainer:
     """One object per rank.  `train_step(x)` = mask draw, eps draw, forward, loss
     cotangents, backward, gradient all-reduce, AdamW -- every launch on the current CUDA
