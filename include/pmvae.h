@@ -250,6 +250,30 @@ int pmvae_argmm_backward(const pmvae_argmm_config* cfg, const float* params, con
                          const float* context, int64_t B, const float* g, float* grads, float* dz,
                          float* dcontext, void* ws, uint64_t ws_bytes, pmvae_stream_t stream);
 
+/* ---- convolutions of the MNIST config's networks (networks.py:9-72), NHWC float32 ----------------
+ * One general operator covers hk.Conv2D and hk.Conv2DTranspose (what lax.conv_general_dilated reduces both to):
+ *   y[b,oy,ox,co] = act(bias[co] + sum_{ky,kx,ci} Xd(b, oy*stride+ky-pad_top, ox*stride+kx-pad_left, ci)
+ *                                                 * w[(ky*KW+kx)*Cin*Cout + ci*w_ci + co*w_co])
+ *   Xd = x dilated by `dil` (zeros between samples and outside), act = leaky_relu(slope) (slope 1 = identity).
+ *   hk.Conv2D(k, s, SAME|VALID), weights [kh,kw,in,out]:          stride = s, dil = 1, w_ci = Cout, w_co = 1
+ *   hk.Conv2DTranspose(k, s, SAME|VALID), weights [kh,kw,out,in]: stride = 1, dil = s, w_ci = 1, w_co = Cin
+ * (padding per lax.padtype_to_pads / lax.conv_transpose; posterior_matching_b200/conv.py builds the descriptors).
+ * Correctness-first direct kernels: this row is not on the tensor cores yet. */
+typedef struct pmvae_conv_desc {
+  int32_t H, W, Cin;          /* input  [B, H, W, Cin]    */
+  int32_t OH, OW, Cout;       /* output [B, OH, OW, Cout] */
+  int32_t KH, KW, stride, dil, pad_top, pad_left;
+  int32_t w_ci, w_co;         /* element strides of ci / co inside one tap of w */
+  float slope;                /* leaky_relu negative slope */
+  int32_t reserved;
+} pmvae_conv_desc;
+int pmvae_conv2d_forward(const pmvae_conv_desc* desc, const float* x, const float* w, const float* bias,
+                         int64_t B, float* y, pmvae_stream_t stream);
+/* VJP: dy (cotangent of y) is overwritten with the pre-activation cotangent; dx may be NULL; dw and dbias are
+ * accumulated into (zero them first). */
+int pmvae_conv2d_backward(const pmvae_conv_desc* desc, const float* x, const float* w, const float* y,
+                          float* dy, int64_t B, float* dx, float* dw, float* dbias, pmvae_stream_t stream);
+
 /* ---- XLA custom-call targets (jax.ffi / xla_client registration, api_version 1) --------------
  * The reference is driven by jax.jit / jax.value_and_grad (bax.Trainer, train_pm_vae.py:85,96;
  * eval_pm_vae_uci.py:96), so the binding a maintainer adds is an XLA custom call per entry

@@ -48,6 +48,12 @@ class TrainStateHost(C.Structure):
 BETA_CONST, BETA_CYCLIC, BETA_MONOTONIC = 0, 1, 2
 
 
+class ConvDesc(C.Structure):
+    """pmvae_conv_desc (include/pmvae.h)."""
+    _fields_ = [(n, C.c_int32) for n in ("H", "W", "Cin", "OH", "OW", "Cout", "KH", "KW", "stride", "dil", "pad_top",
+                                         "pad_left", "w_ci", "w_co")] + [("slope", C.c_float), ("reserved", C.c_int32)]
+
+
 class XlaOpaque(C.Structure):
     """pmvae_xla_opaque (include/pmvae.h): the `opaque` descriptor of the XLA custom-call targets."""
     _fields_ = [("cfg", Config), ("B", C.c_int64), ("K", C.c_int64), ("B_total", C.c_int64), ("row_start", C.c_int64),
@@ -111,6 +117,8 @@ _SIGS = {
     "pmvae_argmm_workspace_bytes": (_u64, [C.POINTER(ArgmmConfig), _i64]),
     "pmvae_argmm_log_prob": (_i32, [C.POINTER(ArgmmConfig), _vp, _vp, _vp, _i64, _vp, _vp, _u64, _vp]),
     "pmvae_argmm_backward": (_i32, [C.POINTER(ArgmmConfig), _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "pmvae_conv2d_forward": (_i32, [C.POINTER(ConvDesc), _vp, _vp, _vp, _i64, _vp, _vp]),
+    "pmvae_conv2d_backward": (_i32, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "pmvae_xla_opaque_size": (_u64, []),
     "pmvae_xla_forward": (None, [_vp, C.POINTER(_vp), C.c_char_p, C.c_size_t, _vp]),
     "pmvae_xla_backward": (None, [_vp, C.POINTER(_vp), C.c_char_p, C.c_size_t, _vp]),
