@@ -274,6 +274,22 @@ int pmvae_conv2d_forward(const pmvae_conv_desc* desc, const float* x, const floa
 int pmvae_conv2d_backward(const pmvae_conv_desc* desc, const float* x, const float* w, const float* y,
                           float* dy, int64_t B, float* dx, float* dw, float* dbias, pmvae_stream_t stream);
 
+/* ---- building blocks for models composed on the host (the MNIST config: posterior_matching_b200/conv_vae.py) --
+ * VJP of pmvae_linear (float32 arithmetic): dw[K,N] += relu?(x)^T dy, db[N] += colsum(dy), dx[B,K] = dy w^T
+ * (dx only for relu_in = 0); any of dx / dw / db may be NULL. */
+int pmvae_linear_backward(const float* x, const float* w, const float* dy, int64_t B, int32_t K, int32_t N,
+                          int32_t relu_in, float* dx, float* dw, float* db, pmvae_stream_t stream);
+/* TriLGaussian head algebra on its own (distributions.py:101-113, vae.py:124,130): par[B, d + d(d+1)/2] raw head
+ * output, eps[B,d] -> z = mu + L eps, kl = KL(q || N(0,I)); and the VJP for cotangents dz[B,d], g_kl[B]. */
+int pmvae_tril_sample_kl(const float* par, const float* eps, int64_t B, int32_t d, float* z, float* kl,
+                         pmvae_stream_t stream);
+int pmvae_tril_sample_kl_backward(const float* par, const float* eps, const float* dz, const float* g_kl,
+                                  int64_t B, int32_t d, float* dpar, pmvae_stream_t stream);
+/* optax chain of train_pm_vae.py:74-83 over a flat arena where weight decay applies to every element
+ * (or wd = 0, the MNIST config). */
+int pmvae_adamw_flat(float* params, const float* grads, float* m, float* v, uint64_t n, int64_t count, float lr,
+                     float wd, float b1, float b2, float eps, pmvae_stream_t stream);
+
 /* ---- XLA custom-call targets (jax.ffi / xla_client registration, api_version 1) --------------
  * The reference is driven by jax.jit / jax.value_and_grad (bax.Trainer, train_pm_vae.py:85,96;
  * eval_pm_vae_uci.py:96), so the binding a maintainer adds is an XLA custom call per entry

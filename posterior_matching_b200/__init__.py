@@ -11,3 +11,4 @@ from .masking import BernoulliMaskGenerator, MNISTMaskGenerator, get_mask_genera
 from .train import HostFeeder, Trainer, get_beta_schedule, cyclical_annealing_schedule  # noqa: F401
 from .evaluate import eval_fn, nrmse_score  # noqa: F401
 from .distributions import AutoregressiveGMM, Bernoulli  # noqa: F401
+from .conv_vae import ConvPosteriorMatchingVAE  # noqa: F401

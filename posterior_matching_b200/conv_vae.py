@@ -1,0 +1,219 @@
+"""PosteriorMatchingVAE for configs/pm_vae_mnist.py, composed on the host from libpmvae operators
+(reference: posterior_matching/models/vae.py:34-144 with ConvEncoder / ConvDecoder networks.py:9-72,
+TriLGaussian, Bernoulli and AutoregressiveGMM heads).
+
+SURVEY.md §8f row N1, first cut: float32, correctness-first (direct convolution kernels, fp32 GEMMs);
+forward (`__call__`) and `backward` (VJP with per-row cotangents) plus `train_step` (loss_fn of
+train_pm_vae.py:58-72 and the optax chain :74-83 with weight_decay = 0, as the MNIST config has).
+`impute` / `is_log_prob` need AR-GMM sampling (row N2) and are not built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Any, Dict, Mapping, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, prng
+from .conv import conv2d_backward, conv2d_forward, conv_desc
+from .distributions import AutoregressiveGMM, Bernoulli
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t, device):
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+class _ConvStack:
+    """ConvEncoder (transpose=False) or ConvDecoder (transpose=True): descriptors + parameter views."""
+
+    def __init__(self, prefix: str, layers, H: int, cin: int, transpose: bool):
+        self.prefix, self.transpose = prefix, transpose
+        self.descs, self.names = [], []
+        base = "conv2_d_transpose" if transpose else "conv2_d"
+        for i, (f, k, s) in enumerate(layers):
+            if transpose:
+                pad = "VALID" if i == 0 else "SAME"
+            else:
+                pad = "VALID" if i == len(layers) - 1 else "SAME"
+            d = conv_desc(H, H, cin, f, k, s, pad, transpose=transpose)
+            self.descs.append(d)
+            self.names.append(f"{prefix}/{base}" if i == 0 else f"{prefix}/{base}_{i}")
+            H, cin = d.OH, f
+        self.out_hw, self.out_c = H, cin
+
+    def leaf_shapes(self):
+        out = []
+        for d, n in zip(self.descs, self.names):
+            shape = (d.KH, d.KW, d.Cout, d.Cin) if self.transpose else (d.KH, d.KW, d.Cin, d.Cout)
+            out.append((n, shape, d.Cout))
+        return out
+
+    def forward(self, params, x):
+        acts = [x]
+        for d, n in zip(self.descs, self.names):
+            acts.append(conv2d_forward(d, acts[-1], params[n]["w"], params[n]["b"]))
+        return acts
+
+    def backward(self, params, grads, acts, dy, need_dx: bool):
+        for i in reversed(range(len(self.descs))):
+            d, n = self.descs[i], self.names[i]
+            dy = conv2d_backward(d, acts[i], params[n]["w"], acts[i + 1], dy, grads[n]["w"], grads[n]["b"],
+                                 need_dx=(i > 0 or need_dx))
+        return dy
+
+
+class ConvPosteriorMatchingVAE:
+    def __init__(self, config: Mapping[str, Any], name: Optional[str] = None, *, device=None, image_size: int = 28,
+                 channels: int = 1):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ConvPosteriorMatchingVAE needs a CUDA device: the hot path has no CPU fallback")
+        if (config["encoder_net"], config["decoder_net"], config["posterior_dist"], config["decoder_dist"],
+                config.get("partial_posterior_dist")) != ("ConvEncoder", "ConvDecoder", "TriLGaussian", "Bernoulli",
+                                                          "AutoregressiveGMM"):
+            raise NotImplementedError("this class covers the combination configs/pm_vae_mnist.py uses")
+        self.name = name
+        self.device = torch.device("cuda" if device is None else device)
+        self.latent_dim = d = int(config["latent_dim"])
+        self._stop = bool(config.get("matching_ll_stop_gradients", False))
+        enc_layers = [tuple(l) for l in config["encoder_net_config"]["conv_layers"]]
+        dec_layers = [tuple(l) for l in config["decoder_net_config"]["conv_layers"]]
+        part_layers = [tuple(l) for l in config.get("partial_encoder_net_config", config["encoder_net_config"])["conv_layers"]]
+        self.enc = _ConvStack("encoder_net", enc_layers, image_size, channels, False)
+        self.dec = _ConvStack("decoder_net", dec_layers, 1, d, True)
+        self.part = _ConvStack("partial_encoder_net", part_layers, image_size, 2 * channels, False)
+        if self.dec.out_hw != image_size or self.dec.out_c != channels:
+            raise ValueError("decoder does not reproduce the image shape")
+        self.P = d + d * (d + 1) // 2
+        self.enc_feat = self.enc.out_hw ** 2 * self.enc.out_c
+        ar_cfg = dict(config.get("partial_posterior_dist_config", {}) or {})
+        self.argmm = AutoregressiveGMM(d, ar_cfg.get("num_components", 10), ar_cfg.get("residual_blocks", 2),
+                                       ar_cfg.get("hidden_units", 256), context_size=self.part.out_hw ** 2 * self.part.out_c,
+                                       device=self.device)
+        self.bern = Bernoulli(device=self.device)
+        # one flat arena for the conv / head leaves (the AR-GMM keeps its own arena inside `self.argmm`)
+        self.leaves = self.enc.leaf_shapes() + [("posterior_dist/linear", (self.enc_feat, self.P), self.P)] + \
+            self.dec.leaf_shapes() + self.part.leaf_shapes()
+        n = sum(int(np.prod(s)) + nb for _, s, nb in self.leaves)
+        self.arena = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.grad_arena = torch.zeros_like(self.arena)
+        self.params, self.grads = self._views(self.arena), self._views(self.grad_arena)
+        self.params.update(self.argmm.params)
+        self.grads.update(self.argmm.grads)
+        self.m = [torch.zeros_like(self.arena), torch.zeros_like(self.argmm.arena)]
+        self.v = [torch.zeros_like(self.arena), torch.zeros_like(self.argmm.arena)]
+        self.step = 0
+        self._last = None
+
+    @classmethod
+    def from_config(cls, config: Mapping[str, Any], name: Optional[str] = None, **kw):
+        return cls(config, name=name, **kw)
+
+    def _views(self, arena):
+        out, off = {}, 0
+        for name, shape, nb in self.leaves:
+            nw = int(np.prod(shape))
+            out[name] = {"w": arena[off:off + nw].view(*shape), "b": arena[off + nw:off + nw + nb]}
+            off += nw + nb
+        return out
+
+    def load_params(self, params):
+        for name, leaf in self.params.items():
+            for k, dst in leaf.items():
+                src = params[name][k]
+                src = src if torch.is_tensor(src) else torch.as_tensor(np.asarray(src))
+                dst.copy_(src.to(device=self.device, dtype=torch.float32).reshape(dst.shape))
+
+    def init(self, seed: int = 0):
+        g = torch.Generator(device="cpu").manual_seed(int(seed))
+        for name, leaf in self.params.items():
+            w = torch.empty(leaf["w"].shape, dtype=torch.float32)
+            fan_in = w[..., 0].numel() if "transpose" not in name else w.shape[0] * w.shape[1] * w.shape[3]
+            torch.nn.init.trunc_normal_(w, mean=0.0, std=1.0, a=-2.0, b=2.0, generator=g)
+            leaf["w"].copy_(w / math.sqrt(fan_in))
+            leaf["b"].zero_()
+        return self.params
+
+    # ---- vae.py:120-144 ---------------------------------------------------------------------------
+    def __call__(self, x: torch.Tensor, b: torch.Tensor, is_training: bool = False, *, rng=None,
+                 eps: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        x, b = _f32c(x, self.device), _f32c(b, self.device)
+        B, d = x.shape[0], self.latent_dim
+        if eps is None:
+            if rng is None:
+                raise ValueError("pass rng= or eps=")
+            key = prng.PRNGSequence(rng).next()        # the conv encoder draws no dropout keys
+            eps = torch.empty((B, d), dtype=torch.float32, device=self.device)
+            _lib.check(_lib.lib.pmvae_normal(_lib.key_arg(key), B * d, 0, B * d, eps.data_ptr(), _stream()), "pmvae_normal")
+        eps = _f32c(eps, self.device)
+        S = _stream()
+        enc_acts = self.enc.forward(self.params, x)
+        feat = enc_acts[-1].reshape(B, self.enc_feat)
+        par = torch.empty((B, self.P), dtype=torch.float32, device=self.device)
+        hw = self.params["posterior_dist/linear"]
+        _lib.check(_lib.lib.pmvae_linear(_lib.PREC_F32, feat.data_ptr(), hw["w"].data_ptr(), hw["b"].data_ptr(), B,
+                                         self.enc_feat, self.P, 0, par.data_ptr(), None, 0, S), "pmvae_linear")
+        z = torch.empty((B, d), dtype=torch.float32, device=self.device)
+        kl = torch.empty(B, dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib.pmvae_tril_sample_kl(par.data_ptr(), eps.data_ptr(), B, d, z.data_ptr(), kl.data_ptr(), S),
+                   "pmvae_tril_sample_kl")
+        dec_acts = self.dec.forward(self.params, z.view(B, 1, 1, d))
+        rec = self.bern.log_prob(dec_acts[-1], x)
+        xob = torch.cat([x * b, b], dim=-1).contiguous()
+        part_acts = self.part.forward(self.params, xob)
+        ctx = part_acts[-1].reshape(B, -1)
+        match = self.argmm.log_prob(z, ctx)
+        self._last = (x, eps, feat, par, z, enc_acts, dec_acts, part_acts, B)
+        return {"reconstruction_ll": rec, "kl": kl, "matching_ll": match}
+
+    def backward(self, g_rec: torch.Tensor, g_kl: torch.Tensor, g_match: torch.Tensor):
+        """VJP of the last __call__ for per-row cotangents -> `self.grads` (overwritten)."""
+        if self._last is None:
+            raise RuntimeError("backward() needs a preceding __call__")
+        x, eps, feat, par, z, enc_acts, dec_acts, part_acts, B = self._last
+        d, S = self.latent_dim, _stream()
+        self.grad_arena.zero_()
+        g_rec, g_kl, g_match = (_f32c(t, self.device) for t in (g_rec, g_kl, g_match))
+        # partial posterior (AR-GMM): parameter grads, dz, dcontext -> partial encoder
+        _, dz_match, dctx = self.argmm.backward(g_match)
+        self.part.backward(self.params, self.grads, part_acts, dctx.view_as(part_acts[-1]).contiguous(), need_dx=False)
+        # decoder: Bernoulli -> conv-transpose stack -> dz
+        dlogits = self.bern.backward(g_rec).view_as(dec_acts[-1]).contiguous()
+        dz = self.dec.backward(self.params, self.grads, dec_acts, dlogits, need_dx=True).reshape(B, d)
+        if not self._stop:
+            dz = dz + dz_match
+        # posterior head: (z, kl) -> par -> Linear -> conv stack
+        dpar = torch.empty_like(par)
+        _lib.check(_lib.lib.pmvae_tril_sample_kl_backward(par.data_ptr(), eps.data_ptr(), dz.contiguous().data_ptr(),
+                                                          g_kl.data_ptr(), B, d, dpar.data_ptr(), S),
+                   "pmvae_tril_sample_kl_backward")
+        hw, hg = self.params["posterior_dist/linear"], self.grads["posterior_dist/linear"]
+        dfeat = torch.empty_like(feat)
+        _lib.check(_lib.lib.pmvae_linear_backward(feat.data_ptr(), hw["w"].data_ptr(), dpar.data_ptr(), B, self.enc_feat,
+                                                  self.P, 0, dfeat.data_ptr(), hg["w"].data_ptr(), hg["b"].data_ptr(), S),
+                   "pmvae_linear_backward")
+        self.enc.backward(self.params, self.grads, enc_acts, dfeat.view_as(enc_acts[-1]).contiguous(), need_dx=False)
+        return self.grads
+
+    # ---- train_pm_vae.py:58-83 (beta = 1: the MNIST config has no beta schedule; weight_decay = 0) ------
+    def train_step(self, x, b, *, rng=None, eps=None, lr_schedule=None, matching_coef: float = 1.0,
+                   adam=(0.9, 0.999, 1e-8)) -> Dict[str, float]:
+        out = self(x, b, is_training=True, rng=rng, eps=eps)
+        B = out["kl"].shape[0]
+        ones = torch.full((B,), 1.0 / B, device=self.device)
+        self.backward(-ones, ones, -matching_coef * ones)
+        lr = float(lr_schedule(self.step)) if lr_schedule else 1e-3
+        for arena, grads, m, v in ((self.arena, self.grad_arena, self.m[0], self.v[0]),
+                                   (self.argmm.arena, self.argmm.grad_arena, self.m[1], self.v[1])):
+            _lib.check(_lib.lib.pmvae_adamw_flat(arena.data_ptr(), grads.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                                 arena.numel(), self.step, lr, 0.0, adam[0], adam[1], adam[2], _stream()),
+                       "pmvae_adamw_flat")
+        self.step += 1
+        rec, kl, match = (float(out[k].mean()) for k in ("reconstruction_ll", "kl", "matching_ll"))
+        return {"reconstruction_ll": rec, "kl": kl, "matching_ll": match, "beta": 1.0,
+                "loss": -(rec - kl) + matching_coef * (-match)}

@@ -80,6 +80,8 @@ int latent_bwd(const float* par_e, const float* par_p, const float* eps, const f
                const float* g_kl, const float* g_match, int stop_grad, float* dpar_e, float* dpar_p,
                __nv_bfloat16* dpar_e_b, __nv_bfloat16* dpar_p_b, int64_t B, int d, cudaStream_t s,
                float* db_e = nullptr, float* db_p = nullptr, bool* db_done = nullptr);
+int tril_sample_bwd(const float* par, const float* eps, const float* dz, const float* g_kl, float* dpar, int64_t B, int d,
+                    cudaStream_t s);
 // latent16.cu: thread-per-row versions for d = 16 (bf16 gradient outputs only)
 int latent_fwd16(const float* par, const float* eps, float* z, float* kl, int64_t B, cudaStream_t s);
 int match_fwd16(const float* par_p, const float* z, float* match, int64_t B, cudaStream_t s);

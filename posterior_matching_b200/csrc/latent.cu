@@ -351,6 +351,50 @@ __global__ void __launch_bounds__(kThreadsL) sample_latents_kernel(const float* 
   }
 }
 
+// ---------------------------------------------------------------- stand-alone VJP of (z, kl) = f(par, eps)
+// d/dpar of  sum_r [ dz[r] . z[r] + g_kl[r] * kl[r] ]  with z = mu + L eps, kl = KL(N(mu, LL^T) || N(0, I)):
+//   loc:  dz + g_kl * mu;   off-diagonal L_ij: dz_i eps_j + g_kl * L_ij;
+//   diagonal raw_ii: (dz_i eps_i + g_kl * (D_ii - 1 / D_ii)) * sigmoid(raw_ii),  D_ii = softplus(raw_ii) + 1e-5
+__global__ void __launch_bounds__(256) tril_sample_bwd_kernel(const float* __restrict__ par, const float* __restrict__ eps,
+                                                              const float* __restrict__ dz, const float* __restrict__ g_kl,
+                                                              float* __restrict__ dpar, int64_t B, int d) {
+  const int m = d * (d + 1) / 2, P = d + m;
+  const int64_t n = B * P;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / P;
+    const int q = (int)(t - r * P);
+    const float kw = g_kl[r];
+    const float raw = par[t];
+    float val;
+    if (q < d) {
+      val = dz[r * d + q] + kw * raw;
+    } else {
+      int i, j;
+      tril_ij(q - d, d, m, i, j);
+      const float base = dz[r * d + i] * eps[r * d + j];
+      if (i == j) {
+        const float dg = softplus_f(raw) + 1e-5f;
+        val = (base + kw * (dg - 1.0f / dg)) * sigmoid_f(raw);
+      } else {
+        val = base + kw * raw;
+      }
+    }
+    dpar[t] = val;
+  }
+}
+
+int tril_sample_bwd(const float* par, const float* eps, const float* dz, const float* g_kl, float* dpar, int64_t B, int d,
+                    cudaStream_t s) {
+  PMVAE_CHECK(d >= 1 && d <= 64, "latent_dim must be in [1, 64]");
+  if (B == 0) return 0;
+  const int P = d + d * (d + 1) / 2;
+  int64_t g = (B * P + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  tril_sample_bwd_kernel<<<(int)g, 256, 0, s>>>(par, eps, dz, g_kl, dpar, B, d);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---------------------------------------------------------------- launchers
 static int grid_for_rows(int64_t rows, int G) {
   const int gpb = kThreadsL / G;

@@ -632,6 +632,52 @@ int pmvae_bernoulli_ll_backward(const float* logits, const float* x, const float
   return bernoulli_ll_bwd(logits, x, w, g, B, D, dlogits, as_stream(stream));
 }
 
+// ---- building blocks exposed for models composed on the host (the MNIST config) ------------------
+int pmvae_linear_backward(const float* x, const float* w, const float* dy, int64_t B, int32_t K, int32_t N,
+                          int32_t relu_in, float* dx, float* dw, float* db, pmvae_stream_t stream) {
+  PMVAE_CHECK(B >= 0 && K > 0 && N > 0, "bad shape");
+  if (B == 0) return 0;
+  PMVAE_CHECK(x && w && dy, "null pointer");
+  cudaStream_t s = as_stream(stream);
+  Leaf lf{};
+  lf.rows = K; lf.cols = N; lf.w = 0; lf.b = 0;
+  if (dw) {
+    GemmF32Args a{};
+    a.M = K; a.N = N; a.K = B;
+    a.A = x; a.lda = K; a.B = dy; a.ldb = N; a.C = dw; a.ldc = N;
+    a.relu_a = relu_in; a.atomic = 1; a.split_k = split_for(K, N, B);
+    PMVAE_TRY(gemm_f32(a, true, false, s));
+  }
+  if (db) PMVAE_TRY(colsum_add(dy, N, db, B, N, s));
+  if (dx) {
+    PMVAE_CHECK(!relu_in, "dx through a fused input relu is not provided: apply the mask on the caller's side");
+    GemmF32Args a{};
+    a.M = B; a.N = K; a.K = N;
+    a.A = dy; a.lda = N; a.B = w; a.ldb = N; a.C = dx; a.ldc = K;
+    PMVAE_TRY(gemm_f32(a, false, true, s));
+  }
+  return 0;
+}
+
+int pmvae_tril_sample_kl(const float* par, const float* eps, int64_t B, int32_t d, float* z, float* kl,
+                         pmvae_stream_t stream) {
+  PMVAE_CHECK(B >= 0 && (B == 0 || (par && eps && z && kl)), "bad arguments");
+  return latent_fwd(par, eps, z, kl, B, d, as_stream(stream));
+}
+int pmvae_tril_sample_kl_backward(const float* par, const float* eps, const float* dz, const float* g_kl, int64_t B,
+                                  int32_t d, float* dpar, pmvae_stream_t stream) {
+  PMVAE_CHECK(B >= 0 && (B == 0 || (par && eps && dz && g_kl && dpar)), "bad arguments");
+  return tril_sample_bwd(par, eps, dz, g_kl, dpar, B, d, as_stream(stream));
+}
+int pmvae_adamw_flat(float* params, const float* grads, float* m, float* v, uint64_t n, int64_t count, float lr,
+                     float wd, float b1, float b2, float eps, pmvae_stream_t stream) {
+  PMVAE_CHECK(params && grads && m && v && count >= 0, "bad arguments");
+  AdamSegs seg{};
+  const double t = (double)count + 1.0;
+  const float bc1 = (float)(1.0 - pow((double)b1, t)), bc2 = (float)(1.0 - pow((double)b2, t));
+  return adamw(params, grads, m, v, n, seg, lr, wd, b1, b2, eps, bc1, bc2, as_stream(stream));
+}
+
 int pmvae_net_apply(const pmvae_config* cfg, const float* params, int32_t which, const float* in, const float* msk,
                     int64_t B, float* out, void* ws, uint64_t ws_bytes, pmvae_stream_t stream) {
   PMVAE_CHECK(cfg != nullptr, "null config");

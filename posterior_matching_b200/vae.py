@@ -138,6 +138,12 @@ class PosteriorMatchingVAE:
         """vae.py:61-118, including its fallbacks: the partial encoder defaults to the
         encoder's type/config, the partial posterior to `posterior_dist`, and both dist
         configs receive event_size = latent_dim."""
+        if config["encoder_net"] == "ConvEncoder":
+            # configs/pm_vae_mnist.py: convolutional networks, Bernoulli decoder, AutoregressiveGMM partial posterior --
+            # composed on the host from libpmvae operators (conv_vae.py; float32, first cut of SURVEY §8f N1)
+            from .conv_vae import ConvPosteriorMatchingVAE
+            kwargs.pop("precision", None)
+            return ConvPosteriorMatchingVAE.from_config(config, name=name, **kwargs)
         encoder_net = get_network(config["encoder_net"], config.get("encoder_net_config"), name="encoder_net")
         decoder_net = get_network(config["decoder_net"], config.get("decoder_net_config"), name="decoder_net")
         partial_encoder_net = get_network(

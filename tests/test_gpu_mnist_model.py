@@ -1,0 +1,58 @@
+"""The MNIST-config PM-VAE composed from libpmvae operators (posterior_matching_b200/conv_vae.py) against the float64
+oracle (oracle/model_mnist.py): per-row terms, loss and every gradient leaf; masks from the MNIST mask generator."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_mnist as MM
+from tests.util import rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(B, seed=0):
+    from posterior_matching_b200 import MNISTMaskGenerator
+    rng = np.random.default_rng(seed)
+    x = torch.tensor((rng.random((B, 28, 28, 1)) < 0.13).astype(np.float64))
+    b = MNISTMaskGenerator(seed=seed + 1)((B, 28, 28, 1)).cpu().double()
+    eps = torch.tensor(rng.standard_normal((B, MM.LATENT)))
+    return x, b, eps
+
+
+def test_mnist_model_forward_loss_and_gradients():
+    from posterior_matching_b200 import pm_vae_config
+    from posterior_matching_b200.conv_vae import ConvPosteriorMatchingVAE
+    cfg = pm_vae_config("mnist")
+    m = ConvPosteriorMatchingVAE.from_config(cfg.model.to_dict())
+    assert [(n, tuple(s), nb) for n, s, nb in m.leaves] == [(n, tuple(s), nb) for n, s, nb in MM.leaf_shapes()[:len(m.leaves)]]
+    p = MM.init_params()
+    m.load_params(p)
+    B = 6
+    x, b, eps = _inputs(B)
+    loss, out, grads = MM.loss_and_grads(p, x, b, eps)
+    got = m(x.float().cuda(), b.float().cuda(), eps=eps.float().cuda())
+    for k in ("reconstruction_ll", "kl", "matching_ll"):
+        assert rel_err(got[k].cpu().numpy(), out[k].numpy()) < 2e-4, k
+    ones = torch.full((B,), 1.0 / B, device="cuda")
+    g = m.backward(-ones, ones, -ones)
+    torch.cuda.synchronize()
+    got_loss = float(-(got["reconstruction_ll"] - got["kl"]).mean() - got["matching_ll"].mean())
+    assert abs(got_loss - float(loss)) < 2e-5 * abs(float(loss))
+    for n in grads:
+        for k in grads[n]:
+            w = grads[n][k].numpy()
+            gg = g[n][k].cpu().numpy().reshape(w.shape)
+            e = rel_l2(gg, w) if np.linalg.norm(w) > 0 else float(np.abs(gg).max())
+            assert e < 2e-3, (n, k, e)
+
+
+def test_mnist_train_step_reduces_the_loss():
+    from posterior_matching_b200 import pm_vae_config
+    from posterior_matching_b200.conv_vae import ConvPosteriorMatchingVAE
+    m = ConvPosteriorMatchingVAE.from_config(pm_vae_config("mnist").model.to_dict())
+    m.load_params(MM.init_params())
+    x, b, eps = (t.float().cuda() for t in _inputs(16, seed=3))
+    first = m.train_step(x, b, eps=eps)
+    for _ in range(12):
+        last = m.train_step(x, b, eps=eps)
+    assert np.isfinite(last["loss"]) and last["loss"] < first["loss"]
