@@ -258,7 +258,7 @@ int pmvae_argmm_backward(const pmvae_argmm_config* cfg, const float* params, con
  *   hk.Conv2D(k, s, SAME|VALID), weights [kh,kw,in,out]:          stride = s, dil = 1, w_ci = Cout, w_co = 1
  *   hk.Conv2DTranspose(k, s, SAME|VALID), weights [kh,kw,out,in]: stride = 1, dil = s, w_ci = 1, w_co = Cin
  * (padding per lax.padtype_to_pads / lax.conv_transpose; posterior_matching_b200/conv.py builds the descriptors).
- * Correctness-first direct kernels: this row is not on the tensor cores yet. */
+ * Float32 first cut: this row is not on the tensor cores yet. */
 typedef struct pmvae_conv_desc {
   int32_t H, W, Cin;          /* input  [B, H, W, Cin]    */
   int32_t OH, OW, Cout;       /* output [B, OH, OW, Cout] */
@@ -267,12 +267,16 @@ typedef struct pmvae_conv_desc {
   float slope;                /* leaky_relu negative slope */
   int32_t reserved;
 } pmvae_conv_desc;
+/* With a workspace (pmvae_conv2d_workspace_bytes, 256-byte aligned) the operator runs as im2col + float32 GEMM;
+ * with ws = NULL as direct one-thread-per-element kernels (slow; kept as an independent cross-check). */
+uint64_t pmvae_conv2d_workspace_bytes(const pmvae_conv_desc* desc, int64_t B);
 int pmvae_conv2d_forward(const pmvae_conv_desc* desc, const float* x, const float* w, const float* bias,
-                         int64_t B, float* y, pmvae_stream_t stream);
+                         int64_t B, float* y, void* ws, uint64_t ws_bytes, pmvae_stream_t stream);
 /* VJP: dy (cotangent of y) is overwritten with the pre-activation cotangent; dx may be NULL; dw and dbias are
  * accumulated into (zero them first). */
 int pmvae_conv2d_backward(const pmvae_conv_desc* desc, const float* x, const float* w, const float* y,
-                          float* dy, int64_t B, float* dx, float* dw, float* dbias, pmvae_stream_t stream);
+                          float* dy, int64_t B, float* dx, float* dw, float* dbias, void* ws, uint64_t ws_bytes,
+                          pmvae_stream_t stream);
 
 /* ---- building blocks for models composed on the host (the MNIST config: posterior_matching_b200/conv_vae.py) --
  * VJP of pmvae_linear (float32 arithmetic): dw[K,N] += relu?(x)^T dy, db[N] += colsum(dy), dx[B,K] = dy w^T

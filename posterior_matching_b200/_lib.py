@@ -121,8 +121,9 @@ _SIGS = {
     "pmvae_tril_sample_kl": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "pmvae_tril_sample_kl_backward": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "pmvae_adamw_flat": (_i32, [_vp, _vp, _vp, _vp, _u64, _i64, _f32, _f32, _f32, _f32, _f32, _vp]),
-    "pmvae_conv2d_forward": (_i32, [C.POINTER(ConvDesc), _vp, _vp, _vp, _i64, _vp, _vp]),
-    "pmvae_conv2d_backward": (_i32, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "pmvae_conv2d_workspace_bytes": (_u64, [C.POINTER(ConvDesc), _i64]),
+    "pmvae_conv2d_forward": (_i32, [C.POINTER(ConvDesc), _vp, _vp, _vp, _i64, _vp, _vp, _u64, _vp]),
+    "pmvae_conv2d_backward": (_i32, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _u64, _vp]),
     "pmvae_xla_opaque_size": (_u64, []),
     "pmvae_xla_forward": (None, [_vp, C.POINTER(_vp), C.c_char_p, C.c_size_t, _vp]),
     "pmvae_xla_backward": (None, [_vp, C.POINTER(_vp), C.c_char_p, C.c_size_t, _vp]),

@@ -58,21 +58,42 @@ def conv_desc(H: int, W: int, Cin: int, Cout: int, k: int, s: int, padding: str,
     return d
 
 
-def conv2d_forward(d: _lib.ConvDesc, x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
+_WS = {}
+
+
+def conv_workspace(d: _lib.ConvDesc, B: int, device) -> torch.Tensor:
+    """One shared, growing scratch buffer per device for the im2col + GEMM form of the operator."""
+    need = int(_lib.lib.pmvae_conv2d_workspace_bytes(C.byref(d), B))
+    ws = _WS.get(device)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need + 256, dtype=torch.uint8, device=device)
+        _WS[device] = ws
+    off = (-ws.data_ptr()) % 256
+    return ws[off:]
+
+
+def conv2d_forward(d: _lib.ConvDesc, x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], *,
+                   direct: bool = False) -> torch.Tensor:
+    """`direct=True` runs the one-thread-per-element kernels instead of im2col + GEMM (cross-check)."""
     B = x.shape[0]
     y = torch.empty((B, d.OH, d.OW, d.Cout), dtype=torch.float32, device=x.device)
+    ws = None if direct else conv_workspace(d, B, x.device)
     _lib.check(_lib.lib.pmvae_conv2d_forward(C.byref(d), x.data_ptr(), w.data_ptr(), b.data_ptr() if b is not None else None,
-                                             B, y.data_ptr(), _stream()), "pmvae_conv2d_forward")
+                                             B, y.data_ptr(), ws.data_ptr() if ws is not None else None,
+                                             ws.numel() if ws is not None else 0, _stream()), "pmvae_conv2d_forward")
     return y
 
 
 def conv2d_backward(d: _lib.ConvDesc, x: torch.Tensor, w: torch.Tensor, y: torch.Tensor, dy: torch.Tensor,
-                    dw: torch.Tensor, db: Optional[torch.Tensor], need_dx: bool = True) -> Optional[torch.Tensor]:
+                    dw: torch.Tensor, db: Optional[torch.Tensor], need_dx: bool = True, *,
+                    direct: bool = False) -> Optional[torch.Tensor]:
     """Accumulates into dw / db, overwrites dy with the pre-activation cotangent, returns dx (or None)."""
     B = x.shape[0]
     dx = torch.empty_like(x) if need_dx else None
+    ws = None if direct else conv_workspace(d, B, x.device)
     _lib.check(_lib.lib.pmvae_conv2d_backward(C.byref(d), x.data_ptr(), w.data_ptr(), y.data_ptr(), dy.data_ptr(), B,
                                               dx.data_ptr() if need_dx else None, dw.data_ptr(),
-                                              db.data_ptr() if db is not None else None, _stream()),
-               "pmvae_conv2d_backward")
+                                              db.data_ptr() if db is not None else None,
+                                              ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
+                                              _stream()), "pmvae_conv2d_backward")
     return dx

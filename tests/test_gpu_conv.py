@@ -27,8 +27,9 @@ def _layer_cases():
     return cases
 
 
+@pytest.mark.parametrize("direct", [False, True], ids=["im2col", "direct"])
 @pytest.mark.parametrize("name,transpose,H,cin,cout,k,s,pad", _layer_cases())
-def test_conv_layer_forward_and_gradients(name, transpose, H, cin, cout, k, s, pad):
+def test_conv_layer_forward_and_gradients(name, transpose, H, cin, cout, k, s, pad, direct):
     from posterior_matching_b200 import conv as PC
     torch.manual_seed(hash(name) % 1000)
     B = 3
@@ -43,9 +44,9 @@ def test_conv_layer_forward_and_gradients(name, transpose, H, cin, cout, k, s, p
     d = PC.conv_desc(H, H, cin, cout, k, s, pad, transpose=transpose)
     assert (d.OH, d.OW) == tuple(want.shape[1:3])
     xc, wc, bc = (t.detach().float().cuda().contiguous() for t in (x, w, b))
-    y = PC.conv2d_forward(d, xc, wc, bc)
+    y = PC.conv2d_forward(d, xc, wc, bc, direct=direct)
     dw, db = torch.zeros_like(wc), torch.zeros_like(bc)
-    dx = PC.conv2d_backward(d, xc, wc, y, g.float().cuda().contiguous(), dw, db)
+    dx = PC.conv2d_backward(d, xc, wc, y, g.float().cuda().contiguous(), dw, db, direct=direct)
     torch.cuda.synchronize()
     assert rel_err(y.cpu().numpy(), want.detach().numpy()) < 2e-5
     assert rel_l2(dx.cpu().numpy(), x.grad.numpy()) < 5e-5
