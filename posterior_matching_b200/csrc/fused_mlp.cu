@@ -111,7 +111,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   const int it_stride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int it_count = CTA2 ? (p.num_tiles + 1) / 2 : p.num_tiles;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
   const int R = p.R;
   const int n_hidden = 2 * R + 1;                 // Linears that feed the operand buffer
   const int nkb0 = (p.k16_0 + 3) >> 2;
@@ -160,23 +160,27 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   };
 
   if (warp == 0) {
-    // ===================== weight producer =====================
-    if (lane == 0) {
+    // ===================== weight producer (converged warp, one elected lane issues the TMA) =====================
+    {
       int stage = 0; uint32_t ph = 0;
       // one K-block of `rows` weight rows starting at row c1 (CTA2: this CTA's half of them)
       auto load = [&](const CUtensorMap* m, int c0, int c1, int rows) {
         mbar_wait_x<CTA2>(w_empty(stage), ph ^ 1u, 1);
         const uint32_t dst = wring + stage * kStgBytes;
-        if (CTA2) {
-          const int half_rows = rows >> 1;
-          if (rank == 0) mbar_arrive_expect_tx(w_full(stage), (uint32_t)rows * 128u);
-          tma_load_2d_cta2(dst, m, mapa_shared(w_full(stage), 0), c0, c1 + (int)rank * half_rows);
-        } else if (p.debug & 2) {
-          mbar_arrive(w_full(stage));
-        } else {
-          mbar_arrive_expect_tx(w_full(stage), (uint32_t)rows * 128u);
-          tma_load_2d(dst, m, w_full(stage), c0, c1);
+        __syncwarp();
+        if (elect_one()) {
+          if (CTA2) {
+            const int half_rows = rows >> 1;
+            if (rank == 0) mbar_arrive_expect_tx(w_full(stage), (uint32_t)rows * 128u);
+            tma_load_2d_cta2(dst, m, mapa_shared(w_full(stage), 0), c0, c1 + (int)rank * half_rows);
+          } else if (p.debug & 2) {
+            mbar_arrive(w_full(stage));
+          } else {
+            mbar_arrive_expect_tx(w_full(stage), (uint32_t)rows * 128u);
+            tma_load_2d(dst, m, w_full(stage), c0, c1);
+          }
         }
+        __syncwarp();
         if (++stage == kStg) { stage = 0; ph ^= 1u; }
       };
       for (int it = it_first; it < it_count; it += it_stride) {
@@ -189,18 +193,19 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (CTA2: the leader CTA issues for the pair) =====================
-    if (lane == 0 && rank == 0) {
+    // The whole warp runs the loop converged; one elected lane issues (see elect_one in tc_ptx.cuh).
+    if (rank == 0) {
       int stage = 0; uint32_t ph = 0;
       uint32_t ready_par = 0, use_cnt0 = 0, use_cnt1 = 0, in_par = 0;
       // wait_mode: 0 = operand already announced, 1 = chunk by chunk (opnd_ready), 2 = first-Linear buffer (in_ready)
       auto step = [&](int s_idx, uint32_t abuf, int nk16, int N, bool accum, int wait_mode) {
         const int region = region_of(s_idx);
         uint32_t& uc = region ? use_cnt1 : use_cnt0;
-        stamp(0, 100 + s_idx);
+        if (lane == 0) stamp(0, 100 + s_idx);
         mbar_wait_x<CTA2>(acc_empty(region), (uc & 1u) ^ 1u, 2);
         ++uc;
         tc_fence_after();
-        stamp(0, 200 + s_idx);
+        if (lane == 0) stamp(0, 200 + s_idx);
         const uint32_t d_tmem = tmem_base + (uint32_t)(region * 256);
         const uint32_t idesc = instr_desc(CTA2 ? 256 : 128, N, 0, 0);
         const int nkb = (nk16 + 3) >> 2;
@@ -212,24 +217,30 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             mbar_wait_x<CTA2>(in_ready, in_par, 9);
             in_par ^= 1u;
           }
-          stamp(0, 300 + kb);
+          if (lane == 0) stamp(0, 300 + kb);
           mbar_wait_x<CTA2>(w_full(stage), ph, 4);
           tc_fence_after();
-          stamp(0, 400 + kb);
+          if (lane == 0) stamp(0, 400 + kb);
           const uint32_t sa = abuf + kb * kChunkBytes;
           const uint32_t sb = wring + stage * kStgBytes;
           const int ks = min(4, nk16 - 4 * kb);
-          for (int k = 0; k < ks && !(p.debug & 4); ++k) {
-            const uint64_t da = smem_desc(sa + k * 32, 16, 1024), db = smem_desc(sb + k * 32, 16, 1024);
-            const uint32_t acc = (accum || kb > 0 || k > 0) ? 1u : 0u;
-            if (CTA2) umma_f16_cta2(d_tmem, da, db, idesc, acc);
-            else umma_f16(d_tmem, da, db, idesc, acc);
+          __syncwarp();
+          if (elect_one()) {
+            for (int k = 0; k < ks && !(p.debug & 4); ++k) {
+              const uint64_t da = smem_desc(sa + k * 32, 16, 1024), db = smem_desc(sb + k * 32, 16, 1024);
+              const uint32_t acc = (accum || kb > 0 || k > 0) ? 1u : 0u;
+              if (CTA2) umma_f16_cta2(d_tmem, da, db, idesc, acc);
+              else umma_f16(d_tmem, da, db, idesc, acc);
+            }
+            if (CTA2) umma_commit_cta2(w_empty(stage), 3); else umma_commit(w_empty(stage));
+            if (kb == nkb - 1) {
+              if (CTA2) umma_commit_cta2(acc_full(region), 3); else umma_commit(acc_full(region));
+            }
           }
-          if (CTA2) umma_commit_cta2(w_empty(stage), 3); else umma_commit(w_empty(stage));
+          __syncwarp();
           if (++stage == kStg) { stage = 0; ph ^= 1u; }
         }
-        if (CTA2) umma_commit_cta2(acc_full(region), 3); else umma_commit(acc_full(region));
-        stamp(0, 500 + s_idx);
+        if (lane == 0) stamp(0, 500 + s_idx);
       };
       for (int it = it_first; it < it_count; it += it_stride) {
         step(0, l0buf, p.k16_0, 256, false, 2);
@@ -607,7 +618,7 @@ net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant
   const uint32_t tmem_slot = bar + 8u * (2 * kWStages + 22);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + kBwdOffBar + 8 * (2 * kWStages + 22));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
   constexpr int n_hidden = 2 * R + 1;
   const int nkb_h = (p.k16_h + 3) >> 2;
 
@@ -632,21 +643,29 @@ net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant
   const uint32_t tmem_base = *tmem_slot_gen;
 
   if (warp == 0) {
-    // ===================== producer: dHead tiles and weight K-blocks =====================
-    if (lane == 0) {
+    // ===================== producer: dHead tiles and weight K-blocks (converged warp, elected lane issues) =====================
+    {
       int stage = 0; uint32_t ph = 0; uint32_t uf_cnt = 0;
       auto load = [&](const CUtensorMap* m, int c0, int c1, uint32_t bytes) {
         mbar_wait(w_empty(stage), ph ^ 1u, 1);
-        mbar_arrive_expect_tx(w_full(stage), bytes);
-        tma_load_2d(wring + stage * kWStageBytes, m, w_full(stage), c0, c1);
+        __syncwarp();
+        if (elect_one()) {
+          mbar_arrive_expect_tx(w_full(stage), bytes);
+          tma_load_2d(wring + stage * kWStageBytes, m, w_full(stage), c0, c1);
+        }
+        __syncwarp();
         if (++stage == kWStages) { stage = 0; ph ^= 1u; }
       };
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         // dHead rows of this tile go into the dU buffer once the previous tile no longer needs it
         mbar_wait(ubuf_free, (uf_cnt & 1u) ^ 1u, 7);
         ++uf_cnt;
-        mbar_arrive_expect_tx(dh_full, (uint32_t)nkb_h * kChunkBytes);
-        for (int kb = 0; kb < nkb_h; ++kb) tma_load_2d(ubuf + kb * kChunkBytes, &map_dh, dh_full, kb * 64, tile * 128);
+        __syncwarp();
+        if (elect_one()) {
+          mbar_arrive_expect_tx(dh_full, (uint32_t)nkb_h * kChunkBytes);
+          for (int kb = 0; kb < nkb_h; ++kb) tma_load_2d(ubuf + kb * kChunkBytes, &map_dh, dh_full, kb * 64, tile * 128);
+        }
+        __syncwarp();
         for (int kb = 0; kb < nkb_h; ++kb) load(&map_wh, kb * 64, 0, kWStageBytes);
         for (int l = 2 * R; l >= 1; --l)
           for (int kb = 0; kb < 4; ++kb) load(&map_w, kb * 64, (l - 1) * 256, kWStageBytes);
@@ -655,8 +674,8 @@ net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (converged warp, one elected lane issues; see elect_one) =====================
+    {
       int stage = 0; uint32_t ph = 0;
       uint32_t ready_par = 0, use_cnt0 = 0, use_cnt1 = 0, dh_par = 0;
       auto step = [&](int s_idx, uint32_t abuf, int nk16, int N, bool wait_opnd) {
@@ -678,13 +697,17 @@ net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant
           const uint32_t sa = abuf + kb * kChunkBytes;
           const uint32_t sb = wring + stage * kWStageBytes;
           const int ks = min(4, nk16 - 4 * kb);
-          for (int k = 0; k < ks; ++k)
-            umma_f16(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sb + k * 32, 16, 1024), idesc,
-                     (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(w_empty(stage));
+          __syncwarp();
+          if (elect_one()) {
+            for (int k = 0; k < ks; ++k)
+              umma_f16(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sb + k * 32, 16, 1024), idesc,
+                       (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(w_empty(stage));
+            if (kb == nkb - 1) umma_commit(acc_full(region));
+          }
+          __syncwarp();
           if (++stage == kWStages) { stage = 0; ph ^= 1u; }
         }
-        umma_commit(acc_full(region));
       };
       int t = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {

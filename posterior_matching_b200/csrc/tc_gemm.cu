@@ -57,7 +57,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * kStageBytes + 8 * (2 * kStages + 2 * kAccStages));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -80,8 +80,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t stage_tx = (uint32_t)(kABytes + n_tile * kBlockK * 2);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (converged warp, one elected lane issues) =====================
+    {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile % p.num_m_tiles;
@@ -92,27 +92,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int kb1 = min(p.num_k_blocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, 1);
-          mbar_arrive_expect_tx(full_bar(stage), stage_tx);
           const uint32_t sa = smem_base + stage * kStageBytes;
           const uint32_t sb = sa + kABytes;
-          if (KIND == 0) {
-            // A box: [64 k] x [128 rows]; B box: [64 k] x [n_tile rows]
-            tma_load_2d(sa, &map_a, full_bar(stage), kb * kBlockK, mt * kBlockM);
-            tma_load_2d(sb, &map_b, full_bar(stage), kb * kBlockK, nt * n_tile);
-          } else {
-            // MN-major: boxes of [64 m-or-n] x [64 k rows], one per 64 columns of the tile
-            for (int j = 0; j < kBlockM / 64; ++j)
-              tma_load_2d(sa + j * 8192, &map_a, full_bar(stage), mt * kBlockM + j * 64, kb * kBlockK);
-            for (int j = 0; j < n_tile / 64; ++j)
-              tma_load_2d(sb + j * 8192, &map_b, full_bar(stage), nt * n_tile + j * 64, kb * kBlockK);
+          __syncwarp();
+          if (elect_one()) {
+            mbar_arrive_expect_tx(full_bar(stage), stage_tx);
+            if (KIND == 0) {
+              // A box: [64 k] x [128 rows]; B box: [64 k] x [n_tile rows]
+              tma_load_2d(sa, &map_a, full_bar(stage), kb * kBlockK, mt * kBlockM);
+              tma_load_2d(sb, &map_b, full_bar(stage), kb * kBlockK, nt * n_tile);
+            } else {
+              // MN-major: boxes of [64 m-or-n] x [64 k rows], one per 64 columns of the tile
+              for (int j = 0; j < kBlockM / 64; ++j)
+                tma_load_2d(sa + j * 8192, &map_a, full_bar(stage), mt * kBlockM + j * 64, kb * kBlockK);
+              for (int j = 0; j < n_tile / 64; ++j)
+                tma_load_2d(sb + j * 8192, &map_b, full_bar(stage), nt * n_tile + j * 64, kb * kBlockK);
+            }
           }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (converged warp, one elected lane issues; see elect_one) =====================
+    {
       const uint32_t idesc = instr_desc(kBlockM, n_tile, KIND, KIND);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -129,24 +133,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_base + stage * kStageBytes;
           const uint32_t sb = sa + kABytes;
+          __syncwarp();
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            uint64_t da, db;
-            if (KIND == 0) {
-              // K-major SW128: 8-row groups 1024 B apart; a K=16 slice is 32 B inside the swizzle row
-              da = smem_desc(sa + k * 32, 16, 1024);
-              db = smem_desc(sb + k * 32, 16, 1024);
-            } else {
-              // MN-major SW128: 64-element column groups 8192 B apart (LBO), 8-k groups 1024 B apart (SBO)
-              da = smem_desc(sa + k * 2048, 8192, 1024);
-              db = smem_desc(sb + k * 2048, 8192, 1024);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              uint64_t da, db;
+              if (KIND == 0) {
+                // K-major SW128: 8-row groups 1024 B apart; a K=16 slice is 32 B inside the swizzle row
+                da = smem_desc(sa + k * 32, 16, 1024);
+                db = smem_desc(sb + k * 32, 16, 1024);
+              } else {
+                // MN-major SW128: 64-element column groups 8192 B apart (LBO), 8-k groups 1024 B apart (SBO)
+                da = smem_desc(sa + k * 2048, 8192, 1024);
+                db = smem_desc(sb + k * 2048, 8192, 1024);
+              }
+              umma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
-            umma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
+            if (kb == kb1 - 1) umma_commit(tfull_bar(acc));   // accumulator ready for the epilogue
           }
-          umma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));              // accumulator ready for the epilogue
+        if (kb1 <= kb0) {                          // empty K range: still hand the (stale) accumulator over
+          if (elect_one()) umma_commit(tfull_bar(acc));
+          __syncwarp();
+        }
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -295,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) tn_grouped_kernel(const __grid_co
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 2 * kAccStages);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * kStageBytes + 8 * (2 * kStages + 2 * kAccStages));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform for ptxas
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < g.n; ++i) { tma_prefetch_desc(&g.p[i].ma); tma_prefetch_desc(&g.p[i].mb); }
@@ -319,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) tn_grouped_kernel(const __grid_co
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
         int pi, mt, sp;
@@ -329,16 +341,20 @@ __global__ void __launch_bounds__(kThreads, 1) tn_grouped_kernel(const __grid_co
         const uint32_t tx = (uint32_t)(kABytes + P.n_tile * kBlockK * 2);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, 1);
-          mbar_arrive_expect_tx(full_bar(stage), tx);
           const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
-          for (int j = 0; j < kBlockM / 64; ++j) tma_load_2d(sa + j * 8192, &P.ma, full_bar(stage), mt * kBlockM + j * 64, kb * kBlockK);
-          for (int j = 0; j < P.n_tile / 64; ++j) tma_load_2d(sb + j * 8192, &P.mb, full_bar(stage), j * 64, kb * kBlockK);
+          __syncwarp();
+          if (elect_one()) {
+            mbar_arrive_expect_tx(full_bar(stage), tx);
+            for (int j = 0; j < kBlockM / 64; ++j) tma_load_2d(sa + j * 8192, &P.ma, full_bar(stage), mt * kBlockM + j * 64, kb * kBlockK);
+            for (int j = 0; j < P.n_tile / 64; ++j) tma_load_2d(sb + j * 8192, &P.mb, full_bar(stage), j * 64, kb * kBlockK);
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
@@ -354,14 +370,22 @@ __global__ void __launch_bounds__(kThreads, 1) tn_grouped_kernel(const __grid_co
           mbar_wait(full_bar(stage), phase, 3);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+          __syncwarp();
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_f16(d_tmem, smem_desc(sa + k * 2048, 8192, 1024), smem_desc(sb + k * 2048, 8192, 1024), idesc,
-                     (kb > kb0 || k > 0) ? 1u : 0u);
-          umma_commit(empty_bar(stage));
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16(d_tmem, smem_desc(sa + k * 2048, 8192, 1024), smem_desc(sb + k * 2048, 8192, 1024), idesc,
+                       (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit(empty_bar(stage));
+            if (kb == kb1 - 1) umma_commit(tfull_bar(acc));
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));
+        if (kb1 <= kb0) {                          // empty K range: still hand the (stale) accumulator over
+          if (elect_one()) umma_commit(tfull_bar(acc));
+          __syncwarp();
+        }
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
       }
     }

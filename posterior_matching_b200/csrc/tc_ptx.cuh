@@ -74,6 +74,19 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// One lane of a converged warp.  The issuing warp runs its loop with all 32 lanes (so addresses and descriptors stay in
+// uniform registers) and only the tcgen05.mma / commit / TMA instructions sit under this predicate: a `lane == 0`
+// branch instead makes ptxas wrap every UTCHMMA in an R2UR + ELECT + BRA.U.ANY waterfall (~90 cycles per issue,
+// scripts/probes/mma_probe.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
