@@ -70,6 +70,23 @@ __device__ __forceinline__ uint32_t relu2(uint32_t v) {
   return o;
 }
 
+// bf16 pair of relu(a), relu(b) in one conversion (a in the low half)
+__device__ __forceinline__ uint32_t pack2_relu(float a, float b) {
+  uint32_t o;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o) : "f"(b), "f"(a));
+  return o;
+}
+// (x0, x1) += (b0, b1) as one packed fp32x2 add
+__device__ __forceinline__ void add2(float& x0, float& x1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ta, tb;\n\t"
+      "mov.b64 ta, {%0, %1};\n\t"
+      "mov.b64 tb, {%2, %3};\n\t"
+      "add.rn.f32x2 ta, ta, tb;\n\t"
+      "mov.b64 {%0, %1}, ta;\n\t}"
+      : "+f"(x0), "+f"(x1)
+      : "f"(b0), "f"(b1));
+}
+
 // CTA2: two CTAs of a cluster run as one tcgen05 pair (cta_group::2, M = 256): each owns a 128-row tile and
 // half of every weight K-block, so the weight traffic from L2 is halved and the ring covers twice the latency.
 // LN: hk.LayerNorm(-1, False, False) after every Linear (networks.py:117-118,123-124,128-129; the bsds config).  The
@@ -198,18 +215,31 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       int stage = 0; uint32_t ph = 0;
       uint32_t ready_par = 0, use_cnt0 = 0, use_cnt1 = 0, in_par = 0;
       // wait_mode: 0 = operand already announced, 1 = chunk by chunk (opnd_ready), 2 = first-Linear buffer (in_ready)
+      // Everything the issuing thread does per K-block is exposed once it exceeds the tensor pipe's small run-ahead
+      // (scripts/probes/mma_probe.cu), so the loop is kept lean: descriptor low words are precomputed (a K=16 slice is
+      // +2 in the address field), both barrier polls are in flight together, debug / trace flags are read once.
+      const bool no_mma = (p.debug & 4) != 0;
+      const bool tracing = p.trace != nullptr;
+      const bool fine = tracing && !(p.debug & 8);       // debug bit 8: per-Linear stamps only
+      constexpr uint32_t kDescHi = 0x40004040u;      // SBO 1024 | version 1 | SWIZZLE_128B (see smem_desc)
+      auto desc_lo = [](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
+      auto mk = [](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
       auto step = [&](int s_idx, uint32_t abuf, int nk16, int N, bool accum, int wait_mode) {
         const int region = region_of(s_idx);
         uint32_t& uc = region ? use_cnt1 : use_cnt0;
-        if (lane == 0) stamp(0, 100 + s_idx);
+        if (tracing && lane == 0) stamp(0, 100 + s_idx);
         mbar_wait_x<CTA2>(acc_empty(region), (uc & 1u) ^ 1u, 2);
         ++uc;
         tc_fence_after();
-        if (lane == 0) stamp(0, 200 + s_idx);
+        if (tracing && lane == 0) stamp(0, 200 + s_idx);
         const uint32_t d_tmem = tmem_base + (uint32_t)(region * 256);
         const uint32_t idesc = instr_desc(CTA2 ? 256 : 128, N, 0, 0);
         const int nkb = (nk16 + 3) >> 2;
-        for (int kb = 0; kb < nkb; ++kb) {
+        uint32_t a_lo = desc_lo(abuf);
+        for (int kb = 0; kb < nkb; ++kb, a_lo += kChunkBytes >> 4) {
+          // poll both barriers of this K-block before looking at either answer
+          const uint32_t b_w = w_full(stage);
+          bool ok_w = CTA2 ? mbar_try_wait_cluster(b_w, ph) : mbar_try_wait(b_w, ph);
           if (wait_mode == 1) {
             mbar_wait_x<CTA2>(opnd_ready(kb), (ready_par >> kb) & 1u, 3);
             ready_par ^= 1u << kb;
@@ -217,20 +247,27 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             mbar_wait_x<CTA2>(in_ready, in_par, 9);
             in_par ^= 1u;
           }
-          if (lane == 0) stamp(0, 300 + kb);
-          mbar_wait_x<CTA2>(w_full(stage), ph, 4);
+          if (fine && lane == 0) stamp(0, 300 + kb);
+          if (!ok_w) mbar_wait_x<CTA2>(b_w, ph, 4);
           tc_fence_after();
-          if (lane == 0) stamp(0, 400 + kb);
-          const uint32_t sa = abuf + kb * kChunkBytes;
-          const uint32_t sb = wring + stage * kStgBytes;
-          const int ks = min(4, nk16 - 4 * kb);
+          if (fine && lane == 0) stamp(0, 400 + kb);
+          const uint32_t b_lo = desc_lo(wring + stage * kStgBytes);
+          const int ks = no_mma ? 0 : min(4, nk16 - 4 * kb);
           __syncwarp();
           if (elect_one()) {
-            for (int k = 0; k < ks && !(p.debug & 4); ++k) {
-              const uint64_t da = smem_desc(sa + k * 32, 16, 1024), db = smem_desc(sb + k * 32, 16, 1024);
-              const uint32_t acc = (accum || kb > 0 || k > 0) ? 1u : 0u;
-              if (CTA2) umma_f16_cta2(d_tmem, da, db, idesc, acc);
-              else umma_f16(d_tmem, da, db, idesc, acc);
+            if (ks == 4) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t acc = (accum || kb > 0 || k > 0) ? 1u : 0u;
+                if (CTA2) umma_f16_cta2(d_tmem, mk(a_lo + 2 * k), mk(b_lo + 2 * k), idesc, acc);
+                else umma_f16(d_tmem, mk(a_lo + 2 * k), mk(b_lo + 2 * k), idesc, acc);
+              }
+            } else {
+              for (int k = 0; k < ks; ++k) {
+                const uint32_t acc = (accum || kb > 0 || k > 0) ? 1u : 0u;
+                if (CTA2) umma_f16_cta2(d_tmem, mk(a_lo + 2 * k), mk(b_lo + 2 * k), idesc, acc);
+                else umma_f16(d_tmem, mk(a_lo + 2 * k), mk(b_lo + 2 * k), idesc, acc);
+              }
             }
             if (CTA2) umma_commit_cta2(w_empty(stage), 3); else umma_commit(w_empty(stage));
             if (kb == nkb - 1) {
@@ -240,7 +277,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           __syncwarp();
           if (++stage == kStg) { stage = 0; ph ^= 1u; }
         }
-        if (lane == 0) stamp(0, 500 + s_idx);
+        if (tracing && lane == 0) stamp(0, 500 + s_idx);
       };
       for (int it = it_first; it < it_count; it += it_stride) {
         step(0, l0buf, p.k16_0, 256, false, 2);
@@ -419,16 +456,18 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 bv = bp[i];
-            const float v0 = __uint_as_float(r[4 * i]) + bv.x, v1 = __uint_as_float(r[4 * i + 1]) + bv.y;
-            const float v2 = __uint_as_float(r[4 * i + 2]) + bv.z, v3 = __uint_as_float(r[4 * i + 3]) + bv.w;
+            float v0 = __uint_as_float(r[4 * i]), v1 = __uint_as_float(r[4 * i + 1]);
+            float v2 = __uint_as_float(r[4 * i + 2]), v3 = __uint_as_float(r[4 * i + 3]);
+            add2(v0, v1, bv.x, bv.y);
+            add2(v2, v3, bv.z, bv.w);
             if (SAVE) {
               neg = __funnelshift_l(__float_as_uint(v0), neg, 1);
               neg = __funnelshift_l(__float_as_uint(v1), neg, 1);
               neg = __funnelshift_l(__float_as_uint(v2), neg, 1);
               neg = __funnelshift_l(__float_as_uint(v3), neg, 1);
             }
-            pk[2 * i] = relu2(pack2(v0, v1));
-            pk[2 * i + 1] = relu2(pack2(v2, v3));
+            pk[2 * i] = pack2_relu(v0, v1);
+            pk[2 * i + 1] = pack2_relu(v2, v3);
           }
           mw[j] = ~neg;
           if (SAVE) mbar_wait(chunk_free(j), (n_writes & 1u) ^ 1u, 13);   // the previous tile in this chunk has been stored
@@ -678,6 +717,10 @@ net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant
     {
       int stage = 0; uint32_t ph = 0;
       uint32_t ready_par = 0, use_cnt0 = 0, use_cnt1 = 0, dh_par = 0;
+      constexpr uint32_t kDescHi = 0x40004040u;      // SBO 1024 | version 1 | SWIZZLE_128B (see smem_desc)
+      auto desc_lo = [](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
+      auto mk = [](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
+      // lean K-loop (see net_fwd_kernel): precomputed descriptor words, both barrier polls in flight together
       auto step = [&](int s_idx, uint32_t abuf, int nk16, int N, bool wait_opnd) {
         const int region = s_idx & 1;
         uint32_t& uc = region ? use_cnt1 : use_cnt0;
@@ -687,21 +730,26 @@ net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant
         const uint32_t d_tmem = tmem_base + (uint32_t)(region * 256);
         const uint32_t idesc = instr_desc(128, N, 0, 0);
         const int nkb = (nk16 + 3) >> 2;
-        for (int kb = 0; kb < nkb; ++kb) {
+        uint32_t a_lo = desc_lo(abuf);
+        for (int kb = 0; kb < nkb; ++kb, a_lo += kChunkBytes >> 4) {
+          const uint32_t b_w = w_full(stage);
+          const bool ok_w = mbar_try_wait(b_w, ph);
           if (wait_opnd) {
             mbar_wait(opnd_ready(kb), (ready_par >> kb) & 1u, 3);
             ready_par ^= 1u << kb;
           }
-          mbar_wait(w_full(stage), ph, 4);
+          if (!ok_w) mbar_wait(b_w, ph, 4);
           tc_fence_after();
-          const uint32_t sa = abuf + kb * kChunkBytes;
-          const uint32_t sb = wring + stage * kWStageBytes;
+          const uint32_t b_lo = desc_lo(wring + stage * kWStageBytes);
           const int ks = min(4, nk16 - 4 * kb);
           __syncwarp();
           if (elect_one()) {
-            for (int k = 0; k < ks; ++k)
-              umma_f16(d_tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sb + k * 32, 16, 1024), idesc,
-                       (kb > 0 || k > 0) ? 1u : 0u);
+            if (ks == 4) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16(d_tmem, mk(a_lo + 2 * k), mk(b_lo + 2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            } else {
+              for (int k = 0; k < ks; ++k) umma_f16(d_tmem, mk(a_lo + 2 * k), mk(b_lo + 2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
             umma_commit(w_empty(stage));
             if (kb == nkb - 1) umma_commit(acc_full(region));
           }

@@ -200,6 +200,64 @@ __global__ void __launch_bounds__(64, 1) prim_probe(long long* out) {
   __syncthreads();
   if (threadIdx.x < 32) tmem_dealloc(slot_s, 32);
 }
+// Latency of the epilogue's per-chunk steps for one warp on an otherwise idle SM (dependent chain, clock64 between).
+__global__ void __launch_bounds__(128, 1) epi_probe(long long* out) {
+  __shared__ __align__(1024) uint8_t buf[16384];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t slot_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bars[0]), 1 << 19); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(smem_u32(&slot_s), 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot_s;
+  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t sb = smem_u32(buf);
+  long long acc[6] = {0, 0, 0, 0, 0, 0};
+  uint32_t sink = 0;
+  for (int it = 0; it < 200; ++it) {
+    uint32_t r[32];
+    long long t0 = clock64();
+    tmem_ld32(t_lane + 32 * (it & 7), r);
+    tmem_ld_wait();
+    long long t1 = clock64();
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float a = __uint_as_float(r[2 * i]) + 1.0f, b = __uint_as_float(r[2 * i + 1]) + 2.0f;
+      asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(b), "f"(a));
+    }
+    long long t2 = clock64();
+    const uint32_t rowaddr = sb + (lane + 32 * (warp & 1)) * 128;
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4)
+      st_shared_v4(rowaddr + (((warp >> 1) * 4 + i4) ^ (lane & 7)) * 16, pk[4 * i4], pk[4 * i4 + 1], pk[4 * i4 + 2], pk[4 * i4 + 3]);
+    long long t3 = clock64();
+    fence_proxy_async();
+    long long t4 = clock64();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&bars[0]));
+    long long t5 = clock64();
+    tc_fence_before();
+    long long t6 = clock64();
+    acc[0] += t1 - t0; acc[1] += t2 - t1; acc[2] += t3 - t2; acc[3] += t4 - t3; acc[4] += t5 - t4; acc[5] += t6 - t5;
+    sink ^= pk[3];
+  }
+  if (threadIdx.x == 0) { for (int i = 0; i < 6; ++i) out[i] = acc[i]; out[7] = sink; }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+static void run_epi(long long* d_out) {
+  epi_probe<<<1, 128>>>(d_out);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("epi: %s\n", cudaGetErrorString(e)); return; }
+  long long h[8];
+  cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
+  const char* names[6] = {"tcgen05.ld x32 + wait::ld", "bias add + relu + bf16 pack (32 values)", "4 x st.shared.v4", "fence.proxy.async",
+                          "syncwarp + mbarrier.arrive", "tcgen05.fence::before_thread_sync"};
+  for (int i = 0; i < 6; ++i) printf("epilogue step %-42s %.1f cycles\n", names[i], h[i] / 200.0);
+}
 static void run_prims(long long* d_out) {
   prim_probe<<<1, 64>>>(d_out);
   cudaError_t e = cudaDeviceSynchronize();
@@ -210,14 +268,15 @@ static void run_prims(long long* d_out) {
                           "tcgen05.fence::after_thread_sync", "fence.proxy.async", "try_wait + arrive", "tcgen05.fence::before_thread_sync", "try_wait + dependent branch"};
   for (int i = 0; i < 9; ++i) printf("prim %-36s %.1f cycles each\n", names[i], h[i] / 1000.0);
 }
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
 // Same ring, but the whole issuer warp runs the loop converged and one elected lane issues (the CUTLASS way): the
 // operands stay in uniform registers and the per-instruction R2UR / ELECT waterfall of a lane-0 branch disappears.
-__global__ void __launch_bounds__(128, 1) ring_probe_w(int stages, int mmas, int nkb, long long* out) {
+// flags: 1 = the producer streams 32 KB per K-block from global memory (bulk copy, L2 resident), 2 = eight more warps
+// spin on a pending mbarrier, 4 = eight warps read TMEM (tcgen05.ld x32) in a loop, 8 = eight warps write shared
+// memory + fence.proxy.async in a loop, 16 = a second (already complete) barrier wait + tcgen05 fence per K-block
+// VAR strips pieces of the issuing loop at compile time (bisecting what makes the K-block slower than 4 x 128 cycles):
+// bit 0: no layered wait block, bit 1: D address fixed, bit 2: accumulate flag fixed, bit 3: no per-Linear commit
+template <int VAR>
+__global__ void __launch_bounds__(320, 1) ring_probe_w(int stages, int mmas, int flags, const uint8_t* wsrc, int nkb, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -226,11 +285,15 @@ __global__ void __launch_bounds__(128, 1) ring_probe_w(int stages, int mmas, int
   for (uint32_t i = threadIdx.x; i < (65536 + 3 * 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sgen)[i] = 0x3C003C00u;
   auto full = [&](int s) { return bar + 8u * s; };
   auto empty = [&](int s) { return bar + 8u * (8 + s); };
-  const uint32_t done = bar + 8u * 16;
+  const uint32_t done = bar + 8u * 16, never = bar + 8u * 17, always = bar + 8u * 18;
+  auto acc_full = [&](int r) { return bar + 8u * (19 + r); };
+  auto acc_empty = [&](int r) { return bar + 8u * (21 + r); };
   if (threadIdx.x == 0) {
     for (int s = 0; s < 8; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    mbar_init(done, 1);
+    mbar_init(done, 1); mbar_init(never, 1); mbar_init(always, 1);
+    for (int r = 0; r < 2; ++r) { mbar_init(acc_full(r), 1); mbar_init(acc_empty(r), 8); }
     fence_barrier_init();
+    mbar_arrive(always);
   }
   if (warp == 0) { tmem_alloc(slot, 512); tmem_relinquish(); }
   fence_proxy_async();
@@ -239,25 +302,48 @@ __global__ void __launch_bounds__(128, 1) ring_probe_w(int stages, int mmas, int
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + (slot - sbase));
   if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0; uint32_t ph = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(empty(stage), ph ^ 1u, 1);
-        mbar_arrive(full(stage));
-        if (++stage == stages) { stage = 0; ph ^= 1u; }
+    int stage = 0; uint32_t ph = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(empty(stage), ph ^ 1u, 1);
+      __syncwarp();
+      if (elect_one()) {
+        if (flags & 1) {
+          mbar_arrive_expect_tx(full(stage), 32768u);
+          const uint8_t* src = wsrc + (size_t)((kb * 7 + blockIdx.x) % 20) * 32768;
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(bbuf + (stage % 3) * 32768), "l"(src), "r"(32768u), "r"(full(stage)) : "memory");
+        } else {
+          mbar_arrive(full(stage));
+        }
       }
+      __syncwarp();
+      if (++stage == stages) { stage = 0; ph ^= 1u; }
     }
   } else if (warp == 0) {
     const uint32_t idesc = instr_desc(128, 256, 0, 0);
     int stage = 0; uint32_t ph = 0;
     const long long t0 = clock64();
+    uint32_t uc[2] = {0, 0};
     for (int kb = 0; kb < nkb; ++kb) {
+      const int layer = kb >> 2, region = (flags & 64) ? 0 : (layer & 1);
+      if (!(VAR & 1) && (flags & 32) && (kb & 3) == 0) {
+        // layered mode: four K-blocks make one Linear whose accumulator region must have been drained
+        mbar_wait(acc_empty(region), (uc[region] & 1u) ^ 1u, 5);
+        ++uc[region];
+        tc_fence_after();
+      }
+      if (flags & 16) { mbar_wait(always, 0, 4); }
       mbar_wait(full(stage), ph, 2);
+      if (flags & 16) tc_fence_after();
       const uint32_t sa = abuf + (kb & 3) * 16384, sb = bbuf + (stage % 3) * 32768;
+      const uint32_t d = (!(VAR & 2) && (flags & 32)) ? tmem + 256u * region : tmem;
+      __syncwarp();
       if (elect_one()) {
         for (int k = 0; k < mmas; ++k)
-          umma_f16(tmem, smem_desc(sa + k * 32, 16, 1024), smem_desc(sb + k * 32, 16, 1024), idesc, 1u);
+          umma_f16(d, smem_desc(sa + k * 32, 16, 1024), smem_desc(sb + k * 32, 16, 1024), idesc,
+                   (!(VAR & 4) && (flags & 32) && (kb & 3) == 0 && k == 0 && !(flags & 128)) ? 0u : 1u);
         umma_commit(empty(stage));
+        if (!(VAR & 8) && (flags & 32) && (kb & 3) == 3) umma_commit(acc_full(region));
       }
       __syncwarp();
       if (++stage == stages) { stage = 0; ph ^= 1u; }
@@ -266,17 +352,59 @@ __global__ void __launch_bounds__(128, 1) ring_probe_w(int stages, int mmas, int
     __syncwarp();
     mbar_wait(done, 0, 3);
     if (lane == 0) out[blockIdx.x] = clock64() - t0;
+  } else {
+    const int q = warp & 3;
+    uint32_t sink = 0;
+    if (flags & 32) {
+      // the drain side of layered mode: wait for the Linear's accumulator, read it, hand the region back
+      uint32_t fp[2] = {0, 0};
+      for (int layer = 0; layer < nkb / 4; ++layer) {
+        const int region = (flags & 64) ? 0 : (layer & 1);
+        mbar_wait(acc_full(region), fp[region] & 1u, 6);
+        fp[region] ^= 1u;
+        tc_fence_after();
+        for (int j = 0; j < 4; ++j) {
+          uint32_t r[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 256u * region + 32 * ((warp - 2) >> 2) + 64 * j, r);
+          tmem_ld_wait();
+          for (int i = 0; i < 32; ++i) sink ^= r[i];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(region));
+      }
+    } else if (flags & 2) {
+      while (!mbar_try_wait(done, 0)) { sink += mbar_try_wait(never, 0); }
+    } else if (flags & 4) {
+      while (!mbar_try_wait(done, 0)) {
+        uint32_t r[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 256 + 32 * (warp & 7), r);
+        tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) sink ^= r[i];
+      }
+    } else if (flags & 8) {
+      const uint32_t dst = sbase + 65536 + 3 * 32768 + (uint32_t)(warp - 2) * 4096 + lane * 16;
+      uint32_t it = 0;
+      while (!mbar_try_wait(done, 0)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) st_shared_v4(dst + j * 512, it, it, it, it);
+        fence_proxy_async();
+        ++it;
+      }
+    }
+    if (sink == 0x12345u) out[200] = sink;
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
-static void run_ring_w(int stages, int mmas, long long* d_out, int sms) {
+template <int VAR>
+static void run_ring_w(int stages, int mmas, int flags, const uint8_t* wsrc, long long* d_out, int sms) {
   const int nkb = 2000;
   const size_t smem = 65536 + 4 * 32768 + 1024 + 512;
-  cudaFuncSetAttribute(ring_probe_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(ring_probe_w<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   for (int rep = 0; rep < 2; ++rep) {
-    ring_probe_w<<<sms, 128, smem>>>(stages, mmas, nkb, d_out);
+    ring_probe_w<VAR><<<sms, 320, smem>>>(stages, mmas, flags, wsrc, nkb, d_out);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("ring_w: %s\n", cudaGetErrorString(e)); return; }
   }
@@ -284,7 +412,8 @@ static void run_ring_w(int stages, int mmas, long long* d_out, int sms) {
   cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
   double tot = 0;
   for (int b = 0; b < sms; ++b) tot += h[b];
-  printf("ring (converged warp, elected lane) stages=%d mmas/kb=%d: %.1f cycles per K-block\n", stages, mmas, tot / sms / nkb);
+  printf("ring (converged warp, elected lane) var=%2d stages=%d mmas/kb=%d flags=%2d: %.1f cycles per K-block\n", VAR, stages, mmas, flags,
+         tot / sms / nkb);
 }
 static void run_ring(int stages, int free_mode, int mmas, int peek, long long* d_out, int sms) {
   const int nkb = 2000;
@@ -338,7 +467,12 @@ int main() {
   long long* d_out;
   cudaMalloc(&d_out, sizeof(long long) * 2 * 160);
   run_prims(d_out);
-  for (int mm : {0, 1, 2, 4, 8}) run_ring_w(3, mm, d_out, sms);
+  run_epi(d_out);
+  uint8_t* wsrc;
+  cudaMalloc(&wsrc, 20 * 32768);
+  cudaMemset(wsrc, 0x3C, 20 * 32768);
+  run_ring_w<15>(3, 4, 0, wsrc, d_out, sms);
+  run_ring_w<0>(3, 4, 32, wsrc, d_out, sms);
   for (int st : {3})
     for (int mm : {0, 2, 4, 8})
       for (int pk : {0, 1}) run_ring(st, 0, mm, pk, d_out, sms);
