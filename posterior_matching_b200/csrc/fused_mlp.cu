@@ -55,7 +55,7 @@ struct FwdArgs {
   int head_tma;                   // 1: head rows staged in the (idle) operand buffer and stored by TMA
   int64_t Bpad; uint32_t* masks;
   long long* trace;   // PMVAE_FUSED_TRACE: per-phase clock64 stamps of block 0 (profiling only)
-  int debug;   // PMVAE_FUSED_DEBUG bits (profiling only): 1 no epilogue math/stores, 2 no weight loads, 4 no MMAs
+  int debug;   // PMVAE_FUSED_DEBUG bits (profiling only): 2 no weight loads, 4 no MMAs, 8 coarse trace stamps
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -319,18 +319,27 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       else if (p.in_lo && kk < 2 * D) { src = kk - D; kind = 1; }
       else if (p.msk && kk < 3 * D) { src = kk - 2 * D; kind = 2; }
       const bool has_m = p.msk != nullptr;
-      const int64_t g0 = (int64_t)tile_n * 128 + q * 32;
+      // branch-free per row (eight independent rows in flight): value = a * b with a = x or the mask itself,
+      // b = mask or 1; the lo columns subtract the bf16 rounding; rows past B and unused columns give 0
+      const int ia = (kind == 2) ? D + src : src;
+      const int ib = (has_m && kind < 2) ? D + src : -1;
+      const bool live = kind != 3;
+      const bool is_lo = kind == 1;
+      const int64_t left = p.B - ((int64_t)tile_n * 128 + q * 32);
+      const int nvalid = left < 0 ? 0 : (left > 32 ? 32 : (int)left);
+      const float* sbase_row = inbuf_gen + (q * 32) * kInPitch;
+      const uint32_t col_off = ((kk & 7) << 1);
+      const int kslot = kk >> 3;
 #pragma unroll 8
       for (int rr = 0; rr < 32; ++rr) {
-        const float* srow = inbuf_gen + (q * 32 + rr) * kInPitch;
-        float v = 0.f;
-        if (kind != 3 && g0 + rr < p.B) {
-          const float m = has_m ? srow[D + src] : 1.f;
-          v = (kind == 2) ? m : srow[src] * m;
-          if (kind == 1) v -= bf16_round(v);
-        }
+        const float* srow = sbase_row + rr * kInPitch;
+        const float a = srow[ia];
+        const float b = ib >= 0 ? srow[ib] : 1.f;
+        float v = (live && rr < nvalid) ? a * b : 0.f;
+        const float lo = v - bf16_round(v);
+        v = is_lo ? lo : v;
         const int r = q * 32 + rr;
-        const uint32_t addr = l0buf + r * 128 + (((kk >> 3) ^ (r & 7)) << 4) + ((kk & 7) << 1);
+        const uint32_t addr = l0buf + r * 128 + ((kslot ^ (r & 7)) << 4) + col_off;
         st_shared_u16(addr, __bfloat16_as_ushort(__float2bfloat16(v)));
       }
       fence_proxy_async();
@@ -423,7 +432,9 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       };
       for (int l = 0; l < n_hidden; ++l) {
         const int region = region_of(l);
-        if (l == n_hidden - 1 && has_next) prefetch_input(tile_next);     // lands while this Linear is drained
+        // the next tile's input rows: requested a whole tile ahead when the staging area is free (one head tile),
+        // else while the last hidden Linear is drained (several head tiles reuse the area as head staging)
+        if (l == (p.head_tiles == 1 ? 0 : n_hidden - 1) && has_next) prefetch_input(tile_next);
         if (LN) { epi_ln(l); continue; }
         if (l == 0 && p.head_tma) {
           // the previous tile's head rows were staged in the operand buffer: their TMA stores must have been read out
@@ -445,11 +456,6 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           uint32_t (&r)[32] = (j & 1) ? rb : ra;
           tmem_ld_wait();
           if (j < 3) tmem_ld32(t_acc + 64 * (j + 1), (j & 1) ? ra : rb);
-          if (p.debug & 1) {
-            __syncwarp();
-            if (lane == 0) arrive_leader(opnd_ready(j));
-            continue;
-          }
           const float4* bp = reinterpret_cast<const float4*>(bias_tbl + l * 256 + 64 * j + 32 * half);
           uint32_t pk[16];
           uint32_t neg = 0;          // sign bits of the pre-activations, element 0 ends up in bit 31
@@ -533,24 +539,35 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
                 __syncwarp();
               }
             }
+            if (p.head_tiles == 1) {
+              // all eight bias vectors first (independent broadcast loads), then packed adds and the staging stores
+              const float4* bp = reinterpret_cast<const float4*>(bias_tbl + n_hidden * 256 + nb);
+              float4 bv[8];
 #pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4) {
-              float v[4];
+              for (int i4 = 0; i4 < 8; ++i4) bv[i4] = bp[i4];
 #pragma unroll
-              if (p.head_tiles == 1) {
-                const float4 bv = *reinterpret_cast<const float4*>(bias_tbl + n_hidden * 256 + nb + 4 * i4);
-                v[0] = __uint_as_float(r[4 * i4]) + bv.x; v[1] = __uint_as_float(r[4 * i4 + 1]) + bv.y;
-                v[2] = __uint_as_float(r[4 * i4 + 2]) + bv.z; v[3] = __uint_as_float(r[4 * i4 + 3]) + bv.w;
-              } else {
+              for (int i4 = 0; i4 < 8; ++i4) {
+                float v0 = __uint_as_float(r[4 * i4]), v1 = __uint_as_float(r[4 * i4 + 1]);
+                float v2 = __uint_as_float(r[4 * i4 + 2]), v3 = __uint_as_float(r[4 * i4 + 3]);
+                add2(v0, v1, bv[i4].x, bv[i4].y);
+                add2(v2, v3, bv[i4].z, bv[i4].w);
+                const int slot = i4 ^ (lane & 7);
+                st_shared_v4(st + lane * 128 + slot * 16, __float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2),
+                             __float_as_uint(v3));
+              }
+            } else {
+#pragma unroll
+              for (int i4 = 0; i4 < 8; ++i4) {
+                float v[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const int n = nb + 4 * i4 + i;
                   v[i] = __uint_as_float(r[4 * i4 + i]) + (n < p.head_N ? __ldg(p.head_bias + n) : 0.f);
                 }
+                const int slot = i4 ^ (lane & 7);
+                st_shared_v4(st + lane * 128 + slot * 16, __float_as_uint(v[0]), __float_as_uint(v[1]),
+                             __float_as_uint(v[2]), __float_as_uint(v[3]));
               }
-              const int slot = i4 ^ (lane & 7);
-              st_shared_v4(st + lane * 128 + slot * 16, __float_as_uint(v[0]), __float_as_uint(v[1]),
-                           __float_as_uint(v[2]), __float_as_uint(v[3]));
             }
             fence_proxy_async();
             __syncwarp();
