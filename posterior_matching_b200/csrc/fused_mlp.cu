@@ -330,17 +330,27 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       const float* sbase_row = inbuf_gen + (q * 32) * kInPitch;
       const uint32_t col_off = ((kk & 7) << 1);
       const int kslot = kk >> 3;
-#pragma unroll 8
-      for (int rr = 0; rr < 32; ++rr) {
-        const float* srow = sbase_row + rr * kInPitch;
-        const float a = srow[ia];
-        const float b = ib >= 0 ? srow[ib] : 1.f;
-        float v = (live && rr < nvalid) ? a * b : 0.f;
-        const float lo = v - bf16_round(v);
-        v = is_lo ? lo : v;
-        const int r = q * 32 + rr;
-        const uint32_t addr = l0buf + r * 128 + ((kslot ^ (r & 7)) << 4) + col_off;
-        st_shared_u16(addr, __bfloat16_as_ushort(__float2bfloat16(v)));
+      // eight rows per batch: all loads first (the volatile stores below would otherwise pin each row's loads behind
+      // the previous row's store and expose the shared-memory latency 32 times)
+#pragma unroll 1
+      for (int r0 = 0; r0 < 32; r0 += 8) {
+        float a[8], b[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float* srow = sbase_row + (r0 + u) * kInPitch;
+          a[u] = srow[ia];
+          b[u] = ib >= 0 ? srow[ib] : 1.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int rr = r0 + u;
+          float v = (live && rr < nvalid) ? a[u] * b[u] : 0.f;
+          const float lo = v - bf16_round(v);
+          v = is_lo ? lo : v;
+          const int r = q * 32 + rr;
+          const uint32_t addr = l0buf + r * 128 + ((kslot ^ (r & 7)) << 4) + col_off;
+          st_shared_u16(addr, __bfloat16_as_ushort(__float2bfloat16(v)));
+        }
       }
       fence_proxy_async();
       __syncwarp();
