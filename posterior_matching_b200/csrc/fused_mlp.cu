@@ -605,6 +605,10 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     if (lane == 0) tma_store_wait_all();
   } else if (SAVE) {
     // ===================== helper warp (training mode): streams every finished operand chunk to HBM =====================
+    // Two stores are kept in flight: chunk j is handed back once the store of chunk j+1 has been issued and the one
+    // before it has been read out (waiting for each store's read before issuing the next made this warp the
+    // bottleneck of the training-mode forward); everything is flushed at the end of each Linear, long before the
+    // next Linear's epilogue (or the head staging) needs the chunk.
     uint32_t cnt = 0;
     for (int it = it_first; it < it_count; it += it_stride) {
       const int tile = CTA2 ? 2 * it + (int)rank : it;
@@ -614,11 +618,18 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           if (lane == 0) {
             tma_store_2d(&map_s, opnd + j * kChunkBytes, 64 * j, (int)((int64_t)l * p.Bpad + (int64_t)tile * 128));
             tma_store_commit();
-            tma_store_wait_read<0>();
-            mbar_arrive(chunk_free(j));
+            if (j > 0) {
+              tma_store_wait_read<1>();
+              mbar_arrive(chunk_free(j - 1));
+            }
           }
           __syncwarp();
         }
+        if (lane == 0) {
+          tma_store_wait_read<0>();
+          mbar_arrive(chunk_free(3));
+        }
+        __syncwarp();
       }
     }
     if (lane == 0) tma_store_wait_all();
