@@ -258,14 +258,14 @@ int pmvae_argmm_backward(const pmvae_argmm_config* cfg, const float* params, con
  *   hk.Conv2D(k, s, SAME|VALID), weights [kh,kw,in,out]:          stride = s, dil = 1, w_ci = Cout, w_co = 1
  *   hk.Conv2DTranspose(k, s, SAME|VALID), weights [kh,kw,out,in]: stride = 1, dil = s, w_ci = 1, w_co = Cin
  * (padding per lax.padtype_to_pads / lax.conv_transpose; posterior_matching_b200/conv.py builds the descriptors).
- * Float32 first cut: this row is not on the tensor cores yet. */
+ * Float32 (exact-parity) or bf16-operand tensor-core GEMMs, selected per descriptor (`reserved` = precision). */
 typedef struct pmvae_conv_desc {
   int32_t H, W, Cin;          /* input  [B, H, W, Cin]    */
   int32_t OH, OW, Cout;       /* output [B, OH, OW, Cout] */
   int32_t KH, KW, stride, dil, pad_top, pad_left;
   int32_t w_ci, w_co;         /* element strides of ci / co inside one tap of w */
   float slope;                /* leaky_relu negative slope */
-  int32_t reserved;
+  int32_t reserved;           /* precision: 0 = float32 GEMMs, 1 = bf16 operands on the tcgen05 GEMMs (fp32 accumulate) */
 } pmvae_conv_desc;
 /* With a workspace (pmvae_conv2d_workspace_bytes, 256-byte aligned) the operator runs as im2col + float32 GEMM;
  * with ws = NULL as direct one-thread-per-element kernels (slow; kept as an independent cross-check). */

@@ -43,8 +43,13 @@ def conv_transpose_pads(size: int, k: int, s: int, padding: str) -> Tuple[int, i
 
 
 def conv_desc(H: int, W: int, Cin: int, Cout: int, k: int, s: int, padding: str, *, transpose: bool = False,
-              slope: float = 0.01) -> _lib.ConvDesc:
+              slope: float = 0.01, precision: str = "fp32") -> _lib.ConvDesc:
+    """`precision="bf16"`: bf16 GEMM operands on the tcgen05 GEMMs with fp32 accumulation (layers whose channel counts
+    do not give 16-byte operand pitches, e.g. the decoder's 1-channel output layer, stay on the float32 GEMM)."""
+    if precision not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
     d = _lib.ConvDesc()
+    d.reserved = 1 if precision == "bf16" else 0
     pads = conv_transpose_pads if transpose else conv_pads
     OH, pt, _ = pads(H, k, s, padding)
     OW, pl, _ = pads(W, k, s, padding)

@@ -32,7 +32,7 @@ def _f32c(t, device):
 class _ConvStack:
     """ConvEncoder (transpose=False) or ConvDecoder (transpose=True): descriptors + parameter views."""
 
-    def __init__(self, prefix: str, layers, H: int, cin: int, transpose: bool):
+    def __init__(self, prefix: str, layers, H: int, cin: int, transpose: bool, precision: str = "fp32"):
         self.prefix, self.transpose = prefix, transpose
         self.descs, self.names = [], []
         base = "conv2_d_transpose" if transpose else "conv2_d"
@@ -41,7 +41,7 @@ class _ConvStack:
                 pad = "VALID" if i == 0 else "SAME"
             else:
                 pad = "VALID" if i == len(layers) - 1 else "SAME"
-            d = conv_desc(H, H, cin, f, k, s, pad, transpose=transpose)
+            d = conv_desc(H, H, cin, f, k, s, pad, transpose=transpose, precision=precision)
             self.descs.append(d)
             self.names.append(f"{prefix}/{base}" if i == 0 else f"{prefix}/{base}_{i}")
             H, cin = d.OH, f
@@ -70,7 +70,7 @@ class _ConvStack:
 
 class ConvPosteriorMatchingVAE:
     def __init__(self, config: Mapping[str, Any], name: Optional[str] = None, *, device=None, image_size: int = 28,
-                 channels: int = 1):
+                 channels: int = 1, precision: str = "fp32"):
         if not torch.cuda.is_available():
             raise RuntimeError("ConvPosteriorMatchingVAE needs a CUDA device: the hot path has no CPU fallback")
         if (config["encoder_net"], config["decoder_net"], config["posterior_dist"], config["decoder_dist"],
@@ -84,9 +84,10 @@ class ConvPosteriorMatchingVAE:
         enc_layers = [tuple(l) for l in config["encoder_net_config"]["conv_layers"]]
         dec_layers = [tuple(l) for l in config["decoder_net_config"]["conv_layers"]]
         part_layers = [tuple(l) for l in config.get("partial_encoder_net_config", config["encoder_net_config"])["conv_layers"]]
-        self.enc = _ConvStack("encoder_net", enc_layers, image_size, channels, False)
-        self.dec = _ConvStack("decoder_net", dec_layers, 1, d, True)
-        self.part = _ConvStack("partial_encoder_net", part_layers, image_size, 2 * channels, False)
+        self.precision = precision       # convolution GEMMs: "fp32" (exact-parity path) or "bf16" (tcgen05, fp32 accumulate)
+        self.enc = _ConvStack("encoder_net", enc_layers, image_size, channels, False, precision)
+        self.dec = _ConvStack("decoder_net", dec_layers, 1, d, True, precision)
+        self.part = _ConvStack("partial_encoder_net", part_layers, image_size, 2 * channels, False, precision)
         if self.dec.out_hw != image_size or self.dec.out_c != channels:
             raise ValueError("decoder does not reproduce the image shape")
         self.P = d + d * (d + 1) // 2

@@ -10,6 +10,7 @@
 // hk.Conv2DTranspose (weights HWOI):   stride = 1, dil = s, w_ci = 1,    w_co = Cin   (lax.conv_transpose, kernel not flipped)
 // Correctness-first direct kernels (row N1 of SURVEY §8f): one thread per output / input / weight element.
 #include "kernels.h"
+#include "tc_gemm.h"
 
 namespace pmvae {
 
@@ -218,6 +219,221 @@ static int split_rows(int64_t out_rows, int64_t out_cols, int64_t K) {
   return (int)sp;
 }
 
+// ---------------------------------------------------------------- bf16 tensor-core path (desc.precision = 1)
+// The same im2col formulation with bf16 GEMM operands and fp32 accumulation on the tcgen05 GEMMs of tc_gemm.cu:
+//   forward   y    = leaky(col @ Wm + b)          gemm_nt(col [rows, Kc], Wm^T [Cout, Kc])
+//   weights   dWm += col^T @ dpre                  gemm_tn(col, dpre)                (fp32 atomics)
+//   data      dcol = dpre @ Wm^T                   gemm_nt(dpre [rows, Cout], Wm [Kc, Cout]) -> bf16, then col2im
+// Row pitches are padded to 8 elements (TMA needs 16-byte pitches; the tensor maps' extents stay exact).
+typedef __nv_bfloat16 bf16c;
+__device__ __forceinline__ float conv_tap_value(const float* __restrict__ X, const pmvae_conv_desc& d, int64_t b, int oy, int ox,
+                                                int k) {
+  const int ci = k % d.Cin, tap = k / d.Cin;
+  const int ky = tap / d.KW, kx = tap - ky * d.KW;
+  const int v = oy * d.stride + ky - d.pad_top, u = ox * d.stride + kx - d.pad_left;
+  if (v < 0 || u < 0) return 0.f;
+  int iy = v, ix = u;
+  if (d.dil != 1) {
+    if (v % d.dil != 0 || u % d.dil != 0) return 0.f;
+    iy = v / d.dil; ix = u / d.dil;
+  }
+  if (iy >= d.H || ix >= d.W) return 0.f;
+  return X[((b * d.H + iy) * d.W + ix) * d.Cin + ci];
+}
+// source pixel of output position (oy, ox) under tap (ky, kx), or false when it falls into padding / a dilation hole
+__device__ __forceinline__ bool conv_src(const pmvae_conv_desc& d, int oy, int ox, int ky, int kx, int& iy, int& ix) {
+  const int v = oy * d.stride + ky - d.pad_top, u = ox * d.stride + kx - d.pad_left;
+  if (v < 0 || u < 0) return false;
+  iy = v; ix = u;
+  if (d.dil != 1) {
+    if (v % d.dil != 0 || u % d.dil != 0) return false;
+    iy = v / d.dil; ix = u / d.dil;
+  }
+  return iy < d.H && ix < d.W;
+}
+// Cin % 8 == 0: one thread per (row, group of 8 channels), looping over the taps: for a tap the 8 channels are
+// contiguous in the image (NHWC) and in the column (k = tap * Cin + ci): two 16-byte loads, one 16-byte store, and
+// the only divisions are the per-thread row decomposition.
+__global__ void __launch_bounds__(256) im2col_bf16_c8_kernel(const float* __restrict__ X, bf16c* __restrict__ col, int64_t B,
+                                                             pmvae_conv_desc d, int Kp) {
+  const int cgs = d.Cin >> 3;
+  const int64_t n = B * d.OH * d.OW * cgs;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(t % cgs);
+    const int64_t r = t / cgs;
+    const int ox = (int)(r % d.OW);
+    const int64_t r2 = r / d.OW;
+    const int oy = (int)(r2 % d.OH);
+    const int64_t b = r2 / d.OH;
+    bf16c* dst = col + r * Kp + cg * 8;
+    for (int ky = 0; ky < d.KH; ++ky)
+      for (int kx = 0; kx < d.KW; ++kx) {
+        int iy, ix;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (conv_src(d, oy, ox, ky, kx, iy, ix)) {
+          const float4* src = reinterpret_cast<const float4*>(X + ((b * d.H + iy) * d.W + ix) * d.Cin + cg * 8);
+          const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(v0.x, v0.y), h1 = __floats2bfloat162_rn(v0.z, v0.w);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v1.x, v1.y), h3 = __floats2bfloat162_rn(v1.z, v1.w);
+          o = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2),
+                         *reinterpret_cast<uint32_t*>(&h3));
+        }
+        *reinterpret_cast<uint4*>(dst + (ky * d.KW + kx) * d.Cin) = o;
+      }
+  }
+}
+// any Cin: one thread per (row, group of 8 k): a 16-byte store; columns [Kc, Kp) are zero
+__global__ void __launch_bounds__(256) im2col_bf16_kernel(const float* __restrict__ X, bf16c* __restrict__ col, int64_t B,
+                                                          pmvae_conv_desc d, int Kc, int Kp) {
+  const int groups = Kp >> 3;
+  const int64_t n = B * d.OH * d.OW * groups;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int gk = (int)(t % groups);
+    int64_t r = t / groups;
+    const int ox = (int)(r % d.OW);
+    const int64_t r2 = r / d.OW;
+    const int oy = (int)(r2 % d.OH);
+    const int64_t b = r2 / d.OH;
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k0 = gk * 8 + 2 * i;
+      const float v0 = k0 < Kc ? conv_tap_value(X, d, b, oy, ox, k0) : 0.f;
+      const float v1 = k0 + 1 < Kc ? conv_tap_value(X, d, b, oy, ox, k0 + 1) : 0.f;
+      __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+      pk[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(col + r * Kp + gk * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+static int im2col_bf16(const float* x, bf16c* col, int64_t B, const pmvae_conv_desc& d, int Kc, int Kp, cudaStream_t s) {
+  const int64_t rows = B * d.OH * d.OW;
+  if (d.Cin % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0)
+    im2col_bf16_c8_kernel<<<grid1d_c(rows * (d.Cin >> 3), 256), 256, 0, s>>>(x, col, B, d, Kp);
+  else
+    im2col_bf16_kernel<<<grid1d_c(rows * (Kp >> 3), 256), 256, 0, s>>>(x, col, B, d, Kc, Kp);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+// dX[b, iy, ix, ci..ci+V) = sum over the taps that reach the pixel of dcol[(b, oy, ox), tap * Cin + ci..]; V = 8 when
+// Cin % 8 == 0 (one 16-byte load per tap), else 1
+template <int V>
+__global__ void __launch_bounds__(256) col2im_bf16_kernel(const bf16c* __restrict__ dcol, float* __restrict__ dX, int64_t B,
+                                                          pmvae_conv_desc d, int Kp) {
+  const int cgs = d.Cin / V;
+  const int64_t n = B * d.H * d.W * cgs;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(t % cgs);
+    int64_t r = t / cgs;
+    const int ix = (int)(r % d.W); r /= d.W;
+    const int iy = (int)(r % d.H);
+    const int64_t b = r / d.H;
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    for (int ky = 0; ky < d.KH; ++ky) {
+      const int vy = iy * d.dil + d.pad_top - ky;
+      if (vy < 0 || vy % d.stride != 0) continue;
+      const int oy = vy / d.stride;
+      if (oy >= d.OH) continue;
+      for (int kx = 0; kx < d.KW; ++kx) {
+        const int vx = ix * d.dil + d.pad_left - kx;
+        if (vx < 0 || vx % d.stride != 0) continue;
+        const int ox = vx / d.stride;
+        if (ox >= d.OW) continue;
+        const bf16c* src = dcol + ((b * d.OH + oy) * d.OW + ox) * (int64_t)Kp + (ky * d.KW + kx) * d.Cin + cg * V;
+        if (V == 8) {
+          const uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
+          const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[2 * i] += __uint_as_float(w4[i] << 16);
+            acc[2 * i + 1] += __uint_as_float(w4[i] & 0xFFFF0000u);
+          }
+        } else {
+          acc[0] += __bfloat162float(src[0]);
+        }
+      }
+    }
+    float* dst = dX + (((b * d.H + iy) * d.W + ix) * d.Cin + cg * V);
+#pragma unroll
+    for (int i = 0; i < V; ++i) dst[i] = acc[i];
+  }
+}
+// bf16 weight images with the output channels padded to Cp: nk[co][k] (pitch Kp) for the forward, kn[k][co] (pitch Cp)
+// for the data gradient; padded rows / columns are zero
+__global__ void __launch_bounds__(256) wpack_bf16_kernel(const float* __restrict__ w, bf16c* __restrict__ nk, bf16c* __restrict__ kn,
+                                                         pmvae_conv_desc d, int Kc, int Kp, int Cp) {
+  const int64_t n = (int64_t)Kp * Cp;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(t % Cp);
+    const int k = (int)(t / Cp);
+    float v = 0.f;
+    if (k < Kc && co < d.Cout) {
+      const int ci = k % d.Cin, tap = k / d.Cin;
+      v = w[(int64_t)tap * d.Cin * d.Cout + (int64_t)ci * d.w_ci + (int64_t)co * d.w_co];
+    }
+    const bf16c h = __float2bfloat16(v);
+    nk[(int64_t)co * Kp + k] = h;
+    if (k < Kc) kn[(int64_t)k * Cp + co] = h;
+  }
+}
+// dpre = dy * act'(y) in place (float32, for the bias gradient) and as bf16 with the channel pitch padded to Cp
+__global__ void __launch_bounds__(256) conv_dpre_bf16_kernel(float* __restrict__ dY, const float* __restrict__ Y,
+                                                             bf16c* __restrict__ out, int64_t rows, int Cout, int Cp, float slope) {
+  const int64_t n = rows * Cp;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % Cp);
+    const int64_t r = t / Cp;
+    float g = 0.f;
+    if (c < Cout) {
+      const int64_t i = r * Cout + c;
+      g = dY[i] * (Y[i] > 0.f ? 1.f : slope);
+      dY[i] = g;
+    }
+    out[t] = __float2bfloat16(g);
+  }
+}
+// y[r, c] = act(tmp[r, c]) from the GEMM's padded output pitch
+__global__ void __launch_bounds__(256) leaky_gather_kernel(const float* __restrict__ tmp, float* __restrict__ y, int64_t rows,
+                                                           int Cout, int Cp, float slope) {
+  const int64_t n = rows * Cout;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const float v = tmp[(t / Cout) * Cp + (t % Cout)];
+    y[t] = v > 0.f ? v : slope * v;
+  }
+}
+// dw (either layout) += wm[(tap, ci), co] with column pitch Cp
+__global__ void __launch_bounds__(256) wmat_unpack_add_p_kernel(const float* __restrict__ wm, float* __restrict__ dw, pmvae_conv_desc d,
+                                                                int Cp) {
+  const int64_t n = (int64_t)d.KH * d.KW * d.Cin * d.Cout;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(t % d.Cout);
+    const int64_t r = t / d.Cout;
+    const int ci = (int)(r % d.Cin), tap = (int)(r / d.Cin);
+    dw[(int64_t)tap * d.Cin * d.Cout + (int64_t)ci * d.w_ci + (int64_t)co * d.w_co] += wm[r * Cp + co];
+  }
+}
+struct ConvWsB { bf16c *col, *dcol, *nk, *kn, *dpre; float *wm, *bias, *ytmp; uint64_t bytes; };
+static ConvWsB plan_conv_ws_b(const pmvae_conv_desc* d, int64_t B, void* ws) {
+  ConvWsB p{};
+  const uint64_t rows = (uint64_t)B * d->OH * d->OW, Kc = (uint64_t)d->KH * d->KW * d->Cin, Kp = (Kc + 7) & ~7ull;
+  const uint64_t Cp = ((uint64_t)d->Cout + 7) & ~7ull;
+  uint64_t off = 0;
+  auto take = [&](uint64_t bytes) { char* q = ws ? reinterpret_cast<char*>(ws) + off : nullptr; off += align_up(bytes, 256); return q; };
+  p.col = reinterpret_cast<bf16c*>(take(rows * Kp * 2));
+  p.dcol = reinterpret_cast<bf16c*>(take(rows * Kp * 2));
+  p.nk = reinterpret_cast<bf16c*>(take(Cp * Kp * 2));
+  p.kn = reinterpret_cast<bf16c*>(take(Kc * Cp * 2));
+  p.dpre = reinterpret_cast<bf16c*>(take(rows * Cp * 2));
+  p.wm = reinterpret_cast<float*>(take(Kc * Cp * 4));
+  p.bias = reinterpret_cast<float*>(take(Cp * 4));
+  p.ytmp = reinterpret_cast<float*>(take(Cp != (uint64_t)d->Cout ? rows * Cp * 4 : 0));
+  p.bytes = off;
+  return p;
+}
+static bool conv_bf16_ok(const pmvae_conv_desc* d) { return d->reserved == 1; }
+
 static int check_desc(const pmvae_conv_desc* d) {
   PMVAE_CHECK(d != nullptr, "null conv descriptor");
   PMVAE_CHECK(d->H > 0 && d->W > 0 && d->Cin > 0 && d->OH > 0 && d->OW > 0 && d->Cout > 0 && d->KH > 0 && d->KW > 0 &&
@@ -235,7 +451,8 @@ extern "C" {
 
 uint64_t pmvae_conv2d_workspace_bytes(const pmvae_conv_desc* desc, int64_t B) {
   if (check_desc(desc) != 0 || B < 0) return 0;
-  return plan_conv_ws(desc, B < 1 ? 1 : B, nullptr).bytes + 256;
+  const uint64_t f32 = plan_conv_ws(desc, B < 1 ? 1 : B, nullptr).bytes, b16 = plan_conv_ws_b(desc, B < 1 ? 1 : B, nullptr).bytes;
+  return (f32 > b16 ? f32 : b16) + 256;
 }
 
 int pmvae_conv2d_forward(const pmvae_conv_desc* desc, const float* x, const float* w, const float* bias, int64_t B,
@@ -243,6 +460,34 @@ int pmvae_conv2d_forward(const pmvae_conv_desc* desc, const float* x, const floa
   PMVAE_TRY(check_desc(desc));
   if (B == 0) return 0;
   PMVAE_CHECK(x && w && y && B > 0, "null pointer");
+  if (ws && conv_bf16_ok(desc)) {
+    ConvWsB p = plan_conv_ws_b(desc, B, ws);
+    PMVAE_CHECK(p.bytes <= ws_bytes && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, "conv workspace too small or misaligned");
+    cudaStream_t s = as_stream(stream);
+    const int64_t rows = B * desc->OH * desc->OW;
+    const int Kc = desc->KH * desc->KW * desc->Cin, Kp = (Kc + 7) & ~7, Cp = (desc->Cout + 7) & ~7;
+    PMVAE_TRY(im2col_bf16(x, p.col, B, *desc, Kc, Kp, s));
+    wpack_bf16_kernel<<<grid1d_c((int64_t)Kp * Cp, 256), 256, 0, s>>>(w, p.nk, p.kn, *desc, Kc, Kp, Cp);
+    PMVAE_LAUNCH_CHECK();
+    tc::TcGemmArgs e{};
+    if (bias) {
+      // parameter leaves are views into a flat arena (4-byte aligned): the epilogue reads the bias in 16-byte vectors
+      PMVAE_CUDA(cudaMemsetAsync(p.bias, 0, (size_t)Cp * sizeof(float), s));
+      PMVAE_CUDA(cudaMemcpyAsync(p.bias, bias, (size_t)desc->Cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      e.bias = p.bias;
+    }
+    const bool padded = Cp != desc->Cout;
+    e.out_f32 = padded ? p.ytmp : y; e.ld_out_f32 = Cp;
+    PMVAE_TRY(tc::gemm_nt(p.col, Kp, p.nk, Kp, rows, Cp, Kc, e, s));
+    if (padded) {
+      leaky_gather_kernel<<<grid1d_c(rows * desc->Cout, 256), 256, 0, s>>>(p.ytmp, y, rows, desc->Cout, Cp, desc->slope);
+      PMVAE_LAUNCH_CHECK();
+    } else if (desc->slope != 1.0f) {
+      leaky_kernel<<<grid1d_c(rows * desc->Cout, 256), 256, 0, s>>>(y, rows * desc->Cout, desc->slope);
+      PMVAE_LAUNCH_CHECK();
+    }
+    return 0;
+  }
   if (ws) {
     // im2col + fp32 GEMM: y = leaky(col @ Wm + bias)
     ConvWs p = plan_conv_ws(desc, B, ws);
@@ -282,6 +527,47 @@ int pmvae_conv2d_backward(const pmvae_conv_desc* desc, const float* x, const flo
   PMVAE_CHECK(x && w && y && dy && B > 0, "null pointer");
   cudaStream_t s = as_stream(stream);
   const int64_t ny = B * desc->OH * desc->OW * desc->Cout;
+  const int Kc_all = desc->KH * desc->KW * desc->Cin;
+  if (ws && conv_bf16_ok(desc) && (dx == nullptr || Kc_all % 8 == 0)) {
+    ConvWsB p = plan_conv_ws_b(desc, B, ws);
+    PMVAE_CHECK(p.bytes <= ws_bytes && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, "conv workspace too small or misaligned");
+    const int64_t rows = B * desc->OH * desc->OW;
+    const int Kc = Kc_all, Kp = (Kc + 7) & ~7, Cp = (desc->Cout + 7) & ~7;
+    // the weight-gradient GEMM accumulates with vector atomics: straight into dw only when it is laid out as the
+    // GEMM matrix and 16-byte aligned (leaves of a flat arena need not be)
+    const bool direct_w = desc->w_co == 1 && desc->w_ci == desc->Cout && Cp == desc->Cout &&
+                          (reinterpret_cast<uintptr_t>(dw) & 15u) == 0;
+    conv_dpre_bf16_kernel<<<grid1d_c(rows * Cp, 256), 256, 0, s>>>(dy, y, p.dpre, rows, desc->Cout, Cp, desc->slope);
+    PMVAE_LAUNCH_CHECK();
+    if (dw) {
+      PMVAE_TRY(im2col_bf16(x, p.col, B, *desc, Kc, Kp, s));
+      float* target = dw;
+      if (!direct_w) {
+        PMVAE_CUDA(cudaMemsetAsync(p.wm, 0, (size_t)Kc * Cp * sizeof(float), s));
+        target = p.wm;
+      }
+      PMVAE_TRY(tc::gemm_tn(p.col, Kp, p.dpre, Cp, Kc, Cp, rows, target, Cp, 1, 0, nullptr, s));
+      if (!direct_w) {
+        wmat_unpack_add_p_kernel<<<grid1d_c((int64_t)Kc * desc->Cout, 256), 256, 0, s>>>(p.wm, dw, *desc, Cp);
+        PMVAE_LAUNCH_CHECK();
+      }
+    }
+    if (dx) {
+      wpack_bf16_kernel<<<grid1d_c((int64_t)Kp * Cp, 256), 256, 0, s>>>(w, p.nk, p.kn, *desc, Kc, Kp, Cp);
+      PMVAE_LAUNCH_CHECK();
+      tc::TcGemmArgs e{};
+      e.out_bf16 = p.dcol; e.ld_out_bf16 = Kp;
+      PMVAE_TRY(tc::gemm_nt(p.dpre, Cp, p.kn, Cp, rows, Kc, Cp, e, s));
+      const int64_t npix = B * desc->H * desc->W;
+      if (desc->Cin % 8 == 0)
+        col2im_bf16_kernel<8><<<grid1d_c(npix * (desc->Cin >> 3), 256), 256, 0, s>>>(p.dcol, dx, B, *desc, Kp);
+      else
+        col2im_bf16_kernel<1><<<grid1d_c(npix * desc->Cin, 256), 256, 0, s>>>(p.dcol, dx, B, *desc, Kp);
+      PMVAE_LAUNCH_CHECK();
+    }
+    if (dbias) PMVAE_TRY(colsum_add(dy, desc->Cout, dbias, rows, desc->Cout, s));
+    return 0;
+  }
   conv_dpre_kernel<<<grid1d_c(ny, 256), 256, 0, s>>>(dy, y, dy, ny, desc->slope);
   PMVAE_LAUNCH_CHECK();
   if (ws) {

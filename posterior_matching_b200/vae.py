@@ -140,10 +140,11 @@ class PosteriorMatchingVAE:
         configs receive event_size = latent_dim."""
         if config["encoder_net"] == "ConvEncoder":
             # configs/pm_vae_mnist.py: convolutional networks, Bernoulli decoder, AutoregressiveGMM partial posterior --
-            # composed on the host from libpmvae operators (conv_vae.py; float32, first cut of SURVEY §8f N1)
+            # composed on the host from libpmvae operators (conv_vae.py; float32 unless precision="bf16": SURVEY §8f N1)
             from .conv_vae import ConvPosteriorMatchingVAE
-            kwargs.pop("precision", None)
-            return ConvPosteriorMatchingVAE.from_config(config, name=name, **kwargs)
+            prec = kwargs.pop("precision", None)
+            return ConvPosteriorMatchingVAE.from_config(config, name=name, precision="bf16" if prec == "bf16" else "fp32",
+                                                        **kwargs)
         encoder_net = get_network(config["encoder_net"], config.get("encoder_net_config"), name="encoder_net")
         decoder_net = get_network(config["decoder_net"], config.get("decoder_net_config"), name="decoder_net")
         partial_encoder_net = get_network(
