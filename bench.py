@@ -26,7 +26,8 @@ if ROOT not in sys.path:
 
 METRIC = "PM-VAE train samples/s"
 UNIT = "samples/s"
-TRAIN_MFLOP = {"gas": 5.259, "power": 5.247, "hepmass": 5.339, "bsds": 18.868}   # SURVEY §8 (6 x sum in*out)
+TRAIN_MFLOP = {"gas": 5.259, "power": 5.247, "hepmass": 5.339, "bsds": 18.868,    # SURVEY §8 (6 x sum in*out)
+               "mnist": 609.5}                                                        # conv stacks + AR-GMM, per image
 CONDLL_GFLOP = {"gas": 0.5507, "power": 0.5496, "hepmass": 0.5575, "bsds": 1.4137}  # is_log_prob, K = 512
 
 
@@ -210,9 +211,173 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+# ----------------------------------------------------------------------------- MNIST config
+def mnist_cpu_baseline(rows=32, min_seconds=6.0, max_iters=6):
+    """oracle/model_mnist.py (PyTorch CPU float64 autograd, all host threads): loss + every gradient of one batch."""
+    import numpy as np
+    import torch
+    from oracle import model_mnist as MM
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p = MM.init_params()
+    rng = np.random.default_rng(0)
+    x = torch.tensor((rng.random((rows, 28, 28, 1)) < 0.13).astype(np.float64))
+    b = torch.tensor((rng.random((rows, 28, 28, 1)) < 0.5).astype(np.float64))
+    eps = torch.tensor(rng.standard_normal((rows, MM.LATENT)))
+    MM.loss_and_grads(p, x, b, eps)
+    times, t_all = [], time.perf_counter()
+    while (time.perf_counter() - t_all < min_seconds or len(times) < 2) and len(times) < max_iters:
+        t0 = time.perf_counter()
+        MM.loss_and_grads(p, x, b, eps)
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": rows / med, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(times)} loss+gradient passes of {rows} images (mnist), PyTorch CPU float64 oracle, median",
+            "ms_per_step": med * 1e3}
+
+
+def main_mnist(args):
+    """configs/pm_vae_mnist.py: ConvEncoder / ConvDecoder, Bernoulli decoder, AutoregressiveGMM partial posterior,
+    MNISTMaskGenerator masks; host-composed from libpmvae operators (conv_vae.py), bf16 convolution GEMMs."""
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        cb = mnist_cpu_baseline(rows=32, min_seconds=3.0 * max(1, min(args.steps, 5)), max_iters=max(2, min(args.steps, 8)))
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": "pm_vae_mnist loss + gradients", "rows_per_step": 32},
+                          "cpu_baseline": cb,
+                          "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import ctypes as C
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from posterior_matching_b200 import MNISTMaskGenerator, PosteriorMatchingVAE, _lib, pm_vae_config
+    from posterior_matching_b200 import conv as PC
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    precision = "fp32" if args.precision == "fp32" else "bf16"
+    B = args.batch or 2048
+    K, W = args.steps, max(args.warmup, 3)
+    m = PosteriorMatchingVAE.from_config(pm_vae_config("mnist").model.to_dict(), precision=precision)
+    m.init(3)
+    m.params["posterior_dist/linear"]["w"].mul_(0.1)
+    rng = np.random.default_rng(100 + rank)
+    x_host = torch.from_numpy((rng.random((B, 28, 28, 1)) < 0.13).astype(np.float32)).pin_memory()
+    x_dev = x_host.cuda()
+    gen = MNISTMaskGenerator(seed=1 + rank)
+    sync = None
+    if world > 1:
+        def sync(ts):
+            for t in ts:
+                dist.all_reduce(t)
+
+    def step(xd, i, read):
+        return m.train_step(xd, gen((B, 28, 28, 1)), rng=(7, i), grad_sync=sync, global_rows=B * world, sync_metrics=read)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for i in range(W):
+        step(x_dev, i, False)
+    barrier()
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 0.6:
+        step(x_dev, 0, False)
+        torch.cuda.synchronize()
+    barrier()
+    l0 = int(_lib.lib.pmvae_launch_count())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step(x_dev, W + i, False)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = int(_lib.lib.pmvae_launch_count()) - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * K / (ms * 1e-3)
+    # end to end: the batch comes from pinned host memory every step, the batch means are read back every step
+    x_buf = torch.empty_like(x_dev)
+    step(x_dev, 0, True)
+    barrier()
+    t0 = time.perf_counter()
+    last = None
+    for i in range(K):
+        x_buf.copy_(x_host, non_blocking=True)
+        last = step(x_buf, W + K + i, True)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": world * B * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 784 * 4, "d2h_bytes_per_step": 12,
+           "ms_per_step": e2e_s / K * 1e3, "feed": "pinned host images copied in every step; masks drawn on the device"}
+    # dominant operator alone: the largest convolution of the encoders (14x14, 32 -> 64 channels, 5x5) forward
+    peaks = measured_peaks()
+    d = PC.conv_desc(14, 14, 32, 64, 5, 1, "SAME", precision=precision)
+    xin = torch.randn(B, 14, 14, 32, device="cuda")
+    wc = torch.randn(5, 5, 32, 64, device="cuda") / 28.0
+    bc = torch.zeros(64, device="cuda")
+    for _ in range(3):
+        PC.conv2d_forward(d, xin, wc, bc)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(10):
+        PC.conv2d_forward(d, xin, wc, bc)
+    k1.record()
+    torch.cuda.synchronize()
+    k_ms = k0.elapsed_time(k1) / 10
+    k_flop = 2.0 * B * 14 * 14 * 800 * 64
+    step_tflops = TRAIN_MFLOP["mnist"] * 1e6 * world * B / (ms / K * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": k_flop / (k_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": k_flop / (k_ms * 1e-3) / 1e12 / peaks["bf16_tflops"], "traffic": None,
+                "kernel": f"pmvae_conv2d_forward 14x14x32 -> 64, 5x5 ({B} images): im2col_bf16 + tc_gemm_kernel<NT> + leaky, "
+                          "timed as one operator (10 calls)",
+                "kernel_ms": k_ms, "peak_source": peaks["source"] + " (bf16 burst)", "algorithmic_flop_per_launch": k_flop,
+                "step_tflops_per_gpu": step_tflops / world,
+                "step_frac_of_sustained_peak": step_tflops / world / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"])}
+    if rank == 0:
+        cb = None if args.no_cpu_baseline else mnist_cpu_baseline()
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": precision if precision != "fp32" else "f32",
+            "data": "synthetic",
+            "config": {"workload": "configs/pm_vae_mnist.py train step (MNIST masks, conv encoders / decoder, Bernoulli + "
+                                   "AR-GMM terms, fwd, bwd, grad all-reduce, Adam)", "rows_per_gpu_per_step": B,
+                       "global_batch": B * world, "parallelism": f"dp{world}", "l2": "activations + im2col buffers >> L2",
+                       "launch": "host-composed libpmvae operator calls (conv_vae.py)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cb,
+            "loss": last.get("loss") if isinstance(last, dict) else None}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def main():
     args = parse()
+    if args.config == "mnist":
+        main_mnist(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return

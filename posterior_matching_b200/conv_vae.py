@@ -203,11 +203,18 @@ class ConvPosteriorMatchingVAE:
 
     # ---- train_pm_vae.py:58-83 (beta = 1: the MNIST config has no beta schedule; weight_decay = 0) ------
     def train_step(self, x, b, *, rng=None, eps=None, lr_schedule=None, matching_coef: float = 1.0,
-                   adam=(0.9, 0.999, 1e-8)) -> Dict[str, float]:
+                   adam=(0.9, 0.999, 1e-8), grad_sync=None, global_rows: Optional[int] = None,
+                   sync_metrics: bool = True) -> Dict[str, float]:
+        """One optimizer step.  Data parallel: every rank passes its own rows, `global_rows` = rows over all ranks (the
+        cotangents are scaled by 1 / global_rows) and `grad_sync(tensors)` sums the two flat gradient arenas across ranks
+        before the update (e.g. one NCCL all-reduce each).  `sync_metrics=False` skips the host read of the batch means
+        (returns device tensors instead), so consecutive steps queue without a host round trip."""
         out = self(x, b, is_training=True, rng=rng, eps=eps)
         B = out["kl"].shape[0]
-        ones = torch.full((B,), 1.0 / B, device=self.device)
+        ones = torch.full((B,), 1.0 / (global_rows or B), device=self.device)
         self.backward(-ones, ones, -matching_coef * ones)
+        if grad_sync is not None:
+            grad_sync([self.grad_arena, self.argmm.grad_arena])
         lr = float(lr_schedule(self.step)) if lr_schedule else 1e-3
         for arena, grads, m, v in ((self.arena, self.grad_arena, self.m[0], self.v[0]),
                                    (self.argmm.arena, self.argmm.grad_arena, self.m[1], self.v[1])):
@@ -215,6 +222,8 @@ class ConvPosteriorMatchingVAE:
                                                  arena.numel(), self.step, lr, 0.0, adam[0], adam[1], adam[2], _stream()),
                        "pmvae_adamw_flat")
         self.step += 1
+        if not sync_metrics:
+            return {k: out[k].mean() for k in ("reconstruction_ll", "kl", "matching_ll")}
         rec, kl, match = (float(out[k].mean()) for k in ("reconstruction_ll", "kl", "matching_ll"))
         return {"reconstruction_ll": rec, "kl": kl, "matching_ll": match, "beta": 1.0,
                 "loss": -(rec - kl) + matching_coef * (-match)}
