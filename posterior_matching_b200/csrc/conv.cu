@@ -362,20 +362,23 @@ __global__ void __launch_bounds__(256) col2im_bf16_kernel(const bf16c* __restric
 }
 // bf16 weight images with the output channels padded to Cp: nk[co][k] (pitch Kp) for the forward, kn[k][co] (pitch Cp)
 // for the data gradient; padded rows / columns are zero
+// flip = 1 reverses the tap order (the adjoint convolution of the data gradient); kn may be NULL
 __global__ void __launch_bounds__(256) wpack_bf16_kernel(const float* __restrict__ w, bf16c* __restrict__ nk, bf16c* __restrict__ kn,
-                                                         pmvae_conv_desc d, int Kc, int Kp, int Cp) {
+                                                         pmvae_conv_desc d, int Kc, int Kp, int Cp, int flip) {
   const int64_t n = (int64_t)Kp * Cp;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
     const int co = (int)(t % Cp);
     const int k = (int)(t / Cp);
     float v = 0.f;
     if (k < Kc && co < d.Cout) {
-      const int ci = k % d.Cin, tap = k / d.Cin;
+      const int ci = k % d.Cin;
+      int tap = k / d.Cin;
+      if (flip) tap = d.KH * d.KW - 1 - tap;
       v = w[(int64_t)tap * d.Cin * d.Cout + (int64_t)ci * d.w_ci + (int64_t)co * d.w_co];
     }
     const bf16c h = __float2bfloat16(v);
     nk[(int64_t)co * Kp + k] = h;
-    if (k < Kc) kn[(int64_t)k * Cp + co] = h;
+    if (kn && k < Kc) kn[(int64_t)k * Cp + co] = h;
   }
 }
 // dpre = dy * act'(y) in place (float32, for the bias gradient) and as bf16 with the channel pitch padded to Cp
@@ -414,21 +417,44 @@ __global__ void __launch_bounds__(256) wmat_unpack_add_p_kernel(const float* __r
     dw[(int64_t)tap * d.Cin * d.Cout + (int64_t)ci * d.w_ci + (int64_t)co * d.w_co] += wm[r * Cp + co];
   }
 }
+// The data gradient as a convolution of its own: dX = conv(dpre) with stride and dilation swapped, pads K-1-pad, the
+// taps reversed and the channel roles exchanged (same operator, so the same im2col + NT GEMM, K = KH*KW*Cout, N = Cin).
+static pmvae_conv_desc adjoint_desc(const pmvae_conv_desc& d) {
+  pmvae_conv_desc a = d;
+  a.H = d.OH; a.W = d.OW; a.Cin = d.Cout;
+  a.OH = d.H; a.OW = d.W; a.Cout = d.Cin;
+  a.stride = d.dil; a.dil = d.stride;
+  a.pad_top = d.KH - 1 - d.pad_top; a.pad_left = d.KW - 1 - d.pad_left;
+  a.w_ci = d.w_co; a.w_co = d.w_ci;
+  a.slope = 1.0f;
+  return a;
+}
+// column-matrix elements of the two ways to get dX: rows(out) x K x Cin (dcol + col2im) against rows(in) x K x Cout
+static bool use_adjoint(const pmvae_conv_desc& d) {
+  if (d.pad_top > d.KH - 1 || d.pad_left > d.KW - 1) return false;
+  const double direct = (double)d.OH * d.OW * d.Cin, adj = (double)d.H * d.W * d.Cout;
+  return adj <= direct;
+}
 struct ConvWsB { bf16c *col, *dcol, *nk, *kn, *dpre; float *wm, *bias, *ytmp; uint64_t bytes; };
 static ConvWsB plan_conv_ws_b(const pmvae_conv_desc* d, int64_t B, void* ws) {
   ConvWsB p{};
   const uint64_t rows = (uint64_t)B * d->OH * d->OW, Kc = (uint64_t)d->KH * d->KW * d->Cin, Kp = (Kc + 7) & ~7ull;
   const uint64_t Cp = ((uint64_t)d->Cout + 7) & ~7ull;
+  // the adjoint convolution of the data gradient reuses col / nk / ytmp with its own shapes
+  const uint64_t rows_a = (uint64_t)B * d->H * d->W, Kc_a = (uint64_t)d->KH * d->KW * d->Cout, Kp_a = (Kc_a + 7) & ~7ull;
+  const uint64_t Cp_a = ((uint64_t)d->Cin + 7) & ~7ull;
+  const bool adj = use_adjoint(*d);
+  auto mx = [](uint64_t a, uint64_t b) { return a > b ? a : b; };
   uint64_t off = 0;
   auto take = [&](uint64_t bytes) { char* q = ws ? reinterpret_cast<char*>(ws) + off : nullptr; off += align_up(bytes, 256); return q; };
-  p.col = reinterpret_cast<bf16c*>(take(rows * Kp * 2));
-  p.dcol = reinterpret_cast<bf16c*>(take(rows * Kp * 2));
-  p.nk = reinterpret_cast<bf16c*>(take(Cp * Kp * 2));
+  p.col = reinterpret_cast<bf16c*>(take(mx(rows * Kp, adj ? rows_a * Kp_a : 0) * 2));
+  p.dcol = reinterpret_cast<bf16c*>(take(adj ? 0 : rows * Kp * 2));
+  p.nk = reinterpret_cast<bf16c*>(take(mx(Cp * Kp, adj ? Cp_a * Kp_a : 0) * 2));
   p.kn = reinterpret_cast<bf16c*>(take(Kc * Cp * 2));
   p.dpre = reinterpret_cast<bf16c*>(take(rows * Cp * 2));
   p.wm = reinterpret_cast<float*>(take(Kc * Cp * 4));
   p.bias = reinterpret_cast<float*>(take(Cp * 4));
-  p.ytmp = reinterpret_cast<float*>(take(Cp != (uint64_t)d->Cout ? rows * Cp * 4 : 0));
+  p.ytmp = reinterpret_cast<float*>(take(mx(Cp != (uint64_t)d->Cout ? rows * Cp * 4 : 0, (adj && Cp_a != (uint64_t)d->Cin) ? rows_a * Cp_a * 4 : 0)));
   p.bytes = off;
   return p;
 }
@@ -467,7 +493,7 @@ int pmvae_conv2d_forward(const pmvae_conv_desc* desc, const float* x, const floa
     const int64_t rows = B * desc->OH * desc->OW;
     const int Kc = desc->KH * desc->KW * desc->Cin, Kp = (Kc + 7) & ~7, Cp = (desc->Cout + 7) & ~7;
     PMVAE_TRY(im2col_bf16(x, p.col, B, *desc, Kc, Kp, s));
-    wpack_bf16_kernel<<<grid1d_c((int64_t)Kp * Cp, 256), 256, 0, s>>>(w, p.nk, p.kn, *desc, Kc, Kp, Cp);
+    wpack_bf16_kernel<<<grid1d_c((int64_t)Kp * Cp, 256), 256, 0, s>>>(w, p.nk, p.kn, *desc, Kc, Kp, Cp, 0);
     PMVAE_LAUNCH_CHECK();
     tc::TcGemmArgs e{};
     if (bias) {
@@ -528,7 +554,7 @@ int pmvae_conv2d_backward(const pmvae_conv_desc* desc, const float* x, const flo
   cudaStream_t s = as_stream(stream);
   const int64_t ny = B * desc->OH * desc->OW * desc->Cout;
   const int Kc_all = desc->KH * desc->KW * desc->Cin;
-  if (ws && conv_bf16_ok(desc) && (dx == nullptr || Kc_all % 8 == 0)) {
+  if (ws && conv_bf16_ok(desc) && (dx == nullptr || Kc_all % 8 == 0 || use_adjoint(*desc))) {
     ConvWsB p = plan_conv_ws_b(desc, B, ws);
     PMVAE_CHECK(p.bytes <= ws_bytes && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, "conv workspace too small or misaligned");
     const int64_t rows = B * desc->OH * desc->OW;
@@ -552,8 +578,23 @@ int pmvae_conv2d_backward(const pmvae_conv_desc* desc, const float* x, const flo
         PMVAE_LAUNCH_CHECK();
       }
     }
-    if (dx) {
-      wpack_bf16_kernel<<<grid1d_c((int64_t)Kp * Cp, 256), 256, 0, s>>>(w, p.nk, p.kn, *desc, Kc, Kp, Cp);
+    if (dx && use_adjoint(*desc)) {
+      const pmvae_conv_desc a = adjoint_desc(*desc);
+      const int64_t rows_a = B * a.OH * a.OW;
+      const int Kc_a = a.KH * a.KW * a.Cin, Kp_a = (Kc_a + 7) & ~7, Cp_a = (a.Cout + 7) & ~7;
+      PMVAE_TRY(im2col_bf16(dy, p.col, B, a, Kc_a, Kp_a, s));          // dy holds dpre (float32) by now
+      wpack_bf16_kernel<<<grid1d_c((int64_t)Kp_a * Cp_a, 256), 256, 0, s>>>(w, p.nk, nullptr, a, Kc_a, Kp_a, Cp_a, 1);
+      PMVAE_LAUNCH_CHECK();
+      tc::TcGemmArgs e{};
+      const bool padded = Cp_a != a.Cout;
+      e.out_f32 = padded ? p.ytmp : dx; e.ld_out_f32 = Cp_a;
+      PMVAE_TRY(tc::gemm_nt(p.col, Kp_a, p.nk, Kp_a, rows_a, Cp_a, Kc_a, e, s));
+      if (padded) {
+        leaky_gather_kernel<<<grid1d_c(rows_a * a.Cout, 256), 256, 0, s>>>(p.ytmp, dx, rows_a, a.Cout, Cp_a, 1.0f);
+        PMVAE_LAUNCH_CHECK();
+      }
+    } else if (dx) {
+      wpack_bf16_kernel<<<grid1d_c((int64_t)Kp * Cp, 256), 256, 0, s>>>(w, p.nk, p.kn, *desc, Kc, Kp, Cp, 0);
       PMVAE_LAUNCH_CHECK();
       tc::TcGemmArgs e{};
       e.out_bf16 = p.dcol; e.ld_out_bf16 = Kp;
