@@ -378,53 +378,67 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           if (lane == 0) tma_store_wait_read<0>();
           named_bar_sync(1 + q, 64);
         }
-        float* xch = bias_tbl + 14 * 256;                       // [2 passes][128 rows][2 halves]
+        // Row statistics in ONE pass over the accumulator: each of the quadrant's two warps sums its 128 columns shifted
+        // by its own first value c (S = sum(v - c), Q = sum((v - c)^2): no cancellation), the halves are combined
+        // exactly: mean = (S0 + S1 + 128 (c0 + c1)) / 256, sum (v - mean)^2 = sum_h Q_h - 2 (mean - c_h) S_h + 128 (mean - c_h)^2.
+        float* xch = bias_tbl + 14 * 256;                       // [128 rows][2 halves][S, Q, c]
         const uint32_t t_u = t_lane + (uint32_t)(32 * half);
         const uint32_t t_h = t_lane + (uint32_t)(256 + 32 * half);
-        const float* brow = bias_tbl + l * 256 + 32 * half;
-        float sum = 0.f;
+        const float4* bq = reinterpret_cast<const float4*>(bias_tbl + l * 256 + 32 * half);   // chunk j: bq[16 j + i]
+        uint32_t ra[32], rb[32];
+        tmem_ld32(t_u, ra);
+        float S = 0.f, Q = 0.f, c = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint32_t r[32];
-          tmem_ld32(t_u + 64 * j, r);
+          uint32_t (&r)[32] = (j & 1) ? rb : ra;
           tmem_ld_wait();
+          if (j < 3) tmem_ld32(t_u + 64 * (j + 1), (j & 1) ? ra : rb);
+          if (j == 0) c = __uint_as_float(r[0]) + bq[0].x;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sum += __uint_as_float(r[i]) + brow[64 * j + i];
+          for (int i = 0; i < 8; ++i) {
+            const float4 bv = bq[16 * j + i];
+            const float d0 = __uint_as_float(r[4 * i]) + bv.x - c, d1 = __uint_as_float(r[4 * i + 1]) + bv.y - c;
+            const float d2 = __uint_as_float(r[4 * i + 2]) + bv.z - c, d3 = __uint_as_float(r[4 * i + 3]) + bv.w - c;
+            S += (d0 + d1) + (d2 + d3);
+            Q = fmaf(d0, d0, Q); Q = fmaf(d1, d1, Q); Q = fmaf(d2, d2, Q); Q = fmaf(d3, d3, Q);
+          }
         }
-        xch[row * 2 + half] = sum;
+        float* mine = xch + (row * 2 + half) * 3;
+        mine[0] = S; mine[1] = Q; mine[2] = c;
+        tmem_ld32(t_u, ra);                                      // second pass: prefetch its first chunk across the exchange
         named_bar_sync(1 + q, 64);
-        const float mean = (xch[row * 2] + xch[row * 2 + 1]) * (1.0f / 256.0f);
-        float sq = 0.f;
+        const float* other = xch + (row * 2 + (half ^ 1)) * 3;
+        const float So = other[0], Qo = other[1], co = other[2];
+        const float mean = (S + So + 128.f * (c + co)) * (1.0f / 256.0f);
+        const float dm = mean - c, dmo = mean - co;
+        float ss = (Q - 2.f * dm * S + 128.f * dm * dm) + (Qo - 2.f * dmo * So + 128.f * dmo * dmo);
+        ss = fmaxf(ss, 0.f);
+        const float rstd = rsqrtf(ss * (1.0f / 256.0f) + 1e-5f);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint32_t r[32];
-          tmem_ld32(t_u + 64 * j, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) { const float v = __uint_as_float(r[i]) + brow[64 * j + i] - mean; sq = fmaf(v, v, sq); }
-        }
-        xch[256 + row * 2 + half] = sq;
-        named_bar_sync(1 + q, 64);
-        const float rstd = rsqrtf((xch[256 + row * 2] + xch[256 + row * 2 + 1]) * (1.0f / 256.0f) + 1e-5f);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t r[32], hreg[32];
-          tmem_ld32(t_u + 64 * j, r);
+          uint32_t (&r)[32] = (j & 1) ? rb : ra;
+          uint32_t hreg[32];
           if ((l & 1) == 0 && l > 0) tmem_ld32(t_h + 64 * j, hreg);
           tmem_ld_wait();
+          if (j < 3) tmem_ld32(t_u + 64 * (j + 1), (j & 1) ? ra : rb);
           uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float v = (__uint_as_float(r[i]) + brow[64 * j + i] - mean) * rstd;
-            if ((l & 1) == 0) {
-              if (l > 0) v += __uint_as_float(hreg[i]);
-              hreg[i] = __float_as_uint(v);
+          for (int i = 0; i < 8; ++i) {
+            const float4 bv = bq[16 * j + i];
+            const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float v = (__uint_as_float(r[4 * i + e]) + bb[e] - mean) * rstd;
+              if ((l & 1) == 0) {
+                if (l > 0) v += __uint_as_float(hreg[4 * i + e]);
+                hreg[4 * i + e] = __float_as_uint(v);
+              }
+              r[4 * i + e] = __float_as_uint(v);
             }
-            r[i] = __float_as_uint(v);
           }
           if ((l & 1) == 0) tmem_st32(t_h + 64 * j, hreg);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = relu2(pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])));
+          for (int i = 0; i < 16; ++i) pk[i] = pack2_relu(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
           const uint32_t rowaddr = opnd + j * kChunkBytes + row * 128;
 #pragma unroll
           for (int i4 = 0; i4 < 4; ++i4) {
