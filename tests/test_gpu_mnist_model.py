@@ -86,3 +86,35 @@ def test_mnist_train_step_reduces_the_loss():
     for _ in range(12):
         last = m.train_step(x, b, eps=eps)
     assert np.isfinite(last["loss"]) and last["loss"] < first["loss"]
+
+
+def test_mnist_train_step_data_parallel_hooks_match_the_full_batch():
+    """Two ranks' worth of rows through `global_rows` + `grad_sync` (the other shard's gradients are added by the hook,
+    as an all-reduce would) give the same parameter update as one full-batch step."""
+    from posterior_matching_b200 import pm_vae_config
+    from posterior_matching_b200.conv_vae import ConvPosteriorMatchingVAE
+    cfg = pm_vae_config("mnist").model.to_dict()
+    p = MM.init_params()
+    full, rank0, rank1 = (ConvPosteriorMatchingVAE.from_config(cfg) for _ in range(3))
+    for m in (full, rank0, rank1):
+        m.load_params(p)
+    B = 8
+    x, b, eps = (t.float().cuda() for t in _inputs(B, seed=11))
+    full.train_step(x, b, eps=eps)
+    # rank 1's shard: gradients only (cotangents scaled by 1 / global rows), no update
+    h = B // 2
+    rank1(x[h:], b[h:], eps=eps[h:])
+    ones = torch.full((h,), 1.0 / B, device="cuda")
+    rank1.backward(-ones, ones, -ones)
+    other = [rank1.grad_arena.clone(), rank1.argmm.grad_arena.clone()]
+
+    def sync(arenas):
+        for a, o in zip(arenas, other):
+            a.add_(o)
+
+    rank0.train_step(x[:h], b[:h], eps=eps[:h], grad_sync=sync, global_rows=B)
+    torch.cuda.synchronize()
+    for a, c in ((full.arena, rank0.arena), (full.argmm.arena, rank0.argmm.arena)):
+        # Adam's first step moves every weight by ~lr * sign(g): compare the updates, not the weights
+        assert rel_l2((c - a).cpu().numpy() + 1.0, np.ones(a.numel())) < 1e-5
+        assert float((a - c).abs().max()) < 2e-4
