@@ -294,6 +294,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t full_par = 0;
     uint32_t n_writes = 0;             // operand tiles written so far (training mode: chunk_free phase tracking)
+    const bool skip_bits = (p.debug & 32) != 0;      // profiling only: no relu-bit extraction
     const int D = p.D_in;
 
     // cp.async of a tile's fp32 input rows (x | mask) into the staging slots: thread (q, half 0, lane) copies row 32q+lane
@@ -490,7 +491,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             float v2 = __uint_as_float(r[4 * i + 2]), v3 = __uint_as_float(r[4 * i + 3]);
             add2(v0, v1, bv.x, bv.y);
             add2(v2, v3, bv.z, bv.w);
-            if (SAVE) {
+            if (SAVE && !skip_bits) {
               neg = __funnelshift_l(__float_as_uint(v0), neg, 1);
               neg = __funnelshift_l(__float_as_uint(v1), neg, 1);
               neg = __funnelshift_l(__float_as_uint(v2), neg, 1);
@@ -630,7 +631,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         for (int j = 0; j < 4; ++j) {
           mbar_wait(written(j), cnt & 1u, 15);
           if (lane == 0) {
-            tma_store_2d(&map_s, opnd + j * kChunkBytes, 64 * j, (int)((int64_t)l * p.Bpad + (int64_t)tile * 128));
+            if (!(p.debug & 16)) tma_store_2d(&map_s, opnd + j * kChunkBytes, 64 * j, (int)((int64_t)l * p.Bpad + (int64_t)tile * 128));
             tma_store_commit();
             if (j > 0) {
               tma_store_wait_read<1>();
@@ -1095,8 +1096,10 @@ int pack_images(const float* params, const Net& n, const Leaf& head, const NetIm
 
 static bool cta2_enabled() {
   static int v = -1;
-  // default off: measured no gain yet (the per-layer hand-offs, not weight streaming from L2, pace the chain)
-  if (v < 0) { const char* e = getenv("PMVAE_FUSED_CTA2"); v = e ? atoi(e) : 0; }
+  // default on: a CTA pair halves the weight bytes written into, and the B-operand bytes read from, each SM's shared
+  // memory, whose port is close to saturated in the forward chain (MMA operand reads + weight TMA + epilogue stores +
+  // activation stores): 96 -> 92 us for the encoder chain, 1.31 -> 1.24 ms per train step (PMVAE_FUSED_CTA2=0 disables)
+  if (v < 0) { const char* e = getenv("PMVAE_FUSED_CTA2"); v = e ? atoi(e) : 1; }
   return v != 0;
 }
 
