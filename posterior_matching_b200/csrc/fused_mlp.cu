@@ -1122,7 +1122,7 @@ static int launch_fwd_t(int grid, const CUtensorMap& mw, const CUtensorMap& mh, 
 }
 static int launch_fwd(bool save, bool cta2, bool ln, int grid, const CUtensorMap& mw, const CUtensorMap& mh,
                       const CUtensorMap& ms, const CUtensorMap& mo, const FwdArgs& a, cudaStream_t s) {
-  if (ln) return launch_fwd_t<false, false, true>(grid, mw, mh, ms, mo, a, s);
+  if (ln) return cta2 ? launch_fwd_t<false, true, true>(grid, mw, mh, ms, mo, a, s) : launch_fwd_t<false, false, true>(grid, mw, mh, ms, mo, a, s);
   if (save) return cta2 ? launch_fwd_t<true, true, false>(grid, mw, mh, ms, mo, a, s) : launch_fwd_t<true, false, false>(grid, mw, mh, ms, mo, a, s);
   return cta2 ? launch_fwd_t<false, true, false>(grid, mw, mh, ms, mo, a, s) : launch_fwd_t<false, false, false>(grid, mw, mh, ms, mo, a, s);
 }
@@ -1144,7 +1144,7 @@ int net_forward(const float* params, const Net& n, const Leaf& head, const NetIm
   a.masks = nullptr;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PMVAE_FUSED_DEBUG"); dbg = e ? atoi(e) : 0; } a.debug = dbg; }
   CUtensorMap mw, mh, ms, mo;
-  const bool cta2 = cta2_enabled() && !n.ln;
+  const bool cta2 = cta2_enabled();
   PMVAE_TRY(make_map_2d(&mw, im.stack_t, 2, (uint64_t)(1 + 2 * n.R) * 256, 256, 256, 64, cta2 ? 128 : 256));
   PMVAE_TRY(make_map_2d(&mh, im.head_t, 2, (uint64_t)im.head_tiles * im.head_NT, 256, 256, 64,
                         (uint32_t)(cta2 ? im.head_NT / 2 : im.head_NT)));
