@@ -24,6 +24,12 @@ static bool fast16() {
   if (v < 0) { const char* e = getenv("PMVAE_LATENT16"); v = e ? atoi(e) : 1; }
   return v != 0;
 }
+// d = 64: the K-sample draw of the evaluators has its own kernel (PMVAE_LATENT64=0 keeps the general one)
+static bool fast64() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PMVAE_LATENT64"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
 
 constexpr int kThreadsL = 128;
 
@@ -351,6 +357,98 @@ __global__ void __launch_bounds__(kThreadsL) sample_latents_kernel(const float* 
   }
 }
 
+// d = 64 (bsds): one warp per (row, 64 samples).  The triangular factor is expanded ONCE per item into a dense,
+// zero-padded, transposed matrix Lt[j][i] in shared memory (the fill_triangular index map is paid 4096 times per item
+// instead of 2080 times per sample), then the samples go through in batches of 16 as a small matrix product:
+// z[s][i] = mu[i] + sum_j Lt[j][i] e[j][s], lane = rows i and i + 32, 32 accumulators per lane, e[j][0..15] read as four
+// broadcast 16-byte loads.  Same words of the same threefry stream as the general kernel (index (k, row, q)).
+constexpr int kS64Batch = 16, kS64Chunk = 64;
+constexpr int kS64SmemFloats = 64 * 64 + 64 * kS64Batch + 64;      // Lt | e | mu per warp
+__global__ void __launch_bounds__(kThreadsL) sample_latents64_kernel(const float* __restrict__ par, Key2 key, int64_t B,
+                                                                     int64_t K, int64_t B_total, int64_t row_start,
+                                                                     float* __restrict__ z, float* __restrict__ base) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int d = 64, m = d * (d + 1) / 2, P = d + m;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float* Lt = smem + (size_t)wib * kS64SmemFloats;
+  float* se = Lt + 64 * 64;                         // [j][16 samples]
+  float* smu = se + 64 * kS64Batch;
+  const int64_t chunks = (K + kS64Chunk - 1) / kS64Chunk;
+  const int64_t items = B * chunks;
+  const uint64_t n_total = (uint64_t)K * (uint64_t)B_total * (uint64_t)d;
+  for (int64_t item = (int64_t)blockIdx.x * wpb + wib; item < items; item += (int64_t)gridDim.x * wpb) {
+    const int64_t r = item / chunks, ck = item - r * chunks;
+    const float* pr = par + r * P;
+    __syncwarp();
+    // dense transposed factor: lane owns columns i = lane and lane + 32 of every row j
+    float logd = 0.f;
+    for (int j = 0; j < 64; ++j) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        float v = 0.f;
+        if (i >= j) {
+          v = __ldg(pr + tril_src(i, j, d, m));
+          if (i == j) { v = softplus_f(v) + 1e-5f; logd += logf(v); }
+        }
+        Lt[j * 64 + i] = v;
+      }
+    }
+    smu[lane] = __ldg(pr + lane); smu[lane + 32] = __ldg(pr + lane + 32);
+    logd = group_sum<32>(logd);
+    __syncwarp();
+    const float mu0 = smu[lane], mu1 = smu[lane + 32];
+    const int64_t kend = min(K, (ck + 1) * kS64Chunk);
+    for (int64_t k0 = ck * kS64Chunk; k0 < kend; k0 += kS64Batch) {
+      const int ns = (int)min((int64_t)kS64Batch, kend - k0);
+      __syncwarp();
+      // eps: lane draws elements q = lane and lane + 32 of every sample of the batch
+      float e2[kS64Batch];
+#pragma unroll
+      for (int sI = 0; sI < kS64Batch; ++sI) {
+        float a = 0.f, b = 0.f;
+        if (sI < ns) {
+          const uint64_t idx = ((uint64_t)(k0 + sI) * B_total + (uint64_t)(row_start + r)) * d;
+          a = bits_to_normal(jax_random_word(key, n_total, idx + lane));
+          b = bits_to_normal(jax_random_word(key, n_total, idx + lane + 32));
+        }
+        se[lane * kS64Batch + sI] = a;
+        se[(lane + 32) * kS64Batch + sI] = b;
+        e2[sI] = fmaf(a, a, b * b);
+      }
+      __syncwarp();
+      float acc0[kS64Batch], acc1[kS64Batch];
+#pragma unroll
+      for (int sI = 0; sI < kS64Batch; ++sI) { acc0[sI] = mu0; acc1[sI] = mu1; }
+      // rows i < 32 only see columns j < 32 (the rest of the factor is zero)
+      for (int j = 0; j < 64; ++j) {
+        const float l1 = Lt[j * 64 + lane + 32];
+        const float4* ev = reinterpret_cast<const float4*>(se + j * kS64Batch);
+        const float4 e0 = ev[0], e1 = ev[1], e2v = ev[2], e3 = ev[3];
+        const float ee[kS64Batch] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w, e2v.x, e2v.y, e2v.z, e2v.w, e3.x, e3.y, e3.z, e3.w};
+#pragma unroll
+        for (int sI = 0; sI < kS64Batch; ++sI) acc1[sI] = fmaf(l1, ee[sI], acc1[sI]);
+        if (j < 32) {
+          const float l0 = Lt[j * 64 + lane];
+#pragma unroll
+          for (int sI = 0; sI < kS64Batch; ++sI) acc0[sI] = fmaf(l0, ee[sI], acc0[sI]);
+        }
+      }
+#pragma unroll
+      for (int sI = 0; sI < kS64Batch; ++sI) {
+        if (sI < ns) {                                   // warp-uniform
+          const int64_t k = k0 + sI;
+          z[(k * B + r) * d + lane] = acc0[sI];
+          z[(k * B + r) * d + lane + 32] = acc1[sI];
+          const float z2 = group_sum<32>(fmaf(acc0[sI], acc0[sI], acc1[sI] * acc1[sI]));
+          const float ee2 = group_sum<32>(e2[sI]);
+          if (lane == 0) base[k * B + r] = -0.5f * z2 + 0.5f * ee2 + logd;
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- stand-alone VJP of (z, kl) = f(par, eps)
 // d/dpar of  sum_r [ dz[r] . z[r] + g_kl[r] * kl[r] ]  with z = mu + L eps, kl = KL(N(mu, LL^T) || N(0, I)):
 //   loc:  dz + g_kl * mu;   off-diagonal L_ij: dz_i eps_j + g_kl * L_ij;
@@ -467,6 +565,21 @@ int sample_latents(const float* par, Key2 key, int64_t B, int64_t K, int64_t B_t
               "K*B_total*d exceeds one 2^32-1 element draw");
   if (B * K == 0) return 0;
   if (d == 16 && fast16()) return sample_latents16(par, key, B, K, B_total, row_start, z, base, s);
+  if (d == 64 && fast64()) {
+    const size_t smem = (size_t)(kThreadsL / 32) * kS64SmemFloats * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      PMVAE_CUDA(cudaFuncSetAttribute(sample_latents64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    const int64_t items = B * ((K + kS64Chunk - 1) / kS64Chunk);
+    int64_t g = (items + kThreadsL / 32 - 1) / (kThreadsL / 32);
+    if (g > 148 * 2) g = 148 * 2;
+    if (g < 1) g = 1;
+    sample_latents64_kernel<<<(int)g, kThreadsL, smem, s>>>(par, key, B, K, B_total, row_start, z, base);
+    PMVAE_LAUNCH_CHECK();
+    return 0;
+  }
   const int P = d + d * (d + 1) / 2;
   const size_t spg = (size_t)(P + 3 * d) * sizeof(float);
   const int64_t items = B * ((K + 15) / 16);

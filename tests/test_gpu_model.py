@@ -106,7 +106,7 @@ def test_loss_and_gradients_match_oracle(name, B, stop, precision):
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
-@pytest.mark.parametrize("name,B,K", [("gas", 32, 64), ("bsds", 5, 16), ("power", 3, 1)])
+@pytest.mark.parametrize("name,B,K", [("gas", 32, 64), ("bsds", 5, 16), ("bsds", 3, 100), ("power", 3, 1)])
 def test_eval_fn_matches_oracle(name, B, K, precision):
     from posterior_matching_b200 import eval_fn
     spec = spec_of(name)
