@@ -4,7 +4,8 @@
 //
 //   warp 0      : TMA producer, streams the bf16 weight K-blocks ([256 n] x [64 k], SWIZZLE_128B) of the
 //                 current Linear through a 3-stage mbarrier ring (the weights come from L2)
-//   warp 1      : MMA issuer (one lane): tcgen05.mma kind::f16, M = 128, N = 256 (head: N <= 256), K = 16
+//   warp 1      : MMA issuer: tcgen05.mma kind::f16, M = 128, N = 256 (head: N <= 256), K = 16; the whole warp runs
+//                 the loop converged and one elect.sync lane issues (a lane-0 branch costs an R2UR waterfall per MMA)
 //   warps 2..9  : epilogue: tcgen05.ld (thread = row) -> + bias -> relu -> bf16 -> st.shared straight into
 //                 the swizzled K-major A-operand buffer of the NEXT Linear, 64 columns (= one K-block) at a
 //                 time, so the next Linear's MMAs start while the rest of the tile is still being drained
@@ -15,6 +16,8 @@
 // accumulator is read (for h: the running sum b0 + sum_r b2_r).  Head tiles alternate between the two
 // regions.  In training mode every bf16 operand tile is also streamed to HBM by TMA (the backward's
 // weight-gradient operands) together with one relu bit per element.
+// By default two CTAs of a cluster work as one tcgen05 pair (cta_group::2, M = 256): each holds half of every weight
+// K-block, which halves the weight bytes through each SM's shared-memory port (PMVAE_FUSED_CTA2=0: single CTAs).
 #include "fused_mlp.cuh"
 
 #include <stdlib.h>
