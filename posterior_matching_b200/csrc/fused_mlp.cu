@@ -425,6 +425,13 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           if ((l & 1) == 0 && l > 0) tmem_ld32(t_h + 64 * j, hreg);
           tmem_ld_wait();
           if (j < 3) tmem_ld32(t_u + 64 * (j + 1), (j & 1) ? ra : rb);
+          if (j == 3) {
+            // the accumulator has been read for the last time: hand it back now, so that the next Linear's first
+            // K-blocks (their operand chunks are already announced) run under this chunk's math and stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) arrive_leader(acc_empty(0));
+          }
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -454,9 +461,6 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           if (lane == 0) arrive_leader(opnd_ready(j));
         }
         tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) arrive_leader(acc_empty(0));
       };
       for (int l = 0; l < n_hidden; ++l) {
         const int region = region_of(l);
