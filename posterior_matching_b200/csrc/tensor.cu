@@ -225,18 +225,27 @@ __global__ void __launch_bounds__(256) in_layer_dinput_kernel(const bf16* __rest
 
 // bf16 image of a net's input, [B, ld] with ld = pad8(K0): in (K0 = D_in) or [in*msk, msk] (K0 = 2 D_in);
 // it is the A operand of the first Linear's weight-gradient GEMM (gW_0 += in^T @ dY_0).
+// One thread per row (the rows are 8 ... 64 elements): no per-element division, contiguous reads and writes per warp.
 __global__ void __launch_bounds__(256) cast_input_kernel(const float* __restrict__ in, const float* __restrict__ msk,
                                                          int D_in, int K0, int ld, int64_t B, bf16* __restrict__ out) {
-  const int64_t n = B * ld;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / ld;
-    const int k = (int)(i - r * ld);
-    float v = 0.f;
-    if (k < K0) {
-      if (msk) v = (k < D_in) ? in[r * D_in + k] * msk[r * D_in + k] : msk[r * D_in + (k - D_in)];
-      else v = in[r * D_in + k];
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < B; r += (int64_t)gridDim.x * blockDim.x) {
+    const float* xi = in + r * D_in;
+    const float* mi = msk ? msk + r * D_in : nullptr;
+    bf16* o = out + r * ld;
+    for (int k = 0; k < ld; k += 2) {
+      float v[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int kk = k + e;
+        float t = 0.f;
+        if (kk < K0) {
+          if (mi) t = (kk < D_in) ? xi[kk] * mi[kk] : mi[kk - D_in];
+          else t = xi[kk];
+        }
+        v[e] = t;
+      }
+      *reinterpret_cast<__nv_bfloat162*>(o + k) = __floats2bfloat162_rn(v[0], v[1]);
     }
-    out[i] = __float2bfloat16(v);
   }
 }
 
@@ -655,7 +664,7 @@ static int net_bwd_b(const float* params, float* grads, const Net& n, const Leaf
     PMVAE_TRY(fused::net_backward(n, head, *fim, dHead, ld_dhead, B, sv.masks, sv.Bpad, dY, grads, dIn, s));
     const Leaf& l0 = n.lin[0];
     const int ld0 = pad8(l0.rows);
-    cast_input_kernel<<<grid1d(B * ld0, 256), 256, 0, s>>>(in, msk, D_in, l0.rows, ld0, B, in_b);
+    cast_input_kernel<<<grid1d(B, 256), 256, 0, s>>>(in, msk, D_in, l0.rows, ld0, B, in_b);
     PMVAE_LAUNCH_CHECK();
     // every weight gradient of the net in one grouped launch
     tc::TnDesc td[2 * kMaxBlocks + 2];
