@@ -82,3 +82,26 @@ def conv_decoder(params, z, layers=MNIST_DECODER):
         w, b = params[i]
         h = conv2d_transpose(h, w, b, s, "VALID" if i == 0 else "SAME")
     return h
+
+
+# ---- the general operator of csrc/conv.cu, restated (test infrastructure; pins the descriptor algebra on the CPU) ----
+def general_conv(x, w_taps, d):
+    """y[b,oy,ox,co] = sum_{ky,kx,ci} Xd(b, oy*stride+ky-pad_top, ox*stride+kx-pad_left, ci) * w_taps[ky,kx,ci,co], where Xd is
+    x with dil-1 zeros inserted between pixels (csrc/conv.cu header).  `d`: dict with H, W, Cin, OH, OW, Cout, KH, KW,
+    stride, dil, pad_top, pad_left.  x [B,H,W,Cin], w_taps [KH,KW,Cin,Cout] (already in tap-major HWIO order)."""
+    B = x.shape[0]
+    Hd, Wd = (d["H"] - 1) * d["dil"] + 1, (d["W"] - 1) * d["dil"] + 1
+    xd = x.new_zeros((B, Hd, Wd, d["Cin"]))
+    xd[:, ::d["dil"], ::d["dil"], :] = x
+    need_h, need_w = (d["OH"] - 1) * d["stride"] + d["KH"], (d["OW"] - 1) * d["stride"] + d["KW"]
+    pb, pr = need_h - Hd - d["pad_top"], need_w - Wd - d["pad_left"]
+    xp = F.pad(_nchw(xd), (d["pad_left"], max(pr, 0), d["pad_top"], max(pb, 0)))
+    xp = xp[:, :, :need_h, :need_w]
+    return _nhwc(F.conv2d(xp, w_taps.permute(3, 2, 0, 1).contiguous(), stride=d["stride"]))
+
+
+def adjoint_desc(d):
+    """Descriptor of the data gradient as a convolution of its own (csrc/conv.cu::adjoint_desc): stride and dilation swap,
+    pads become K-1-pad, channels swap; the weights are used with reversed taps and transposed channels."""
+    return dict(H=d["OH"], W=d["OW"], Cin=d["Cout"], OH=d["H"], OW=d["W"], Cout=d["Cin"], KH=d["KH"], KW=d["KW"],
+                stride=d["dil"], dil=d["stride"], pad_top=d["KH"] - 1 - d["pad_top"], pad_left=d["KW"] - 1 - d["pad_left"])
