@@ -205,3 +205,27 @@ def test_is_log_prob_converges_to_exact_for_linear_gaussian_sanity():
     lpx, cond = M.is_log_prob(p, spec, x, b, e1, e1)
     assert torch.isfinite(lpx).all() and torch.isfinite(cond).all()
     assert math.isfinite(float(cond.mean()))
+
+
+def test_shifted_one_pass_layernorm_statistics_are_exact():
+    """The row statistics of the fused LayerNorm epilogue (csrc/fused_mlp.cu::epi_ln): two halves of 128 columns each sum
+    S = sum(v - c), Q = sum((v - c)^2) around their own first value c and are combined as
+    mean = (S0 + S1 + 128 (c0 + c1)) / 256, sum (v - mean)^2 = sum_h Q_h - 2 (mean - c_h) S_h + 128 (mean - c_h)^2.
+    In float32 this must agree with the two-pass variance also when |mean| >> std."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    for mean, std in ((0.0, 1.0), (300.0, 0.5), (-4000.0, 2.0), (1e-3, 1e-4)):
+        v = (mean + std * rng.standard_normal((64, 256))).astype(np.float32)
+        halves = [v[:, :128], v[:, 128:]]
+        c = [h[:, :1] for h in halves]
+        S = [np.sum(h - ch, axis=1, dtype=np.float32) for h, ch in zip(halves, c)]
+        Q = [np.sum((h - ch) ** 2, axis=1, dtype=np.float32) for h, ch in zip(halves, c)]
+        mu = (S[0] + S[1] + np.float32(128) * (c[0][:, 0] + c[1][:, 0])) * np.float32(1 / 256)
+        ss = np.zeros_like(mu)
+        for h in range(2):
+            dm = mu - c[h][:, 0]
+            ss += Q[h] - 2 * dm * S[h] + np.float32(128) * dm * dm
+        var = np.maximum(ss, 0) * np.float32(1 / 256)
+        v64 = v.astype(np.float64)
+        assert np.allclose(mu, v64.mean(axis=1), rtol=1e-6, atol=1e-6 * max(1.0, abs(mean)))
+        assert np.allclose(var, v64.var(axis=1), rtol=2e-4), (mean, std)
