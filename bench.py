@@ -358,7 +358,7 @@ def main_mnist(args):
                 "step_tflops_per_gpu": step_tflops / world,
                 "step_frac_of_sustained_peak": step_tflops / world / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"])}
     if rank == 0:
-        cb = None if args.no_cpu_baseline else mnist_cpu_baseline()
+        cb = None if (args.no_cpu_baseline or world > 1) else mnist_cpu_baseline()      # rank 0 at N = 1 only
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": precision if precision != "fp32" else "f32",
