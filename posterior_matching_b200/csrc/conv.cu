@@ -503,6 +503,7 @@ int pmvae_conv2d_forward(const pmvae_conv_desc* desc, const float* x, const floa
       e.bias = p.bias;
     }
     const bool padded = Cp != desc->Cout;
+    PMVAE_CHECK(padded || (reinterpret_cast<uintptr_t>(y) & 15u) == 0, "bf16 convolution path: y must be 16-byte aligned");
     e.out_f32 = padded ? p.ytmp : y; e.ld_out_f32 = Cp;
     PMVAE_TRY(tc::gemm_nt(p.col, Kp, p.nk, Kp, rows, Cp, Kc, e, s));
     if (padded) {
@@ -587,6 +588,7 @@ int pmvae_conv2d_backward(const pmvae_conv_desc* desc, const float* x, const flo
       PMVAE_LAUNCH_CHECK();
       tc::TcGemmArgs e{};
       const bool padded = Cp_a != a.Cout;
+      PMVAE_CHECK(padded || (reinterpret_cast<uintptr_t>(dx) & 15u) == 0, "bf16 convolution path: dx must be 16-byte aligned");
       e.out_f32 = padded ? p.ytmp : dx; e.ld_out_f32 = Cp_a;
       PMVAE_TRY(tc::gemm_nt(p.col, Kp_a, p.nk, Kp_a, rows_a, Cp_a, Kc_a, e, s));
       if (padded) {
