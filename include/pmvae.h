@@ -153,7 +153,10 @@ int pmvae_adamw(const pmvae_config* cfg, float* params, const float* grads, floa
  *   which = 1: decoder(z[B,d])             -> out[B,D]  IdentityGaussian loc
  *   which = 2: partial_encoder([x*b, b])   -> out[B,P]  (in = x, msk = b, both [B,D])
  * P = d + d(d+1)/2. */
-enum { PMVAE_NET_ENCODER = 0, PMVAE_NET_DECODER = 1, PMVAE_NET_PARTIAL_ENCODER = 2 };
+enum { PMVAE_NET_ENCODER = 0, PMVAE_NET_DECODER = 1, PMVAE_NET_PARTIAL_ENCODER = 2,
+       /* OR-ed into `which`: run the training-mode forward of that net (what pmvae_forward launches for it: the
+        * saved activations / relu bits of pmvae_backward are written into `ws` as well) -- bench.py's roofline leg */
+       PMVAE_NET_SAVE = 0x100 };
 int pmvae_net_apply(const pmvae_config* cfg, const float* params, int32_t which, const float* in,
                     const float* msk, int64_t B, float* out, void* ws, uint64_t ws_bytes,
                     pmvae_stream_t stream);
@@ -173,6 +176,34 @@ int pmvae_impute_mean(const pmvae_config* cfg, const float* params, const float*
                       int64_t B, int64_t K, const uint32_t key[2], int64_t B_total,
                       int64_t row_start, float* out /* [B,D] */, void* ws, uint64_t ws_bytes,
                       pmvae_stream_t stream);
+
+/* PosteriorMatchingVAE.impute (vae.py:146-169): K imputations per row, out_samples[K, B, D] =
+ * where(b == 1, x_o, decoder mean of z_k), z_k ~ q(z | x_o) drawn as in pmvae_impute_mean (same key, same stream);
+ * out_mean[B, D] (optional) is their mean over K.  Either output may be NULL, not both. */
+int pmvae_impute(const pmvae_config* cfg, const float* params, const float* x, const float* b,
+                 int64_t B, int64_t K, const uint32_t key[2], int64_t B_total, int64_t row_start,
+                 float* out_samples /* [K,B,D] */, float* out_mean /* [B,D] or NULL */, void* ws,
+                 uint64_t ws_bytes, pmvae_stream_t stream);
+
+/* ---- distribution objects behind .encoder / .partial_encoder / .decoder / .prior (vae.py:47-57) ---------------
+ * What lookahead.py:126-133,219-222 and the evaluation scripts call on the returned tfd objects, as row kernels over
+ * the raw head output `par[B, d + d(d+1)/2]` of pmvae_net_apply (TriLGaussian, distributions.py:101-113):
+ *   pmvae_tril_log_prob   MultivariateNormalTriL.log_prob(z)            out[B]
+ *   pmvae_tril_entropy    MultivariateNormalTriL.entropy()              out[B]
+ *   pmvae_tril_sample     .sample(seed=key, sample_shape=K): z[K,B,d] = mu + L eps, eps = rows
+ *                         [row_start, row_start+B) of normal(key, [K, B_total, d]); log_ratio[K,B] =
+ *                         log N(z; 0, I) - log q(z) (the importance-weight term of vae.py:203-212)
+ * (one sample with caller-provided eps + the KL to the prior: pmvae_tril_sample_kl below)
+ *   pmvae_normal_log_prob IdentityGaussian (distributions.py:41-55): Normal(loc, exp(log_scale)).log_prob(x)
+ *                         elementwise, out[rows, D]; x has rows_x rows and is repeated rows / rows_x times
+ *   pmvae_std_normal_log_prob  the prior MultivariateNormalDiag(0, 1).log_prob(z) (vae.py:55-57), out[B] */
+int pmvae_tril_log_prob(const float* par, const float* z, int64_t B, int32_t d, float* out, pmvae_stream_t stream);
+int pmvae_tril_entropy(const float* par, int64_t B, int32_t d, float* out, pmvae_stream_t stream);
+int pmvae_tril_sample(const float* par, const uint32_t key[2], int64_t B, int64_t K, int64_t B_total,
+                      int64_t row_start, int32_t d, float* z, float* log_ratio, pmvae_stream_t stream);
+int pmvae_normal_log_prob(const float* x, const float* loc, const float* log_scale /* device scalar */,
+                          int64_t rows, int64_t rows_x, int32_t D, float* out, pmvae_stream_t stream);
+int pmvae_std_normal_log_prob(const float* z, int64_t B, int32_t d, float* out, pmvae_stream_t stream);
 
 /* ---- the whole training step as one launch sequence ---------------------------------------------
  * train_pm_vae.py's step (mask draw, eps draw, loss_fn forward, value_and_grad, optax update) enqueued by ONE
@@ -294,14 +325,16 @@ int pmvae_tril_sample_kl_backward(const float* par, const float* eps, const floa
 int pmvae_adamw_flat(float* params, const float* grads, float* m, float* v, uint64_t n, int64_t count, float lr,
                      float wd, float b1, float b2, float eps, pmvae_stream_t stream);
 
-/* ---- XLA custom-call targets (jax.ffi / xla_client registration, api_version 1) --------------
+/* ---- XLA custom-call targets (jax.ffi / xla_client registration; CustomCallApiVersion
+ *      API_VERSION_STATUS_RETURNING = 2, i.e. `custom_call_api_version=2`) --------------
  * The reference is driven by jax.jit / jax.value_and_grad (bax.Trainer, train_pm_vae.py:85,96;
  * eval_pm_vae_uci.py:96), so the binding a maintainer adds is an XLA custom call per entry
  * point.  Each target has the status-returning legacy signature
  *     void target(cudaStream_t stream, void** buffers, const char* opaque, size_t opaque_len,
  *                 XlaCustomCallStatus* status)
  * with `buffers` = the operands followed by the results (all device pointers owned by XLA) and
- * `opaque` = one pmvae_xla_opaque.  Scratch (`ws`) is a result buffer XLA allocates; the forward's
+ * `opaque` = one pmvae_xla_opaque.  Scratch (`ws`) is a result buffer of ws_bytes + PMVAE_XLA_WS_SLACK bytes that
+ * XLA allocates (XLA aligns to 256 bytes at most, the tensor path needs 1024: the targets round the pointer up); the forward's
  * `ws` is a residual of the custom_vjp and is passed to the backward as an operand aliased to a
  * result.  posterior_matching_b200/jax_ffi.py registers them; INTEGRATION.md shows the wiring.
  *
@@ -311,6 +344,7 @@ int pmvae_adamw_flat(float* params, const float* grads, float* m, float* v, uint
  *   pmvae_xla_impute_mean  operands [params, x_o, b]                           results [mean, ws]
  *   pmvae_xla_mask_bernoulli  operands []                                      results [mask]
  */
+#define PMVAE_XLA_WS_SLACK 1024
 typedef struct pmvae_xla_opaque {
   pmvae_config cfg;
   int64_t B, K, B_total, row_start;

@@ -73,6 +73,35 @@ def random_bits(key, n: int):
     return np.concatenate([a, b])[:n]
 
 
+def random_bits_at(key, n: int, idx):
+    """Elements `idx` (flat indices) of `random_bits(key, n)` without forming the whole draw: element i < h is the
+    first word of threefry(key; i, i + h), element i >= h the second word of threefry(key; i - h, i), h = ceil(n / 2)
+    (the counter appended for odd n is 0)."""
+    n = int(n)
+    idx = np.asarray(idx, dtype=np.uint64)
+    h = (n + (n & 1)) // 2
+    first = idx < h
+    c0 = np.where(first, idx, idx - h)
+    c1 = c0 + np.uint64(h)
+    if n & 1:
+        c1 = np.where(c1 == n, 0, c1)          # the padding counter
+    a, b = threefry2x32(key, c0.astype(U32), c1.astype(U32))
+    return np.where(first, a, b)
+
+
+def normal_rows(key, K: int, B: int, d: int, row_start: int, rows: int):
+    """Rows [row_start, row_start + rows) of `normal(key, (K, B, d))` -> [K, rows, d] float32."""
+    k = np.arange(K, dtype=np.uint64)[:, None, None]
+    r = (np.uint64(row_start) + np.arange(rows, dtype=np.uint64))[None, :, None]
+    j = np.arange(d, dtype=np.uint64)[None, None, :]
+    idx = ((k * np.uint64(B) + r) * np.uint64(d) + j).reshape(-1)
+    bits = random_bits_at(key, K * B * d, idx)
+    f = ((bits >> U32(9)) | U32(0x3F800000)).view(np.float32) - np.float32(1.0)
+    lo = np.nextafter(np.float32(-1.0), np.float32(0.0))
+    u = np.maximum(lo, f * (np.float32(1.0) - lo) + lo).astype(np.float32)
+    return (np.float32(np.sqrt(2.0)) * erfinv_f32(u)).astype(np.float32).reshape(K, rows, d)
+
+
 def split(key, num: int = 2):
     """[V] `jax.random.split(key, num)` -> [num, 2] uint32."""
     return random_bits(key, 2 * num).reshape(num, 2)

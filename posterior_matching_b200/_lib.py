@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpmvae.so")
 
 PREC_F32, PREC_BF16 = 0, 1
+NET_SAVE = 0x100      # PMVAE_NET_SAVE
 
 
 class Config(C.Structure):
@@ -131,6 +132,12 @@ _SIGS = {
     "pmvae_xla_impute_mean": (None, [_vp, C.POINTER(_vp), C.c_char_p, C.c_size_t, _vp]),
     "pmvae_xla_mask_bernoulli": (None, [_vp, C.POINTER(_vp), C.c_char_p, C.c_size_t, _vp]),
     "pmvae_impute_mean": (_i32, [_cfgp, _vp, _vp, _vp, _i64, _i64, _u32p, _i64, _i64, _vp, _vp, _u64, _vp]),
+    "pmvae_tril_log_prob": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "pmvae_tril_entropy": (_i32, [_vp, _i64, _i32, _vp, _vp]),
+    "pmvae_tril_sample": (_i32, [_vp, _u32p, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
+    "pmvae_normal_log_prob": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp]),
+    "pmvae_std_normal_log_prob": (_i32, [_vp, _i64, _i32, _vp, _vp]),
+    "pmvae_impute": (_i32, [_cfgp, _vp, _vp, _vp, _i64, _i64, _u32p, _i64, _i64, _vp, _vp, _vp, _u64, _vp]),
 }
 EXPORTS = tuple(_SIGS)
 

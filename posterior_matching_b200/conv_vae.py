@@ -142,15 +142,20 @@ class ConvPosteriorMatchingVAE:
 
     # ---- vae.py:120-144 ---------------------------------------------------------------------------
     def __call__(self, x: torch.Tensor, b: torch.Tensor, is_training: bool = False, *, rng=None,
-                 eps: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                 eps: Optional[torch.Tensor] = None, row_start: int = 0,
+                 total_rows: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """`row_start` / `total_rows`: this call's rows inside a global batch (data parallelism): eps is rows
+        [row_start, row_start + B) of normal(key, [total_rows, d]), like PosteriorMatchingVAE.draw_eps."""
         x, b = _f32c(x, self.device), _f32c(b, self.device)
         B, d = x.shape[0], self.latent_dim
         if eps is None:
             if rng is None:
                 raise ValueError("pass rng= or eps=")
             key = prng.PRNGSequence(rng).next()        # the conv encoder draws no dropout keys (SURVEY §8a-R)
+            total = B if total_rows is None else int(total_rows)
             eps = torch.empty((B, d), dtype=torch.float32, device=self.device)
-            _lib.check(_lib.lib.pmvae_normal(_lib.key_arg(key), B * d, 0, B * d, eps.data_ptr(), _stream()), "pmvae_normal")
+            _lib.check(_lib.lib.pmvae_normal(_lib.key_arg(key), total * d, int(row_start) * d, B * d, eps.data_ptr(),
+                                             _stream()), "pmvae_normal")
         eps = _f32c(eps, self.device)
         S = _stream()
         enc_acts = self.enc.forward(self.params, x)
@@ -204,12 +209,12 @@ class ConvPosteriorMatchingVAE:
     # ---- train_pm_vae.py:58-83 (beta = 1: the MNIST config has no beta schedule; weight_decay = 0) ------
     def train_step(self, x, b, *, rng=None, eps=None, lr_schedule=None, matching_coef: float = 1.0,
                    adam=(0.9, 0.999, 1e-8), grad_sync=None, global_rows: Optional[int] = None,
-                   sync_metrics: bool = True) -> Dict[str, float]:
+                   row_start: int = 0, sync_metrics: bool = True) -> Dict[str, float]:
         """One optimizer step.  Data parallel: every rank passes its own rows, `global_rows` = rows over all ranks (the
         cotangents are scaled by 1 / global_rows) and `grad_sync(tensors)` sums the two flat gradient arenas across ranks
         before the update (e.g. one NCCL all-reduce each).  `sync_metrics=False` skips the host read of the batch means
         (returns device tensors instead), so consecutive steps queue without a host round trip."""
-        out = self(x, b, is_training=True, rng=rng, eps=eps)
+        out = self(x, b, is_training=True, rng=rng, eps=eps, row_start=row_start, total_rows=global_rows)
         B = out["kl"].shape[0]
         ones = torch.full((B,), 1.0 / (global_rows or B), device=self.device)
         self.backward(-ones, ones, -matching_coef * ones)

@@ -1,0 +1,104 @@
+// Stand-alone distribution algebra behind the module attributes of PosteriorMatchingVAE (vae.py:47-57): the
+// objects `.encoder(x)`, `.partial_encoder(x_o_b)` (tfd.MultivariateNormalTriL, distributions.py:101-113),
+// `.decoder(z)` (tfd.Normal with one shared scale, distributions.py:41-55) and `.prior`
+// (tfd.MultivariateNormalDiag(0, 1), vae.py:55-57) expose .mean() / .sample() / .log_prob() / .entropy();
+// lookahead.py:126-133,219-222 and the evaluation scripts call them.  Small HBM-bound row kernels; the
+// K-sample draw and the TriL log-prob reuse the kernels of the training / evaluation path (latent.cu).
+#include "kernels.h"
+
+namespace pmvae {
+
+static int grid_rows(int64_t work, int block) {
+  int64_t g = ceil_div(work, block);
+  if (g > 148 * 8) g = 148 * 8;
+  return (int)(g < 1 ? 1 : g);
+}
+
+// entropy of N(mu, L L^T): d/2 (1 + log 2 pi) + sum_i log L_ii, L_ii = softplus(raw_ii) + 1e-5 (FillScaleTriL);
+// the diagonal (i, i) of tfp's fill_triangular sits at c[i*d + i], c = concat(v[d:], reverse(v))
+__global__ void __launch_bounds__(256) tril_entropy_kernel(const float* __restrict__ par, int64_t B, int d,
+                                                           float* __restrict__ out) {
+  const int m = d * (d + 1) / 2, P = d + m;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < B; r += (int64_t)gridDim.x * blockDim.x) {
+    const float* v = par + r * P + d;
+    float acc = 0.f;
+    for (int i = 0; i < d; ++i) {
+      const int k = i * d + i;
+      const float raw = v[(k < m - d) ? (d + k) : (m - 1 - (k - (m - d)))];
+      acc += logf(softplus_f(raw) + 1e-5f);
+    }
+    out[r] = 0.5f * d * (1.0f + kLog2Pi) + acc;
+  }
+}
+
+// tfd.Normal(loc, exp(log_scale)).log_prob(x), elementwise over [rows, D] (loc has row pitch ld_loc); x is
+// broadcast over `reps` leading repetitions of its `rows_x` rows (the [K, B, D] case of vae.py:197-199)
+__global__ void __launch_bounds__(256) normal_log_prob_kernel(const float* __restrict__ x, const float* __restrict__ loc,
+                                                              int64_t ld_loc, const float* __restrict__ log_scale,
+                                                              int64_t rows, int64_t rows_x, int D,
+                                                              float* __restrict__ out) {
+  const float ls = *log_scale, inv = __expf(-ls);
+  const int64_t n = rows * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / D;
+    const int j = (int)(i - r * D);
+    const float t = (x[(r % rows_x) * D + j] - loc[r * ld_loc + j]) * inv;
+    out[i] = -0.5f * t * t - ls - 0.5f * kLog2Pi;
+  }
+}
+
+// tfd.MultivariateNormalDiag(0, 1).log_prob(z): -|z|^2 / 2 - d/2 log 2 pi
+__global__ void __launch_bounds__(256) std_normal_log_prob_kernel(const float* __restrict__ z, int64_t B, int d,
+                                                                  float* __restrict__ out) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < B; r += (int64_t)gridDim.x * blockDim.x) {
+    float q = 0.f;
+    for (int j = 0; j < d; ++j) { const float v = z[r * d + j]; q = fmaf(v, v, q); }
+    out[r] = -0.5f * q - 0.5f * d * kLog2Pi;
+  }
+}
+
+}  // namespace pmvae
+
+using namespace pmvae;
+
+extern "C" {
+
+int pmvae_tril_log_prob(const float* par, const float* z, int64_t B, int32_t d, float* out, pmvae_stream_t stream) {
+  PMVAE_CHECK(B >= 0 && (B == 0 || (par && z && out)), "bad arguments");
+  return match_fwd(par, z, out, B, d, as_stream(stream));
+}
+
+int pmvae_tril_entropy(const float* par, int64_t B, int32_t d, float* out, pmvae_stream_t stream) {
+  PMVAE_CHECK(B >= 0 && d >= 1 && d <= 64 && (B == 0 || (par && out)), "bad arguments");
+  if (B == 0) return 0;
+  tril_entropy_kernel<<<grid_rows(B, 256), 256, 0, as_stream(stream)>>>(par, B, d, out);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int pmvae_tril_sample(const float* par, const uint32_t key[2], int64_t B, int64_t K, int64_t B_total, int64_t row_start,
+                      int32_t d, float* z, float* log_ratio, pmvae_stream_t stream) {
+  PMVAE_CHECK(B >= 0 && K >= 1 && row_start >= 0 && row_start + B <= B_total, "bad K / row range");
+  PMVAE_CHECK(B == 0 || (par && key && z && log_ratio), "null pointer");
+  return sample_latents(par, Key2{key[0], key[1]}, B, K, B_total, row_start, d, z, log_ratio, as_stream(stream));
+}
+
+int pmvae_normal_log_prob(const float* x, const float* loc, const float* log_scale, int64_t rows, int64_t rows_x,
+                          int32_t D, float* out, pmvae_stream_t stream) {
+  PMVAE_CHECK(rows >= 0 && D >= 1 && rows_x >= 1 && (rows == 0 || (x && loc && log_scale && out)), "bad arguments");
+  PMVAE_CHECK(rows % rows_x == 0, "rows must be a multiple of the rows of x");
+  if (rows == 0) return 0;
+  normal_log_prob_kernel<<<grid_rows(rows * D, 256), 256, 0, as_stream(stream)>>>(x, loc, D, log_scale, rows, rows_x, D, out);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int pmvae_std_normal_log_prob(const float* z, int64_t B, int32_t d, float* out, pmvae_stream_t stream) {
+  PMVAE_CHECK(B >= 0 && d >= 1 && (B == 0 || (z && out)), "bad arguments");
+  if (B == 0) return 0;
+  std_normal_log_prob_kernel<<<grid_rows(B, 256), 256, 0, as_stream(stream)>>>(z, B, d, out);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

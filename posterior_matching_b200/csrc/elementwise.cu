@@ -368,4 +368,27 @@ int impute_mean(const float* x, const float* b, const float* loc, int64_t ld_loc
   return 0;
 }
 
+// vae.py:164-165: imputations = where(b == 1, x_o, decoder mean) for every sample k of a chunk of nb data rows:
+// out[(k * B_all + r) * D + j] with r counted inside the whole call (out already points at the chunk's first row)
+__global__ void __launch_bounds__(256) impute_samples_kernel(const float* __restrict__ x, const float* __restrict__ b,
+                                                             const float* __restrict__ loc, int64_t ld_loc,
+                                                             float* __restrict__ out, int64_t nb, int64_t B_all, int64_t K,
+                                                             int D) {
+  const int64_t n = K * nb * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t kr = i / D;
+    const int j = (int)(i - kr * D);
+    const int64_t k = kr / nb, r = kr - k * nb;
+    const float bv = b[r * D + j];
+    out[(k * B_all + r) * D + j] = bv != 0.f ? x[r * D + j] * bv : loc[kr * ld_loc + j];
+  }
+}
+int impute_samples(const float* x, const float* b, const float* loc, int64_t ld_loc, float* out, int64_t nb, int64_t B_all,
+                   int64_t K, int D, cudaStream_t s) {
+  if (nb == 0) return 0;
+  impute_samples_kernel<<<grid1d(K * nb * D, 256), 256, 0, s>>>(x, b, loc, ld_loc, out, nb, B_all, K, D);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace pmvae

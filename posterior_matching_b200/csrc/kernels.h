@@ -56,7 +56,9 @@ int rec_ll_bwd(const float* x, const float* loc, int64_t ld_loc, const float* lo
 int loss_cotangents(int64_t B, int64_t B_global, float beta, float coef, const float* rec, const float* kl,
                     const float* match, float* g_rec, float* g_kl, float* g_match, float* out_sums, cudaStream_t s,
                     const StepState* st = nullptr);
-struct AdamSegs { int n; uint32_t beg[48]; uint32_t end[48]; };  // no-decay (bias) ranges
+// no-decay (bias) ranges: one per Linear of the three nets (<= 2 * kMaxBlocks + 1 = 17 each) + three heads
+constexpr int kAdamSegCap = 3 * (2 * 8 + 1) + 3;
+struct AdamSegs { int n; uint32_t beg[kAdamSegCap]; uint32_t end[kAdamSegCap]; };
 // st (optional): lr and the bias corrections are read from the device step state instead
 int adamw(float* p, const float* g, float* m, float* v, uint64_t n, const AdamSegs& nodecay, float lr, float wd,
           float b1, float b2, float eps, float bc1, float bc2, cudaStream_t s, const StepState* st = nullptr);
@@ -72,6 +74,9 @@ int eval_rows_ll(const float* x, const float* w, const float* loc, int64_t ld_lo
 int logmeanexp_rows(const float* a, const float* c, float* out, int64_t B, int64_t K, cudaStream_t s);
 int impute_mean(const float* x, const float* b, const float* loc, int64_t ld_loc, float* out, int64_t B, int64_t K,
                 int D, cudaStream_t s);
+// out[(k * B_all + r) * D + j] = b ? x * b : loc[(k * nb + r) * ld_loc + j]   (one chunk of nb data rows, K samples)
+int impute_samples(const float* x, const float* b, const float* loc, int64_t ld_loc, float* out, int64_t nb, int64_t B_all,
+                   int64_t K, int D, cudaStream_t s);
 
 // ---- latent.cu  (par = raw TriL head output [B, P], P = d + d(d+1)/2)
 int latent_fwd(const float* par, const float* eps, float* z, float* kl, int64_t B, int d, cudaStream_t s);

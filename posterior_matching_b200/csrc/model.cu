@@ -317,15 +317,28 @@ int backward(const pmvae_config* c, const float* params, const float* x, const f
   return 0;
 }
 
+// Bias leaves of the arena (ndim == 1: no weight decay, train_pm_vae.py:77-79), bound-checked against AdamSegs.
+static_assert(kAdamSegCap >= 3 * (2 * kMaxBlocks + 1) + 3, "AdamSegs must hold every bias leaf kMaxBlocks allows");
+static int bias_ranges(const Layout& L, AdamSegs* seg) {
+  seg->n = 0;
+  bool ok = true;
+  auto add = [&](const Leaf& lf) {
+    if (seg->n >= kAdamSegCap) { ok = false; return; }
+    seg->beg[seg->n] = (uint32_t)lf.b; seg->end[seg->n] = (uint32_t)(lf.b + pad64(lf.cols)); ++seg->n;
+  };
+  auto addnet = [&](const Net& n) { for (int i = 0; i <= 2 * n.R; ++i) add(n.lin[i]); };
+  addnet(L.enc); add(L.post); addnet(L.dec); add(L.ddist); addnet(L.part); add(L.ppost);
+  PMVAE_CHECK(ok, "too many bias leaves for AdamSegs");
+  return 0;
+}
+
 int adamw_step(const pmvae_config* c, float* params, const float* grads, float* m, float* v, int64_t count, float lr,
                float wd, float b1, float b2, float eps, cudaStream_t s) {
   Layout L;
   PMVAE_TRY(build_layout(c, &L));
   PMVAE_CHECK(params && grads && m && v && count >= 0, "bad arguments");
   AdamSegs seg{};
-  auto add = [&](const Leaf& lf) { seg.beg[seg.n] = (uint32_t)lf.b; seg.end[seg.n] = (uint32_t)(lf.b + pad64(lf.cols)); ++seg.n; };
-  auto addnet = [&](const Net& n) { for (int i = 0; i <= 2 * n.R; ++i) add(n.lin[i]); };
-  addnet(L.enc); add(L.post); addnet(L.dec); add(L.ddist); addnet(L.part); add(L.ppost);
+  PMVAE_TRY(bias_ranges(L, &seg));
   const double t = (double)count + 1.0;
   const float bc1 = (float)(1.0 - pow((double)b1, t)), bc2 = (float)(1.0 - pow((double)b2, t));
   return adamw(params, grads, m, v, L.total, seg, lr, wd, b1, b2, eps, bc1, bc2, s);
@@ -375,16 +388,16 @@ int is_log_prob(const pmvae_config* c, const float* params, const float* x, cons
 }
 
 int impute_mean_seq(const pmvae_config* c, const float* params, const float* x, const float* b, int64_t B, int64_t K,
-                    const uint32_t key[2], int64_t B_total, int64_t row_start, float* out, void* ws, uint64_t ws_bytes,
-                    cudaStream_t s) {
+                    const uint32_t key[2], int64_t B_total, int64_t row_start, float* out, float* out_samples, void* ws,
+                    uint64_t ws_bytes, cudaStream_t s) {
   Layout L;
   PMVAE_TRY(build_layout(c, &L));
   if (B == 0) return 0;
-  PMVAE_CHECK(params && x && b && key && out && ws, "null pointer");
+  PMVAE_CHECK(params && x && b && key && (out || out_samples) && ws, "null pointer");
   PMVAE_CHECK(K >= 1 && B >= 0 && row_start >= 0 && row_start + B <= B_total, "bad K / row range");
   if (B == 0) return 0;
   if (c->precision == PMVAE_PREC_BF16)
-    return impute_mean_bf16(c, L, params, x, b, B, K, key, B_total, row_start, out, ws, ws_bytes, s);
+    return impute_mean_bf16(c, L, params, x, b, B, K, key, B_total, row_start, out, out_samples, ws, ws_bytes, s);
   EvalPlan p = plan_eval(c, L, B, K, ws);
   PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_workspace_bytes)");
   PMVAE_TRY(eval_common(c, L, params, x, b, B, p, false, s));
@@ -392,7 +405,9 @@ int impute_mean_seq(const pmvae_config* c, const float* params, const float* x, 
     const int64_t nb = (B - r0 < p.rows_per_chunk) ? (B - r0) : p.rows_per_chunk;
     PMVAE_TRY(sample_latents(p.par_p + r0 * L.P, Key2{key[0], key[1]}, nb, K, B_total, row_start + r0, c->d, p.z, p.base, s));
     PMVAE_TRY(net_fwd_f32(params, L.dec, L.ddist, c->H, p.z, nb * K, p.dec, p.loc, s));
-    PMVAE_TRY(impute_mean(x + r0 * c->D, b + r0 * c->D, p.loc, c->D, out + r0 * c->D, nb, K, c->D, s));
+    if (out) PMVAE_TRY(impute_mean(x + r0 * c->D, b + r0 * c->D, p.loc, c->D, out + r0 * c->D, nb, K, c->D, s));
+    if (out_samples)
+      PMVAE_TRY(impute_samples(x + r0 * c->D, b + r0 * c->D, p.loc, c->D, out_samples + r0 * c->D, nb, B, K, c->D, s));
   }
   return 0;
 }
@@ -402,9 +417,7 @@ int adamw_step_dev(const pmvae_config* c, float* params, const float* grads, flo
   Layout L;
   PMVAE_TRY(build_layout(c, &L));
   AdamSegs seg{};
-  auto add = [&](const Leaf& lf) { seg.beg[seg.n] = (uint32_t)lf.b; seg.end[seg.n] = (uint32_t)(lf.b + pad64(lf.cols)); ++seg.n; };
-  auto addnet = [&](const Net& n) { for (int i = 0; i <= 2 * n.R; ++i) add(n.lin[i]); };
-  addnet(L.enc); add(L.post); addnet(L.dec); add(L.ddist); addnet(L.part); add(L.ppost);
+  PMVAE_TRY(bias_ranges(L, &seg));
   return adamw(params, grads, m, v, L.total, seg, 0.f, wd, b1, b2, eps, 1.f, 1.f, s, st);
 }
 
@@ -492,10 +505,12 @@ int net_apply(const pmvae_config* c, const float* params, int which, const float
               float* out, void* ws, uint64_t ws_bytes, cudaStream_t s) {
   Layout L;
   PMVAE_TRY(build_layout(c, &L));
+  const bool save = (which & PMVAE_NET_SAVE) != 0;     // training-mode forward (fp32 path: it always saves)
+  which &= ~PMVAE_NET_SAVE;
   PMVAE_CHECK(which >= 0 && which <= 2, "net id must be 0 (encoder), 1 (decoder) or 2 (partial encoder)");
   if (B == 0) return 0;
   PMVAE_CHECK(params && in && out && ws && B >= 0 && (which != 2 || msk), "null pointer");
-  if (c->precision == PMVAE_PREC_BF16) return net_apply_bf16(c, L, params, which, in, msk, B, out, ws, ws_bytes, s);
+  if (c->precision == PMVAE_PREC_BF16) return net_apply_bf16(c, L, params, which, in, msk, B, out, save, ws, ws_bytes, s);
   TrainPlan p = plan_train(c, L, B, ws);
   PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_workspace_bytes)");
   if (which == 0) return net_fwd_f32(params, L.enc, L.post, c->H, in, B, p.enc, out, s);
@@ -687,7 +702,14 @@ int pmvae_net_apply(const pmvae_config* cfg, const float* params, int32_t which,
 int pmvae_impute_mean(const pmvae_config* cfg, const float* params, const float* x, const float* b, int64_t B,
                       int64_t K, const uint32_t key[2], int64_t B_total, int64_t row_start, float* out, void* ws,
                       uint64_t ws_bytes, pmvae_stream_t stream) {
-  return impute_mean_seq(cfg, params, x, b, B, K, key, B_total, row_start, out, ws, ws_bytes, as_stream(stream));
+  return impute_mean_seq(cfg, params, x, b, B, K, key, B_total, row_start, out, nullptr, ws, ws_bytes, as_stream(stream));
+}
+
+int pmvae_impute(const pmvae_config* cfg, const float* params, const float* x, const float* b, int64_t B, int64_t K,
+                 const uint32_t key[2], int64_t B_total, int64_t row_start, float* out_samples, float* out_mean, void* ws,
+                 uint64_t ws_bytes, pmvae_stream_t stream) {
+  return impute_mean_seq(cfg, params, x, b, B, K, key, B_total, row_start, out_mean, out_samples, ws, ws_bytes,
+                         as_stream(stream));
 }
 
 }  // extern "C"

@@ -30,13 +30,13 @@ int backward_bf16(const pmvae_config* c, const Layout& L, const float* params, c
                   const float* eps, int64_t B, const float* g_rec, const float* g_kl, const float* g_match,
                   float* grads, void* ws, uint64_t ws_bytes, cudaStream_t s);
 int net_apply_bf16(const pmvae_config* c, const Layout& L, const float* params, int which, const float* in,
-                   const float* msk, int64_t B, float* out, void* ws, uint64_t ws_bytes, cudaStream_t s);
+                   const float* msk, int64_t B, float* out, bool save, void* ws, uint64_t ws_bytes, cudaStream_t s);
 int is_log_prob_bf16(const pmvae_config* c, const Layout& L, const float* params, const float* x, const float* b,
                      int64_t B, int64_t K, const uint32_t key_z[2], const uint32_t key_zxo[2], int64_t B_total,
                      int64_t row_start, float* out_log_p_x, float* out_cond, void* ws, uint64_t ws_bytes,
                      cudaStream_t s);
 int impute_mean_bf16(const pmvae_config* c, const Layout& L, const float* params, const float* x, const float* b,
                      int64_t B, int64_t K, const uint32_t key[2], int64_t B_total, int64_t row_start, float* out,
-                     void* ws, uint64_t ws_bytes, cudaStream_t s);
+                     float* out_samples, void* ws, uint64_t ws_bytes, cudaStream_t s);
 
 }  // namespace pmvae

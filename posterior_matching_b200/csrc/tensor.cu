@@ -834,7 +834,7 @@ int is_log_prob_bf16(const pmvae_config* c, const Layout& L, const float* params
 
 int impute_mean_bf16(const pmvae_config* c, const Layout& L, const float* params, const float* x, const float* b,
                      int64_t B, int64_t K, const uint32_t key[2], int64_t B_total, int64_t row_start, float* out,
-                     void* ws, uint64_t ws_bytes, cudaStream_t s) {
+                     float* out_samples, void* ws, uint64_t ws_bytes, cudaStream_t s) {
   PMVAE_CHECK(c->H == 256, "the tensor path is specialised for hidden_units = 256");
   EvalPlanB p = plan_eval_b(c, L, B, K, ws);
   CHECK_WS(p);
@@ -845,7 +845,9 @@ int impute_mean_bf16(const pmvae_config* c, const Layout& L, const float* params
     PMVAE_TRY(sample_latents(p.par_p + r0 * L.P, Key2{key[0], key[1]}, nb, K, B_total, row_start + r0, c->d, p.z, p.base, s));
     PMVAE_TRY(net_fwd_b(params, L.dec, p.img.dec, L.ddist, p.img.ddist, p.Dp, p.z, nullptr, c->d, nb * K, p.dec, p.h,
                         p.ytmp, p.loc, p.Dp, p.img.f_dec_ok ? &p.img.f_dec : nullptr, false, s));
-    PMVAE_TRY(impute_mean(x + r0 * c->D, b + r0 * c->D, p.loc, p.Dp, out + r0 * c->D, nb, K, c->D, s));
+    if (out) PMVAE_TRY(impute_mean(x + r0 * c->D, b + r0 * c->D, p.loc, p.Dp, out + r0 * c->D, nb, K, c->D, s));
+    if (out_samples)
+      PMVAE_TRY(impute_samples(x + r0 * c->D, b + r0 * c->D, p.loc, p.Dp, out_samples + r0 * c->D, nb, B, K, c->D, s));
   }
   return 0;
 }
@@ -853,18 +855,18 @@ int impute_mean_bf16(const pmvae_config* c, const Layout& L, const float* params
 // One net + its distribution head on its own (the module's .encoder / .decoder / .partial_encoder):
 // which = 0 encoder(x) -> [B, P], 1 decoder(z) -> [B, D], 2 partial_encoder([x*b, b]) -> [B, P].
 int net_apply_bf16(const pmvae_config* c, const Layout& L, const float* params, int which, const float* in,
-                   const float* msk, int64_t B, float* out, void* ws, uint64_t ws_bytes, cudaStream_t s) {
+                   const float* msk, int64_t B, float* out, bool save, void* ws, uint64_t ws_bytes, cudaStream_t s) {
   PMVAE_CHECK(c->H == 256, "the tensor path is specialised for hidden_units = 256");
   TrainPlanB p = plan_train_b(c, L, B, ws);
   CHECK_WS(p);
   if (which == 0)
     return net_fwd_b(params, L.enc, p.img.enc, L.post, p.img.post, L.P, in, nullptr, c->D, B, p.enc, p.h, p.ytmp, out,
-                     L.P, p.img.f_enc_ok ? &p.img.f_enc : nullptr, false, s);
+                     L.P, p.img.f_enc_ok ? &p.img.f_enc : nullptr, save, s);
   if (which == 2)
     return net_fwd_b(params, L.part, p.img.part, L.ppost, p.img.ppost, L.P, in, msk, c->D, B, p.part, p.h, p.ytmp, out,
-                     L.P, p.img.f_part_ok ? &p.img.f_part : nullptr, false, s);
+                     L.P, p.img.f_part_ok ? &p.img.f_part : nullptr, save, s);
   PMVAE_TRY(net_fwd_b(params, L.dec, p.img.dec, L.ddist, p.img.ddist, p.Dp, in, nullptr, c->d, B, p.dec, p.h, p.ytmp,
-                      p.loc, p.Dp, p.img.f_dec_ok ? &p.img.f_dec : nullptr, false, s));
+                      p.loc, p.Dp, p.img.f_dec_ok ? &p.img.f_dec : nullptr, save, s));
   PMVAE_CUDA(cudaMemcpy2DAsync(out, (size_t)c->D * 4, p.loc, (size_t)p.Dp * 4, (size_t)c->D * 4, (size_t)B,
                                cudaMemcpyDeviceToDevice, s));
   return 0;

@@ -1,6 +1,7 @@
 // XLA custom-call targets over the C ABI (include/pmvae.h): what jax.ffi / xla_client registers so that the
 // reference's jitted loss_fn / eval_fn (train_pm_vae.py:58-72, eval_pm_vae_uci.py:82-96) reach the CUDA path.
-// Status-returning legacy signature (api_version 1); failures go through XlaCustomCallStatusSetFailure,
+// Status-returning legacy signature (XLA CustomCallApiVersion API_VERSION_STATUS_RETURNING = 2: the trailing
+// XlaCustomCallStatus* argument; 1 = API_VERSION_ORIGINAL has none); failures go through XlaCustomCallStatusSetFailure,
 // which is resolved from the hosting process (jaxlib) at run time so that this library links without XLA.
 #include <dlfcn.h>
 #include <string.h>
@@ -28,6 +29,11 @@ const pmvae_xla_opaque* decode(const char* opaque, size_t len, void* status) {
   return reinterpret_cast<const pmvae_xla_opaque*>(opaque);
 }
 
+// XLA aligns its buffers to 256 bytes at most; the tensor path wants 1024 (TMA / swizzle atoms).  The workspace
+// buffer XLA allocates is therefore ws_bytes + PMVAE_XLA_WS_SLACK bytes and every target rounds the pointer up
+// (the same offset in the forward and the backward, which receive the same buffer).
+void* align_ws(void* p) { return reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(p) + 1023u) & ~uintptr_t(1023)); }
+
 int maybe_prepare(const pmvae_xla_opaque* o, const float* params, void* ws, pmvae_stream_t s) {
   return o->prepare ? pmvae_prepare_params(&o->cfg, params, ws, o->ws_bytes, s) : 0;
 }
@@ -42,7 +48,7 @@ void pmvae_xla_forward(pmvae_stream_t s, void** buf, const char* opaque, size_t 
   const pmvae_xla_opaque* o = decode(opaque, len, status);
   if (!o) return;
   const float* params = static_cast<const float*>(buf[0]);
-  void* ws = buf[7];
+  void* ws = align_ws(buf[7]);
   if (maybe_prepare(o, params, ws, s) != 0 ||
       pmvae_forward(&o->cfg, params, static_cast<const float*>(buf[1]), static_cast<const float*>(buf[2]),
                     static_cast<const float*>(buf[3]), o->B, static_cast<float*>(buf[4]), static_cast<float*>(buf[5]),
@@ -62,7 +68,7 @@ void pmvae_xla_backward(pmvae_stream_t s, void** buf, const char* opaque, size_t
   if (pmvae_backward(&o->cfg, static_cast<const float*>(buf[0]), static_cast<const float*>(buf[1]),
                      static_cast<const float*>(buf[2]), static_cast<const float*>(buf[3]), o->B,
                      static_cast<const float*>(buf[4]), static_cast<const float*>(buf[5]),
-                     static_cast<const float*>(buf[6]), static_cast<float*>(buf[8]), buf[7], o->ws_bytes, s) != 0)
+                     static_cast<const float*>(buf[6]), static_cast<float*>(buf[8]), align_ws(buf[7]), o->ws_bytes, s) != 0)
     report(status, "pmvae_xla_backward");
 }
 
@@ -70,7 +76,7 @@ void pmvae_xla_is_log_prob(pmvae_stream_t s, void** buf, const char* opaque, siz
   const pmvae_xla_opaque* o = decode(opaque, len, status);
   if (!o) return;
   const float* params = static_cast<const float*>(buf[0]);
-  void* ws = buf[5];
+  void* ws = align_ws(buf[5]);
   if (maybe_prepare(o, params, ws, s) != 0 ||
       pmvae_is_log_prob(&o->cfg, params, static_cast<const float*>(buf[1]), static_cast<const float*>(buf[2]), o->B,
                         o->K, o->key0, o->key1, o->B_total, o->row_start, static_cast<float*>(buf[3]),
@@ -82,7 +88,7 @@ void pmvae_xla_impute_mean(pmvae_stream_t s, void** buf, const char* opaque, siz
   const pmvae_xla_opaque* o = decode(opaque, len, status);
   if (!o) return;
   const float* params = static_cast<const float*>(buf[0]);
-  void* ws = buf[4];
+  void* ws = align_ws(buf[4]);
   if (maybe_prepare(o, params, ws, s) != 0 ||
       pmvae_impute_mean(&o->cfg, params, static_cast<const float*>(buf[1]), static_cast<const float*>(buf[2]), o->B,
                         o->K, o->key0, o->B_total, o->row_start, static_cast<float*>(buf[3]), ws, o->ws_bytes, s) != 0)

@@ -2,7 +2,7 @@
 wrapper through which the reference's `loss_fn` (train_pm_vae.py:58-72) and `eval_fn`
 (eval_pm_vae_uci.py:82-94) would call the CUDA path from inside `jax.jit`.
 
-JAX is NOT installed in the image this repository is built and tested in,
+EXPERIMENTAL: JAX is NOT installed in the image this repository is built and tested in,
 so this module is import-guarded and UNEXERCISED here: the targets themselves are tested
 through ctypes with the exact calling convention XLA uses (tests/test_gpu_xla_shim.py);
 the JAX side below is the thin part a maintainer checks once against their jaxlib.
@@ -15,6 +15,7 @@ from typing import Any, Mapping
 
 from . import _lib
 
+WS_SLACK = 1024      # PMVAE_XLA_WS_SLACK (include/pmvae.h)
 TARGETS = ("pmvae_xla_forward", "pmvae_xla_backward", "pmvae_xla_is_log_prob", "pmvae_xla_impute_mean",
            "pmvae_xla_mask_bernoulli")
 
@@ -40,7 +41,9 @@ def opaque(cfg: _lib.Config, *, B: int, K: int = 0, B_total: int = 0, row_start:
 
 
 def register() -> None:
-    """Registers every target for platform "CUDA".  Raises ImportError without JAX."""
+    """Registers every target for platform "CUDA".  Raises ImportError without JAX.  The targets have the legacy
+    (untyped) custom-call signature with a trailing XlaCustomCallStatus*: `api_version=0` here selects the legacy
+    registration path of jax.ffi, and the call sites pass `custom_call_api_version=2` (API_VERSION_STATUS_RETURNING)."""
     import jax  # noqa: F401  (ImportError here = this environment has no JAX)
     try:  # jax >= 0.4.31
         from jax import ffi as jffi
@@ -69,10 +72,11 @@ def make_pmvae_call(config: Mapping[str, Any], B: int, precision: str = "bf16"):
     fwd_opaque = opaque(cfg, B=B, ws_bytes=ws_bytes, prepare=True)
     bwd_opaque = opaque(cfg, B=B, ws_bytes=ws_bytes, prepare=False)
     row = jax.ShapeDtypeStruct((B,), f32)
-    ws_t = jax.ShapeDtypeStruct((ws_bytes,), jnp.uint8)
+    # + PMVAE_XLA_WS_SLACK: XLA aligns buffers to <= 256 bytes, the targets round the pointer up to 1024
+    ws_t = jax.ShapeDtypeStruct((ws_bytes + WS_SLACK,), jnp.uint8)
 
     def _fwd_call(arena, x, b, eps):
-        return jffi.ffi_call("pmvae_xla_forward", (row, row, row, ws_t), custom_call_api_version=1,
+        return jffi.ffi_call("pmvae_xla_forward", (row, row, row, ws_t), custom_call_api_version=2,
                              legacy_backend_config=fwd_opaque)(arena, x, b, eps)
 
     @jax.custom_vjp
@@ -88,7 +92,7 @@ def make_pmvae_call(config: Mapping[str, Any], B: int, precision: str = "bf16"):
         arena, x, b, eps, ws = res
         g_rec, g_kl, g_match = cot
         grads, _ = jffi.ffi_call("pmvae_xla_backward", (jax.ShapeDtypeStruct((n_arena,), f32), ws_t),
-                                 custom_call_api_version=1, legacy_backend_config=bwd_opaque,
+                                 custom_call_api_version=2, legacy_backend_config=bwd_opaque,
                                  input_output_aliases={7: 1})(arena, x, b, eps, g_rec, g_kl, g_match, ws)
         return grads, None, None, None     # x, b, eps are data: no cotangent is produced for them
 

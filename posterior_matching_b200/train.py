@@ -89,6 +89,10 @@ class Trainer:
                  process_group=None, model: Optional[PosteriorMatchingVAE] = None):
         self.config = config
         self.model = model or PosteriorMatchingVAE.from_config(config["model"], precision=precision, device=device)
+        if not isinstance(self.model, PosteriorMatchingVAE):
+            raise NotImplementedError(
+                "Trainer drives the ResidualMLP / TriLGaussian model (the four UCI configs); "
+                "ConvPosteriorMatchingVAE (configs/pm_vae_mnist.py) has its own train_step")
         if model is None:
             self.model.init(seed)
         self.device = self.model.device
@@ -168,6 +172,13 @@ class Trainer:
         if not isinstance(self.mask_generator, __import__("posterior_matching_b200.masking", fromlist=["x"]).BernoulliMaskGenerator):
             raise NotImplementedError("the fused step draws Bernoulli masks (the four UCI configs)")
         f = self._fused if (self._fused is not None and self._fused["B"] == B) else self._fused_setup(B)
+        if f.get("stale"):
+            # host-driven steps (train_step) ran since the last fused one: the device state block (keys, mask-call
+            # counter, step) is re-seeded from the host mirrors; same buffer, so captured graphs stay valid
+            _lib.check(_lib.lib.pmvae_train_state_init(f["state"].data_ptr(), _lib.key_arg(self._rng.key),
+                                                       _lib.key_arg(self.mask_generator._key), self.step,
+                                                       self.mask_generator._calls, _stream()), "pmvae_train_state_init")
+            f["stale"] = False
         f["x"].copy_(x, non_blocking=True)
         ws = mdl.workspace(B)
         if f.get("ws_ptr") != ws.data_ptr():          # the workspace moved (e.g. an evaluator grew it): re-capture
@@ -257,6 +268,8 @@ class Trainer:
         mdl.mark_params_changed()
         self.step += 1
         self._last_Bg = Bg
+        if self._fused is not None:
+            self._fused["stale"] = True      # the device step state is now one step behind the host mirrors
         return self._sums
 
     def metrics(self) -> Dict[str, float]:

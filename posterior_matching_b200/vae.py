@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib, prng
+from .dist_objects import MultivariateNormalDiagStd, MultivariateNormalTriL, Normal
 
 
 # ----------------------------------------------------------------------------- specs
@@ -131,6 +132,7 @@ class PosteriorMatchingVAE:
         self._ws_key = (0, 0)
         self._params_dirty = True
         self._last = None
+        self.prior = MultivariateNormalDiagStd(self.latent_dim, self.device)       # vae.py:55-57
 
     # ---- construction -------------------------------------------------------------
     @classmethod
@@ -290,19 +292,40 @@ class PosteriorMatchingVAE:
                                             ws.data_ptr(), ws.numel(), _stream()), "pmvae_net_apply")
         return out
 
-    def encoder(self, x: torch.Tensor) -> torch.Tensor:
-        """`self.encoder(x)` of vae.py:47-49 as raw TriLGaussian parameters [B, d + d(d+1)/2]."""
-        return self.net_apply(0, x)
+    def encoder(self, x: torch.Tensor, is_training: bool = False) -> MultivariateNormalTriL:
+        """`self.encoder(x)` (vae.py:47-49): q(z | x) as a distribution object; `.parameters` is the raw
+        TriLGaussian head output [B, d + d(d+1)/2]."""
+        return MultivariateNormalTriL(self.net_apply(0, x), self.latent_dim)
 
-    def decoder(self, z: torch.Tensor) -> torch.Tensor:
-        """`self.decoder(z).mean()` of vae.py:50-51: the IdentityGaussian loc [B, D]."""
-        return self.net_apply(1, z)
+    def decoder(self, z: torch.Tensor, is_training: bool = False) -> Normal:
+        """`self.decoder(z)` (vae.py:50-51): p(x | z) = Normal(loc, exp(log_scale)) (IdentityGaussian)."""
+        return Normal(self.net_apply(1, z), self.params["decoder_dist"]["log_scale"])
 
-    def partial_encoder(self, x_o_b: torch.Tensor) -> torch.Tensor:
-        """`self.partial_encoder(concat([x_o, b]))` of vae.py:52-53,132-134: takes the
-        concatenated [B, 2D] input like the reference and returns raw TriL parameters."""
+    def partial_encoder(self, x_o_b: torch.Tensor, is_training: bool = False) -> MultivariateNormalTriL:
+        """`self.partial_encoder(concat([x_o, b]))` (vae.py:52-53,132-134): takes the concatenated [B, 2D] input
+        like the reference and returns q(z | x_o)."""
         D = self.num_features
-        return self.net_apply(2, x_o_b[:, :D], x_o_b[:, D:])
+        return MultivariateNormalTriL(self.net_apply(2, x_o_b[:, :D], x_o_b[:, D:]), self.latent_dim)
+
+    def impute(self, x_o: torch.Tensor, b: torch.Tensor, num_samples: int = 100, *, rng=None, key=None,
+               row_start: int = 0, total_rows: Optional[int] = None) -> torch.Tensor:
+        """vae.py:146-169 -> [num_samples, B, D]: imputed values where b == 0, x_o elsewhere.  `rng` replays the Haiku
+        chain of a stand-alone call (the partial encoder's dropout keys come first); `key` passes the sample key."""
+        x_o = _f32c(x_o, self.device)
+        b = _f32c(b, self.device)
+        B = x_o.shape[0]
+        if key is None:
+            if rng is None:
+                raise ValueError("pass rng= or key=")
+            key = prng.PRNGSequence(rng).skip(self.cfg.R_part).next()
+        total = B if total_rows is None else int(total_rows)
+        out = torch.empty((int(num_samples), B, self.num_features), dtype=torch.float32, device=self.device)
+        ws = self.workspace(B, num_samples)
+        self._prepare(ws)
+        _lib.check(_lib.lib.pmvae_impute(self._cfgp, self.arena.data_ptr(), x_o.data_ptr(), b.data_ptr(), B,
+                                         int(num_samples), _lib.key_arg(key), total, row_start, out.data_ptr(), None,
+                                         ws.data_ptr(), ws.numel(), _stream()), "pmvae_impute")
+        return out
 
     def impute_mean(self, x_o: torch.Tensor, b: torch.Tensor, num_samples: int = 100, *, key,
                     row_start: int = 0, total_rows: Optional[int] = None) -> torch.Tensor:

@@ -106,7 +106,7 @@ def test_loss_and_gradients_match_oracle(name, B, stop, precision):
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
-@pytest.mark.parametrize("name,B,K", [("gas", 32, 64), ("bsds", 5, 16), ("bsds", 3, 100), ("power", 3, 1)])
+@pytest.mark.parametrize("name,B,K", [("gas", 256, 64), ("bsds", 64, 16), ("bsds", 48, 100), ("power", 257, 1)])
 def test_eval_fn_matches_oracle(name, B, K, precision):
     from posterior_matching_b200 import eval_fn
     spec = spec_of(name)
@@ -124,7 +124,9 @@ def test_eval_fn_matches_oracle(name, B, K, precision):
     tol = ROW_TOL[precision]
     assert rel_err(imp.cpu().numpy(), want_imp.numpy()) < tol
     assert np.abs(ll.cpu().numpy() - want_ll.numpy()).max() < tol * max(1.0, np.abs(want_ll.numpy()).max())
-    assert abs(ll.mean().item() - want_ll.mean().item()) < LOSS_TOL[precision] * max(1.0, abs(want_ll.mean().item())) * 5
+    # the contract (north star): <= 1e-3 relative on the per-batch conditional log-likelihood; benchmark-scale
+    # batches (B = 2048, K = 512 / 4096) are held to the same bound in tests/test_gpu_condll_scale.py
+    assert abs(ll.mean().item() - want_ll.mean().item()) <= LOSS_TOL[precision] * abs(want_ll.mean().item())
     assert rel_err(lpx.cpu().numpy(), want_lpx.numpy()) < tol
 
 
@@ -321,3 +323,87 @@ def test_fused_graph_train_step_equals_host_driven_step(name, precision):
             d0 = p[n][k].float().cuda()
             move = float((a - d0.reshape(a.shape)).norm())
             assert float((a - c).norm()) <= tol * max(move, 1e-12), (n, k)
+
+
+def test_fp32_path_at_raw_haiku_init_d16():
+    """Step 0 of the reference runs at raw Haiku init (no conditioning of the TriL heads).  For d = 16 the float32 path
+    stays within 1e-3 of the float64 oracle on every batch mean there too (for d = 64 the forward substitution through
+    a random lower-triangular factor amplifies rounding beyond any fixed tolerance, in the reference as well: DESIGN §1)."""
+    for name in ("gas", "power", "hepmass"):
+        spec = spec_of(name)
+        p = M.init_params(spec, 3)
+        B = 512
+        x, b, eps = make_inputs(spec, B, seed=5)
+        want = M.forward(p, spec, x, b, eps)
+        m = _model(name, "fp32", p)
+        got = m(_cuda(x), _cuda(b), eps=_cuda(eps))
+        torch.cuda.synchronize()
+        for k in ("reconstruction_ll", "kl", "matching_ll"):
+            g, w = got[k].cpu().double(), want[k].detach()
+            assert torch.isfinite(g).all()
+            assert abs(float(g.mean() - w.mean())) <= 1e-3 * abs(float(w.mean())), (name, k, float(g.mean()), float(w.mean()))
+
+
+def test_bf16_and_fp32_training_trajectories_agree_over_200_steps():
+    """Convergence evidence for the bf16 operand format: 200 optimizer steps of the fused train step (same seeds, so the
+    same masks, eps and schedules) in bf16 and in fp32 -- the smoothed loss curves stay together and both descend."""
+    if "bf16" not in PRECISIONS or "fp32" not in PRECISIONS:
+        pytest.skip("needs both precisions")
+    from posterior_matching_b200 import Trainer, pm_vae_config, PosteriorMatchingVAE
+    cfg = pm_vae_config("gas")
+    spec = spec_of("gas")
+    p = conditioned_params(spec)
+    B, steps = 512, 200
+    g = torch.Generator(device="cuda").manual_seed(11)
+    mix = torch.randn(spec.D, spec.D, device="cuda", generator=g) * 0.5
+    data = torch.randn(64 * B, spec.D, device="cuda", generator=g) @ mix     # correlated features: something to learn
+    curves = {}
+    for precision in ("fp32", "bf16"):
+        m = PosteriorMatchingVAE.from_config(cfg.model, precision=precision)
+        m.load_params(p)
+        tr = Trainer(cfg, seed=3, precision=precision, model=m)
+        tr.step = 26000            # beta = 1 plateau of the cyclic schedule, lr ~ 5.8e-4
+        losses = []
+        for i in range(steps):
+            tr.train_step_fused(data[(i % 64) * B:(i % 64 + 1) * B])
+            losses.append(tr.metrics()["loss"])
+        curves[precision] = np.array(losses)
+    a, c = curves["bf16"], curves["fp32"]
+    assert np.isfinite(a).all() and np.isfinite(c).all()
+    sm = lambda v: np.convolve(v, np.ones(10) / 10, mode="valid")            # noqa: E731
+    rel = np.abs(sm(a) - sm(c)) / np.abs(sm(c))
+    print(f"trajectory: fp32 {c[:10].mean():.4f} -> {c[-10:].mean():.4f}, bf16 {a[:10].mean():.4f} -> {a[-10:].mean():.4f}, "
+          f"max smoothed rel diff {rel.max():.2e}")
+    assert c[-10:].mean() < c[:10].mean() and a[-10:].mean() < a[:10].mean()
+    assert rel.max() < 2e-2, rel.max()
+    assert abs(a[-10:].mean() - c[-10:].mean()) < 1e-2 * abs(c[-10:].mean())
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_host_and_fused_steps_can_be_mixed(precision):
+    """A host-driven step between fused steps re-seeds the device step state (keys, mask-call counter, step), so
+    host, fused, host, fused walks the same trajectory as four host-driven steps."""
+    from posterior_matching_b200 import Trainer, pm_vae_config, PosteriorMatchingVAE
+    cfg = pm_vae_config("gas")
+    spec = spec_of("gas")
+    p = conditioned_params(spec)
+    B = 200
+    xs = [torch.randn(B, spec.D, device="cuda", generator=torch.Generator(device="cuda").manual_seed(70 + i)) for i in range(5)]
+    runs = []
+    for pattern in ("hhhhh", "fhfhf"):
+        m = PosteriorMatchingVAE.from_config(cfg.model, precision=precision)
+        m.load_params(p)
+        tr = Trainer(cfg, seed=9, precision=precision, model=m)
+        tr.step = 1500
+        out = []
+        for x, c in zip(xs, pattern):
+            (tr.train_step if c == "h" else tr.train_step_fused)(x)
+            out.append(tr.metrics())
+        if "f" in pattern:
+            st = tr.fused_state()
+            assert st.step == tr.step and st.mask_calls == tr.mask_generator._calls
+        runs.append(out)
+    for i, (mh, mf) in enumerate(zip(*runs)):
+        for k in ("reconstruction_ll", "kl", "matching_ll"):
+            assert abs(mh[k] - mf[k]) <= LOSS_TOL[precision] * (1 + i) * max(1.0, abs(mh[k])), (i, k, mh[k], mf[k])
+        assert abs(mh["beta"] - mf["beta"]) < 1e-7

@@ -29,9 +29,9 @@ def test_net_apply_matches_oracle_networks(name, B, precision):
     want_enc = M.net_head(p, spec, "encoder_net", "posterior_dist/linear", x)
     want_dec = M.net_head(p, spec, "decoder_net", "decoder_dist/linear", z)
     want_part = M.net_head(p, spec, "partial_encoder_net", "partial_posterior_dist/linear", torch.cat([x * b, b], -1))
-    got_enc = m.encoder(x.float().cuda())
-    got_dec = m.decoder(z.float().cuda())
-    got_part = m.partial_encoder(torch.cat([x * b, b], -1).float().cuda())
+    got_enc = m.encoder(x.float().cuda()).parameters
+    got_dec = m.decoder(z.float().cuda()).mean()
+    got_part = m.partial_encoder(torch.cat([x * b, b], -1).float().cuda()).parameters
     torch.cuda.synchronize()
     tol = 1e-4 if precision == "fp32" else 3e-2
     for g, w in ((got_enc, want_enc), (got_dec, want_dec), (got_part, want_part)):

@@ -14,9 +14,13 @@ pytestmark = pytest.mark.gpu
 
 
 def _aligned_ws(nbytes):
-    raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device="cuda")
-    off = (-raw.data_ptr()) % 1024
-    return raw[off:off + nbytes]
+    """A workspace the way XLA hands it over: ws_bytes + PMVAE_XLA_WS_SLACK bytes, aligned to 256 only (the targets
+    round the pointer up to the 1024 bytes the tensor path needs)."""
+    raw = torch.empty(nbytes + 2048, dtype=torch.uint8, device="cuda")
+    off = (256 - raw.data_ptr()) % 1024
+    ws = raw[off:off + nbytes + 1024]
+    assert ws.data_ptr() % 1024 == 256
+    return ws
 
 
 def _buffers(*tensors):

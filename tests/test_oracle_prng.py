@@ -66,3 +66,13 @@ def test_prng_sequence_is_split_chain():
         ks = prng.split(k)
         assert np.array_equal(seq.next(), ks[1])
         k = ks[0]
+
+
+def test_normal_rows_equals_a_row_slice_of_the_full_draw():
+    """`normal_rows` (used by the benchmark-scale cond-LL parity tests to draw only a chunk's eps) is a slice of
+    `normal(key, (K, B, d))`, odd element counts included."""
+    key = prng.PRNGKey(7)
+    for K, B, d in ((3, 5, 4), (3, 5, 3), (1, 7, 1)):
+        full = prng.normal(key, (K, B, d))
+        for r0, nb in ((0, B), (2, 3), (B - 1, 1)):
+            assert np.array_equal(prng.normal_rows(key, K, B, d, r0, nb), full[:, r0:r0 + nb])

@@ -46,3 +46,28 @@ def rel_l2(a, b):
     a = np.asarray(a, dtype=np.float64).ravel()
     b = np.asarray(b, dtype=np.float64).ravel()
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def oracle_eval_chunked(p, spec, x, b, keys, K, rows=128, dtype=torch.float64, want_imp=True):
+    """oracle eval_fn (+ log p(x)) over B rows in chunks of `rows`, eps drawn from the three JAX keys exactly as the
+    device draws them (normal(key, [K, B, d]) restricted to the chunk's rows): the [K * B, 256] activations of the
+    decoder never exist at once."""
+    from oracle import prng
+    B = x.shape[0]
+    k_imp, k_z, k_zxo = keys
+    imp, ll, lpx = [], [], []
+    pd = M.cast_params(p, dtype)
+    for r0 in range(0, B, rows):
+        nb = min(rows, B - r0)
+        e = []
+        for k in ((k_imp, k_z, k_zxo) if want_imp else (k_z, k_zxo)):
+            full = prng.normal_rows(k, K, B, spec.d, r0, nb)
+            e.append(torch.tensor(full, dtype=dtype))
+        xs, bs = x[r0:r0 + nb].to(dtype), b[r0:r0 + nb].to(dtype)
+        with torch.no_grad():
+            if want_imp:
+                imp.append(M.impute(pd, spec, xs, bs, e[0]).mean(0))
+            a, c = M.is_log_prob(pd, spec, xs, bs, e[-2], e[-1])
+        lpx.append(a)
+        ll.append(c)
+    return (torch.cat(imp) if want_imp else None), torch.cat(ll), torch.cat(lpx)
