@@ -240,7 +240,13 @@ int pmvae_train_state_init(void* state, const uint32_t seq_key[2], const uint32_
 int pmvae_train_state_read(const void* state, pmvae_train_state_host* out, pmvae_stream_t stream);
 /* phase bit 0: advance state, draw mask + eps, forward, loss cotangents (+ batch sums into out_sums[3]), backward
  * (grads overwritten);  phase bit 1: AdamW, refresh of the operand images, step counter.  With several ranks call
- * phase 1, all-reduce `grads` and `out_sums`, then phase 2.  `scratch`: pmvae_train_scratch_floats floats. */
+ * phase 1, all-reduce `grads` and `out_sums`, then phase 2.  `scratch`: pmvae_train_scratch_floats floats.
+ * Bucketed exchange: PMVAE_STEP_FWD_BWD | PMVAE_STEP_SPLIT_BWD stops the backward after the decoder + latent stage
+ * (the decoder's gradient range [decoder_net/linear .. decoder_dist] is final), PMVAE_STEP_BWD_ENC then
+ * PMVAE_STEP_BWD_PART finish the encoder's and the partial encoder's ranges; each range can be all-reduced on a side
+ * stream while the next stage runs (Trainer.train_step_fused does, inside one captured CUDA graph). */
+enum { PMVAE_STEP_FWD_BWD = 1, PMVAE_STEP_UPDATE = 2, PMVAE_STEP_BWD_ENC = 4, PMVAE_STEP_BWD_PART = 8,
+       PMVAE_STEP_SPLIT_BWD = 16 };
 int pmvae_train_step(const pmvae_config* cfg, const pmvae_train_config* tc, float* params, float* m, float* v,
                      float* grads, void* state, const float* x, int64_t B, int64_t B_global, int64_t row_start,
                      float* scratch, float* out_sums, void* ws, uint64_t ws_bytes, int32_t phase,

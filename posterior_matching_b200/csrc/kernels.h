@@ -85,6 +85,7 @@ int latent_bwd(const float* par_e, const float* par_p, const float* eps, const f
                const float* g_kl, const float* g_match, int stop_grad, float* dpar_e, float* dpar_p,
                __nv_bfloat16* dpar_e_b, __nv_bfloat16* dpar_p_b, int64_t B, int d, cudaStream_t s,
                float* db_e = nullptr, float* db_p = nullptr, bool* db_done = nullptr);
+bool latent_bwd_bias_fused(int d);
 int tril_sample_bwd(const float* par, const float* eps, const float* dz, const float* g_kl, float* dpar, int64_t B, int d,
                     cudaStream_t s);
 // latent16.cu: thread-per-row versions for d = 16 (bf16 gradient outputs only)

@@ -539,6 +539,9 @@ int match_fwd(const float* par_p, const float* z, float* match, int64_t B, int d
   return 0;
 }
 
+// whether latent_bwd with bf16 outputs and db_e / db_p also accumulates the two head bias gradients (d = 16 kernels)
+bool latent_bwd_bias_fused(int d) { return d == 16 && fast16(); }
+
 int latent_bwd(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
                const float* g_kl, const float* g_match, int stop_grad, float* dpar_e, float* dpar_p,
                __nv_bfloat16* dpar_e_b, __nv_bfloat16* dpar_p_b, int64_t B, int d, cudaStream_t s, float* db_e,

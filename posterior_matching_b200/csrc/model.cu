@@ -297,24 +297,33 @@ int forward(const pmvae_config* c, const float* params, const float* x, const fl
   return 0;
 }
 
-int backward(const pmvae_config* c, const float* params, const float* x, const float* b, const float* eps, int64_t B,
-             const float* g_rec, const float* g_kl, const float* g_match, float* grads, void* ws, uint64_t ws_bytes,
-             cudaStream_t s) {
+int backward_staged(const pmvae_config* c, const float* params, const float* x, const float* b, const float* eps, int64_t B,
+                    const float* g_rec, const float* g_kl, const float* g_match, float* grads, int stages, void* ws,
+                    uint64_t ws_bytes, cudaStream_t s) {
   Layout L;
   PMVAE_TRY(build_layout(c, &L));
   PMVAE_CHECK(grads != nullptr && B >= 0, "null gradient arena / negative batch");
-  PMVAE_CUDA(cudaMemsetAsync(grads, 0, L.total * sizeof(float), s));
+  if (stages & 1) PMVAE_CUDA(cudaMemsetAsync(grads, 0, L.total * sizeof(float), s));
   if (B == 0) return 0;            // an empty batch contributes zero gradients
   PMVAE_CHECK(params && x && b && eps && g_rec && g_kl && g_match && ws, "null pointer");
-  if (c->precision == PMVAE_PREC_BF16) return backward_bf16(c, L, params, x, b, eps, B, g_rec, g_kl, g_match, grads, ws, ws_bytes, s);
+  if (c->precision == PMVAE_PREC_BF16)
+    return backward_bf16(c, L, params, x, b, eps, B, g_rec, g_kl, g_match, grads, stages, ws, ws_bytes, s);
   TrainPlan p = plan_train(c, L, B, ws);
   PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_workspace_bytes)");
-  PMVAE_TRY(rec_ll_bwd(x, p.loc, c->D, params + L.log_scale, g_rec, p.dloc, nullptr, c->D, grads + L.log_scale, B, c->D, s));
-  PMVAE_TRY(net_bwd_f32(params, grads, L.dec, L.ddist, c->H, p.z, B, p.dec, p.dloc, p.dH, p.tmp1, p.tmp2, p.dz, s));
-  PMVAE_TRY(latent_bwd(p.par_e, p.par_p, eps, p.z, p.dz, g_kl, g_match, c->stop_grad, p.dpar_e, p.dpar_p, nullptr, nullptr, B, c->d, s));
-  PMVAE_TRY(net_bwd_f32(params, grads, L.enc, L.post, c->H, x, B, p.enc, p.dpar_e, p.dH, p.tmp1, p.tmp2, nullptr, s));
-  PMVAE_TRY(net_bwd_f32(params, grads, L.part, L.ppost, c->H, p.xob, B, p.part, p.dpar_p, p.dH, p.tmp1, p.tmp2, nullptr, s));
+  if (stages & 1) {
+    PMVAE_TRY(rec_ll_bwd(x, p.loc, c->D, params + L.log_scale, g_rec, p.dloc, nullptr, c->D, grads + L.log_scale, B, c->D, s));
+    PMVAE_TRY(net_bwd_f32(params, grads, L.dec, L.ddist, c->H, p.z, B, p.dec, p.dloc, p.dH, p.tmp1, p.tmp2, p.dz, s));
+    PMVAE_TRY(latent_bwd(p.par_e, p.par_p, eps, p.z, p.dz, g_kl, g_match, c->stop_grad, p.dpar_e, p.dpar_p, nullptr, nullptr, B, c->d, s));
+  }
+  if (stages & 2) PMVAE_TRY(net_bwd_f32(params, grads, L.enc, L.post, c->H, x, B, p.enc, p.dpar_e, p.dH, p.tmp1, p.tmp2, nullptr, s));
+  if (stages & 4) PMVAE_TRY(net_bwd_f32(params, grads, L.part, L.ppost, c->H, p.xob, B, p.part, p.dpar_p, p.dH, p.tmp1, p.tmp2, nullptr, s));
   return 0;
+}
+
+int backward(const pmvae_config* c, const float* params, const float* x, const float* b, const float* eps, int64_t B,
+             const float* g_rec, const float* g_kl, const float* g_match, float* grads, void* ws, uint64_t ws_bytes,
+             cudaStream_t s) {
+  return backward_staged(c, params, x, b, eps, B, g_rec, g_kl, g_match, grads, 7, ws, ws_bytes, s);
 }
 
 // Bias leaves of the arena (ndim == 1: no weight decay, train_pm_vae.py:77-79), bound-checked against AdamSegs.

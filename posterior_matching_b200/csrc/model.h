@@ -28,7 +28,11 @@ int forward_bf16(const pmvae_config* c, const Layout& L, const float* params, co
                  uint64_t ws_bytes, cudaStream_t s);
 int backward_bf16(const pmvae_config* c, const Layout& L, const float* params, const float* x, const float* b,
                   const float* eps, int64_t B, const float* g_rec, const float* g_kl, const float* g_match,
-                  float* grads, void* ws, uint64_t ws_bytes, cudaStream_t s);
+                  float* grads, int stages, void* ws, uint64_t ws_bytes, cudaStream_t s);
+// backward of the whole model in stages (bit 0: decoder + latent algebra, bit 1: encoder, bit 2: partial encoder)
+int backward_staged(const pmvae_config* c, const float* params, const float* x, const float* b, const float* eps, int64_t B,
+                    const float* g_rec, const float* g_kl, const float* g_match, float* grads, int stages, void* ws,
+                    uint64_t ws_bytes, cudaStream_t s);
 int net_apply_bf16(const pmvae_config* c, const Layout& L, const float* params, int which, const float* in,
                    const float* msk, int64_t B, float* out, bool save, void* ws, uint64_t ws_bytes, cudaStream_t s);
 int is_log_prob_bf16(const pmvae_config* c, const Layout& L, const float* params, const float* x, const float* b,

@@ -770,33 +770,47 @@ int forward_bf16(const pmvae_config* c, const Layout& L, const float* params, co
   return 0;
 }
 
+// `stages` (bit 0: decoder + latent algebra, bit 1: encoder, bit 2: partial encoder) lets the caller put a gradient
+// exchange of the finished parameter range between them (Trainer: bucketed all-reduce overlapped with the remaining
+// backward); a batch of more than one micro-batch runs everything under bit 0 (the temporaries are per micro-batch).
 int backward_bf16(const pmvae_config* c, const Layout& L, const float* params, const float* x, const float* b,
                   const float* eps, int64_t B, const float* g_rec, const float* g_kl, const float* g_match,
-                  float* grads, void* ws, uint64_t ws_bytes, cudaStream_t s) {
+                  float* grads, int stages, void* ws, uint64_t ws_bytes, cudaStream_t s) {
   TrainPlanB p = plan_train_b(c, L, B, ws);
   CHECK_WS(p);
   const int D = c->D, d = c->d;
   const int64_t kMicroRows = micro_rows();
+  if (B > kMicroRows) {
+    if (!(stages & 1)) return 0;
+    stages = 7;
+  }
   for (int64_t r0 = 0; r0 < B; r0 += kMicroRows) {
     const int64_t nb = (B - r0 < kMicroRows) ? (B - r0) : kMicroRows;
     const float* xc = x + r0 * D;
     // gradient temporaries (dloc, dH, dU, dG, dz, dpar) are reused by every micro-batch
     const bool dec_db = D <= 16;     // wider decoders keep the separate column-sum kernel (shared-memory atomics serialise)
-    PMVAE_TRY(rec_ll_bwd(xc, p.loc + r0 * p.Dp, p.Dp, params + L.log_scale, g_rec + r0, nullptr, p.dloc_b, p.Dp,
-                         grads + L.log_scale, nb, D, s, dec_db ? grads + L.ddist.b : nullptr));
-    PMVAE_TRY(net_bwd_b(params, grads, L.dec, p.img.dec, L.ddist, p.img.ddist, p.dloc_b, p.Dp, p.Dp, p.z + r0 * d,
-                        nullptr, d, nb, shift_saved(p.dec, L.dec, r0), p.dH, p.dU, p.dG, p.wtmp, p.dz,
-                        p.img.f_dec_ok ? &p.img.f_dec : nullptr, p.dY, p.in_b, dec_db, s));
-    bool lat_db = false;
-    PMVAE_TRY(latent_bwd(p.par_e + r0 * L.P, p.par_p + r0 * L.P, eps + r0 * d, p.z + r0 * d, p.dz, g_kl + r0,
-                         g_match + r0, c->stop_grad, nullptr, nullptr, p.dpar_e_b, p.dpar_p_b, nb, d, s, grads + L.post.b,
-                         grads + L.ppost.b, &lat_db));
-    PMVAE_TRY(net_bwd_b(params, grads, L.enc, p.img.enc, L.post, p.img.post, p.dpar_e_b, L.P, L.P, xc, nullptr, D, nb,
-                        shift_saved(p.enc, L.enc, r0), p.dH, p.dU, p.dG, p.wtmp, nullptr,
-                        p.img.f_enc_ok ? &p.img.f_enc : nullptr, p.dY, p.in_b, lat_db, s));
-    PMVAE_TRY(net_bwd_b(params, grads, L.part, p.img.part, L.ppost, p.img.ppost, p.dpar_p_b, L.P, L.P, xc, b + r0 * D,
-                        D, nb, shift_saved(p.part, L.part, r0), p.dH, p.dU, p.dG, p.wtmp, nullptr,
-                        p.img.f_part_ok ? &p.img.f_part : nullptr, p.dY, p.in_b, lat_db, s));
+    // latent_bwd16 (d = 16, bf16 outputs) also takes the two head bias gradients
+    const bool lat_db = latent_bwd_bias_fused(d);
+    if (stages & 1) {
+      PMVAE_TRY(rec_ll_bwd(xc, p.loc + r0 * p.Dp, p.Dp, params + L.log_scale, g_rec + r0, nullptr, p.dloc_b, p.Dp,
+                           grads + L.log_scale, nb, D, s, dec_db ? grads + L.ddist.b : nullptr));
+      PMVAE_TRY(net_bwd_b(params, grads, L.dec, p.img.dec, L.ddist, p.img.ddist, p.dloc_b, p.Dp, p.Dp, p.z + r0 * d,
+                          nullptr, d, nb, shift_saved(p.dec, L.dec, r0), p.dH, p.dU, p.dG, p.wtmp, p.dz,
+                          p.img.f_dec_ok ? &p.img.f_dec : nullptr, p.dY, p.in_b, dec_db, s));
+      bool done = false;
+      PMVAE_TRY(latent_bwd(p.par_e + r0 * L.P, p.par_p + r0 * L.P, eps + r0 * d, p.z + r0 * d, p.dz, g_kl + r0,
+                           g_match + r0, c->stop_grad, nullptr, nullptr, p.dpar_e_b, p.dpar_p_b, nb, d, s, grads + L.post.b,
+                           grads + L.ppost.b, &done));
+      PMVAE_CHECK(done == lat_db, "latent_bwd bias-gradient contract changed");
+    }
+    if (stages & 2)
+      PMVAE_TRY(net_bwd_b(params, grads, L.enc, p.img.enc, L.post, p.img.post, p.dpar_e_b, L.P, L.P, xc, nullptr, D, nb,
+                          shift_saved(p.enc, L.enc, r0), p.dH, p.dU, p.dG, p.wtmp, nullptr,
+                          p.img.f_enc_ok ? &p.img.f_enc : nullptr, p.dY, p.in_b, lat_db, s));
+    if (stages & 4)
+      PMVAE_TRY(net_bwd_b(params, grads, L.part, p.img.part, L.ppost, p.img.ppost, p.dpar_p_b, L.P, L.P, xc, b + r0 * D,
+                          D, nb, shift_saved(p.part, L.part, r0), p.dH, p.dU, p.dG, p.wtmp, nullptr,
+                          p.img.f_part_ok ? &p.img.f_part : nullptr, p.dY, p.in_b, lat_db, s));
   }
   return 0;
 }

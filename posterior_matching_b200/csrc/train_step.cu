@@ -104,8 +104,11 @@ int pmvae_train_state_read(const void* state, pmvae_train_state_host* out, pmvae
   return 0;
 }
 
-// phase bit 0: state advance, mask + eps draw, forward, loss cotangents (+ batch sums), backward
-// phase bit 1: AdamW + refresh of the bf16 operand images + step counter
+// phase bit 0 (PMVAE_STEP_FWD_BWD): state advance, mask + eps draw, forward, loss cotangents (+ batch sums), backward
+// phase bit 1 (PMVAE_STEP_UPDATE):  AdamW + refresh of the bf16 operand images + step counter
+// With PMVAE_STEP_SPLIT_BWD OR-ed into bit 0 the backward stops after the decoder + latent stage; PMVAE_STEP_BWD_ENC and
+// PMVAE_STEP_BWD_PART run the remaining two stages, so that the caller can exchange each finished gradient range
+// (decoder / encoder / partial encoder are contiguous in the arena) while the next stage computes.
 int pmvae_train_step(const pmvae_config* cfg, const pmvae_train_config* tc, float* params, float* m, float* v,
                      float* grads, void* state, const float* x, int64_t B, int64_t B_global, int64_t row_start,
                      float* scratch, float* out_sums, void* ws, uint64_t ws_bytes, int32_t phase,
@@ -128,7 +131,13 @@ int pmvae_train_step(const pmvae_config* cfg, const pmvae_train_config* tc, floa
     PMVAE_TRY(pmvae_forward(cfg, params, x, b, eps, B, terms, terms + B, terms + 2 * B, ws, ws_bytes, stream));
     PMVAE_TRY(loss_cotangents(B, B_global, 0.f, tc->matching_coef, terms, terms + B, terms + 2 * B, cot, cot + B,
                               cot + 2 * B, out_sums, s, st));
-    PMVAE_TRY(pmvae_backward(cfg, params, x, b, eps, B, cot, cot + B, cot + 2 * B, grads, ws, ws_bytes, stream));
+    PMVAE_TRY(backward_staged(cfg, params, x, b, eps, B, cot, cot + B, cot + 2 * B, grads,
+                              (phase & PMVAE_STEP_SPLIT_BWD) ? 1 : 7, ws, ws_bytes, s));
+  }
+  if (phase & (PMVAE_STEP_BWD_ENC | PMVAE_STEP_BWD_PART)) {
+    PMVAE_CHECK(!(phase & 1) || (phase & PMVAE_STEP_SPLIT_BWD), "BWD_ENC / BWD_PART follow a SPLIT_BWD call");
+    const int st_bits = ((phase & PMVAE_STEP_BWD_ENC) ? 2 : 0) | ((phase & PMVAE_STEP_BWD_PART) ? 4 : 0);
+    PMVAE_TRY(backward_staged(cfg, params, x, b, eps, B, cot, cot + B, cot + 2 * B, grads, st_bits, ws, ws_bytes, s));
   }
   if (phase & 2) {
     PMVAE_TRY(adamw_step_dev(cfg, params, grads, m, v, tc->weight_decay, tc->adam_b1, tc->adam_b2, tc->adam_eps, st, s));
