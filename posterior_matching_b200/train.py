@@ -6,6 +6,7 @@ all-reduce (NCCL through torch.distributed) of the flat gradient arena.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Any, Callable, Dict, Mapping, Optional
 
 import torch
@@ -121,6 +122,17 @@ class Trainer:
         self.last_beta = 1.0
         self._seed = seed
         self._fused = None                          # state of train_step_fused (device step state, graphs)
+        self._comm_stream = None
+        # gradient ranges of the three nets (contiguous in the arena, in backward order: decoder, encoder, partial
+        # encoder); the last one carries the 64-float tail with the batch sums
+        starts = {}
+        for name, rows, cols, w_off, b_off in self.model.leaves:
+            grp = "enc" if name.startswith(("encoder_net", "posterior_dist")) else (
+                "dec" if name.startswith(("decoder_net", "decoder_dist")) else "part")
+            starts[grp] = min(starts.get(grp, w_off), w_off)
+        n_store = self.model._grad_store.numel()
+        assert starts["enc"] == 0 and starts["enc"] < starts["dec"] < starts["part"]
+        self._buckets = {"enc": (0, starts["dec"]), "dec": (starts["dec"], starts["part"]), "part": (starts["part"], n_store)}
 
     # ---- the step as one launch sequence / CUDA graph --------------------------------------------
     def _train_config(self) -> "_lib.TrainConfig":
@@ -163,6 +175,40 @@ class Trainer:
             self.rank * f["B"], f["scratch"].data_ptr(), self._sums.data_ptr(), ws.data_ptr(), ws.numel(), phase,
             _stream()), "pmvae_train_step")
 
+    def _step_sequence(self):
+        """The launch sequence of one step on the current stream.  One rank: a single pmvae_train_step.  Several ranks:
+        the backward runs in three stages (decoder, encoder, partial encoder) and each finished gradient range is
+        all-reduced (NCCL) on a communication stream while the next stage computes; only the last range's exchange is
+        exposed before AdamW.  The whole sequence (both streams) is what `train_step_fused` captures in ONE CUDA graph."""
+        mdl = self.model
+        if self.world == 1:
+            self._fused_call(3)
+            return
+        if os.environ.get("PMVAE_DP_OVERLAP", "1") == "0":      # serial exchange (tests compare the two)
+            self._fused_call(1)
+            torch.distributed.all_reduce(mdl._grad_store, group=self.pg)
+            self._fused_call(2)
+            return
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        main, comm = torch.cuda.current_stream(), self._comm_stream
+        store = mdl._grad_store
+
+        def exchange(bucket):
+            lo, hi = self._buckets[bucket]
+            comm.wait_stream(main)
+            with torch.cuda.stream(comm):
+                torch.distributed.all_reduce(store[lo:hi], group=self.pg)
+
+        self._fused_call(1 | 16)          # forward, loss, decoder + latent backward
+        exchange("dec")
+        self._fused_call(4)               # encoder backward
+        exchange("enc")
+        self._fused_call(8)               # partial-encoder backward
+        exchange("part")                  # + the three batch sums in the arena's tail
+        main.wait_stream(comm)
+        self._fused_call(2)               # AdamW on the summed gradients, operand-image refresh
+
     def train_step_fused(self, x: torch.Tensor, graph: bool = True):
         """Same step as `train_step(x)` (same keys, schedules and arithmetic) issued through pmvae_train_step:
         one C call per step, every step-dependent scalar derived on the device.  With `graph=True` the launch
@@ -185,35 +231,26 @@ class Trainer:
             f["ws_ptr"], f["graphs"] = ws.data_ptr(), None
         mdl._prepare(ws)
         if not graph:
-            self._fused_call(1)
-            if self.world > 1:
-                torch.distributed.all_reduce(mdl._grad_store, group=self.pg)
-            self._fused_call(2)
+            self._step_sequence()
         else:
             if f["graphs"] is None:
-                if f.get("warm", 0) < 1:             # one eager step first (lazy kernel attributes, workspace)
+                if f.get("warm", 0) < 1:             # one eager step first (lazy kernel attributes, workspace, NCCL channels)
                     f["warm"] = 1
                     return self.train_step_fused(x, graph=False)
                 torch.cuda.synchronize()
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
-                graphs = []
                 n0 = int(_lib.lib.pmvae_launch_count())
                 with torch.cuda.stream(side):
-                    for phase in ((1, 2) if self.world > 1 else (3,)):
-                        g = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g, stream=side):
-                            self._fused_call(phase)
-                        graphs.append(g)
+                    g = torch.cuda.CUDAGraph()
+                    # thread_local: the NCCL watchdog thread may query events while this thread captures
+                    with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                        self._step_sequence()
                 torch.cuda.current_stream().wait_stream(side)
                 f["launches"] = int(_lib.lib.pmvae_launch_count()) - n0    # kernels one replayed step launches
                 # capturing does not execute: the state block is untouched, so the first replay is this step
-                f["graphs"] = graphs
-            gs = f["graphs"]
-            gs[0].replay()
-            if self.world > 1:
-                torch.distributed.all_reduce(mdl._grad_store, group=self.pg)
-                gs[1].replay()
+                f["graphs"] = [g]
+            f["graphs"][0].replay()
         mdl._params_dirty = False                    # phase 2 refreshed the operand images
         # keep the host-side mirrors in step (so train_step / metrics keep working)
         self._rng.next()
