@@ -33,6 +33,7 @@ typedef __nv_bfloat16 bf16;
 
 constexpr int kThreads = 320;
 constexpr int kFwdThreads = kThreads + 32;      // + 1 helper warp (training mode: TMA stores of the saved activations)
+constexpr int kFwdThreadsLN = kFwdThreads + 32; // LayerNorm training mode: + 1 helper warp for the normalised pre-activations
 constexpr int kEpiWarps = 8;
 constexpr int kChunkBytes = 16384;             // [128 rows] x [64 k] bf16
 constexpr int kOpndBytes = 4 * kChunkBytes;
@@ -46,7 +47,8 @@ constexpr int kOffL0 = kOffW + kWStages * kWStageBytes;   // A operand of the fi
 constexpr int kOffIn = kOffL0 + kChunkBytes;
 constexpr int kOffBias = kOffIn + kInBytes;
 constexpr int kOffBar = kOffBias + kMaxLayers * 1024;
-constexpr int kSmemBytes = kOffBar + 256 + 1024;
+constexpr int kSmemBytes = kOffBar + 512 + 1024;   // 227 KB: the whole opt-in shared memory of an SM
+static_assert(kSmemBytes <= 232448, "shared-memory plan exceeds 227 KB");
 
 struct FwdArgs {
   const float* in; const float* msk;
@@ -57,6 +59,8 @@ struct FwdArgs {
   float* out; int64_t ld_out;     // head output [B, ld_out] fp32
   int head_tma;                   // 1: head rows staged in the (idle) operand buffer and stored by TMA
   int64_t Bpad; uint32_t* masks;
+  float* rstd;                    // LayerNorm training mode: 1 / sigma of every LayerNorm, [(2R+1), Bpad]
+  int in_wide;                    // masked input too wide for one K-block: first Linear = (x*b) @ W_x then += b @ W_b
   long long* trace;   // PMVAE_FUSED_TRACE: per-phase clock64 stamps of block 0 (profiling only)
   int debug;   // PMVAE_FUSED_DEBUG bits (profiling only): 2 no weight loads, 4 no MMAs, 8 coarse trace stamps
 };
@@ -95,10 +99,15 @@ __device__ __forceinline__ void add2(float& x0, float& x1, float b0, float b1) {
 // LN: hk.LayerNorm(-1, False, False) after every Linear (networks.py:117-118,123-124,128-129; the bsds config).  The
 // residual stream then cannot be accumulated by the MMA, so the epilogue keeps it in TMEM columns [256, 512) with
 // tcgen05.ld / tcgen05.st and every hidden Linear writes columns [0, 256); forward only (evaluators).
+// LN && SAVE (bsds training): besides the operand tiles and relu bits, every LayerNorm's normalised pre-activation
+// xhat (signed, bf16: map_x, same slab layout as the operand stack) and 1 / sigma (p.rstd) are kept for the backward.
+// xhat chunks are staged in the first-Linear operand buffer, which is idle between a tile's first Linear and the next
+// tile's prologue, and stored by a second helper warp.
 template <bool SAVE, bool CTA2, bool LN>
-__global__ void __launch_bounds__(kFwdThreads, 1)
+__global__ void __launch_bounds__(kFwdThreadsLN, 1)
 net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_h,
-               const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_o, FwdArgs p) {
+               const __grid_constant__ CUtensorMap map_s, const __grid_constant__ CUtensorMap map_o,
+               const __grid_constant__ CUtensorMap map_x, FwdArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -120,6 +129,10 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   // helper warp's TMA store of it (the saved activation tile) has been read out
   auto written = [&](int c) { return bar + 8u * (2 * kStg + 10 + c); };
   auto chunk_free = [&](int c) { return bar + 8u * (2 * kStg + 14 + c); };
+  // LN training mode: xs_written = an xhat chunk is complete in the staging buffer (8 epilogue warps), xs_free = its
+  // TMA store has been read out;  l0_free = the MMAs of the first half of a wide first Linear have read l0buf
+  const uint32_t xs_written = bar + 8u * (2 * kStg + 18), xs_free = bar + 8u * (2 * kStg + 19);
+  const uint32_t l0_free = bar + 8u * (2 * kStg + 20);
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;               // 0 = the CTA that issues the pair's MMAs
   // barriers the MMA issuer waits on live in the leader CTA; the peer's warps arrive there remotely
   auto arrive_leader = [&](uint32_t b) {
@@ -142,11 +155,13 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_h); tma_prefetch_desc(&map_o);
     if (SAVE) tma_prefetch_desc(&map_s);
+    if (SAVE && LN) tma_prefetch_desc(&map_x);
     for (int s = 0; s < kStg; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
     for (int c = 0; c < 4; ++c) mbar_init(opnd_ready(c), kArrive);
     for (int r = 0; r < 2; ++r) { mbar_init(acc_full(r), 1); mbar_init(acc_empty(r), kArrive); }
     mbar_init(in_ready, kArrive);
     for (int c = 0; c < 4; ++c) { mbar_init(written(c), kEpiWarps); mbar_init(chunk_free(c), 1); }
+    mbar_init(xs_written, kEpiWarps); mbar_init(xs_free, 1); mbar_init(l0_free, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -204,7 +219,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         if (++stage == kStg) { stage = 0; ph ^= 1u; }
       };
       for (int it = it_first; it < it_count; it += it_stride) {
-        for (int kb = 0; kb < nkb0; ++kb) load(&map_w, kb * 64, 0, 256);
+        for (int kb = 0; kb < (p.in_wide ? 2 : nkb0); ++kb) load(&map_w, kb * 64, 0, 256);
         for (int l = 1; l < n_hidden; ++l)
           for (int kb = 0; kb < 4; ++kb) load(&map_w, kb * 64, l * 256, 256);
         for (int t = 0; t < p.head_tiles; ++t)
@@ -227,12 +242,16 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       constexpr uint32_t kDescHi = 0x40004040u;      // SBO 1024 | version 1 | SWIZZLE_128B (see smem_desc)
       auto desc_lo = [](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
       auto mk = [](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
-      auto step = [&](int s_idx, uint32_t abuf, int nk16, int N, bool accum, int wait_mode) {
+      // part: 0 = a whole contraction; 1 / 2 = first / second half of a wide first Linear (the operand buffer is
+      // rebuilt between them: the first half hands l0buf back through l0_free instead of announcing the accumulator)
+      auto step = [&](int s_idx, uint32_t abuf, int nk16, int N, bool accum, int wait_mode, int part) {
         const int region = region_of(s_idx);
         uint32_t& uc = region ? use_cnt1 : use_cnt0;
         if (tracing && lane == 0) stamp(0, 100 + s_idx);
-        mbar_wait_x<CTA2>(acc_empty(region), (uc & 1u) ^ 1u, 2);
-        ++uc;
+        if (part != 2) {
+          mbar_wait_x<CTA2>(acc_empty(region), (uc & 1u) ^ 1u, 2);
+          ++uc;
+        }
         tc_fence_after();
         if (tracing && lane == 0) stamp(0, 200 + s_idx);
         const uint32_t d_tmem = tmem_base + (uint32_t)(region * 256);
@@ -274,7 +293,8 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             }
             if (CTA2) umma_commit_cta2(w_empty(stage), 3); else umma_commit(w_empty(stage));
             if (kb == nkb - 1) {
-              if (CTA2) umma_commit_cta2(acc_full(region), 3); else umma_commit(acc_full(region));
+              const uint32_t done = part == 1 ? l0_free : acc_full(region);
+              if (CTA2) umma_commit_cta2(done, 3); else umma_commit(done);
             }
           }
           __syncwarp();
@@ -283,9 +303,14 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         if (tracing && lane == 0) stamp(0, 500 + s_idx);
       };
       for (int it = it_first; it < it_count; it += it_stride) {
-        step(0, l0buf, p.k16_0, 256, false, 2);
-        for (int l = 1; l < n_hidden; ++l) step(l, opnd, 16, 256, !LN && (l & 1) == 0, 1);
-        for (int t = 0; t < p.head_tiles; ++t) step(n_hidden + t, opnd, 16, p.head_NT, false, t == 0 ? 1 : 0);
+        if (p.in_wide) {
+          step(0, l0buf, p.k16_0, 256, false, 2, 1);
+          step(0, l0buf, p.k16_0, 256, true, 2, 2);
+        } else {
+          step(0, l0buf, p.k16_0, 256, false, 2, 0);
+        }
+        for (int l = 1; l < n_hidden; ++l) step(l, opnd, 16, 256, !LN && (l & 1) == 0, 1, 0);
+        for (int t = 0; t < p.head_tiles; ++t) step(n_hidden + t, opnd, 16, p.head_NT, false, t == 0 ? 1 : 0, 0);
       }
     }
   } else if (warp < 2 + kEpiWarps) {
@@ -297,6 +322,8 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t full_par = 0;
     uint32_t n_writes = 0;             // operand tiles written so far (training mode: chunk_free phase tracking)
+    uint32_t n_xs = 0;                 // xhat chunks staged so far (LN training mode: xs_free phase tracking)
+    uint32_t l0_par = 0;               // wide first Linear: parity of l0_free
     const bool skip_bits = (p.debug & 32) != 0;      // profiling only: no relu-bit extraction
     const int D = p.D_in;
 
@@ -361,8 +388,44 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       if (lane == 0) arrive_leader(in_ready);
     };
 
-    if (it_first < it_count) prefetch_input(CTA2 ? 2 * it_first + (int)rank : it_first);
-    if (it_first < it_count) prologue(CTA2 ? 2 * it_first + (int)rank : it_first);
+    // Wide masked input (2 D > 64, e.g. bsds: D = 63): the first Linear runs as two K-blocks through the one operand
+    // buffer, [x*b] @ W[:D] then += b @ W[D:] (part 0 / 1), built straight from global memory (lane = column, the rows
+    // are contiguous, so a warp reads whole rows; the latency is exposed once per part and tile).
+    auto prologue_wide = [&](int tile_n, int part) {
+      const int kk = 32 * half + lane;
+      const int64_t g0 = (int64_t)tile_n * 128 + q * 32;
+      const bool live = kk < D;
+      const uint32_t col_off = ((kk & 7) << 1);
+      const int kslot = kk >> 3;
+#pragma unroll 1
+      for (int r0 = 0; r0 < 32; r0 += 8) {
+        float a[8], b[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int64_t gr = g0 + r0 + u;
+          const bool ok = live && gr < p.B;
+          b[u] = ok ? __ldg(p.msk + gr * D + kk) : 0.f;
+          a[u] = (ok && part == 0) ? __ldg(p.in + gr * D + kk) : 1.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = q * 32 + r0 + u;
+          const uint32_t addr = l0buf + r * 128 + ((kslot ^ (r & 7)) << 4) + col_off;
+          st_shared_u16(addr, __bfloat16_as_ushort(__float2bfloat16(a[u] * b[u])));
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) arrive_leader(in_ready);
+    };
+    auto first_operand = [&](int tile_n) {
+      if (SAVE && LN) mbar_wait(xs_free, (n_xs & 1u) ^ 1u, 16);     // the last staged xhat chunk has been stored
+      if (p.in_wide) prologue_wide(tile_n, 0);
+      else prologue(tile_n);
+    };
+
+    if (it_first < it_count && !p.in_wide) prefetch_input(CTA2 ? 2 * it_first + (int)rank : it_first);
+    if (it_first < it_count) first_operand(CTA2 ? 2 * it_first + (int)rank : it_first);
     for (int it = it_first; it < it_count; it += it_stride) {
       const int tile = CTA2 ? 2 * it + (int)rank : it;
       const bool has_next = it + it_stride < it_count;
@@ -374,7 +437,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       // LayerNorm epilogue of hidden Linear l: y = acc + b_l; xhat = (y - mean) / sqrt(var + 1e-5) over the 256
       // columns of the row (each of the two warps of a quadrant holds 128 of them; partial sums meet in shared memory);
       // l even: h (+)= xhat kept in TMEM, operand = relu(h);  l odd: operand = relu(xhat).
-      auto epi_ln = [&](int l) {
+      auto epi_ln = [&](int l, int64_t g_row) {
         mbar_wait_x<CTA2>(acc_full(0), full_par & 1u, 5);
         full_par ^= 1u;
         tc_fence_after();
@@ -418,6 +481,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         float ss = (Q - 2.f * dm * S + 128.f * dm * dm) + (Qo - 2.f * dmo * So + 128.f * dmo * dmo);
         ss = fmaxf(ss, 0.f);
         const float rstd = rsqrtf(ss * (1.0f / 256.0f) + 1e-5f);
+        uint32_t mw[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint32_t (&r)[32] = (j & 1) ? rb : ra;
@@ -433,32 +497,58 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             if (lane == 0) arrive_leader(acc_empty(0));
           }
           uint32_t pk[16];
+          uint32_t xk[16];           // training mode: xhat itself (signed), kept for the LayerNorm backward
+          uint32_t neg = 0;          // sign bits of what the relu sees, element 0 ends up in bit 31
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 bv = bq[16 * j + i];
             const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+            float xh[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float v = (__uint_as_float(r[4 * i + e]) + bb[e] - mean) * rstd;
+              xh[e] = v;
               if ((l & 1) == 0) {
                 if (l > 0) v += __uint_as_float(hreg[4 * i + e]);
                 hreg[4 * i + e] = __float_as_uint(v);
               }
               r[4 * i + e] = __float_as_uint(v);
+              if (SAVE) neg = __funnelshift_l(__float_as_uint(v), neg, 1);
             }
+            if (SAVE) { xk[2 * i] = pack2(xh[0], xh[1]); xk[2 * i + 1] = pack2(xh[2], xh[3]); }
           }
+          mw[j] = ~neg;
           if ((l & 1) == 0) tmem_st32(t_h + 64 * j, hreg);
 #pragma unroll
           for (int i = 0; i < 16; ++i) pk[i] = pack2_relu(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+          if (SAVE) mbar_wait(chunk_free(j), (n_writes & 1u) ^ 1u, 13);   // the previous tile in this chunk has been stored
           const uint32_t rowaddr = opnd + j * kChunkBytes + row * 128;
 #pragma unroll
           for (int i4 = 0; i4 < 4; ++i4) {
             const int slot = (half * 4 + i4) ^ (row & 7);
             st_shared_v4(rowaddr + slot * 16, pk[4 * i4], pk[4 * i4 + 1], pk[4 * i4 + 2], pk[4 * i4 + 3]);
           }
+          if (SAVE) {
+            // xhat chunk -> staging (the idle first-Linear operand buffer), same swizzled row layout
+            mbar_wait(xs_free, (n_xs & 1u) ^ 1u, 18);
+            ++n_xs;
+            const uint32_t xaddr = l0buf + row * 128;
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const int slot = (half * 4 + i4) ^ (row & 7);
+              st_shared_v4(xaddr + slot * 16, xk[4 * i4], xk[4 * i4 + 1], xk[4 * i4 + 2], xk[4 * i4 + 3]);
+            }
+          }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) arrive_leader(opnd_ready(j));
+          if (SAVE && lane == 0) { mbar_arrive(written(j)); mbar_arrive(xs_written); }
+        }
+        if (SAVE) {
+          ++n_writes;
+          if (p.masks)
+            *reinterpret_cast<uint4*>(p.masks + (((int64_t)l * p.Bpad + g_row) * 8 + half * 4)) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+          if (half == 0 && p.rstd) p.rstd[(int64_t)l * p.Bpad + g_row] = rstd;
         }
         tmem_st_wait();
       };
@@ -466,8 +556,14 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         const int region = region_of(l);
         // the next tile's input rows: requested a whole tile ahead when the staging area is free (one head tile),
         // else while the last hidden Linear is drained (several head tiles reuse the area as head staging)
-        if (l == (p.head_tiles == 1 ? 0 : n_hidden - 1) && has_next) prefetch_input(tile_next);
-        if (LN) { epi_ln(l); continue; }
+        if (l == (p.head_tiles == 1 ? 0 : n_hidden - 1) && has_next && !p.in_wide) prefetch_input(tile_next);
+        if (l == 0 && p.in_wide) {
+          // second half of the wide first Linear: the first half's MMAs have read the operand buffer
+          mbar_wait(l0_free, l0_par, 17);
+          l0_par ^= 1u;
+          prologue_wide(tile, 1);
+        }
+        if (LN) { epi_ln(l, g); continue; }
         if (l == 0 && p.head_tma) {
           // the previous tile's head rows were staged in the operand buffer: their TMA stores must have been read out
           if (lane == 0) tma_store_wait_read<0>();
@@ -529,7 +625,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         if (lane == 0) arrive_leader(acc_empty(region));
       }
       // ---- the next tile's first Linear can run while this tile's head is stored
-      if (has_next) prologue(tile_next);
+      if (has_next) first_operand(tile_next);
       // ---- head Linear: accumulator + bias -> fp32 rows (thread = row, 128 contiguous bytes per 32 columns)
       for (int t = 0; t < p.head_tiles; ++t) {
         const int region = region_of(n_hidden + t);
@@ -625,7 +721,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       }
     }
     if (lane == 0) tma_store_wait_all();
-  } else if (SAVE) {
+  } else if (SAVE && warp == 2 + kEpiWarps) {
     // ===================== helper warp (training mode): streams every finished operand chunk to HBM =====================
     // Two stores are kept in flight: chunk j is handed back once the store of chunk j+1 has been issued and the one
     // before it has been read out (waiting for each store's read before issuing the next made this warp the
@@ -652,6 +748,25 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           mbar_arrive(chunk_free(3));
         }
         __syncwarp();
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  } else if (SAVE && LN && warp == 3 + kEpiWarps) {
+    // ===================== second helper warp (LayerNorm training mode): xhat chunks, one staging buffer =====================
+    uint32_t cnt = 0;
+    for (int it = it_first; it < it_count; it += it_stride) {
+      const int tile = CTA2 ? 2 * it + (int)rank : it;
+      for (int l = 0; l < n_hidden; ++l) {
+        for (int j = 0; j < 4; ++j, ++cnt) {
+          mbar_wait(xs_written, cnt & 1u, 19);
+          if (lane == 0) {
+            tma_store_2d(&map_x, l0buf, 64 * j, (int)((int64_t)l * p.Bpad + (int64_t)tile * 128));
+            tma_store_commit();
+            tma_store_wait_read<0>();
+            mbar_arrive(xs_free);
+          }
+          __syncwarp();
+        }
       }
     }
     if (lane == 0) tma_store_wait_all();
@@ -996,6 +1111,396 @@ net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------- backward chain, LayerNorm nets
+// Input-gradient chain of a ResidualMLP with hk.LayerNorm(-1, False, False) after every Linear (networks.py:117-129, the
+// bsds config) + head, the VJP of net_fwd_kernel<SAVE, ., LN>.  With s = dL/dh (residual stream), X_l / rstd_l the
+// normalised pre-activation and 1/sigma of LayerNorm l, M_l the relu bits, and
+//     LNbwd(v; X, rstd) = rstd . (v - mean(v) - X . mean(v . X))            (means over the 256 columns of a row)
+// a 128-row tile runs
+//     s    = M_2R . (dHead @ W_head^T);                 g_2R   = LNbwd(s; X_2R)
+//     for r = R-1 .. 0:   t = M_{2r+1} . (g_{2r+2} @ W_{2r+2}^T);   g_{2r+1} = LNbwd(t; X_{2r+1})
+//                         s += M_{2r} . (g_{2r+1} @ W_{2r+1}^T);    g_{2r}   = LNbwd(s; X_{2r})
+//     dIn  = g_0 @ W_0^T                                 (decoder only)
+// g_l is dY_l, the gradient with respect to the output of Linear l: the A operand of the next contraction (bf16, built
+// 64 columns at a time in shared memory like every other chain), streamed to HBM by TMA for the weight-gradient GEMMs, and
+// column-summed for the bias gradients.  s lives in TMEM columns [256, 512) (fp32), the contraction results in [0, 256).
+// X_l tiles arrive by TMA (four 64-column chunks, refilled as soon as the second pass of the previous epilogue has read
+// them).  Every epilogue makes two passes over its row: sums first (the accumulator is handed back after this pass: odd
+// Linears stash the masked values, rounded to bf16, in the operand buffer they are about to overwrite), then the output.
+// The head contraction streams dHead through the operand buffer as a 4-chunk ring, so any head width works (the TriL
+// heads of bsds have 2144 columns).
+constexpr int kLnOffX = kOpndBytes;
+constexpr int kLnOffW = 2 * kOpndBytes;
+constexpr int kLnOffExch = kLnOffW + kWStages * kWStageBytes;
+constexpr int kLnOffBar = kLnOffExch + 128 * 2 * 2 * 4;
+constexpr int kLnSmemBytes = kLnOffBar + 512;
+static_assert(kLnSmemBytes <= 232448, "shared-memory plan exceeds 227 KB");
+
+struct BwdLnArgs {
+  int64_t B; int num_tiles;
+  int k16_h;                  // K = 16 steps of the head contraction (ceil(head_N / 16))
+  int din_N, din_cols;        // dIn: MMA N (multiple of 16, 0 = none) and valid columns
+  float* dIn;                 // [B, din_cols] fp32
+  const uint32_t* masks; const float* rstd; int64_t Bpad;
+  float* db[kMaxLayers];      // bias-gradient destinations (atomicAdd), Linear 0..2R
+};
+
+template <int R, bool DIN>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant__ CUtensorMap map_wh,
+                  const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w0,
+                  const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, BwdLnArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if ((sbase & 1023u) != 0) { if (threadIdx.x == 0) printf("pmvae net_bwd_ln_kernel: shared memory base is not 1024-byte aligned\n"); __trap(); }
+  const uint32_t abuf = sbase, xbuf = sbase + kLnOffX, wring = sbase + kLnOffW, bar = sbase + kLnOffBar;
+  float* exch = reinterpret_cast<float*>(smem_raw + kLnOffExch);           // [128 rows][2 halves][2]
+  auto w_full = [&](int s) { return bar + 8u * s; };
+  auto w_empty = [&](int s) { return bar + 8u * (3 + s); };
+  auto opnd_ready = [&](int c) { return bar + 8u * (6 + c); };
+  auto hd_full = [&](int c) { return bar + 8u * (10 + c); };
+  auto hd_empty = [&](int c) { return bar + 8u * (14 + c); };
+  auto x_full = [&](int c) { return bar + 8u * (18 + c); };
+  auto x_free = [&](int c) { return bar + 8u * (22 + c); };
+  auto written = [&](int c) { return bar + 8u * (26 + c); };
+  auto chunk_free = [&](int c) { return bar + 8u * (30 + c); };
+  const uint32_t acc_full = bar + 8u * 34, acc_empty = bar + 8u * 35, bufa_free = bar + 8u * 36;
+  const uint32_t tmem_slot = bar + 8u * 37;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + kLnOffBar + 8 * 37);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  constexpr int n_hidden = 2 * R + 1;
+  const int nkb_h = (p.k16_h + 3) >> 2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_dh); tma_prefetch_desc(&map_wh); tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_dy);
+    tma_prefetch_desc(&map_x);
+    if (DIN) tma_prefetch_desc(&map_w0);
+    for (int s = 0; s < 3; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    for (int c = 0; c < 4; ++c) {
+      mbar_init(opnd_ready(c), kEpiWarps); mbar_init(hd_full(c), 1); mbar_init(hd_empty(c), 1);
+      mbar_init(x_full(c), 1); mbar_init(x_free(c), kEpiWarps);
+      mbar_init(written(c), kEpiWarps); mbar_init(chunk_free(c), 1);
+    }
+    mbar_init(acc_full, 1); mbar_init(acc_empty, kEpiWarps);
+    mbar_init(bufa_free, DIN ? 5 : 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ===================== producer: dHead chunks, weight K-blocks, xhat tiles =====================
+    int stage = 0; uint32_t ph = 0;
+    uint32_t hd_cnt = 0, x_cnt = 0, t_cnt = 0;
+    auto load_w = [&](const CUtensorMap* m, int c0, int c1, uint32_t bytes) {
+      mbar_wait(w_empty(stage), ph ^ 1u, 1);
+      __syncwarp();
+      if (elect_one()) {
+        mbar_arrive_expect_tx(w_full(stage), bytes);
+        tma_load_2d(wring + stage * kWStageBytes, m, w_full(stage), c0, c1);
+      }
+      __syncwarp();
+      if (++stage == kWStages) { stage = 0; ph ^= 1u; }
+    };
+    auto load_x = [&](int l, int tile) {
+      for (int j = 0; j < 4; ++j) {
+        mbar_wait(x_free(j), (x_cnt & 1u) ^ 1u, 20);
+        __syncwarp();
+        if (elect_one()) {
+          mbar_arrive_expect_tx(x_full(j), (uint32_t)kChunkBytes);
+          tma_load_2d(xbuf + j * kChunkBytes, &map_x, x_full(j), 64 * j, (int)((int64_t)l * p.Bpad + (int64_t)tile * 128));
+        }
+        __syncwarp();
+      }
+      ++x_cnt;
+    };
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t_cnt) {
+      // the operand buffer is the dHead ring now: the previous tile's last gradient tile has been stored (and multiplied)
+      mbar_wait(bufa_free, (t_cnt & 1u) ^ 1u, 21);
+      load_x(2 * R, tile);
+      for (int kb = 0; kb < nkb_h; ++kb, ++hd_cnt) {
+        const int slot = (int)(hd_cnt & 3u);
+        mbar_wait(hd_empty(slot), ((hd_cnt >> 2) & 1u) ^ 1u, 22);
+        __syncwarp();
+        if (elect_one()) {
+          mbar_arrive_expect_tx(hd_full(slot), (uint32_t)kChunkBytes);
+          tma_load_2d(abuf + slot * kChunkBytes, &map_dh, hd_full(slot), kb * 64, tile * 128);
+        }
+        __syncwarp();
+        load_w(&map_wh, kb * 64, 0, kWStageBytes);
+      }
+      for (int l = 2 * R; l >= 1; --l) {
+        for (int kb = 0; kb < 4; ++kb) load_w(&map_w, kb * 64, (l - 1) * 256, kWStageBytes);
+        load_x(l - 1, tile);
+      }
+      if (DIN)
+        for (int kb = 0; kb < 4; ++kb) load_w(&map_w0, kb * 64, 0, (uint32_t)p.din_N * 128u);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (converged warp, one elected lane issues) =====================
+    int stage = 0; uint32_t ph = 0;
+    uint32_t ready_par = 0, acc_uses = 0, hd_cnt = 0;
+    constexpr uint32_t kDescHi = 0x40004040u;      // SBO 1024 | version 1 | SWIZZLE_128B (see smem_desc)
+    auto desc_lo = [](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };
+    auto mk = [](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
+    const uint32_t d_tmem = tmem_base;
+    auto acquire_acc = [&]() {
+      mbar_wait(acc_empty, (acc_uses & 1u) ^ 1u, 2);
+      ++acc_uses;
+      tc_fence_after();
+    };
+    // one 64-wide K-block: A chunk at `a_addr`, B = the ring stage; `ks` K = 16 slices
+    auto kblock = [&](uint32_t a_addr, int ks, uint32_t idesc, bool first, uint32_t extra_commit, bool last) {
+      const uint32_t b_w = w_full(stage);
+      mbar_wait(b_w, ph, 4);
+      tc_fence_after();
+      const uint32_t a_lo = desc_lo(a_addr), b_lo = desc_lo(wring + stage * kWStageBytes);
+      __syncwarp();
+      if (elect_one()) {
+        for (int k = 0; k < ks; ++k) umma_f16(d_tmem, mk(a_lo + 2 * k), mk(b_lo + 2 * k), idesc, (!first || k > 0) ? 1u : 0u);
+        umma_commit(w_empty(stage));
+        if (extra_commit) umma_commit(extra_commit);
+        if (last) umma_commit(acc_full);
+      }
+      __syncwarp();
+      if (++stage == kWStages) { stage = 0; ph ^= 1u; }
+    };
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      // head: s_raw = dHead @ W_head^T, dHead streamed through the 4-chunk ring
+      acquire_acc();
+      for (int kb = 0; kb < nkb_h; ++kb, ++hd_cnt) {
+        const int slot = (int)(hd_cnt & 3u);
+        mbar_wait(hd_full(slot), (hd_cnt >> 2) & 1u, 8);
+        kblock(abuf + slot * kChunkBytes, min(4, p.k16_h - 4 * kb), instr_desc(128, 256, 0, 0), kb == 0, hd_empty(slot), kb == nkb_h - 1);
+      }
+      for (int st = 0; st < 2 * R; ++st) {
+        acquire_acc();
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(opnd_ready(kb), (ready_par >> kb) & 1u, 3);
+          ready_par ^= 1u << kb;
+          kblock(abuf + kb * kChunkBytes, 4, instr_desc(128, 256, 0, 0), kb == 0, 0u, kb == 3);
+        }
+      }
+      if (DIN) {
+        acquire_acc();
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(opnd_ready(kb), (ready_par >> kb) & 1u, 3);
+          ready_par ^= 1u << kb;
+          kblock(abuf + kb * kChunkBytes, 4, instr_desc(128, p.din_N, 0, 0), kb == 0, kb == 3 ? bufa_free : 0u, kb == 3);
+        }
+      }
+    }
+  } else if (warp < 2 + kEpiWarps) {
+    // ===================== epilogue (8 warps): thread = row, two threads (half 0 / 1) per row =====================
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_acc = t_lane + (uint32_t)(32 * half);
+    const uint32_t t_s = t_lane + (uint32_t)(256 + 32 * half);
+    uint32_t full_par = 0, e_cnt = 0;
+    float* mine = exch + (row * 2 + half) * 2;
+    const float* other = exch + (row * 2 + (half ^ 1)) * 2;
+
+    // One epilogue: v = M_l . acc (+ s), row sums, g_l = LNbwd(v; X_l) -> operand buffer chunk by chunk.
+    auto epi = [&](int l, bool first, int64_t g, bool has_consumer) {
+      const bool even = (l & 1) == 0;
+      const uint4 mq = *reinterpret_cast<const uint4*>(p.masks + (((int64_t)l * p.Bpad + g) * 8 + half * 4));
+      const uint32_t mw[4] = {mq.x, mq.y, mq.z, mq.w};
+      const float rstd = p.rstd[(int64_t)l * p.Bpad + g];
+      const uint32_t cf_par = (e_cnt & 1u) ^ 1u;      // chunk_free: the previous gradient tile in this chunk has been stored
+      const uint32_t x_par = e_cnt & 1u;
+      ++e_cnt;
+      mbar_wait(acc_full, full_par, 5);
+      full_par ^= 1u;
+      tc_fence_after();
+      float S1 = 0.f, S2 = 0.f;
+      // ---- pass 1: masked values, row sums; s -> TMEM (even) or bf16 stash in the operand buffer (odd)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t r[32], so[32];
+        tmem_ld32(t_acc + 64 * j, r);
+        if (even && !first) tmem_ld32(t_s + 64 * j, so);
+        mbar_wait(x_full(j), x_par, 23);
+        uint32_t xq[16];
+        const uint32_t xrow = xbuf + j * kChunkBytes + row * 128;
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int slot = (half * 4 + i4) ^ (row & 7);
+          ld_shared_v4(xrow + slot * 16, xq[4 * i4], xq[4 * i4 + 1], xq[4 * i4 + 2], xq[4 * i4 + 3]);
+        }
+        tmem_ld_wait();
+        const uint32_t m = mw[j];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float a0 = ((int32_t)(m << (2 * i)) < 0) ? __uint_as_float(r[2 * i]) : 0.f;
+          float a1 = ((int32_t)(m << (2 * i + 1)) < 0) ? __uint_as_float(r[2 * i + 1]) : 0.f;
+          if (even && !first) { a0 += __uint_as_float(so[2 * i]); a1 += __uint_as_float(so[2 * i + 1]); }
+          S1 += a0 + a1;
+          S2 = fmaf(a0, bf16_lo(xq[i]), S2);
+          S2 = fmaf(a1, bf16_hi(xq[i]), S2);
+          r[2 * i] = __float_as_uint(a0); r[2 * i + 1] = __float_as_uint(a1);
+        }
+        if (even) {
+          tmem_st32(t_s + 64 * j, r);
+        } else {
+          mbar_wait(chunk_free(j), cf_par, 10);
+          const uint32_t rowaddr = abuf + j * kChunkBytes + row * 128;
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const int slot = (half * 4 + i4) ^ (row & 7);
+            st_shared_v4(rowaddr + slot * 16, pack2(__uint_as_float(r[8 * i4]), __uint_as_float(r[8 * i4 + 1])),
+                         pack2(__uint_as_float(r[8 * i4 + 2]), __uint_as_float(r[8 * i4 + 3])),
+                         pack2(__uint_as_float(r[8 * i4 + 4]), __uint_as_float(r[8 * i4 + 5])),
+                         pack2(__uint_as_float(r[8 * i4 + 6]), __uint_as_float(r[8 * i4 + 7])));
+          }
+        }
+      }
+      if (even) tmem_st_wait();
+      // the accumulator has been read for the last time
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+      mine[0] = S1; mine[1] = S2;
+      named_bar_sync(1 + q, 64);
+      const float c1 = (S1 + other[0]) * (1.0f / 256.0f), c2 = (S2 + other[1]) * (1.0f / 256.0f);
+      // ---- pass 2: g = rstd (v - c1 - x c2)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t r[32];
+        uint32_t vq[16];
+        const uint32_t rowaddr = abuf + j * kChunkBytes + row * 128;
+        if (even) {
+          tmem_ld32(t_s + 64 * j, r);
+        } else {
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const int slot = (half * 4 + i4) ^ (row & 7);
+            ld_shared_v4(rowaddr + slot * 16, vq[4 * i4], vq[4 * i4 + 1], vq[4 * i4 + 2], vq[4 * i4 + 3]);
+          }
+        }
+        uint32_t xq[16];
+        const uint32_t xrow = xbuf + j * kChunkBytes + row * 128;
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int slot = (half * 4 + i4) ^ (row & 7);
+          ld_shared_v4(xrow + slot * 16, xq[4 * i4], xq[4 * i4 + 1], xq[4 * i4 + 2], xq[4 * i4 + 3]);
+        }
+        if (even) {
+          tmem_ld_wait();
+          mbar_wait(chunk_free(j), cf_par, 10);
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float v0 = even ? __uint_as_float(r[2 * i]) : bf16_lo(vq[i]);
+          const float v1 = even ? __uint_as_float(r[2 * i + 1]) : bf16_hi(vq[i]);
+          const float g0 = rstd * (v0 - c1 - bf16_lo(xq[i]) * c2);
+          const float g1 = rstd * (v1 - c1 - bf16_hi(xq[i]) * c2);
+          pk[i] = pack2(g0, g1);
+        }
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int slot = (half * 4 + i4) ^ (row & 7);
+          st_shared_v4(rowaddr + slot * 16, pk[4 * i4], pk[4 * i4 + 1], pk[4 * i4 + 2], pk[4 * i4 + 3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (has_consumer) mbar_arrive(opnd_ready(j));
+          mbar_arrive(written(j));
+          mbar_arrive(x_free(j));
+        }
+      }
+      named_bar_sync(1 + q, 64);        // the exchange slots are rewritten by the next epilogue
+    };
+
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int64_t g = (int64_t)tile * 128 + row;
+      epi(2 * R, true, g, true);
+#pragma unroll
+      for (int r = R - 1; r >= 0; --r) {
+        epi(2 * r + 1, false, g, true);
+        epi(2 * r, false, g, DIN || r > 0);
+      }
+      if (DIN) {
+        mbar_wait(acc_full, full_par, 6);
+        full_par ^= 1u;
+        tc_fence_after();
+        for (int pc = half; pc * 32 < p.din_N; pc += 2) {
+          uint32_t r[32];
+          tmem_ld32(t_lane + (uint32_t)(pc * 32), r);
+          tmem_ld_wait();
+          if (g < p.B) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (pc * 32 + i < p.din_cols) p.dIn[g * p.din_cols + pc * 32 + i] = __uint_as_float(r[i]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+      }
+    }
+  } else {
+    // ===================== helpers (4 warps): warp j owns chunk j of every gradient tile =====================
+    const int j = warp - (2 + kEpiWarps);
+    float cs[n_hidden][2];
+#pragma unroll
+    for (int l = 0; l < n_hidden; ++l) { cs[l][0] = 0.f; cs[l][1] = 0.f; }
+    uint32_t wr_cnt = 0;
+    auto help = [&](int l, int tile, float (&c2)[2]) {
+      const uint32_t src = abuf + j * kChunkBytes;
+      mbar_wait(written(j), wr_cnt & 1u, 11);
+      ++wr_cnt;
+      if (lane == 0) {
+        tma_store_2d(&map_dy, src, 64 * j, (int)((int64_t)l * p.Bpad + (int64_t)tile * 128));
+        tma_store_commit();
+      }
+      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < 128; r += 2) {
+        const uint32_t w0 = ld_shared_u32(src + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+        const uint32_t w1 = ld_shared_u32(src + (r + 1) * 128 + ((((lane >> 2) ^ ((r + 1) & 7)) << 4) | ((lane & 3) << 2)));
+        a0 += bf16_lo(w0); a1 += bf16_hi(w0);
+        b0 += bf16_lo(w1); b1 += bf16_hi(w1);
+      }
+      c2[0] += a0 + b0; c2[1] += a1 + b1;
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(chunk_free(j));
+    };
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      help(2 * R, tile, cs[2 * R]);
+#pragma unroll
+      for (int r = R - 1; r >= 0; --r) {
+        help(2 * r + 1, tile, cs[2 * r + 1]);
+        help(2 * r, tile, cs[2 * r]);
+      }
+      if (lane == 0) mbar_arrive(bufa_free);      // this chunk of the tile's last gradient tile has been stored
+    }
+    if (lane == 0) tma_store_wait_all();
+#pragma unroll
+    for (int l = 0; l < n_hidden; ++l)
+      if (p.db[l]) {
+        atomicAdd(p.db[l] + 64 * j + 2 * lane, cs[l][0]);
+        atomicAdd(p.db[l] + 64 * j + 2 * lane + 1, cs[l][1]);
+      }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---------------------------------------------------------------- weight images
 struct PackSlab { uint64_t dst, w; int rows, cols, kind, src_rows, src_cols, D, tile0; };
 struct PackTable { int n; PackSlab s[2 * kMaxLayers + 4]; };
@@ -1026,6 +1531,10 @@ __global__ void __launch_bounds__(256) pack_fused_kernel(const float* __restrict
     const int kk = tcn * 32 + i, n = tr * 32 + tx;
     int sr = -1;
     if (sl.kind == 0) sr = kk < sl.src_rows ? kk : -1;
+    else if (sl.kind == 4) {                                      // wide masked input: K-block 0 = W[:D], K-block 1 = W[D:2D]
+      if (kk < sl.D) sr = kk;
+      else if (kk >= 64 && kk < 64 + sl.D) sr = sl.D + (kk - 64);
+    }
     else if (kk < sl.D) sr = kk;
     else if (kk < 2 * sl.D) sr = kk - sl.D;
     else if (sl.kind == 2 && kk < 3 * sl.D) sr = kk - sl.D;      // rows D..2D-1 of W multiply b
@@ -1040,7 +1549,9 @@ __global__ void __launch_bounds__(256) pack_fused_kernel(const float* __restrict
 
 // expanded first-Linear operand: plain input [hi | lo] when both fit one 64-wide K-block, else [hi] only (fan-in up
 // to 64: operand rounding like every other Linear); masked input [hi(x*b) | lo(x*b) | b]
+static bool wide_masked(const Net& n, int in_kind) { return in_kind == 1 && 3 * (n.in_dim / 2) > 64 && n.in_dim / 2 <= 64; }
 static int first_kext(const Net& n, int in_kind, int* in_lo) {
+  if (wide_masked(n, in_kind)) { *in_lo = 0; return n.in_dim / 2; }   // per half: [x*b] then [b], one K-block each
   if (in_kind == 1) { *in_lo = 1; return 3 * (n.in_dim / 2); }
   *in_lo = 2 * n.in_dim <= 64 ? 1 : 0;
   return *in_lo ? 2 * n.in_dim : n.in_dim;
@@ -1051,14 +1562,17 @@ bool forward_supported(const Net& n, int H, int in_kind) {
   const int kext = first_kext(n, in_kind, &lo);
   // one K-block for the first Linear; a row's fp32 inputs (x | mask) fit its staging slot; LayerNorm nets keep the
   // exchange buffer in the tail of the bias table
-  return kext <= 64 && n.in_dim <= kInPitch - 1 && n.R < (n.ln ? 6 : kMaxBlocks);
+  return kext <= 64 && (n.in_dim <= kInPitch - 1 || wide_masked(n, in_kind)) && n.R < (n.ln ? 6 : kMaxBlocks);
 }
 bool supported(const Net& n, int H, int in_kind) { return !n.ln && forward_supported(n, H, in_kind); }
+// training-mode forward (saved activations) of LayerNorm nets; their backward chain is fused_ln.cu
+bool ln_train_supported(const Net& n, int H, int in_kind) { return n.ln && forward_supported(n, H, in_kind) && n.R >= 1; }
 
 NetImages plan_images(const Net& n, const Leaf& head, int in_kind, bf16* base) {
   NetImages im{};
   im.R = n.R; im.in_kind = in_kind;
   im.D_in = (in_kind == 1) ? n.in_dim / 2 : n.in_dim;
+  im.in_wide = wide_masked(n, in_kind) ? 1 : 0;
   const int kext = first_kext(n, in_kind, &im.in_lo);
   im.k16_0 = (kext + 15) / 16;
   im.head_N = head.cols;
@@ -1090,7 +1604,7 @@ int pack_images(const float* params, const Net& n, const Leaf& head, const NetIm
     sl.src_rows = src_rows; sl.src_cols = src_cols; sl.D = im.D_in; sl.tile0 = tiles;
     tiles += ((rows + 31) / 32) * ((cols + 31) / 32);
   };
-  add(im.stack_t, n.lin[0].w, 256, 256, im.in_kind == 1 ? 2 : (im.in_lo ? 1 : 0), n.lin[0].rows, 256);
+  add(im.stack_t, n.lin[0].w, 256, 256, im.in_wide ? 4 : (im.in_kind == 1 ? 2 : (im.in_lo ? 1 : 0)), n.lin[0].rows, 256);
   for (int l = 1; l <= 2 * n.R; ++l) add(im.stack_t + (uint64_t)l * 65536, n.lin[l].w, 256, 256, 0, 256, 256);
   add(im.head_t, head.w, im.head_tiles * im.head_NT, 256, 0, 256, head.cols);
   for (int l = 1; l <= 2 * n.R; ++l) add(im.stack_n + (uint64_t)(l - 1) * 65536, n.lin[l].w, 256, 256, 3, 256, 256);
@@ -1099,6 +1613,13 @@ int pack_images(const float* params, const Net& n, const Leaf& head, const NetIm
   pack_fused_kernel<<<tiles, 256, 0, s>>>(params, const_cast<bf16*>(base), tb);
   PMVAE_LAUNCH_CHECK();
   return 0;
+}
+
+// PMVAE_FUSED_MAXGRID (tests): cap on the persistent grids, so that small batches exercise several tiles per CTA
+static int grid_cap(int grid) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PMVAE_FUSED_MAXGRID"); v = e ? atoi(e) : 0; }
+  return (v > 0 && grid > v) ? v : grid;
 }
 
 static bool cta2_enabled() {
@@ -1112,33 +1633,37 @@ static bool cta2_enabled() {
 
 template <bool SAVE, bool CTA2, bool LN>
 static int launch_fwd_t(int grid, const CUtensorMap& mw, const CUtensorMap& mh, const CUtensorMap& ms,
-                        const CUtensorMap& mo, const FwdArgs& a, cudaStream_t s) {
+                        const CUtensorMap& mo, const CUtensorMap& mx, const FwdArgs& a, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     PMVAE_CUDA(cudaFuncSetAttribute(net_fwd_kernel<SAVE, CTA2, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kFwdThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = s;
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((SAVE && LN) ? kFwdThreadsLN : kFwdThreads);
+  cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CTA2 ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  PMVAE_CUDA(cudaLaunchKernelEx(&cfg, net_fwd_kernel<SAVE, CTA2, LN>, mw, mh, ms, mo, a));
+  PMVAE_CUDA(cudaLaunchKernelEx(&cfg, net_fwd_kernel<SAVE, CTA2, LN>, mw, mh, ms, mo, mx, a));
   return 0;
 }
 static int launch_fwd(bool save, bool cta2, bool ln, int grid, const CUtensorMap& mw, const CUtensorMap& mh,
-                      const CUtensorMap& ms, const CUtensorMap& mo, const FwdArgs& a, cudaStream_t s) {
-  if (ln) return cta2 ? launch_fwd_t<false, true, true>(grid, mw, mh, ms, mo, a, s) : launch_fwd_t<false, false, true>(grid, mw, mh, ms, mo, a, s);
-  if (save) return cta2 ? launch_fwd_t<true, true, false>(grid, mw, mh, ms, mo, a, s) : launch_fwd_t<true, false, false>(grid, mw, mh, ms, mo, a, s);
-  return cta2 ? launch_fwd_t<false, true, false>(grid, mw, mh, ms, mo, a, s) : launch_fwd_t<false, false, false>(grid, mw, mh, ms, mo, a, s);
+                      const CUtensorMap& ms, const CUtensorMap& mo, const CUtensorMap& mx, const FwdArgs& a, cudaStream_t s) {
+  if (ln && save) return cta2 ? launch_fwd_t<true, true, true>(grid, mw, mh, ms, mo, mx, a, s) : launch_fwd_t<true, false, true>(grid, mw, mh, ms, mo, mx, a, s);
+  if (ln) return cta2 ? launch_fwd_t<false, true, true>(grid, mw, mh, ms, mo, mx, a, s) : launch_fwd_t<false, false, true>(grid, mw, mh, ms, mo, mx, a, s);
+  if (save) return cta2 ? launch_fwd_t<true, true, false>(grid, mw, mh, ms, mo, mx, a, s) : launch_fwd_t<true, false, false>(grid, mw, mh, ms, mo, mx, a, s);
+  return cta2 ? launch_fwd_t<false, true, false>(grid, mw, mh, ms, mo, mx, a, s) : launch_fwd_t<false, false, false>(grid, mw, mh, ms, mo, mx, a, s);
 }
 
 int net_forward(const float* params, const Net& n, const Leaf& head, const NetImages& im, const float* in,
                 const float* msk, int64_t B, bf16* saved, uint32_t* masks, int64_t Bpad, float* out, int64_t ld_out,
-                cudaStream_t s) {
+                cudaStream_t s, bf16* xhat, float* rstd) {
   if (B <= 0) return 0;
-  PMVAE_CHECK(forward_supported(n, 256, im.in_kind) && (saved == nullptr || !n.ln), "net not covered by the fused kernels");
+  PMVAE_CHECK(forward_supported(n, 256, im.in_kind), "net not covered by the fused kernels");
+  PMVAE_CHECK(saved == nullptr || !n.ln || (xhat != nullptr && rstd != nullptr),
+              "LayerNorm nets in training mode also save xhat and 1/sigma");
   PMVAE_CHECK((im.in_kind == 1) == (msk != nullptr), "mask pointer does not match the first-layer layout");
   PMVAE_CHECK(B < (1ll << 30), "too many rows");
   FwdArgs a{};
@@ -1149,8 +1674,10 @@ int net_forward(const float* params, const Net& n, const Leaf& head, const NetIm
   a.out = out; a.ld_out = ld_out;
   a.Bpad = Bpad;
   a.masks = nullptr;
+  a.rstd = nullptr;
+  a.in_wide = im.in_wide;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PMVAE_FUSED_DEBUG"); dbg = e ? atoi(e) : 0; } a.debug = dbg; }
-  CUtensorMap mw, mh, ms, mo;
+  CUtensorMap mw, mh, ms, mo, mx;
   const bool cta2 = cta2_enabled();
   PMVAE_TRY(make_map_2d(&mw, im.stack_t, 2, (uint64_t)(1 + 2 * n.R) * 256, 256, 256, 64, cta2 ? 128 : 256));
   PMVAE_TRY(make_map_2d(&mh, im.head_t, 2, (uint64_t)im.head_tiles * im.head_NT, 256, 256, 64,
@@ -1161,16 +1688,22 @@ int net_forward(const float* params, const Net& n, const Leaf& head, const NetIm
     PMVAE_CHECK((int64_t)(2 * n.R + 1) * Bpad < (1ll << 31), "saved activation stack too large");
     PMVAE_TRY(make_map_2d(&ms, saved, 2, (uint64_t)(2 * n.R + 1) * Bpad, 256, 256, 64, 128));
     a.masks = masks;
+    if (n.ln) {
+      PMVAE_TRY(make_map_2d(&mx, xhat, 2, (uint64_t)(2 * n.R + 1) * Bpad, 256, 256, 64, 128));
+      a.rstd = rstd;
+    } else {
+      mx = mw;
+    }
   } else {
-    ms = mw;
+    ms = mw; mx = mw;
   }
   a.head_tma = ((ld_out * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) ? 1 : 0;
   if (a.head_tma) PMVAE_TRY(make_map_2d(&mo, out, 4, (uint64_t)B, (uint64_t)im.head_N, (uint64_t)ld_out, 32, 32));
   else mo = mw;
-  int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
+  int grid = grid_cap(a.num_tiles < num_sms() ? a.num_tiles : num_sms());
   if (cta2) {
     const int pairs = (a.num_tiles + 1) / 2;
-    grid = 2 * (pairs < num_sms() / 2 ? pairs : num_sms() / 2);
+    grid = 2 * grid_cap(pairs < num_sms() / 2 ? pairs : num_sms() / 2);
     PMVAE_CHECK(saved == nullptr || Bpad % 256 == 0, "CTA pairs need a 256-row padded slab pitch");
   }
   static long long* trace_buf = nullptr;
@@ -1181,7 +1714,7 @@ int net_forward(const float* params, const Net& n, const Leaf& head, const NetIm
     cudaMemsetAsync(trace_buf, 0, 2 * 2048 * sizeof(long long), s);
     a.trace = trace_buf;
   }
-  PMVAE_TRY(launch_fwd(saved != nullptr, cta2, n.ln != 0, grid, mw, mh, ms, mo, a, s));
+  PMVAE_TRY(launch_fwd(saved != nullptr, cta2, n.ln != 0, grid, mw, mh, ms, mo, mx, a, s));
   PMVAE_LAUNCH_CHECK();
   if (trace_on) {
     static long long host[2 * 2048];
@@ -1208,7 +1741,7 @@ static int launch_bwd(const CUtensorMap& mdh, const CUtensorMap& mwh, const CUte
     PMVAE_CUDA(cudaFuncSetAttribute(net_bwd_kernel<R, DIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes));
     attr_set = true;
   }
-  const int grid = a.num_tiles < num_sms() ? a.num_tiles : num_sms();
+  const int grid = grid_cap(a.num_tiles < num_sms() ? a.num_tiles : num_sms());
   net_bwd_kernel<R, DIN><<<grid, kBwdThreads, kBwdSmemBytes, s>>>(mdh, mwh, mw, mw0, mdy, a);
   PMVAE_LAUNCH_CHECK();
   return 0;
@@ -1245,6 +1778,58 @@ int net_backward(const Net& n, const Leaf& head, const NetImages& im, const bf16
     PMVAE_BWD_CASE(4);
   }
 #undef PMVAE_BWD_CASE
+  PMVAE_CHECK(false, "unsupported number of residual blocks");
+  return 1;
+}
+
+template <int R, bool DIN>
+static int launch_bwd_ln(const CUtensorMap& mdh, const CUtensorMap& mwh, const CUtensorMap& mw, const CUtensorMap& mw0,
+                         const CUtensorMap& mdy, const CUtensorMap& mx, const BwdLnArgs& a, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PMVAE_CUDA(cudaFuncSetAttribute(net_bwd_ln_kernel<R, DIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnSmemBytes));
+    attr_set = true;
+  }
+  const int grid = grid_cap(a.num_tiles < num_sms() ? a.num_tiles : num_sms());
+  net_bwd_ln_kernel<R, DIN><<<grid, kBwdThreads, kLnSmemBytes, s>>>(mdh, mwh, mw, mw0, mdy, mx, a);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+bool backward_ln_supported(const Net& n, int H, int in_kind) { return ln_train_supported(n, H, in_kind) && n.R <= 5; }
+
+int net_backward_ln(const Net& n, const Leaf& head, const NetImages& im, const bf16* dHead, int64_t ld_dhead, int64_t B,
+                    const uint32_t* masks, const bf16* xhat, const float* rstd, int64_t Bpad, bf16* dY, float* grads,
+                    float* dIn, cudaStream_t s) {
+  if (B <= 0) return 0;
+  PMVAE_CHECK(backward_ln_supported(n, 256, im.in_kind), "net not covered by the fused LayerNorm backward kernel");
+  PMVAE_CHECK(dIn == nullptr || im.has_w0_n, "no first-layer image for the input gradient");
+  PMVAE_CHECK(Bpad % 128 == 0 && Bpad >= B && (int64_t)(2 * n.R + 1) * Bpad < (1ll << 31), "bad slab pitch");
+  PMVAE_CHECK((ld_dhead * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(dHead) & 15u) == 0, "dHead must be 16-byte aligned with a 16-byte pitch");
+  BwdLnArgs a{};
+  a.B = B; a.num_tiles = (int)ceil_div(B, 128);
+  a.k16_h = (im.head_N + 15) / 16;
+  a.din_N = dIn ? im.din_N : 0; a.din_cols = n.in_dim; a.dIn = dIn;
+  a.masks = masks; a.rstd = rstd; a.Bpad = Bpad;
+  for (int l = 0; l <= 2 * n.R; ++l) a.db[l] = grads + n.lin[l].b;
+  CUtensorMap mdh, mwh, mw, mw0, mdy, mx;
+  PMVAE_TRY(make_map_2d(&mdh, dHead, 2, (uint64_t)B, (uint64_t)im.head_N, (uint64_t)ld_dhead, 64, 128));
+  PMVAE_TRY(make_map_2d(&mwh, im.head_n, 2, 256, (uint64_t)im.head_Kp, (uint64_t)im.head_Kp, 64, 256));
+  PMVAE_TRY(make_map_2d(&mw, im.stack_n, 2, (uint64_t)(2 * n.R) * 256, 256, 256, 64, 256));
+  PMVAE_TRY(make_map_2d(&mdy, dY, 2, (uint64_t)(2 * n.R + 1) * Bpad, 256, 256, 64, 128));
+  PMVAE_TRY(make_map_2d(&mx, xhat, 2, (uint64_t)(2 * n.R + 1) * Bpad, 256, 256, 64, 128));
+  if (dIn) PMVAE_TRY(make_map_2d(&mw0, im.w0_n, 2, (uint64_t)im.din_N, 256, 256, 64, (uint32_t)im.din_N));
+  else mw0 = mw;
+#define PMVAE_BWD_LN_CASE(RR)                                                                                    \
+  case RR: return dIn ? launch_bwd_ln<RR, true>(mdh, mwh, mw, mw0, mdy, mx, a, s) : launch_bwd_ln<RR, false>(mdh, mwh, mw, mw0, mdy, mx, a, s)
+  switch (n.R) {
+    PMVAE_BWD_LN_CASE(1);
+    PMVAE_BWD_LN_CASE(2);
+    PMVAE_BWD_LN_CASE(3);
+    PMVAE_BWD_LN_CASE(4);
+    PMVAE_BWD_LN_CASE(5);
+  }
+#undef PMVAE_BWD_LN_CASE
   PMVAE_CHECK(false, "unsupported number of residual blocks");
   return 1;
 }

@@ -23,6 +23,7 @@ struct NetImages {
   const __nv_bfloat16* w0_n;            // [din_N, 256] first Linear (natural), in_kind 0 only: dL/d(input)
   bool has_w0_n; int din_N;
   int R, D_in, in_kind, in_lo, k16_0;   // k16_0 = ceil(K_ext / 16); in_lo: the [lo(v)] columns are present
+  int in_wide;                          // masked input with 3 D > 64: first Linear as two K-blocks, [x*b] @ W[:D] + b @ W[D:]
   int head_N, head_NT, head_tiles, head_Kp;
   uint64_t elems;                       // bf16 elements used by the four images
 };
@@ -31,6 +32,7 @@ struct NetImages {
 // supported: forward with saved activations + backward (no LayerNorm)
 bool forward_supported(const Net& n, int H, int in_kind);
 bool supported(const Net& n, int H, int in_kind);
+bool ln_train_supported(const Net& n, int H, int in_kind);
 
 // plans the images at `base` (may be null to size only)
 NetImages plan_images(const Net& n, const Leaf& head, int in_kind, __nv_bfloat16* base);
@@ -44,9 +46,11 @@ int pack_images(const float* params, const Net& n, const Leaf& head, const NetIm
 // [64 j + 32 half, +32)).
 //   in/msk : [B, D_in] float32 (msk only for in_kind 1)
 //   out    : [B, ld_out] float32 head output (columns < head_N written)
+// LayerNorm nets in training mode additionally keep xhat of every LayerNorm (`xhat`, bf16, same slab layout as
+// `saved`) and 1 / sigma (`rstd`, [(2R+1), Bpad] float32).
 int net_forward(const float* params, const Net& n, const Leaf& head, const NetImages& im, const float* in,
                 const float* msk, int64_t B, __nv_bfloat16* saved, uint32_t* masks, int64_t Bpad, float* out,
-                int64_t ld_out, cudaStream_t s);
+                int64_t ld_out, cudaStream_t s, __nv_bfloat16* xhat = nullptr, float* rstd = nullptr);
 
 // Input-gradient chain of the same net (the activations' VJP): reads dHead [B, ld_dhead] (bf16, columns >=
 // head_N zero) and the relu bits of the forward, writes dY_l (bf16, slab l of [(2R+1), Bpad, 256]) = the
@@ -56,6 +60,13 @@ bool backward_supported(const Net& n, int H, int in_kind);
 int net_backward(const Net& n, const Leaf& head, const NetImages& im, const __nv_bfloat16* dHead, int64_t ld_dhead,
                  int64_t B, const uint32_t* masks, int64_t Bpad, __nv_bfloat16* dY, float* grads, float* dIn,
                  cudaStream_t s);
+
+// The same chain for LayerNorm nets (VJP of the training-mode LayerNorm forward): additionally reads xhat / 1/sigma of
+// every LayerNorm; dY_l is the gradient with respect to the (pre-LayerNorm) output of Linear l.  Any head width.
+bool backward_ln_supported(const Net& n, int H, int in_kind);
+int net_backward_ln(const Net& n, const Leaf& head, const NetImages& im, const __nv_bfloat16* dHead, int64_t ld_dhead,
+                    int64_t B, const uint32_t* masks, const __nv_bfloat16* xhat, const float* rstd, int64_t Bpad,
+                    __nv_bfloat16* dY, float* grads, float* dIn, cudaStream_t s);
 
 }  // namespace fused
 }  // namespace pmvae

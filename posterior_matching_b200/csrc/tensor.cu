@@ -417,16 +417,26 @@ struct NetSavedB {
   // LN nets: normalised pre-activations and 1/sigma
   bf16* X0; bf16* XU[kMaxBlocks]; bf16* XV[kMaxBlocks];
   float* rstd0; float* rstdU[kMaxBlocks]; float* rstdV[kMaxBlocks];
+  // LN nets on the fused chains: xhat of LayerNorm l = slab l of [(2R+1), Bpad, 256], 1/sigma = row l of [(2R+1), Bpad]
+  bf16* xstack; float* rstd_stack;
 };
 
-static void plan_net_b(Bump& bp, const Net& n, int64_t B, NetSavedB& s) {
+static bool ln_fused_train(const Net& n, int in_kind) {
+  return in_kind >= 0 && n.ln && fused_enabled() && fused::backward_ln_supported(n, 256, in_kind);
+}
+
+static void plan_net_b(Bump& bp, const Net& n, int64_t B, NetSavedB& s, int in_kind) {
   const uint64_t e = (uint64_t)B * 256;
   s.Bpad = (B + 255) / 256 * 256;        // whole tiles for a CTA pair (2 x 128 rows)
   s.stack = bp.take<bf16>((uint64_t)(2 * n.R + 1) * s.Bpad * 256);
   s.masks = bp.take<uint32_t>((uint64_t)(2 * n.R + 1) * s.Bpad * 8);
   for (int r = 0; r <= n.R; ++r) s.A[r] = s.stack + (uint64_t)(2 * r) * s.Bpad * 256;
   for (int r = 0; r < n.R; ++r) s.T[r] = s.stack + (uint64_t)(2 * r + 1) * s.Bpad * 256;
-  if (n.ln) {
+  s.xstack = nullptr; s.rstd_stack = nullptr;
+  if (ln_fused_train(n, in_kind)) {
+    s.xstack = bp.take<bf16>((uint64_t)(2 * n.R + 1) * s.Bpad * 256);
+    s.rstd_stack = bp.take<float>((uint64_t)(2 * n.R + 1) * s.Bpad);
+  } else if (n.ln) {
     s.X0 = bp.take<bf16>(e);
     s.rstd0 = bp.take<float>(B);
     for (int r = 0; r < n.R; ++r) {
@@ -440,9 +450,10 @@ static NetSavedB shift_saved(const NetSavedB& s, const Net& n, int64_t r0) {
   NetSavedB o = s;
   o.stack = s.stack + r0 * 256;
   o.masks = s.masks + r0 * 8;
+  if (s.xstack) { o.xstack = s.xstack + r0 * 256; o.rstd_stack = s.rstd_stack + r0; }
   for (int r = 0; r <= n.R; ++r) o.A[r] = s.A[r] + r0 * 256;
   for (int r = 0; r < n.R; ++r) o.T[r] = s.T[r] + r0 * 256;
-  if (n.ln) {
+  if (n.ln && !s.xstack) {
     o.X0 = s.X0 + r0 * 256; o.rstd0 = s.rstd0 + r0;
     for (int r = 0; r < n.R; ++r) {
       o.XU[r] = s.XU[r] + r0 * 256; o.XV[r] = s.XV[r] + r0 * 256;
@@ -482,9 +493,9 @@ static TrainPlanB plan_train_b(const pmvae_config* c, const Layout& L, int64_t B
   plan_images(L, ws, &p.img, nullptr);
   Bump bp(ws, p.img.bytes);
   p.Dp = pad8(c->D);
-  plan_net_b(bp, L.enc, B, p.enc);
-  plan_net_b(bp, L.dec, B, p.dec);
-  plan_net_b(bp, L.part, B, p.part);
+  plan_net_b(bp, L.enc, B, p.enc, 0);
+  plan_net_b(bp, L.dec, B, p.dec, 0);
+  plan_net_b(bp, L.part, B, p.part, 1);
   const bool any_ln = L.enc.ln || L.dec.ln || L.part.ln;
   p.h = bp.take<float>((uint64_t)B * 256);
   p.ytmp = any_ln ? bp.take<float>((uint64_t)B * 256) : nullptr;
@@ -533,9 +544,9 @@ static EvalPlanB plan_eval_b(const pmvae_config* c, const Layout& L, int64_t B, 
   p.rows_per_chunk = rpc;
   const int64_t M = rpc * K;
   const int64_t Mmax = M > B ? M : B;
-  plan_net_b(bp, L.enc, B, p.enc);
-  plan_net_b(bp, L.part, B, p.part);
-  plan_net_b(bp, L.dec, M, p.dec);
+  plan_net_b(bp, L.enc, B, p.enc, -1);      // evaluators save nothing on the fused chains (in_kind -1: no xhat stacks)
+  plan_net_b(bp, L.part, B, p.part, -1);
+  plan_net_b(bp, L.dec, M, p.dec, -1);
   const bool any_ln = L.enc.ln || L.dec.ln || L.part.ln;
   p.h = bp.take<float>((uint64_t)Mmax * 256);
   p.ytmp = any_ln ? bp.take<float>((uint64_t)Mmax * 256) : nullptr;
@@ -595,9 +606,9 @@ static int net_fwd_b(const float* params, const Net& n, const LeafImg* img, cons
                      float* h, float* ytmp, float* head_out, int64_t ld_head, const fused::NetImages* fim, bool save,
                      cudaStream_t s) {
   using tc::TcGemmArgs;
-  if (fim && (!save || !n.ln))   // one persistent kernel for the whole net + head, activations stay on chip
+  if (fim && (!save || !n.ln || sv.xstack))   // one persistent kernel for the whole net + head, activations stay on chip
     return fused::net_forward(params, n, head, *fim, in, msk, B, save ? sv.stack : nullptr, save ? sv.masks : nullptr,
-                              sv.Bpad, head_out, ld_head, s);
+                              sv.Bpad, head_out, ld_head, s, save ? sv.xstack : nullptr, save ? sv.rstd_stack : nullptr);
   if (!n.ln) {
     PMVAE_TRY(in_layer_fwd(params, n.lin[0], in, msk, D_in, B, h, sv.A[0], s));
   } else {
@@ -658,10 +669,15 @@ static int net_bwd_b(const float* params, float* grads, const Net& n, const Leaf
                      const float* msk, int D_in, int64_t B, const NetSavedB& sv, bf16* dH, bf16* dU, bf16* dG,
                      float* wtmp, float* dIn, const fused::NetImages* fim, bf16* dY, bf16* in_b, bool head_db_done, cudaStream_t s) {
   using tc::TcGemmArgs;
-  if (fim && fused::backward_supported(n, 256, fim->in_kind) && (dIn == nullptr || fim->has_w0_n)) {
+  const bool ln_chain = fim && sv.xstack && fused::backward_ln_supported(n, 256, fim->in_kind);
+  if (fim && (ln_chain || fused::backward_supported(n, 256, fim->in_kind)) && (dIn == nullptr || fim->has_w0_n)) {
     // head Linear parameters, then the fused input-gradient chain (dY_l of every Linear + bias gradients),
     // then one tensor-core weight-gradient GEMM per Linear: gW_l += act_{l-1}^T @ dY_l
-    PMVAE_TRY(fused::net_backward(n, head, *fim, dHead, ld_dhead, B, sv.masks, sv.Bpad, dY, grads, dIn, s));
+    if (ln_chain)
+      PMVAE_TRY(fused::net_backward_ln(n, head, *fim, dHead, ld_dhead, B, sv.masks, sv.xstack, sv.rstd_stack, sv.Bpad, dY,
+                                       grads, dIn, s));
+    else
+      PMVAE_TRY(fused::net_backward(n, head, *fim, dHead, ld_dhead, B, sv.masks, sv.Bpad, dY, grads, dIn, s));
     const Leaf& l0 = n.lin[0];
     const int ld0 = pad8(l0.rows);
     cast_input_kernel<<<grid1d(B, 256), 256, 0, s>>>(in, msk, D_in, l0.rows, ld0, B, in_b);
