@@ -342,8 +342,19 @@ class Dist:
         return self.max_over_ranks(e0.elapsed_time(e1)) / reps
 
     def close(self):
+        """Multi-rank exit: synchronise, then leave without tearing the NCCL communicator down.  With CUDA graphs alive
+        that captured NCCL kernels (the overlapped gradient exchange), destroy_process_group / interpreter exit blocked
+        for minutes on this driver + NCCL build (measured in round 2); every result has been printed by now."""
         if self.world > 1:
-            self.dist.destroy_process_group()
+            self.torch.cuda.synchronize()
+            try:
+                self.dist.barrier()
+                self.torch.cuda.synchronize()
+            except Exception:  # noqa: BLE001
+                pass
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
 
 
 def mnist_leg(dd: Dist, precision, B, K, W, with_e2e=True, load_seconds=0.6):

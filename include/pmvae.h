@@ -287,6 +287,21 @@ int pmvae_argmm_backward(const pmvae_argmm_config* cfg, const float* params, con
                          const float* context, int64_t B, const float* g, float* grads, float* dz,
                          float* dcontext, void* ws, uint64_t ws_bytes, pmvae_stream_t stream);
 
+/* _AutoregressiveDistribution._sample_n (distributions.py:168-189): out[n, B, d], n samples per context row, drawn
+ * dimension by dimension (one ResidualMLP pass over the n * B rows per dimension).  Noise contract [R: TFP's seed
+ * plumbing is recollection, so parity with the reference is distributional]: (k_comp, k_cat) = split(key);
+ * eps = normal(k_comp, [n, d, K]), u = uniform(k_cat, [n, d, K]); at step i component c = argmax_k(logits_k -
+ * log(-log(u[s, i, k]))) and x_i = mean_c + scale_c * eps[s, i, c] -- the same draws for every batch row and every
+ * step, as the reference's jax.vmap over the batch with one key does. */
+uint64_t pmvae_argmm_sample_workspace_bytes(const pmvae_argmm_config* cfg, int64_t B, int64_t n);
+int pmvae_argmm_sample(const pmvae_argmm_config* cfg, const float* params, const float* context, int64_t B,
+                       int64_t n, const uint32_t key[2], float* out /* [n,B,d] */, void* ws, uint64_t ws_bytes,
+                       pmvae_stream_t stream);
+/* reduce_logmeanexp over the leading axis (vae.py:222-223): out[r] = logsumexp_k a[k*B + r] - log K
+ * [ - (logsumexp_k c[k*B + r] - log K) when c is given: log p(x) - log p(x_o), vae.py:224 ]. */
+int pmvae_logmeanexp_rows(const float* a, const float* c /* or NULL */, float* out, int64_t B, int64_t K,
+                          pmvae_stream_t stream);
+
 /* ---- convolutions of the MNIST config's networks (networks.py:9-72), NHWC float32 ----------------
  * One general operator covers hk.Conv2D and hk.Conv2DTranspose (what lax.conv_general_dilated reduces both to):
  *   y[b,oy,ox,co] = act(bias[co] + sum_{ky,kx,ci} Xd(b, oy*stride+ky-pad_top, ox*stride+kx-pad_left, ci)

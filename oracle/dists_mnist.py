@@ -96,3 +96,33 @@ def bernoulli_log_prob(logits, x):
     [0, 1] (the MNIST pipeline feeds binarised floats)."""
     sp = torch.nn.functional.softplus
     return -x * sp(-logits) - (1.0 - x) * sp(logits)
+
+
+def argmm_sample(p: Params, spec: ArgmmSpec, context, n: int, key):
+    """_AutoregressiveDistribution._sample_n (distributions.py:168-189) -> [n, B, d].  The reference hands the SAME key
+    to `out.sample` at every step and vmaps over the batch with that one key, so the noise depends on
+    (sample, dimension, component) only.  Noise contract shared with the device (include/pmvae.h, pmvae_argmm_sample)
+    [R: TFP's MixtureSameFamily seed plumbing is recollection -> parity with the reference is distributional]:
+    (k_comp, k_cat) = split(key); eps = normal(k_comp, [n, d, K]); u = uniform(k_cat, [n, d, K]);
+    component = argmax_k(logits_k - log(-log(u))) (jax.random.categorical); x_i = mean_c + scale_c * eps_c."""
+    from . import prng
+    B, d, K = context.shape[0], spec.d, spec.n_comp
+    ks = prng.split(key, 2)
+    eps = torch.tensor(prng.normal(ks[0], (n, d, K)).astype(np.float64))
+    u = prng.uniform(ks[1], (n, d, K)).astype(np.float32)
+    u = np.where(u > 0, u, np.float32(1.17549435e-38))
+    gumbel = torch.tensor(-np.log(-np.log(u.astype(np.float64))))
+    x = torch.zeros(n, B, d, dtype=context.dtype)
+    ar = torch.arange(d, dtype=context.dtype)
+    ctx = context.unsqueeze(0).expand(n, B, context.shape[1]).reshape(n * B, -1)
+    for i in range(d):
+        mask = (ar < i).to(context.dtype).expand(n * B, d)
+        inp = torch.cat([x.reshape(n * B, d) * mask, mask, ctx], -1)
+        h = residual_mlp(p, NET, inp, spec.R, False)
+        params = linear(p, HEAD, h).reshape(n, B, d, 3 * K)[:, :, i, :]
+        logits, means = params[..., :K], params[..., K:2 * K]
+        scales = torch.nn.functional.softplus(params[..., 2 * K:]) + 1e-5
+        comp = torch.argmax(logits + gumbel[:, i, :].unsqueeze(1), -1, keepdim=True)
+        e = eps[:, i, :].unsqueeze(1).expand(n, B, K)
+        x[:, :, i] = (means.gather(-1, comp) + scales.gather(-1, comp) * e.gather(-1, comp)).squeeze(-1)
+    return x

@@ -87,3 +87,52 @@ def loss_and_grads(p, x, b, eps, beta: float = 1.0, coef: float = 1.0):
     loss, out = loss_fn(q, x, b, eps, beta, coef)
     loss.backward()
     return loss.detach(), {k: v.detach() for k, v in out.items()}, {n: {k: t.grad for k, t in leaf.items()} for n, leaf in q.items()}
+
+
+def _posterior(p, x):
+    B = x.shape[0]
+    h = OC.conv_encoder(_convs(p, "encoder_net", "conv2_d", 5), x).reshape(B, -1)
+    par = h @ p["posterior_dist/linear"]["w"] + p["posterior_dist/linear"]["b"]
+    return par[:, :LATENT], fill_scale_tril(par[:, LATENT:], LATENT)
+
+
+def _context(p, x, b):
+    return OC.conv_encoder(_convs(p, "partial_encoder_net", "conv2_d", 5), torch.cat([x * b, b], -1)).reshape(x.shape[0], -1)
+
+
+ARGMM_SPEC = DM.ArgmmSpec(d=LATENT, n_comp=10, R=2, H=256, C=128)
+
+
+def impute(p, x_o, b, z_xo):
+    """vae.py:146-169 given the AR-GMM samples z_xo [K,B,32] of q(z | x_o): [K,B,28,28,1], the Bernoulli mean
+    (sigmoid of the decoder logits) where b == 0, x_o elsewhere."""
+    K, B, d = z_xo.shape
+    x_o = x_o * b
+    logits = OC.conv_decoder(_convs(p, "decoder_net", "conv2_d_transpose", 6), z_xo.reshape(K * B, d))
+    mean = torch.sigmoid(logits).reshape(K, *x_o.shape)
+    return torch.where(b.unsqueeze(0) != 0, x_o.unsqueeze(0), mean)
+
+
+def is_log_prob(p, x, b, eps_z, z_xo):
+    """vae.py:171-226 for this config: eps_z [K,B,32] drives z ~ q(z|x) (TriL); z_xo [K,B,32] are samples of the
+    AutoregressiveGMM partial posterior -> (log p(x), log p(x_u | x_o))."""
+    from .model import std_normal_log_prob, tril_log_prob
+    K, B, d = eps_z.shape
+    mu, L = _posterior(p, x)
+    ctx = _context(p, x, b)
+    z = mu.unsqueeze(0) + torch.einsum("bij,kbj->kbi", L, eps_z)
+    dec = _convs(p, "decoder_net", "conv2_d_transpose", 6)
+
+    def dec_ll(zz, weight):
+        logits = OC.conv_decoder(dec, zz.reshape(K * B, d)).reshape(K, *x.shape)
+        ll = DM.bernoulli_log_prob(logits, x.unsqueeze(0))
+        if weight is not None:
+            ll = ll * weight.unsqueeze(0)
+        return ll.reshape(K, B, -1).sum(-1)
+
+    log_q_zgx = tril_log_prob(z, mu.unsqueeze(0), L.unsqueeze(0))
+    log_q_zgxo = DM.argmm_log_prob(p, ARGMM_SPEC, z_xo.reshape(K * B, d), ctx.repeat(K, 1)).reshape(K, B)
+    lk = math.log(K)
+    log_p_x = torch.logsumexp(dec_ll(z, None) + std_normal_log_prob(z) - log_q_zgx, 0) - lk
+    log_p_xo = torch.logsumexp(dec_ll(z_xo, b) + std_normal_log_prob(z_xo) - log_q_zgxo, 0) - lk
+    return log_p_x, log_p_x - log_p_xo

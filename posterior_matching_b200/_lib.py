@@ -118,6 +118,9 @@ _SIGS = {
     "pmvae_argmm_workspace_bytes": (_u64, [C.POINTER(ArgmmConfig), _i64]),
     "pmvae_argmm_log_prob": (_i32, [C.POINTER(ArgmmConfig), _vp, _vp, _vp, _i64, _vp, _vp, _u64, _vp]),
     "pmvae_argmm_backward": (_i32, [C.POINTER(ArgmmConfig), _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "pmvae_argmm_sample_workspace_bytes": (_u64, [C.POINTER(ArgmmConfig), _i64, _i64]),
+    "pmvae_argmm_sample": (_i32, [C.POINTER(ArgmmConfig), _vp, _vp, _i64, _i64, _u32p, _vp, _vp, _u64, _vp]),
+    "pmvae_logmeanexp_rows": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "pmvae_linear_backward": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "pmvae_tril_sample_kl": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "pmvae_tril_sample_kl_backward": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),

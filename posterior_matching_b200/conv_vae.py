@@ -5,7 +5,8 @@ TriLGaussian, Bernoulli and AutoregressiveGMM heads).
 SURVEY.md §8f row N1, first cut: float32, correctness-first (direct convolution kernels, fp32 GEMMs);
 forward (`__call__`) and `backward` (VJP with per-row cotangents) plus `train_step` (loss_fn of
 train_pm_vae.py:58-72 and the optax chain :74-83 with weight_decay = 0, as the MNIST config has).
-`impute` / `is_log_prob` need AR-GMM sampling (row N2) and are not built.
+`impute` / `is_log_prob` (vae.py:146-226) sample the AutoregressiveGMM partial posterior (distributions.py:168-189,
+SURVEY §8f N2).
 """
 from __future__ import annotations
 
@@ -205,6 +206,75 @@ class ConvPosteriorMatchingVAE:
                    "pmvae_linear_backward")
         self.enc.backward(self.params, self.grads, enc_acts, dfeat.view_as(enc_acts[-1]).contiguous(), need_dx=False)
         return self.grads
+
+    # ---- vae.py:146-226 for the MNIST config -------------------------------------------------------
+    def _posterior_par(self, x):
+        """raw TriLGaussian parameters of q(z | x): conv encoder + Linear head (vae.py:47-49)."""
+        B = x.shape[0]
+        feat = self.enc.forward(self.params, x)[-1].reshape(B, self.enc_feat)
+        par = torch.empty((B, self.P), dtype=torch.float32, device=self.device)
+        hw = self.params["posterior_dist/linear"]
+        _lib.check(_lib.lib.pmvae_linear(_lib.PREC_F32, feat.data_ptr(), hw["w"].data_ptr(), hw["b"].data_ptr(), B,
+                                         self.enc_feat, self.P, 0, par.data_ptr(), None, 0, _stream()), "pmvae_linear")
+        return par
+
+    def _context(self, x, b):
+        xob = torch.cat([x * b, b], dim=-1).contiguous()
+        return self.part.forward(self.params, xob)[-1].reshape(x.shape[0], -1)
+
+    def _decode_logits(self, z):
+        """decoder logits [K*B, 28, 28, 1] of latent samples z [K, B, d]."""
+        K, B, d = z.shape
+        return self.dec.forward(self.params, z.reshape(K * B, 1, 1, d).contiguous())[-1]
+
+    def impute(self, x_o: torch.Tensor, b: torch.Tensor, num_samples: int = 100, *, rng=None, key=None) -> torch.Tensor:
+        """vae.py:146-169 -> [num_samples, B, 28, 28, 1]: z ~ q(z | x_o) (AR-GMM), decoder mean = sigmoid(logits)
+        (tfd.Bernoulli.mean), observed pixels kept."""
+        x_o, b = _f32c(x_o, self.device), _f32c(b, self.device)
+        if key is None:
+            if rng is None:
+                raise ValueError("pass rng= or key=")
+            key = prng.PRNGSequence(rng).next()        # conv nets draw no dropout keys (SURVEY §8a-R)
+        x_o = x_o * b
+        K, B = int(num_samples), x_o.shape[0]
+        z = self.argmm.sample(self._context(x_o, b), K, key=key)
+        mean = torch.sigmoid(self._decode_logits(z)).view(K, *x_o.shape)
+        return torch.where(b.unsqueeze(0) != 0, x_o.unsqueeze(0), mean)
+
+    def is_log_prob(self, x: torch.Tensor, b: torch.Tensor, num_samples: int = 100, *, rng=None, keys=None):
+        """vae.py:171-226 -> (log p(x), log p(x_u | x_o)), each [B]."""
+        x, b = _f32c(x, self.device), _f32c(b, self.device)
+        if keys is None:
+            if rng is None:
+                raise ValueError("pass rng= or keys=")
+            seq = prng.PRNGSequence(rng)
+            keys = (seq.next(), seq.next())
+        K, B, d, S = int(num_samples), x.shape[0], self.latent_dim, _stream()
+        D = x[0].numel()
+        par = self._posterior_par(x)
+        ctx = self._context(x, b)
+        # z ~ q(z | x): samples and log p(z) - log q(z | x) in one kernel
+        z = torch.empty((K, B, d), dtype=torch.float32, device=self.device)
+        ratio = torch.empty((K, B), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib.pmvae_tril_sample(par.data_ptr(), _lib.key_arg(keys[0]), B, K, B, 0, d, z.data_ptr(),
+                                              ratio.data_ptr(), S), "pmvae_tril_sample")
+        xk = x.reshape(1, B, D).expand(K, B, D).reshape(K * B, D).contiguous()
+        ll = self.bern.log_prob(self._decode_logits(z).reshape(K * B, D), xk).view(K, B) + ratio
+        # z' ~ q(z | x_o): AR-GMM samples, their log-density, the prior, and the observed-pixel likelihood
+        z_xo = self.argmm.sample(ctx, K, key=keys[1])
+        ctx_k = ctx.unsqueeze(0).expand(K, B, ctx.shape[1]).reshape(K * B, -1).contiguous()
+        log_q = self.argmm.log_prob(z_xo.reshape(K * B, d), ctx_k).view(K, B)
+        log_pz = torch.empty(K * B, dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib.pmvae_std_normal_log_prob(z_xo.data_ptr(), K * B, d, log_pz.data_ptr(), S),
+                   "pmvae_std_normal_log_prob")
+        bk = b.reshape(1, B, D).expand(K, B, D).reshape(K * B, D).contiguous()
+        ll_o = self.bern.log_prob(self._decode_logits(z_xo).reshape(K * B, D), xk, bk).view(K, B) + log_pz.view(K, B) - log_q
+        ll, ll_o = ll.contiguous(), ll_o.contiguous()
+        out = torch.empty((2, B), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib.pmvae_logmeanexp_rows(ll.data_ptr(), None, out[0].data_ptr(), B, K, S), "pmvae_logmeanexp_rows")
+        _lib.check(_lib.lib.pmvae_logmeanexp_rows(ll.data_ptr(), ll_o.data_ptr(), out[1].data_ptr(), B, K, S),
+                   "pmvae_logmeanexp_rows")
+        return out[0], out[1]
 
     # ---- train_pm_vae.py:58-83 (beta = 1: the MNIST config has no beta schedule; weight_decay = 0) ------
     def train_step(self, x, b, *, rng=None, eps=None, lr_schedule=None, matching_coef: float = 1.0,

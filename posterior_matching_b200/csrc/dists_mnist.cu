@@ -192,6 +192,64 @@ int argmm_lp_bwd(const float* head_out, const float* z, const float* g, int64_t 
   PMVAE_LAUNCH_CHECK();
   return 0;
 }
+// ---- sampling (distributions.py:168-189 `_sample_n`) ------------------------------------------------------------
+// input rows of sampling step i for M = n * B rows (row m = s * B + b): [x * (arange(d) < i), (arange(d) < i), context[b]]
+__global__ void __launch_bounds__(256) argmm_sample_input_kernel(const float* __restrict__ x, const float* __restrict__ ctx,
+                                                                 int64_t M, int64_t B, int d, int C, int step,
+                                                                 float* __restrict__ X) {
+  const int F = 2 * d + C;
+  const int64_t n = M * F;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = t / F;
+    const int j = (int)(t - m * F);
+    float v;
+    if (j < d) v = (j < step) ? x[m * d + j] : 0.f;
+    else if (j < 2 * d) v = (j - d < step) ? 1.f : 0.f;
+    else v = ctx[(m % B) * C + (j - 2 * d)];
+    X[t] = v;
+  }
+}
+
+// x[m, step] = mean_c + scale_c * eps[s, step, c], c = argmax_k(logits_k + gumbel[s, step, k]) with
+// gumbel = -log(-log(u)), u = uniform(minval = tiny, maxval = 1) (jax.random.categorical / gumbel); eps and u are
+// [n, d, K] draws shared by every batch row and every step (the reference passes the same key to every step under
+// jax.vmap over the batch: distributions.py:168-189).
+__global__ void __launch_bounds__(128) argmm_sample_step_kernel(const float* __restrict__ head_out, const float* __restrict__ eps,
+                                                                const float* __restrict__ u, int64_t M, int64_t B, int d, int K,
+                                                                int step, float* __restrict__ x) {
+  const int ld = 3 * K * d;
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    const float* p = head_out + m * ld + (int64_t)step * 3 * K;
+    const int64_t s = m / B;
+    const float* us = u + (s * d + step) * K;
+    int best = 0;
+    float bv = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+      float uk = us[k];
+      uk = uk > 0.f ? uk : 1.17549435e-38f;
+      const float v = p[k] - logf(-logf(uk));
+      if (v > bv) { bv = v; best = k; }
+    }
+    const float sc = softplus_f(p[2 * K + best]) + 1e-5f;
+    x[m * d + step] = p[K + best] + sc * eps[(s * d + step) * K + best];
+  }
+}
+
+int argmm_sample_input(const float* x, const float* ctx, int64_t M, int64_t B, int d, int C, int step, float* X, cudaStream_t s) {
+  if (M == 0) return 0;
+  argmm_sample_input_kernel<<<grid1d(M * (2 * d + C), 256), 256, 0, s>>>(x, ctx, M, B, d, C, step, X);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+int argmm_sample_step(const float* head_out, const float* eps, const float* u, int64_t M, int64_t B, int d, int K, int step,
+                      float* x, cudaStream_t s) {
+  PMVAE_CHECK(K >= 1 && K <= kMaxComp, "num_components must be in [1, 32]");
+  if (M == 0) return 0;
+  argmm_sample_step_kernel<<<grid1d(M, 128), 128, 0, s>>>(head_out, eps, u, M, B, d, K, step, x);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
 int argmm_reduce_dx(const float* dX, const float* dz_direct, int64_t B, int d, int C, float* dz, float* dctx,
                     cudaStream_t s) {
   argmm_reduce_dx_kernel<<<grid1d(B * (d + C), 256), 256, 0, s>>>(dX, dz_direct, B, d, C, dz, dctx);

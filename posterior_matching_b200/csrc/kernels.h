@@ -109,6 +109,9 @@ int argmm_input(const float* z, const float* ctx, int64_t B, int d, int C, float
 int argmm_lp(const float* head_out, const float* z, int64_t B, int d, int K, float* out, cudaStream_t s);
 int argmm_lp_bwd(const float* head_out, const float* z, const float* g, int64_t B, int d, int K, float* d_head,
                  float* dz_direct, cudaStream_t s);
+int argmm_sample_input(const float* x, const float* ctx, int64_t M, int64_t B, int d, int C, int step, float* X, cudaStream_t s);
+int argmm_sample_step(const float* head_out, const float* eps, const float* u, int64_t M, int64_t B, int d, int K, int step,
+                      float* x, cudaStream_t s);
 int argmm_reduce_dx(const float* dX, const float* dz_direct, int64_t B, int d, int C, float* dz, float* dctx,
                     cudaStream_t s);
 

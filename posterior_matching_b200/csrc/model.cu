@@ -510,6 +510,47 @@ int argmm_backward(const pmvae_argmm_config* c, const float* params, const float
   return 0;
 }
 
+// _AutoregressiveDistribution._sample_n (distributions.py:168-189): n samples per context row, one ResidualMLP pass over
+// all n * B rows per latent dimension.  Workspace: the net's activations for n * B rows, the step input, the head output
+// and the two [n, d, K] noise draws.
+struct ArgmmSamplePlan { NetSaved sv; float *X, *out, *eps, *u; uint64_t bytes; };
+static ArgmmSamplePlan plan_argmm_sample(const pmvae_argmm_config* c, const ArgmmLayout& L, int64_t M, int64_t n, void* ws) {
+  ArgmmSamplePlan p{};
+  Bump bp(ws);
+  plan_net(bp, L.net, M, c->H, p.sv, false);
+  p.X = bp.take<float>((uint64_t)M * L.F);
+  p.out = bp.take<float>((uint64_t)M * L.cols);
+  p.eps = bp.take<float>((uint64_t)n * c->d * c->n_comp);
+  p.u = bp.take<float>((uint64_t)n * c->d * c->n_comp);
+  p.bytes = bp.off;
+  return p;
+}
+
+int argmm_sample(const pmvae_argmm_config* c, const float* params, const float* ctx, int64_t B, int64_t n,
+                 const uint32_t key[2], float* out, void* ws, uint64_t ws_bytes, cudaStream_t s) {
+  ArgmmLayout L;
+  PMVAE_TRY(build_argmm_layout(c, &L));
+  PMVAE_CHECK(B >= 0 && n >= 1, "bad sample count / batch");
+  if (B == 0) return 0;
+  PMVAE_CHECK(params && (ctx || c->C == 0) && key && out && ws, "null pointer");
+  const int64_t M = n * B;
+  ArgmmSamplePlan p = plan_argmm_sample(c, L, M, n, ws);
+  PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_argmm_sample_workspace_bytes)");
+  // TFP's MixtureSameFamily.sample splits its seed in two [R]: components first, then the categorical
+  uint32_t ks[4];
+  PMVAE_TRY(pmvae_key_split_host(key, 2, ks));
+  const uint64_t nn = (uint64_t)n * c->d * c->n_comp;
+  PMVAE_TRY(pmvae_normal(ks, nn, 0, nn, p.eps, s));
+  PMVAE_TRY(pmvae_uniform(ks + 2, nn, 0, nn, p.u, s));
+  PMVAE_CUDA(cudaMemsetAsync(out, 0, (size_t)M * c->d * sizeof(float), s));
+  for (int i = 0; i < c->d; ++i) {
+    PMVAE_TRY(argmm_sample_input(out, ctx, M, B, c->d, c->C, i, p.X, s));
+    PMVAE_TRY(net_fwd_f32(params, L.net, L.head, c->H, p.X, M, p.sv, p.out, s));
+    PMVAE_TRY(argmm_sample_step(p.out, p.eps, p.u, M, B, c->d, c->n_comp, i, out, s));
+  }
+  return 0;
+}
+
 int net_apply(const pmvae_config* c, const float* params, int which, const float* in, const float* msk, int64_t B,
               float* out, void* ws, uint64_t ws_bytes, cudaStream_t s) {
   Layout L;
@@ -639,6 +680,20 @@ uint64_t pmvae_argmm_workspace_bytes(const pmvae_argmm_config* cfg, int64_t B) {
 int pmvae_argmm_log_prob(const pmvae_argmm_config* cfg, const float* params, const float* z, const float* context,
                          int64_t B, float* out, void* ws, uint64_t ws_bytes, pmvae_stream_t stream) {
   return argmm_log_prob(cfg, params, z, context, B, out, ws, ws_bytes, as_stream(stream));
+}
+uint64_t pmvae_argmm_sample_workspace_bytes(const pmvae_argmm_config* cfg, int64_t B, int64_t n) {
+  ArgmmLayout L;
+  if (build_argmm_layout(cfg, &L) != 0 || n < 1) return 0;
+  return plan_argmm_sample(cfg, L, n * (B < 1 ? 1 : B), n, nullptr).bytes + 256;
+}
+int pmvae_argmm_sample(const pmvae_argmm_config* cfg, const float* params, const float* context, int64_t B, int64_t n,
+                       const uint32_t key[2], float* out, void* ws, uint64_t ws_bytes, pmvae_stream_t stream) {
+  return argmm_sample(cfg, params, context, B, n, key, out, ws, ws_bytes, as_stream(stream));
+}
+int pmvae_logmeanexp_rows(const float* a, const float* c, float* out, int64_t B, int64_t K, pmvae_stream_t stream) {
+  PMVAE_CHECK(B >= 0 && K >= 1 && (B == 0 || (a && out)), "bad arguments");
+  if (B == 0) return 0;
+  return logmeanexp_rows(a, c, out, B, K, as_stream(stream));
 }
 int pmvae_argmm_backward(const pmvae_argmm_config* cfg, const float* params, const float* z, const float* context,
                          int64_t B, const float* g, float* grads, float* dz, float* dcontext, void* ws,

@@ -2,10 +2,10 @@
 `Bernoulli` (distributions.py:20-25) and `AutoregressiveGMM` (distributions.py:192-223 with
 `OneDimensionalGMM` :116-134 and `_AutoregressiveDistribution.log_prob` :152-166).
 
-They are stand-alone operators with the reference's constructor arguments: the MNIST
-config's convolutional encoder / decoder (networks.py:9-72) are not on the CUDA path yet
-(SURVEY.md §8f N1), so `PosteriorMatchingVAE.from_config` still refuses that config, but the
-two heads it needs are built, differentiable and parity-tested on their own.
+They are stand-alone operators with the reference's constructor arguments; `ConvPosteriorMatchingVAE`
+(conv_vae.py, what `PosteriorMatchingVAE.from_config` returns for the MNIST config) composes them with the
+convolutional encoder / decoder (networks.py:9-72).  Both are differentiable and parity-tested on their own; the
+AR-GMM also samples (distributions.py:168-189), which `impute` / `is_log_prob` of the MNIST config need.
 """
 from __future__ import annotations
 
@@ -133,6 +133,23 @@ class AutoregressiveGMM:
                                                  out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
                    "pmvae_argmm_log_prob")
         self._last = (z, context, B)
+        return out
+
+    def sample(self, context: torch.Tensor, num_samples: int, *, key) -> torch.Tensor:
+        """`_AutoregressiveDistribution._sample_n(key, n)` (distributions.py:168-189) -> [n, B, d]: n samples per context
+        row, drawn one latent dimension at a time.  Noise contract in include/pmvae.h (pmvae_argmm_sample)."""
+        B = context.shape[0]
+        context = _f32c(context.reshape(B, -1), self.device)
+        if context.shape[1] != self.cfg.C:
+            raise ValueError(f"expected context [B, {self.cfg.C}]")
+        n = int(num_samples)
+        out = torch.empty((n, B, self.cfg.d), dtype=torch.float32, device=self.device)
+        need = int(_lib.lib.pmvae_argmm_sample_workspace_bytes(self._cfgp, B, n))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        _lib.check(_lib.lib.pmvae_argmm_sample(self._cfgp, self.arena.data_ptr(), context.data_ptr(), B, n,
+                                               _lib.key_arg(key), out.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                                               _stream()), "pmvae_argmm_sample")
         return out
 
     def backward(self, g: torch.Tensor) -> Tuple[Dict[str, Dict[str, torch.Tensor]], torch.Tensor, torch.Tensor]:

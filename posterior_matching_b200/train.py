@@ -260,6 +260,13 @@ class Trainer:
         self._last_Bg = B * self.world
         return self._sums
 
+    def release_graphs(self):
+        """Drops the captured step graph(s) and the device step state (re-created by the next fused step).  Call it
+        before torch.distributed.destroy_process_group(): graphs that captured NCCL kernels keep the communicator busy."""
+        if self._fused is not None:
+            torch.cuda.synchronize()
+            self._fused = None
+
     @property
     def graph_launches_per_step(self) -> int:
         """Kernels of this library inside one replayed step (counted while the graph was captured)."""

@@ -40,7 +40,9 @@ def main():
         np.savez(out_path, params=m.arena.cpu().numpy(), init=init.cpu().numpy(), metrics=np.array(metrics))
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)      # see bench.py Dist.close: communicator teardown blocks while captured NCCL graphs are alive
 
 
 if __name__ == "__main__":

@@ -28,7 +28,7 @@ def _run(nproc, out, name, steps, mode, env_extra=None):
     env.pop("NCCL_DEBUG", None)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), WORKER, out, name, str(steps), mode]
-    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240, cwd=ROOT)
     assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
     return dict(np.load(out))
 

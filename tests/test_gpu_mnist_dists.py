@@ -71,3 +71,30 @@ def test_argmm_rejects_bad_shapes_and_configs():
     dist = AutoregressiveGMM(4, 2, 1, 32, context_size=3)
     with pytest.raises(ValueError):
         dist.log_prob(torch.zeros(2, 5), torch.zeros(2, 3))
+
+
+@pytest.mark.parametrize("d,K,R,H,Cx,B,n", [(32, 10, 2, 256, 128, 3, 50), (5, 3, 1, 64, 7, 4, 200)])
+def test_argmm_sample_matches_oracle_contract(d, K, R, H, Cx, B, n):
+    """pmvae_argmm_sample against oracle.dists_mnist.argmm_sample on the same key (the noise contract of
+    include/pmvae.h): identical draws up to float32 rounding, except where two mixture components tie within rounding
+    at the Gumbel arg-max (a handful of entries at most; later dimensions of those samples then differ too)."""
+    from oracle import prng as oprng
+    from posterior_matching_b200.distributions import AutoregressiveGMM
+    spec = DM.ArgmmSpec(d=d, n_comp=K, R=R, H=H, C=Cx)
+    p = DM.argmm_init(spec)
+    torch.manual_seed(d)
+    ctx = torch.randn(B, Cx, dtype=torch.float64)
+    key = oprng.PRNGKey(23)
+    want = DM.argmm_sample(p, spec, ctx, n, key)
+    dist = AutoregressiveGMM(d, K, R, H, context_size=Cx)
+    dist.load_params(p)
+    got = dist.sample(ctx.float().cuda(), n, key=tuple(int(v) for v in key))
+    torch.cuda.synchronize()
+    assert got.shape == (n, B, d) and torch.isfinite(got).all()
+    err = (got.cpu().double() - want).abs().amax(-1)              # per (sample, row)
+    close = (err < 1e-3 * (1 + want.abs().amax(-1))).double().mean()
+    assert float(close) > 0.97, float(close)
+    # the device's samples are high-density points of the device's own log_prob
+    lp = dist.log_prob(got.reshape(n * B, d), ctx.float().cuda().repeat(n, 1))
+    want_lp = DM.argmm_log_prob(p, spec, got.cpu().double().reshape(n * B, d), ctx.repeat(n, 1))
+    assert rel_err(lp.cpu().numpy(), want_lp.numpy()) < 5e-4

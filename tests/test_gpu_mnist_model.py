@@ -118,3 +118,34 @@ def test_mnist_train_step_data_parallel_hooks_match_the_full_batch():
         # Adam's first step moves every weight by ~lr * sign(g): compare the updates, not the weights
         assert rel_l2((c - a).cpu().numpy() + 1.0, np.ones(a.numel())) < 1e-5
         assert float((a - c).abs().max()) < 2e-4
+
+
+def test_mnist_model_impute_and_is_log_prob():
+    """`impute` / `is_log_prob` of the MNIST config (vae.py:146-226) -- AR-GMM samples from the device
+    sampler (its noise contract is tested in test_gpu_mnist_dists.py), everything downstream against the float64 oracle
+    fed the same samples."""
+    from oracle import prng as oprng
+    from posterior_matching_b200 import pm_vae_config
+    from posterior_matching_b200.conv_vae import ConvPosteriorMatchingVAE
+    m = ConvPosteriorMatchingVAE.from_config(pm_vae_config("mnist").model.to_dict())
+    p = MM.init_params()
+    m.load_params(p)
+    B, K = 3, 6
+    x, b, _ = _inputs(B, seed=8)
+    xc, bc = x.float().cuda(), b.float().cuda()
+    k_z, k_zxo = (5, 6), (7, 8)
+    ctx = m._context(xc * bc, bc)
+    z_xo = m.argmm.sample(ctx, K, key=k_zxo).cpu().double()
+    # impute: observed pixels kept, unobserved = Bernoulli mean of the decoded samples
+    imp = m.impute(xc, bc, K, key=k_zxo)
+    want_imp = MM.impute(p, x, b, z_xo)
+    torch.cuda.synchronize()
+    assert imp.shape == (K, B, 28, 28, 1)
+    assert rel_err(imp.cpu().numpy(), want_imp.numpy()) < 2e-4
+    # is_log_prob
+    eps_z = torch.tensor(oprng.normal(np.array(k_z, dtype=np.uint32), (K, B, MM.LATENT)).astype(np.float64))
+    want_lpx, want_cond = MM.is_log_prob(p, x, b, eps_z, z_xo)
+    lpx, cond = m.is_log_prob(xc, bc, K, keys=(k_z, k_zxo))
+    torch.cuda.synchronize()
+    assert rel_err(lpx.cpu().numpy(), want_lpx.numpy()) < 2e-4
+    assert np.abs(cond.cpu().numpy() - want_cond.numpy()).max() < 2e-3 * max(1.0, np.abs(want_cond.numpy()).max())

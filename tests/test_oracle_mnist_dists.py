@@ -57,3 +57,31 @@ def test_argmm_is_a_normalised_autoregressive_density():
     t1, t2 = terms(v), terms(v2)
     assert torch.allclose(t1[:-1], t2[:-1], atol=1e-12) and not torch.allclose(t1[-1], t2[-1])
     assert torch.allclose(t1.sum(0), base, atol=1e-12)
+
+
+def test_argmm_sample_follows_the_mixture_of_the_first_dimension():
+    """Dimension 0 of the autoregressive sampler sees only the context: its samples follow the first 1-D mixture
+    (analytic mean / variance), and the samples' own log-density is what argmm_log_prob computes (finite, and higher
+    on average than that of shuffled samples)."""
+    from oracle import prng
+    spec = DM.ArgmmSpec(d=3, n_comp=4, R=1, H=32, C=5)
+    p = DM.argmm_init(spec)
+    torch.manual_seed(3)
+    ctx = torch.randn(2, spec.C, dtype=torch.float64)
+    n = 4000
+    x = DM.argmm_sample(p, spec, ctx, n, prng.PRNGKey(11))
+    assert x.shape == (n, 2, 3) and torch.isfinite(x).all()
+    from oracle.model import linear, residual_mlp
+    inp = torch.cat([torch.zeros(2, 3, dtype=torch.float64), torch.zeros(2, 3, dtype=torch.float64), ctx], -1)
+    par = linear(p, DM.HEAD, residual_mlp(p, DM.NET, inp, spec.R, False)).reshape(2, 3, 12)[:, 0]
+    w = torch.softmax(par[:, :4], -1)
+    mu, sc = par[:, 4:8], torch.nn.functional.softplus(par[:, 8:]) + 1e-5
+    mean = (w * mu).sum(-1)
+    var = (w * (sc ** 2 + mu ** 2)).sum(-1) - mean ** 2
+    se = (var / n).sqrt()
+    assert torch.all((x[:, :, 0].mean(0) - mean).abs() < 5 * se)
+    assert torch.all((x[:, :, 0].var(0) / var - 1).abs() < 0.15)
+    lp = DM.argmm_log_prob(p, spec, x.reshape(n * 2, 3), ctx.repeat(n, 1))
+    perm = torch.randperm(n * 2)
+    lp_shuffled = DM.argmm_log_prob(p, spec, x.reshape(n * 2, 3)[perm], ctx.repeat(n, 1))
+    assert torch.isfinite(lp).all() and lp.mean() >= lp_shuffled.mean() - 1e-9
