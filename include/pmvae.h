@@ -204,6 +204,13 @@ int pmvae_tril_sample(const float* par, const uint32_t key[2], int64_t B, int64_
 int pmvae_normal_log_prob(const float* x, const float* loc, const float* log_scale /* device scalar */,
                           int64_t rows, int64_t rows_x, int32_t D, float* out, pmvae_stream_t stream);
 int pmvae_std_normal_log_prob(const float* z, int64_t B, int32_t d, float* out, pmvae_stream_t stream);
+/* DiagonalGaussian (distributions.py:58-84), the posterior of the VaDE models (vade.py:61-63): par[B, 2d] = raw head
+ * output [loc | raw scale], scale = softplus(raw) + 1e-5.
+ *   pmvae_diag_sample    z = loc + scale * eps            (posterior.sample, vade.py:259, for the PM-VaDE matching term)
+ *   pmvae_diag_log_prob  MultivariateNormalDiag.log_prob(z) and / or .entropy(), each [B] (either output may be NULL) */
+int pmvae_diag_sample(const float* par, const float* eps, int64_t B, int32_t d, float* z, pmvae_stream_t stream);
+int pmvae_diag_log_prob(const float* par, const float* z, int64_t B, int32_t d, float* out_log_prob,
+                        float* out_entropy, pmvae_stream_t stream);
 
 /* ---- the whole training step as one launch sequence ---------------------------------------------
  * train_pm_vae.py's step (mask draw, eps draw, loss_fn forward, value_and_grad, optax update) enqueued by ONE

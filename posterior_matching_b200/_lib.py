@@ -140,6 +140,8 @@ _SIGS = {
     "pmvae_tril_sample": (_i32, [_vp, _u32p, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
     "pmvae_normal_log_prob": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp]),
     "pmvae_std_normal_log_prob": (_i32, [_vp, _i64, _i32, _vp, _vp]),
+    "pmvae_diag_sample": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "pmvae_diag_log_prob": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "pmvae_impute": (_i32, [_cfgp, _vp, _vp, _vp, _i64, _i64, _u32p, _i64, _i64, _vp, _vp, _vp, _u64, _vp]),
 }
 EXPORTS = tuple(_SIGS)

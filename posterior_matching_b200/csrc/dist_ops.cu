@@ -57,6 +57,34 @@ __global__ void __launch_bounds__(256) std_normal_log_prob_kernel(const float* _
   }
 }
 
+// DiagonalGaussian (distributions.py:58-84): par[B, 2d] = [loc | raw], scale = softplus(raw) + 1e-5.
+// z = loc + scale * eps (the reparameterised sample behind posterior.sample, vade.py:259);
+// log_prob(z) = sum_j -0.5 ((z - loc) / scale)^2 - log scale - 0.5 log 2 pi;  entropy = sum_j 0.5 (1 + log 2 pi) + log scale
+__global__ void __launch_bounds__(256) diag_sample_kernel(const float* __restrict__ par, const float* __restrict__ eps,
+                                                          int64_t B, int d, float* __restrict__ z) {
+  const int64_t n = B * d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / d;
+    const int j = (int)(i - r * d);
+    z[i] = par[r * 2 * d + j] + (softplus_f(par[r * 2 * d + d + j]) + 1e-5f) * eps[i];
+  }
+}
+__global__ void __launch_bounds__(256) diag_log_prob_kernel(const float* __restrict__ par, const float* __restrict__ z,
+                                                            int64_t B, int d, float* __restrict__ out_lp,
+                                                            float* __restrict__ out_ent) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < B; r += (int64_t)gridDim.x * blockDim.x) {
+    float lp = 0.f, ent = 0.f;
+    for (int j = 0; j < d; ++j) {
+      const float sc = softplus_f(par[r * 2 * d + d + j]) + 1e-5f;
+      const float ls = logf(sc);
+      if (z) { const float t = (z[r * d + j] - par[r * 2 * d + j]) / sc; lp += -0.5f * t * t - ls - 0.5f * kLog2Pi; }
+      ent += 0.5f * (1.0f + kLog2Pi) + ls;
+    }
+    if (out_lp) out_lp[r] = lp;
+    if (out_ent) out_ent[r] = ent;
+  }
+}
+
 }  // namespace pmvae
 
 using namespace pmvae;
@@ -97,6 +125,24 @@ int pmvae_std_normal_log_prob(const float* z, int64_t B, int32_t d, float* out, 
   PMVAE_CHECK(B >= 0 && d >= 1 && (B == 0 || (z && out)), "bad arguments");
   if (B == 0) return 0;
   std_normal_log_prob_kernel<<<grid_rows(B, 256), 256, 0, as_stream(stream)>>>(z, B, d, out);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int pmvae_diag_sample(const float* par, const float* eps, int64_t B, int32_t d, float* z, pmvae_stream_t stream) {
+  PMVAE_CHECK(B >= 0 && d >= 1 && (B == 0 || (par && eps && z)), "bad arguments");
+  if (B == 0) return 0;
+  diag_sample_kernel<<<grid_rows(B * d, 256), 256, 0, as_stream(stream)>>>(par, eps, B, d, z);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int pmvae_diag_log_prob(const float* par, const float* z, int64_t B, int32_t d, float* out_log_prob, float* out_entropy,
+                        pmvae_stream_t stream) {
+  PMVAE_CHECK(B >= 0 && d >= 1 && (B == 0 || (par && (out_log_prob || out_entropy))), "bad arguments");
+  PMVAE_CHECK(out_log_prob == nullptr || z != nullptr, "log_prob needs z");
+  if (B == 0) return 0;
+  diag_log_prob_kernel<<<grid_rows(B, 256), 256, 0, as_stream(stream)>>>(par, z, B, d, out_log_prob, out_entropy);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -419,7 +419,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       if (lane == 0) arrive_leader(in_ready);
     };
     auto first_operand = [&](int tile_n) {
-      if (SAVE && LN) mbar_wait(xs_free, (n_xs & 1u) ^ 1u, 16);     // the last staged xhat chunk has been stored
+      if (SAVE && LN && !(p.debug & 64)) mbar_wait(xs_free, (n_xs & 1u) ^ 1u, 16);     // the last staged xhat chunk has been stored
       if (p.in_wide) prologue_wide(tile_n, 0);
       else prologue(tile_n);
     };
@@ -528,7 +528,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
             const int slot = (half * 4 + i4) ^ (row & 7);
             st_shared_v4(rowaddr + slot * 16, pk[4 * i4], pk[4 * i4 + 1], pk[4 * i4 + 2], pk[4 * i4 + 3]);
           }
-          if (SAVE) {
+          if (SAVE && !(p.debug & 64)) {
             // xhat chunk -> staging (the idle first-Linear operand buffer), same swizzled row layout
             mbar_wait(xs_free, (n_xs & 1u) ^ 1u, 18);
             ++n_xs;
@@ -539,16 +539,17 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
               st_shared_v4(xaddr + slot * 16, xk[4 * i4], xk[4 * i4 + 1], xk[4 * i4 + 2], xk[4 * i4 + 3]);
             }
           }
+          if (p.debug & 256) tmem_st_wait();
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) arrive_leader(opnd_ready(j));
-          if (SAVE && lane == 0) { mbar_arrive(written(j)); mbar_arrive(xs_written); }
+          if (SAVE && lane == 0) { mbar_arrive(written(j)); if (!(p.debug & 64)) mbar_arrive(xs_written); }
         }
         if (SAVE) {
           ++n_writes;
-          if (p.masks)
+          if (p.masks && !(p.debug & 128))
             *reinterpret_cast<uint4*>(p.masks + (((int64_t)l * p.Bpad + g_row) * 8 + half * 4)) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-          if (half == 0 && p.rstd) p.rstd[(int64_t)l * p.Bpad + g_row] = rstd;
+          if (half == 0 && p.rstd && !(p.debug & 128)) p.rstd[(int64_t)l * p.Bpad + g_row] = rstd;
         }
         tmem_st_wait();
       };
@@ -626,6 +627,9 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       }
       // ---- the next tile's first Linear can run while this tile's head is stored
       if (has_next) first_operand(tile_next);
+      // several head tiles are staged in the input area: every warp must be done reading the next tile's input rows
+      // (prologue) before any warp overwrites them
+      if (has_next && p.head_tiles > 1 && p.head_tma && !p.in_wide) named_bar_sync(9, kEpiWarps * 32);
       // ---- head Linear: accumulator + bias -> fp32 rows (thread = row, 128 contiguous bytes per 32 columns)
       for (int t = 0; t < p.head_tiles; ++t) {
         const int region = region_of(n_hidden + t);
@@ -754,7 +758,7 @@ net_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   } else if (SAVE && LN && warp == 3 + kEpiWarps) {
     // ===================== second helper warp (LayerNorm training mode): xhat chunks, one staging buffer =====================
     uint32_t cnt = 0;
-    for (int it = it_first; it < it_count; it += it_stride) {
+    for (int it = it_first; it < it_count && !(p.debug & 64); it += it_stride) {
       const int tile = CTA2 ? 2 * it + (int)rank : it;
       for (int l = 0; l < n_hidden; ++l) {
         for (int j = 0; j < 4; ++j, ++cnt) {
@@ -1579,6 +1583,11 @@ NetImages plan_images(const Net& n, const Leaf& head, int in_kind, bf16* base) {
   const int np16 = (head.cols + 15) / 16 * 16;
   im.head_tiles = (np16 + 255) / 256;
   im.head_NT = ((np16 + im.head_tiles - 1) / im.head_tiles + 15) / 16 * 16;
+  // Several head tiles: the epilogue stores 32-column pieces, so a tile width that is not a multiple of 32 lets the last
+  // piece of tile t spill 16 never-written accumulator columns over the first 16 columns of tile t + 1, and the two TMA
+  // stores (issued by different warps) are not ordered: whenever the TMA unit was busy enough for the earlier store to
+  // land last (the training-mode LayerNorm forward: ~1 tile in 500), those columns came out stale.
+  if (im.head_tiles > 1) im.head_NT = (im.head_NT + 31) / 32 * 32;
   im.head_Kp = (head.cols + 63) / 64 * 64;
   uint64_t off = 0;
   auto take = [&](uint64_t elems) { bf16* p = base ? base + off : nullptr; off += align_up(elems, 512); return p; };
