@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 CSRC = os.path.dirname(os.path.abspath(__file__))
 HERE = os.path.dirname(CSRC)
 OUT = os.path.join(HERE, "libpmvae.so")
-SOURCES = ["rng.cu", "gemm_f32.cu", "elementwise.cu", "latent.cu", "latent16.cu", "dists_mnist.cu", "dist_ops.cu", "conv.cu", "tc_gemm.cu", "fused_mlp.cu", "tensor.cu", "model.cu", "train_step.cu", "xla_shim.cu"]
+SOURCES = ["rng.cu", "gemm_f32.cu", "elementwise.cu", "latent.cu", "latent16.cu", "latent64.cu", "dists_mnist.cu", "dist_ops.cu", "conv.cu", "tc_gemm.cu", "fused_mlp.cu", "tensor.cu", "model.cu", "train_step.cu", "xla_shim.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

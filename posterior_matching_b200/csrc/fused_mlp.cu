@@ -1138,6 +1138,8 @@ constexpr int kLnOffW = 2 * kOpndBytes;
 constexpr int kLnOffExch = kLnOffW + kWStages * kWStageBytes;
 constexpr int kLnOffBar = kLnOffExch + 128 * 2 * 2 * 4;
 constexpr int kLnSmemBytes = kLnOffBar + 512;
+constexpr int kLnHelpers = 2;                               // helper warps, two operand chunks each
+constexpr int kLnThreads = kThreads + kLnHelpers * 32;      // 384: leaves 168 registers per thread (no spills in the epilogue)
 static_assert(kLnSmemBytes <= 232448, "shared-memory plan exceeds 227 KB");
 
 struct BwdLnArgs {
@@ -1150,7 +1152,7 @@ struct BwdLnArgs {
 };
 
 template <int R, bool DIN>
-__global__ void __launch_bounds__(kBwdThreads, 1)
+__global__ void __launch_bounds__(kLnThreads, 1)
 net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant__ CUtensorMap map_wh,
                   const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w0,
                   const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, BwdLnArgs p) {
@@ -1187,7 +1189,7 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
       mbar_init(written(c), kEpiWarps); mbar_init(chunk_free(c), 1);
     }
     mbar_init(acc_full, 1); mbar_init(acc_empty, kEpiWarps);
-    mbar_init(bufa_free, DIN ? 5 : 4);
+    mbar_init(bufa_free, 2 * kLnHelpers + (DIN ? 1 : 0));
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -1452,32 +1454,36 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
       }
     }
   } else {
-    // ===================== helpers (4 warps): warp j owns chunk j of every gradient tile =====================
-    const int j = warp - (2 + kEpiWarps);
-    float cs[n_hidden][2];
+    // ===================== helpers (2 warps): warp h owns chunks 2h, 2h + 1 of every gradient tile =====================
+    const int h = warp - (2 + kEpiWarps);
+    float cs[n_hidden][2][2];
 #pragma unroll
-    for (int l = 0; l < n_hidden; ++l) { cs[l][0] = 0.f; cs[l][1] = 0.f; }
+    for (int l = 0; l < n_hidden; ++l) { cs[l][0][0] = cs[l][0][1] = cs[l][1][0] = cs[l][1][1] = 0.f; }
     uint32_t wr_cnt = 0;
-    auto help = [&](int l, int tile, float (&c2)[2]) {
-      const uint32_t src = abuf + j * kChunkBytes;
-      mbar_wait(written(j), wr_cnt & 1u, 11);
-      ++wr_cnt;
-      if (lane == 0) {
-        tma_store_2d(&map_dy, src, 64 * j, (int)((int64_t)l * p.Bpad + (int64_t)tile * 128));
-        tma_store_commit();
-      }
-      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+    auto help = [&](int l, int tile, float (&c2)[2][2]) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = 2 * h + u;
+        const uint32_t src = abuf + j * kChunkBytes;
+        mbar_wait(written(j), wr_cnt & 1u, 11);
+        if (lane == 0) {
+          tma_store_2d(&map_dy, src, 64 * j, (int)((int64_t)l * p.Bpad + (int64_t)tile * 128));
+          tma_store_commit();
+        }
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll 8
-      for (int r = 0; r < 128; r += 2) {
-        const uint32_t w0 = ld_shared_u32(src + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
-        const uint32_t w1 = ld_shared_u32(src + (r + 1) * 128 + ((((lane >> 2) ^ ((r + 1) & 7)) << 4) | ((lane & 3) << 2)));
-        a0 += bf16_lo(w0); a1 += bf16_hi(w0);
-        b0 += bf16_lo(w1); b1 += bf16_hi(w1);
+        for (int r = 0; r < 128; r += 2) {
+          const uint32_t w0 = ld_shared_u32(src + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+          const uint32_t w1 = ld_shared_u32(src + (r + 1) * 128 + ((((lane >> 2) ^ ((r + 1) & 7)) << 4) | ((lane & 3) << 2)));
+          a0 += bf16_lo(w0); a1 += bf16_hi(w0);
+          b0 += bf16_lo(w1); b1 += bf16_hi(w1);
+        }
+        c2[u][0] += a0 + b0; c2[u][1] += a1 + b1;
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(chunk_free(j));
       }
-      c2[0] += a0 + b0; c2[1] += a1 + b1;
-      if (lane == 0) tma_store_wait_read<0>();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(chunk_free(j));
+      ++wr_cnt;
     };
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       help(2 * R, tile, cs[2 * R]);
@@ -1486,14 +1492,17 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
         help(2 * r + 1, tile, cs[2 * r + 1]);
         help(2 * r, tile, cs[2 * r]);
       }
-      if (lane == 0) mbar_arrive(bufa_free);      // this chunk of the tile's last gradient tile has been stored
+      if (lane == 0) { mbar_arrive(bufa_free); mbar_arrive(bufa_free); }   // both chunks of the tile's last gradient tile stored
     }
     if (lane == 0) tma_store_wait_all();
 #pragma unroll
     for (int l = 0; l < n_hidden; ++l)
       if (p.db[l]) {
-        atomicAdd(p.db[l] + 64 * j + 2 * lane, cs[l][0]);
-        atomicAdd(p.db[l] + 64 * j + 2 * lane + 1, cs[l][1]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          atomicAdd(p.db[l] + 64 * (2 * h + u) + 2 * lane, cs[l][u][0]);
+          atomicAdd(p.db[l] + 64 * (2 * h + u) + 2 * lane + 1, cs[l][u][1]);
+        }
       }
   }
 
@@ -1800,7 +1809,7 @@ static int launch_bwd_ln(const CUtensorMap& mdh, const CUtensorMap& mwh, const C
     attr_set = true;
   }
   const int grid = grid_cap(a.num_tiles < num_sms() ? a.num_tiles : num_sms());
-  net_bwd_ln_kernel<R, DIN><<<grid, kBwdThreads, kLnSmemBytes, s>>>(mdh, mwh, mw, mw0, mdy, mx, a);
+  net_bwd_ln_kernel<R, DIN><<<grid, kLnThreads, kLnSmemBytes, s>>>(mdh, mwh, mw, mw0, mdy, mx, a);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -521,6 +521,7 @@ int latent_fwd(const float* par, const float* eps, float* z, float* kl, int64_t 
   PMVAE_CHECK(d >= 1 && d <= 64, "latent_dim must be in [1, 64]");
   if (B == 0) return 0;
   if (d == 16 && fast16()) return latent_fwd16(par, eps, z, kl, B, s);
+  if (d == 64 && fast64()) return latent_fwd64(par, eps, z, kl, B, s);
   const int P = d + d * (d + 1) / 2;
   const size_t spg = (size_t)(P + 3 * d) * sizeof(float);
   DISPATCH_D(latent_fwd_kernel, d, B, spg, s, par, eps, z, kl, B, d);
@@ -532,6 +533,7 @@ int match_fwd(const float* par_p, const float* z, float* match, int64_t B, int d
   PMVAE_CHECK(d >= 1 && d <= 64, "latent_dim must be in [1, 64]");
   if (B == 0) return 0;
   if (d == 16 && fast16()) return match_fwd16(par_p, z, match, B, s);
+  if (d == 64 && fast64()) return match_fwd64(par_p, z, match, B, s);
   const int P = d + d * (d + 1) / 2;
   const size_t spg = (size_t)(P + 4 * d) * sizeof(float);
   DISPATCH_D(match_fwd_kernel, d, B, spg, s, par_p, z, match, B, d);
@@ -540,7 +542,7 @@ int match_fwd(const float* par_p, const float* z, float* match, int64_t B, int d
 }
 
 // whether latent_bwd with bf16 outputs and db_e / db_p also accumulates the two head bias gradients (d = 16 kernels)
-bool latent_bwd_bias_fused(int d) { return d == 16 && fast16(); }
+bool latent_bwd_bias_fused(int d) { return (d == 16 && fast16()) || (d == 64 && fast64()); }
 
 int latent_bwd(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
                const float* g_kl, const float* g_match, int stop_grad, float* dpar_e, float* dpar_p,
@@ -552,6 +554,10 @@ int latent_bwd(const float* par_e, const float* par_p, const float* eps, const f
   if (d == 16 && fast16() && dpar_e == nullptr && dpar_p == nullptr && dpar_e_b && dpar_p_b) {
     if (db_done) *db_done = (db_e != nullptr && db_p != nullptr);     // head bias gradients are taken here as well
     return latent_bwd16(par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad, dpar_e_b, dpar_p_b, db_e, db_p, B, s);
+  }
+  if (d == 64 && fast64() && dpar_e == nullptr && dpar_p == nullptr && dpar_e_b && dpar_p_b) {
+    if (db_done) *db_done = (db_e != nullptr && db_p != nullptr);
+    return latent_bwd64(par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad, dpar_e_b, dpar_p_b, db_e, db_p, B, s);
   }
   const int P = d + d * (d + 1) / 2;
   const size_t spg = (size_t)(P + 6 * d) * sizeof(float);
