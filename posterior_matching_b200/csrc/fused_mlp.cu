@@ -1149,7 +1149,10 @@ struct BwdLnArgs {
   float* dIn;                 // [B, din_cols] fp32
   const uint32_t* masks; const float* rstd; int64_t Bpad;
   float* db[kMaxLayers];      // bias-gradient destinations (atomicAdd), Linear 0..2R
+  int debug;                  // PMVAE_FUSED_DEBUG bits (profiling only): 1024 no column sums, 2048 no dY stores, 4096 no xhat loads
 };
+
+__device__ long long g_ln_trace[1024];      // PMVAE_FUSED_DEBUG bit 8192: clock64 stamps of block 0 (profiling only)
 
 template <int R, bool DIN>
 __global__ void __launch_bounds__(kLnThreads, 1)
@@ -1217,8 +1220,12 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
         mbar_wait(x_free(j), (x_cnt & 1u) ^ 1u, 20);
         __syncwarp();
         if (elect_one()) {
-          mbar_arrive_expect_tx(x_full(j), (uint32_t)kChunkBytes);
-          tma_load_2d(xbuf + j * kChunkBytes, &map_x, x_full(j), 64 * j, (int)((int64_t)l * p.Bpad + (int64_t)tile * 128));
+          if (p.debug & 4096) {
+            mbar_arrive(x_full(j));
+          } else {
+            mbar_arrive_expect_tx(x_full(j), (uint32_t)kChunkBytes);
+            tma_load_2d(xbuf + j * kChunkBytes, &map_x, x_full(j), 64 * j, (int)((int64_t)l * p.Bpad + (int64_t)tile * 128));
+          }
         }
         __syncwarp();
       }
@@ -1322,9 +1329,12 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
       const uint32_t cf_par = (e_cnt & 1u) ^ 1u;      // chunk_free: the previous gradient tile in this chunk has been stored
       const uint32_t x_par = e_cnt & 1u;
       ++e_cnt;
+      const bool tr = (p.debug & 8192) && blockIdx.x == 0 && ew == 0 && lane == 0 && e_cnt <= 24;
+      if (tr) g_ln_trace[8 * e_cnt + 0] = clock64();
       mbar_wait(acc_full, full_par, 5);
       full_par ^= 1u;
       tc_fence_after();
+      if (tr) g_ln_trace[8 * e_cnt + 1] = clock64();
       float S1 = 0.f, S2 = 0.f;
       // ---- pass 1: masked values, row sums; s -> TMEM (even) or bf16 stash in the operand buffer (odd)
 #pragma unroll
@@ -1332,7 +1342,9 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
         uint32_t r[32], so[32];
         tmem_ld32(t_acc + 64 * j, r);
         if (even && !first) tmem_ld32(t_s + 64 * j, so);
+        if (tr && e_cnt == 6) g_ln_trace[512 + 8 * j + 0] = clock64();
         mbar_wait(x_full(j), x_par, 23);
+        if (tr && e_cnt == 6) g_ln_trace[512 + 8 * j + 1] = clock64();
         uint32_t xq[16];
         const uint32_t xrow = xbuf + j * kChunkBytes + row * 128;
 #pragma unroll
@@ -1341,6 +1353,7 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
           ld_shared_v4(xrow + slot * 16, xq[4 * i4], xq[4 * i4 + 1], xq[4 * i4 + 2], xq[4 * i4 + 3]);
         }
         tmem_ld_wait();
+        if (tr && e_cnt == 6) g_ln_trace[512 + 8 * j + 2] = clock64();
         const uint32_t m = mw[j];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -1352,10 +1365,12 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
           S2 = fmaf(a1, bf16_hi(xq[i]), S2);
           r[2 * i] = __float_as_uint(a0); r[2 * i + 1] = __float_as_uint(a1);
         }
+        if (tr && e_cnt == 6) g_ln_trace[512 + 8 * j + 3] = clock64();
         if (even) {
           tmem_st32(t_s + 64 * j, r);
         } else {
           mbar_wait(chunk_free(j), cf_par, 10);
+          if (tr && e_cnt == 6) g_ln_trace[512 + 8 * j + 4] = clock64();
           const uint32_t rowaddr = abuf + j * kChunkBytes + row * 128;
 #pragma unroll
           for (int i4 = 0; i4 < 4; ++i4) {
@@ -1372,8 +1387,10 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
+      if (tr) g_ln_trace[8 * e_cnt + 2] = clock64();
       mine[0] = S1; mine[1] = S2;
       named_bar_sync(1 + q, 64);
+      if (tr) g_ln_trace[8 * e_cnt + 3] = clock64();
       const float c1 = (S1 + other[0]) * (1.0f / 256.0f), c2 = (S2 + other[1]) * (1.0f / 256.0f);
       // ---- pass 2: g = rstd (v - c1 - x c2)
 #pragma unroll
@@ -1423,6 +1440,7 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
           mbar_arrive(x_free(j));
         }
       }
+      if (tr) g_ln_trace[8 * e_cnt + 4] = clock64();
       named_bar_sync(1 + q, 64);        // the exchange slots are rewritten by the next epilogue
     };
 
@@ -1467,12 +1485,12 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
         const uint32_t src = abuf + j * kChunkBytes;
         mbar_wait(written(j), wr_cnt & 1u, 11);
         if (lane == 0) {
-          tma_store_2d(&map_dy, src, 64 * j, (int)((int64_t)l * p.Bpad + (int64_t)tile * 128));
+          if (!(p.debug & 2048)) tma_store_2d(&map_dy, src, 64 * j, (int)((int64_t)l * p.Bpad + (int64_t)tile * 128));
           tma_store_commit();
         }
         float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll 8
-        for (int r = 0; r < 128; r += 2) {
+        for (int r = 0; r < ((p.debug & 1024) ? 0 : 128); r += 2) {
           const uint32_t w0 = ld_shared_u32(src + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
           const uint32_t w1 = ld_shared_u32(src + (r + 1) * 128 + ((((lane >> 2) ^ ((r + 1) & 7)) << 4) | ((lane & 3) << 2)));
           a0 += bf16_lo(w0); a1 += bf16_hi(w0);
@@ -1811,6 +1829,25 @@ static int launch_bwd_ln(const CUtensorMap& mdh, const CUtensorMap& mwh, const C
   const int grid = grid_cap(a.num_tiles < num_sms() ? a.num_tiles : num_sms());
   net_bwd_ln_kernel<R, DIN><<<grid, kLnThreads, kLnSmemBytes, s>>>(mdh, mwh, mw, mw0, mdy, mx, a);
   PMVAE_LAUNCH_CHECK();
+  if (a.debug & 8192) {
+    static int printed = 0;
+    if (printed < 2) {
+      ++printed;
+      static long long host[1024];
+      cudaStreamSynchronize(s);
+      cudaMemcpyFromSymbol(host, g_ln_trace, sizeof(host));
+      const long long t0 = host[8 + 0];
+      printf("pass 1 of epilogue 5 (odd), per chunk: start, x_full, loads, math, chunk_free\n");
+      for (int j = 0; j < 4; ++j)
+        printf("  j %d: %8lld %8lld %8lld %8lld %8lld\n", j, host[512 + 8 * j] - t0, host[512 + 8 * j + 1] - t0,
+               host[512 + 8 * j + 2] - t0, host[512 + 8 * j + 3] - t0, host[512 + 8 * j + 4] - t0);
+      printf("net_bwd_ln trace (block 0, epilogue warp 0): epilogue e: start, acc_full, pass1 end, exchange, pass2 end (cycles)\n");
+      for (int e = 1; e <= 24; ++e)
+        printf("  e %2d: %8lld %8lld %8lld %8lld %8lld\n", e, host[8 * e] - t0, host[8 * e + 1] - t0, host[8 * e + 2] - t0,
+               host[8 * e + 3] - t0, host[8 * e + 4] - t0);
+      fflush(stdout);
+    }
+  }
   return 0;
 }
 
@@ -1830,6 +1867,7 @@ int net_backward_ln(const Net& n, const Leaf& head, const NetImages& im, const b
   a.din_N = dIn ? im.din_N : 0; a.din_cols = n.in_dim; a.dIn = dIn;
   a.masks = masks; a.rstd = rstd; a.Bpad = Bpad;
   for (int l = 0; l <= 2 * n.R; ++l) a.db[l] = grads + n.lin[l].b;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("PMVAE_FUSED_DEBUG"); dbg = e ? atoi(e) : 0; } a.debug = dbg; }
   CUtensorMap mdh, mwh, mw, mw0, mdy, mx;
   PMVAE_TRY(make_map_2d(&mdh, dHead, 2, (uint64_t)B, (uint64_t)im.head_N, (uint64_t)ld_dhead, 64, 128));
   PMVAE_TRY(make_map_2d(&mwh, im.head_n, 2, 256, (uint64_t)im.head_Kp, (uint64_t)im.head_Kp, 64, 256));

@@ -547,7 +547,7 @@ bool latent_bwd_bias_fused(int d) { return (d == 16 && fast16()) || (d == 64 && 
 int latent_bwd(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
                const float* g_kl, const float* g_match, int stop_grad, float* dpar_e, float* dpar_p,
                __nv_bfloat16* dpar_e_b, __nv_bfloat16* dpar_p_b, int64_t B, int d, cudaStream_t s, float* db_e,
-               float* db_p, bool* db_done) {
+               float* db_p, bool* db_done, float* dz_scratch) {
   if (db_done) *db_done = false;
   PMVAE_CHECK(d >= 1 && d <= 64, "latent_dim must be in [1, 64]");
   if (B == 0) return 0;
@@ -555,9 +555,9 @@ int latent_bwd(const float* par_e, const float* par_p, const float* eps, const f
     if (db_done) *db_done = (db_e != nullptr && db_p != nullptr);     // head bias gradients are taken here as well
     return latent_bwd16(par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad, dpar_e_b, dpar_p_b, db_e, db_p, B, s);
   }
-  if (d == 64 && fast64() && dpar_e == nullptr && dpar_p == nullptr && dpar_e_b && dpar_p_b) {
+  if (d == 64 && fast64() && dpar_e == nullptr && dpar_p == nullptr && dpar_e_b && dpar_p_b && dz_scratch) {
     if (db_done) *db_done = (db_e != nullptr && db_p != nullptr);
-    return latent_bwd64(par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad, dpar_e_b, dpar_p_b, db_e, db_p, B, s);
+    return latent_bwd64(par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad, dpar_e_b, dpar_p_b, db_e, db_p, dz_scratch, B, s);
   }
   const int P = d + d * (d + 1) / 2;
   const size_t spg = (size_t)(P + 6 * d) * sizeof(float);

@@ -21,7 +21,7 @@ constexpr int kPitch = D + 1;
 constexpr int kWarps = 4;                                  // per block
 constexpr int kThreads = kWarps * 32;
 constexpr int kLFloats = D * kPitch;                       // dense factor
-constexpr int kVecs = 7;                                   // per-warp vectors of D floats
+constexpr int kVecs = 4;                                   // per-warp vectors of D floats
 constexpr int kWarpFloats = kLFloats + kVecs * D;
 constexpr size_t kSmemBytes = (size_t)kWarps * kWarpFloats * sizeof(float);
 
@@ -36,24 +36,38 @@ __device__ __forceinline__ void v_to_ij(int q, int& i, int& j) {
   i = k2 >> 6; j = k2 & 63;
 }
 
+// index into v of the diagonal element (i, i)
+__device__ __forceinline__ int diag_q(int i) { return i < 32 ? D + 65 * i : 4095 - 65 * i; }
+
 // Stages L (diagonal = softplus(raw) + 1e-5) into Lp[64][65]; sraw[i] = raw diagonal, sinv[i] = 1 / L_ii.
-// Returns this lane's share of sum_i log L_ii.
+// Returns this lane's share of sum_i log L_ii.  The 65 loads of a lane are issued in batches of 13 before anything is
+// stored (stores to shared memory would otherwise pin every load behind the previous iteration: one HBM round trip
+// per element), and the transcendental work of the 64 diagonal elements is done once, two per lane, after the copy.
 __device__ __forceinline__ float stage_factor(const float* __restrict__ pr, float* Lp, float* sraw, float* sinv, int lane) {
-  float logd = 0.f;
   const float* v = pr + D;
-#pragma unroll 5
-  for (int it = 0; it < M / 32; ++it) {
-    const int q = lane + 32 * it;
-    float val = __ldg(v + q);
-    int i, j;
-    v_to_ij(q, i, j);
-    if (i == j) {
-      sraw[i] = val;
-      val = softplus_f(val) + 1e-5f;
-      sinv[i] = 1.0f / val;
-      logd += logf(val);
+#pragma unroll 1
+  for (int it0 = 0; it0 < M / 32; it0 += 13) {
+    float buf[13];
+#pragma unroll
+    for (int u = 0; u < 13; ++u) buf[u] = __ldg(v + lane + 32 * (it0 + u));
+#pragma unroll
+    for (int u = 0; u < 13; ++u) {
+      int i, j;
+      v_to_ij(lane + 32 * (it0 + u), i, j);
+      Lp[i * kPitch + j] = buf[u];
     }
-    Lp[i * kPitch + j] = val;
+  }
+  __syncwarp();
+  float logd = 0.f;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = lane + 32 * h;
+    const float raw = Lp[i * kPitch + i];
+    const float dg = softplus_f(raw) + 1e-5f;
+    sraw[i] = raw;
+    sinv[i] = 1.0f / dg;
+    Lp[i * kPitch + i] = dg;
+    logd += logf(dg);
   }
   return logd;
 }
@@ -144,31 +158,31 @@ __global__ void __launch_bounds__(kThreads) match_fwd64_kernel(const float* __re
 // Cotangents g_kl[r], g_match[r] and dz_dec (decoder) -> d / d par_e, d / d par_p (bf16, the A operands of the two head
 // Linears' backward), formulas as latent.cu::latent_bwd_kernel.  Optionally also the two head bias gradients (column
 // sums of the bf16 values), accumulated per block in shared memory and flushed with one atomicAdd per column.
+template <bool CS>
 __global__ void __launch_bounds__(kThreads) latent_bwd64_kernel(
     const float* __restrict__ par_e, const float* __restrict__ par_p, const float* __restrict__ eps,
     const float* __restrict__ z, const float* __restrict__ dz_dec, const float* __restrict__ g_kl,
     const float* __restrict__ g_match, int stop_grad, __nv_bfloat16* __restrict__ dpar_e_b,
-    __nv_bfloat16* __restrict__ dpar_p_b, float* __restrict__ db_e, float* __restrict__ db_p, int64_t B) {
+    __nv_bfloat16* __restrict__ dpar_p_b, float* __restrict__ db_e, float* __restrict__ db_p, float* __restrict__ dz_total,
+    int64_t B) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   float* Lp = smem + (size_t)wib * kWarpFloats;
   float* sr = Lp + kLFloats;     // r = L_p^-1 (z - mu_p)
   float* sg = sr + D;            // g = L_p^-T r
-  float* se = sg + D;            // eps
-  float* sdz = se + D;           // dz_total
-  float* sraw = sdz + D;
+  float* sraw = sg + D;
   float* sinv = sraw + D;
-  float* cs = smem + (size_t)kWarps * kWarpFloats;      // [2][P] column sums of this block (only with db_e / db_p)
-  const bool do_cs = db_e != nullptr && db_p != nullptr;
-  if (do_cs) {
-    for (int q = threadIdx.x; q < 2 * P; q += kThreads) cs[q] = 0.f;
-    __syncthreads();
+  // CS: column sums of the bf16 outputs (the two head bias gradients) in registers: lane keeps column 32 it + lane of
+  // both outputs over all rows of its warp (shared-memory atomics cost 64 cycles per warp and column: 4 ms per step)
+  constexpr int kIt = P / 32;                 // 67
+  float acc_p[CS ? kIt : 1], dacc_p[2] = {0.f, 0.f};
+  if (CS) {
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) acc_p[it] = 0.f;
   }
   for (int64_t r = (int64_t)blockIdx.x * kWarps + wib; r < B; r += (int64_t)gridDim.x * kWarps) {
     const float* pp = par_p + r * P;
-    const float* pe = par_e + r * P;
     __syncwarp();
-    se[lane] = eps[r * D + lane]; se[lane + 32] = eps[r * D + lane + 32];
     stage_factor(pp, Lp, sraw, sinv, lane);
     __syncwarp();
     // ---- partial posterior: r, g
@@ -176,64 +190,106 @@ __global__ void __launch_bounds__(kThreads) latent_bwd64_kernel(
     solve_lower(Lp, sinv, s0, s1, sr, lane);
     solve_upper_t(Lp, sinv, sr[lane], sr[lane + 32], sg, lane);
     const float mw = g_match[r];
-    // d match / d par_p: loc -> mw g; L_ij -> mw (g_i r_j - [i == j] / L_ii) (diagonal through softplus)
+    // d match / d par_p: loc -> mw g; L_ij -> mw (g_i r_j - [i == j] / L_ii) (diagonal through softplus: second pass)
     __nv_bfloat16* op = dpar_p_b + r * P;
-#pragma unroll 1
-    for (int q0 = 0; q0 < P; q0 += 32) {
-      const int q = q0 + lane;
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      const int q = 32 * it + lane;
       float val;
-      if (q < D) {
+      bool diag = false;
+      if (it < D / 32) {
         val = mw * sg[q];
       } else {
         int i, j;
         v_to_ij(q - D, i, j);
-        val = sg[i] * sr[j];
-        if (i == j) val = (val - sinv[i]) * sigmoid_f(sraw[i]);
-        val *= mw;
+        val = mw * sg[i] * sr[j];
+        diag = i == j;
       }
-      const __nv_bfloat16 hv = __float2bfloat16(val);
-      op[q] = hv;
-      if (do_cs) atomicAdd(cs + P + q, __bfloat162float(hv));
+      if (!diag) {
+        const __nv_bfloat16 hv = __float2bfloat16(val);
+        op[q] = hv;
+        if (CS) acc_p[it] += __bfloat162float(hv);
+      }
     }
-    // ---- dz_total = dz_dec - (stop_grad ? 0 : mw g)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = lane + 32 * h;
+      const float val = mw * (sg[i] * sr[i] - sinv[i]) * sigmoid_f(sraw[i]);
+      const __nv_bfloat16 hv = __float2bfloat16(val);
+      op[D + diag_q(i)] = hv;
+      if (CS) dacc_p[h] += __bfloat162float(hv);
+    }
+    // ---- dz_total = dz_dec - (stop_grad ? 0 : mw g): consumed by the posterior part (post_bwd64_kernel)
     {
       float v0 = dz_dec ? dz_dec[r * D + lane] : 0.f, v1 = dz_dec ? dz_dec[r * D + lane + 32] : 0.f;
       if (!stop_grad) { v0 -= mw * sg[lane]; v1 -= mw * sg[lane + 32]; }
-      sdz[lane] = v0; sdz[lane + 32] = v1;
-    }
-    __syncwarp();
-    // ---- posterior: z = mu + L eps and kw * KL
-    const float kw = g_kl[r];
-    __nv_bfloat16* oe = dpar_e_b + r * P;
-#pragma unroll 1
-    for (int q0 = 0; q0 < P; q0 += 32) {
-      const int q = q0 + lane;
-      const float raw = __ldg(pe + q);
-      float val;
-      if (q < D) {
-        val = sdz[q] + kw * raw;
-      } else {
-        int i, j;
-        v_to_ij(q - D, i, j);
-        if (i == j) {
-          const float dg = softplus_f(raw) + 1e-5f;
-          val = (sdz[i] * se[j] + kw * (dg - 1.0f / dg)) * sigmoid_f(raw);
-        } else {
-          val = sdz[i] * se[j] + kw * raw;
-        }
-      }
-      const __nv_bfloat16 hv = __float2bfloat16(val);
-      oe[q] = hv;
-      if (do_cs) atomicAdd(cs + q, __bfloat162float(hv));
+      dz_total[r * D + lane] = v0; dz_total[r * D + lane + 32] = v1;
     }
   }
-  if (do_cs) {
+  if (CS) {
+    // block reduction in the (now idle) factor tiles: warp w writes its 2 x P sums, then every column is summed over
+    // the four warps and added to the gradient arena with one atomic per column and block
+    __syncthreads();
+    float* mine = smem + (size_t)wib * kWarpFloats;
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) mine[32 * it + lane] = acc_p[it];
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) mine[D + diag_q(lane + 32 * h)] += dacc_p[h];
     __syncthreads();
     for (int q = threadIdx.x; q < P; q += kThreads) {
-      atomicAdd(db_e + q, cs[q]);
-      atomicAdd(db_p + q, cs[P + q]);
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) t += smem[(size_t)w * kWarpFloats + q];
+      atomicAdd(db_p + q, t);
     }
   }
+}
+
+// ---------------------------------------------------------------- posterior part: d / d par_e (streaming)
+// d / d par_e of z = mu + L eps (cotangent dz_total) and kw KL: loc -> dz_i + kw mu_i; L_ij -> dz_i eps_j + kw L_ij;
+// diagonal (through softplus) -> (dz_i eps_i + kw (D_ii - 1 / D_ii)) sigmoid(raw).  No triangular algebra: thread =
+// column q, block = kPostRows consecutive rows, so reads and writes are coalesced and the head bias gradient (column
+// sums of the bf16 values) is one register per thread and one atomicAdd per column and block.
+constexpr int kPostThreads = 256, kPostRows = 64;
+__global__ void __launch_bounds__(kPostThreads) post_bwd64_kernel(const float* __restrict__ par_e, const float* __restrict__ eps,
+                                                                  const float* __restrict__ dz_total,
+                                                                  const float* __restrict__ g_kl,
+                                                                  __nv_bfloat16* __restrict__ dpar_e_b,
+                                                                  float* __restrict__ db_e, int64_t B) {
+  __shared__ float sdz[kPostRows][D], se[kPostRows][D], skw[kPostRows];
+  const int64_t r0 = (int64_t)blockIdx.y * kPostRows;
+  const int nr = (int)((B - r0 < kPostRows) ? (B - r0) : kPostRows);
+  const int q = blockIdx.x * kPostThreads + threadIdx.x;
+  for (int t = threadIdx.x; t < nr * D; t += kPostThreads) {
+    sdz[t / D][t % D] = dz_total[r0 * D + t];
+    se[t / D][t % D] = eps[r0 * D + t];
+  }
+  if (threadIdx.x < nr) skw[threadIdx.x] = g_kl[r0 + threadIdx.x];
+  __syncthreads();
+  if (q >= P) return;
+  int i = 0, j = 0;
+  if (q >= D) v_to_ij(q - D, i, j);
+  const bool is_loc = q < D, diag = !is_loc && i == j;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int rr = 0; rr < nr; ++rr) {
+    const float raw = __ldg(par_e + (r0 + rr) * P + q);
+    const float kw = skw[rr];
+    float val;
+    if (is_loc) {
+      val = sdz[rr][q] + kw * raw;
+    } else if (diag) {
+      const float dg = softplus_f(raw) + 1e-5f;
+      val = (sdz[rr][i] * se[rr][i] + kw * (dg - 1.0f / dg)) * sigmoid_f(raw);
+    } else {
+      val = sdz[rr][i] * se[rr][j] + kw * raw;
+    }
+    const __nv_bfloat16 hv = __float2bfloat16(val);
+    dpar_e_b[(r0 + rr) * P + q] = hv;
+    acc += __bfloat162float(hv);
+  }
+  if (db_e) atomicAdd(db_e + q, acc);
 }
 
 static int grid_rows(int64_t B, int blocks_per_sm) {
@@ -265,14 +321,26 @@ int match_fwd64(const float* par_p, const float* z, float* match, int64_t B, cud
 
 int latent_bwd64(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
                  const float* g_kl, const float* g_match, int stop_grad, __nv_bfloat16* dpar_e_b, __nv_bfloat16* dpar_p_b,
-                 float* db_e, float* db_p, int64_t B, cudaStream_t s) {
+                 float* db_e, float* db_p, float* dz_total, int64_t B, cudaStream_t s) {
   using namespace l64;
   const bool do_cs = db_e != nullptr && db_p != nullptr;
-  const size_t smem = kSmemBytes + (do_cs ? (size_t)2 * P * sizeof(float) : 0);
-  static size_t attr = 0;
-  if (attr < smem) { PMVAE_CUDA(cudaFuncSetAttribute(latent_bwd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
-  latent_bwd64_kernel<<<grid_rows(B, do_cs ? 2 : 3), kThreads, smem, s>>>(par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad,
-                                                                         dpar_e_b, dpar_p_b, db_e, db_p, B);
+  static bool attr = false;
+  if (!attr) {
+    PMVAE_CUDA(cudaFuncSetAttribute(latent_bwd64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    PMVAE_CUDA(cudaFuncSetAttribute(latent_bwd64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    attr = true;
+  }
+  // partial posterior (two triangular solves per row) -> d / d par_p, dz_total
+  if (do_cs)
+    latent_bwd64_kernel<true><<<grid_rows(B, 3), kThreads, kSmemBytes, s>>>(par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad,
+                                                                             dpar_e_b, dpar_p_b, db_e, db_p, dz_total, B);
+  else
+    latent_bwd64_kernel<false><<<grid_rows(B, 3), kThreads, kSmemBytes, s>>>(par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad,
+                                                                              dpar_e_b, dpar_p_b, db_e, db_p, dz_total, B);
+  PMVAE_LAUNCH_CHECK();
+  // posterior: streaming elementwise kernel
+  const dim3 grid((P + kPostThreads - 1) / kPostThreads, (unsigned)((B + kPostRows - 1) / kPostRows));
+  post_bwd64_kernel<<<grid, kPostThreads, 0, s>>>(par_e, eps, dz_total, g_kl, dpar_e_b, do_cs ? db_e : nullptr, B);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }

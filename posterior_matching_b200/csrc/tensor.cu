@@ -480,7 +480,7 @@ static int64_t micro_rows() {
 struct TrainPlanB {
   Images img;
   NetSavedB enc, dec, part;
-  float *h, *ytmp, *par_e, *par_p, *z, *loc, *dz, *wtmp;
+  float *h, *ytmp, *par_e, *par_p, *z, *loc, *dz, *dz2, *wtmp;
   bf16 *dH, *dU, *dG, *dpar_e_b, *dpar_p_b, *dloc_b;
   bf16* in_b; // [B, pad8(2 D)] bf16 image of a net's input (first-Linear weight gradient)
   bf16* dY;   // [(2 Rmax + 1), Bpad, 256] gradient operands of the fused backward (shared by the three nets)
@@ -504,6 +504,7 @@ static TrainPlanB plan_train_b(const pmvae_config* c, const Layout& L, int64_t B
   p.z = bp.take<float>((uint64_t)B * c->d);
   p.loc = bp.take<float>((uint64_t)B * p.Dp);
   p.dz = bp.take<float>((uint64_t)B * c->d);
+  p.dz2 = bp.take<float>((uint64_t)B * c->d);             // dz_total of the d = 64 latent backward (two kernels)
   p.wtmp = bp.take<float>((uint64_t)256 * p.Dp);         // padded-pitch dW of the decoder head
   p.dH = bp.take<bf16>((uint64_t)B * 256);
   p.dU = bp.take<bf16>((uint64_t)B * 256);
@@ -816,7 +817,7 @@ int backward_bf16(const pmvae_config* c, const Layout& L, const float* params, c
       bool done = false;
       PMVAE_TRY(latent_bwd(p.par_e + r0 * L.P, p.par_p + r0 * L.P, eps + r0 * d, p.z + r0 * d, p.dz, g_kl + r0,
                            g_match + r0, c->stop_grad, nullptr, nullptr, p.dpar_e_b, p.dpar_p_b, nb, d, s, grads + L.post.b,
-                           grads + L.ppost.b, &done));
+                           grads + L.ppost.b, &done, p.dz2));
       PMVAE_CHECK(done == lat_db, "latent_bwd bias-gradient contract changed");
     }
     if (stages & 2)
