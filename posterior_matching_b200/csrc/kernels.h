@@ -101,7 +101,7 @@ int latent_fwd64(const float* par, const float* eps, float* z, float* kl, int64_
 int match_fwd64(const float* par_p, const float* z, float* match, int64_t B, cudaStream_t s);
 int latent_bwd64(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
                  const float* g_kl, const float* g_match, int stop_grad, __nv_bfloat16* dpar_e_b,
-                 __nv_bfloat16* dpar_p_b, float* db_e, float* db_p, float* dz_total /* [B,64] scratch */, int64_t B,
+                 __nv_bfloat16* dpar_p_b, float* db_e, float* db_p, float* scratch /* [3, B, 64] floats */, int64_t B,
                  cudaStream_t s);
 // z[k,r,:] = mu_r + L_r eps[k,r,:], eps = normal(key, [K, B_total, d]) rows row_start..;
 // base[k,r] = log N(z;0,I) - log q(z) = -0.5|z|^2 + 0.5|eps|^2 + sum log L_ii

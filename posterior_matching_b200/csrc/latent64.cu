@@ -155,141 +155,108 @@ __global__ void __launch_bounds__(kThreads) match_fwd64_kernel(const float* __re
 }
 
 // ---------------------------------------------------------------- backward of both heads
-// Cotangents g_kl[r], g_match[r] and dz_dec (decoder) -> d / d par_e, d / d par_p (bf16, the A operands of the two head
-// Linears' backward), formulas as latent.cu::latent_bwd_kernel.  Optionally also the two head bias gradients (column
-// sums of the bf16 values), accumulated per block in shared memory and flushed with one atomicAdd per column.
-template <bool CS>
-__global__ void __launch_bounds__(kThreads) latent_bwd64_kernel(
-    const float* __restrict__ par_e, const float* __restrict__ par_p, const float* __restrict__ eps,
-    const float* __restrict__ z, const float* __restrict__ dz_dec, const float* __restrict__ g_kl,
-    const float* __restrict__ g_match, int stop_grad, __nv_bfloat16* __restrict__ dpar_e_b,
-    __nv_bfloat16* __restrict__ dpar_p_b, float* __restrict__ db_e, float* __restrict__ db_p, float* __restrict__ dz_total,
-    int64_t B) {
+// Two kernels.  (1) solve64_bwd_kernel: the triangular algebra of the partial posterior, one warp per row:
+// r = L_p^-1 (z - mu_p), g = L_p^-T r, and dz_total = dz_dec - (stop_grad ? 0 : mw g); writes the three 64-vectors.
+// (2) heads_bwd64_kernel: everything else is elementwise in the P = 2144 head columns, so it streams: thread = column q,
+// block = kPostRows consecutive rows (coalesced reads and bf16 writes, the head bias gradients are one register per
+// thread and output):
+//     d / d par_p: loc -> mw g;  L_ij -> mw g_i r_j;  diagonal -> mw (g_i r_i - 1 / D_ii) sigmoid(raw_ii)
+//     d / d par_e: loc -> dz_i + kw mu_i;  L_ij -> dz_i eps_j + kw L_ij;  diagonal -> (dz_i eps_i + kw (D_ii - 1 / D_ii)) sigmoid(raw_ii)
+// (formulas as latent.cu::latent_bwd_kernel; D_ii = softplus(raw_ii) + 1e-5).
+__global__ void __launch_bounds__(kThreads) solve64_bwd_kernel(const float* __restrict__ par_p, const float* __restrict__ z,
+                                                               const float* __restrict__ dz_dec,
+                                                               const float* __restrict__ g_match, int stop_grad,
+                                                               float* __restrict__ out_r, float* __restrict__ out_g,
+                                                               float* __restrict__ dz_total, int64_t B) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   float* Lp = smem + (size_t)wib * kWarpFloats;
-  float* sr = Lp + kLFloats;     // r = L_p^-1 (z - mu_p)
-  float* sg = sr + D;            // g = L_p^-T r
+  float* sr = Lp + kLFloats;
+  float* sg = sr + D;
   float* sraw = sg + D;
   float* sinv = sraw + D;
-  // CS: column sums of the bf16 outputs (the two head bias gradients) in registers: lane keeps column 32 it + lane of
-  // both outputs over all rows of its warp (shared-memory atomics cost 64 cycles per warp and column: 4 ms per step)
-  constexpr int kIt = P / 32;                 // 67
-  float acc_p[CS ? kIt : 1], dacc_p[2] = {0.f, 0.f};
-  if (CS) {
-#pragma unroll
-    for (int it = 0; it < kIt; ++it) acc_p[it] = 0.f;
-  }
   for (int64_t r = (int64_t)blockIdx.x * kWarps + wib; r < B; r += (int64_t)gridDim.x * kWarps) {
     const float* pp = par_p + r * P;
     __syncwarp();
     stage_factor(pp, Lp, sraw, sinv, lane);
     __syncwarp();
-    // ---- partial posterior: r, g
     const float s0 = z[r * D + lane] - __ldg(pp + lane), s1 = z[r * D + lane + 32] - __ldg(pp + lane + 32);
     solve_lower(Lp, sinv, s0, s1, sr, lane);
     solve_upper_t(Lp, sinv, sr[lane], sr[lane + 32], sg, lane);
     const float mw = g_match[r];
-    // d match / d par_p: loc -> mw g; L_ij -> mw (g_i r_j - [i == j] / L_ii) (diagonal through softplus: second pass)
-    __nv_bfloat16* op = dpar_p_b + r * P;
-#pragma unroll
-    for (int it = 0; it < kIt; ++it) {
-      const int q = 32 * it + lane;
-      float val;
-      bool diag = false;
-      if (it < D / 32) {
-        val = mw * sg[q];
-      } else {
-        int i, j;
-        v_to_ij(q - D, i, j);
-        val = mw * sg[i] * sr[j];
-        diag = i == j;
-      }
-      if (!diag) {
-        const __nv_bfloat16 hv = __float2bfloat16(val);
-        op[q] = hv;
-        if (CS) acc_p[it] += __bfloat162float(hv);
-      }
-    }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int i = lane + 32 * h;
-      const float val = mw * (sg[i] * sr[i] - sinv[i]) * sigmoid_f(sraw[i]);
-      const __nv_bfloat16 hv = __float2bfloat16(val);
-      op[D + diag_q(i)] = hv;
-      if (CS) dacc_p[h] += __bfloat162float(hv);
-    }
-    // ---- dz_total = dz_dec - (stop_grad ? 0 : mw g): consumed by the posterior part (post_bwd64_kernel)
-    {
-      float v0 = dz_dec ? dz_dec[r * D + lane] : 0.f, v1 = dz_dec ? dz_dec[r * D + lane + 32] : 0.f;
-      if (!stop_grad) { v0 -= mw * sg[lane]; v1 -= mw * sg[lane + 32]; }
-      dz_total[r * D + lane] = v0; dz_total[r * D + lane + 32] = v1;
-    }
-  }
-  if (CS) {
-    // block reduction in the (now idle) factor tiles: warp w writes its 2 x P sums, then every column is summed over
-    // the four warps and added to the gradient arena with one atomic per column and block
-    __syncthreads();
-    float* mine = smem + (size_t)wib * kWarpFloats;
-#pragma unroll
-    for (int it = 0; it < kIt; ++it) mine[32 * it + lane] = acc_p[it];
-    __syncwarp();
-#pragma unroll
-    for (int h = 0; h < 2; ++h) mine[D + diag_q(lane + 32 * h)] += dacc_p[h];
-    __syncthreads();
-    for (int q = threadIdx.x; q < P; q += kThreads) {
-      float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) t += smem[(size_t)w * kWarpFloats + q];
-      atomicAdd(db_p + q, t);
-    }
+    float v0 = dz_dec ? dz_dec[r * D + lane] : 0.f, v1 = dz_dec ? dz_dec[r * D + lane + 32] : 0.f;
+    if (!stop_grad) { v0 -= mw * sg[lane]; v1 -= mw * sg[lane + 32]; }
+    dz_total[r * D + lane] = v0; dz_total[r * D + lane + 32] = v1;
+    out_r[r * D + lane] = sr[lane]; out_r[r * D + lane + 32] = sr[lane + 32];
+    out_g[r * D + lane] = sg[lane]; out_g[r * D + lane + 32] = sg[lane + 32];
   }
 }
 
-// ---------------------------------------------------------------- posterior part: d / d par_e (streaming)
-// d / d par_e of z = mu + L eps (cotangent dz_total) and kw KL: loc -> dz_i + kw mu_i; L_ij -> dz_i eps_j + kw L_ij;
-// diagonal (through softplus) -> (dz_i eps_i + kw (D_ii - 1 / D_ii)) sigmoid(raw).  No triangular algebra: thread =
-// column q, block = kPostRows consecutive rows, so reads and writes are coalesced and the head bias gradient (column
-// sums of the bf16 values) is one register per thread and one atomicAdd per column and block.
-constexpr int kPostThreads = 256, kPostRows = 64;
-__global__ void __launch_bounds__(kPostThreads) post_bwd64_kernel(const float* __restrict__ par_e, const float* __restrict__ eps,
-                                                                  const float* __restrict__ dz_total,
-                                                                  const float* __restrict__ g_kl,
-                                                                  __nv_bfloat16* __restrict__ dpar_e_b,
-                                                                  float* __restrict__ db_e, int64_t B) {
-  __shared__ float sdz[kPostRows][D], se[kPostRows][D], skw[kPostRows];
+constexpr int kPostThreads = 256, kPostRows = 32;
+__global__ void __launch_bounds__(kPostThreads) heads_bwd64_kernel(
+    const float* __restrict__ par_e, const float* __restrict__ par_p, const float* __restrict__ eps,
+    const float* __restrict__ dz_total, const float* __restrict__ vec_r, const float* __restrict__ vec_g,
+    const float* __restrict__ g_kl, const float* __restrict__ g_match, __nv_bfloat16* __restrict__ dpar_e_b,
+    __nv_bfloat16* __restrict__ dpar_p_b, float* __restrict__ db_e, float* __restrict__ db_p, int64_t B) {
+  __shared__ float sdz[kPostRows][D], se[kPostRows][D], sr[kPostRows][D], sg[kPostRows][D], skw[kPostRows], smw[kPostRows];
   const int64_t r0 = (int64_t)blockIdx.y * kPostRows;
   const int nr = (int)((B - r0 < kPostRows) ? (B - r0) : kPostRows);
   const int q = blockIdx.x * kPostThreads + threadIdx.x;
-  for (int t = threadIdx.x; t < nr * D; t += kPostThreads) {
-    sdz[t / D][t % D] = dz_total[r0 * D + t];
-    se[t / D][t % D] = eps[r0 * D + t];
+  for (int t = threadIdx.x; t < kPostRows * D; t += kPostThreads) {
+    const bool ok = t < nr * D;
+    sdz[t / D][t % D] = ok ? dz_total[r0 * D + t] : 0.f;
+    se[t / D][t % D] = ok ? eps[r0 * D + t] : 0.f;
+    sr[t / D][t % D] = ok ? vec_r[r0 * D + t] : 0.f;
+    sg[t / D][t % D] = ok ? vec_g[r0 * D + t] : 0.f;
   }
-  if (threadIdx.x < nr) skw[threadIdx.x] = g_kl[r0 + threadIdx.x];
+  if (threadIdx.x < kPostRows) {
+    skw[threadIdx.x] = threadIdx.x < nr ? g_kl[r0 + threadIdx.x] : 0.f;
+    smw[threadIdx.x] = threadIdx.x < nr ? g_match[r0 + threadIdx.x] : 0.f;
+  }
   __syncthreads();
   if (q >= P) return;
   int i = 0, j = 0;
   if (q >= D) v_to_ij(q - D, i, j);
   const bool is_loc = q < D, diag = !is_loc && i == j;
-  float acc = 0.f;
-#pragma unroll 8
-  for (int rr = 0; rr < nr; ++rr) {
-    const float raw = __ldg(par_e + (r0 + rr) * P + q);
-    const float kw = skw[rr];
-    float val;
-    if (is_loc) {
-      val = sdz[rr][q] + kw * raw;
-    } else if (diag) {
-      const float dg = softplus_f(raw) + 1e-5f;
-      val = (sdz[rr][i] * se[rr][i] + kw * (dg - 1.0f / dg)) * sigmoid_f(raw);
-    } else {
-      val = sdz[rr][i] * se[rr][j] + kw * raw;
+  float acc_e = 0.f, acc_p = 0.f;
+#pragma unroll 1
+  for (int rb = 0; rb < kPostRows; rb += 8) {
+    // all loads of eight rows first, then the arithmetic and the stores
+    float raw_e[8], raw_p[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const bool ok = rb + u < nr;
+      raw_e[u] = ok ? __ldg(par_e + (r0 + rb + u) * P + q) : 0.f;
+      raw_p[u] = (ok && diag) ? __ldg(par_p + (r0 + rb + u) * P + q) : 0.f;
     }
-    const __nv_bfloat16 hv = __float2bfloat16(val);
-    dpar_e_b[(r0 + rr) * P + q] = hv;
-    acc += __bfloat162float(hv);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int rr = rb + u;
+      if (rr < nr) {
+        const float kw = skw[rr], mw = smw[rr];
+        float ve, vp;
+        if (is_loc) {
+          ve = sdz[rr][q] + kw * raw_e[u];
+          vp = mw * sg[rr][q];
+        } else if (diag) {
+          const float dg = softplus_f(raw_e[u]) + 1e-5f;
+          ve = (sdz[rr][i] * se[rr][i] + kw * (dg - 1.0f / dg)) * sigmoid_f(raw_e[u]);
+          const float dgp = softplus_f(raw_p[u]) + 1e-5f;
+          vp = mw * (sg[rr][i] * sr[rr][i] - 1.0f / dgp) * sigmoid_f(raw_p[u]);
+        } else {
+          ve = sdz[rr][i] * se[rr][j] + kw * raw_e[u];
+          vp = mw * sg[rr][i] * sr[rr][j];
+        }
+        const __nv_bfloat16 he = __float2bfloat16(ve), hp = __float2bfloat16(vp);
+        dpar_e_b[(r0 + rr) * P + q] = he;
+        dpar_p_b[(r0 + rr) * P + q] = hp;
+        acc_e += __bfloat162float(he);
+        acc_p += __bfloat162float(hp);
+      }
+    }
   }
-  if (db_e) atomicAdd(db_e + q, acc);
+  if (db_e) atomicAdd(db_e + q, acc_e);
+  if (db_p) atomicAdd(db_p + q, acc_p);
 }
 
 static int grid_rows(int64_t B, int blocks_per_sm) {
@@ -321,26 +288,18 @@ int match_fwd64(const float* par_p, const float* z, float* match, int64_t B, cud
 
 int latent_bwd64(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
                  const float* g_kl, const float* g_match, int stop_grad, __nv_bfloat16* dpar_e_b, __nv_bfloat16* dpar_p_b,
-                 float* db_e, float* db_p, float* dz_total, int64_t B, cudaStream_t s) {
+                 float* db_e, float* db_p, float* scratch /* [3, B, 64] */, int64_t B, cudaStream_t s) {
   using namespace l64;
-  const bool do_cs = db_e != nullptr && db_p != nullptr;
   static bool attr = false;
-  if (!attr) {
-    PMVAE_CUDA(cudaFuncSetAttribute(latent_bwd64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    PMVAE_CUDA(cudaFuncSetAttribute(latent_bwd64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr = true;
-  }
-  // partial posterior (two triangular solves per row) -> d / d par_p, dz_total
-  if (do_cs)
-    latent_bwd64_kernel<true><<<grid_rows(B, 3), kThreads, kSmemBytes, s>>>(par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad,
-                                                                             dpar_e_b, dpar_p_b, db_e, db_p, dz_total, B);
-  else
-    latent_bwd64_kernel<false><<<grid_rows(B, 3), kThreads, kSmemBytes, s>>>(par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad,
-                                                                              dpar_e_b, dpar_p_b, db_e, db_p, dz_total, B);
+  if (!attr) { PMVAE_CUDA(cudaFuncSetAttribute(solve64_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes)); attr = true; }
+  float* dz_total = scratch;
+  float* vec_r = scratch + (uint64_t)B * D;
+  float* vec_g = scratch + 2 * (uint64_t)B * D;
+  solve64_bwd_kernel<<<grid_rows(B, 3), kThreads, kSmemBytes, s>>>(par_p, z, dz_dec, g_match, stop_grad, vec_r, vec_g, dz_total, B);
   PMVAE_LAUNCH_CHECK();
-  // posterior: streaming elementwise kernel
   const dim3 grid((P + kPostThreads - 1) / kPostThreads, (unsigned)((B + kPostRows - 1) / kPostRows));
-  post_bwd64_kernel<<<grid, kPostThreads, 0, s>>>(par_e, eps, dz_total, g_kl, dpar_e_b, do_cs ? db_e : nullptr, B);
+  heads_bwd64_kernel<<<grid, kPostThreads, 0, s>>>(par_e, par_p, eps, dz_total, vec_r, vec_g, g_kl, g_match, dpar_e_b, dpar_p_b,
+                                                   db_e, db_p, B);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }

@@ -504,7 +504,7 @@ static TrainPlanB plan_train_b(const pmvae_config* c, const Layout& L, int64_t B
   p.z = bp.take<float>((uint64_t)B * c->d);
   p.loc = bp.take<float>((uint64_t)B * p.Dp);
   p.dz = bp.take<float>((uint64_t)B * c->d);
-  p.dz2 = bp.take<float>((uint64_t)B * c->d);             // dz_total of the d = 64 latent backward (two kernels)
+  p.dz2 = bp.take<float>((uint64_t)3 * B * c->d);         // dz_total, r, g of the d = 64 latent backward (two kernels)
   p.wtmp = bp.take<float>((uint64_t)256 * p.Dp);         // padded-pitch dW of the decoder head
   p.dH = bp.take<bf16>((uint64_t)B * 256);
   p.dU = bp.take<bf16>((uint64_t)B * 256);
