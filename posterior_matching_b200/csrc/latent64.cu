@@ -214,21 +214,41 @@ __global__ void __launch_bounds__(kPostThreads) heads_bwd64_kernel(
     smw[threadIdx.x] = threadIdx.x < nr ? g_match[r0 + threadIdx.x] : 0.f;
   }
   __syncthreads();
-  if (q >= P) return;
+  // The 64 diagonal elements go through softplus / sigmoid.  They sit 65 columns apart, i.e. one in almost every warp:
+  // handled in line, every warp would pay the transcendental path (one active lane) for every row.  The spare threads
+  // past the last column (9 x 256 = 2304 > 2144) take them instead, thread = diagonal index.
+  float acc_e = 0.f, acc_p = 0.f;
+  if (q >= P) {
+    const int i = q - P;
+    if (i >= D) return;
+    const int qd = D + diag_q(i);
+#pragma unroll 4
+    for (int rr = 0; rr < nr; ++rr) {
+      const float raw_e = __ldg(par_e + (r0 + rr) * P + qd), raw_p = __ldg(par_p + (r0 + rr) * P + qd);
+      const float dg = softplus_f(raw_e) + 1e-5f;
+      const float ve = (sdz[rr][i] * se[rr][i] + skw[rr] * (dg - 1.0f / dg)) * sigmoid_f(raw_e);
+      const float dgp = softplus_f(raw_p) + 1e-5f;
+      const float vp = smw[rr] * (sg[rr][i] * sr[rr][i] - 1.0f / dgp) * sigmoid_f(raw_p);
+      const __nv_bfloat16 he = __float2bfloat16(ve), hp = __float2bfloat16(vp);
+      dpar_e_b[(r0 + rr) * P + qd] = he;
+      dpar_p_b[(r0 + rr) * P + qd] = hp;
+      acc_e += __bfloat162float(he);
+      acc_p += __bfloat162float(hp);
+    }
+    if (db_e) atomicAdd(db_e + qd, acc_e);
+    if (db_p) atomicAdd(db_p + qd, acc_p);
+    return;
+  }
   int i = 0, j = 0;
   if (q >= D) v_to_ij(q - D, i, j);
-  const bool is_loc = q < D, diag = !is_loc && i == j;
-  float acc_e = 0.f, acc_p = 0.f;
+  const bool is_loc = q < D;
+  if (!is_loc && i == j) return;                 // diagonal: the spare threads above
 #pragma unroll 1
   for (int rb = 0; rb < kPostRows; rb += 8) {
     // all loads of eight rows first, then the arithmetic and the stores
-    float raw_e[8], raw_p[8];
+    float raw_e[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const bool ok = rb + u < nr;
-      raw_e[u] = ok ? __ldg(par_e + (r0 + rb + u) * P + q) : 0.f;
-      raw_p[u] = (ok && diag) ? __ldg(par_p + (r0 + rb + u) * P + q) : 0.f;
-    }
+    for (int u = 0; u < 8; ++u) raw_e[u] = (rb + u < nr) ? __ldg(par_e + (r0 + rb + u) * P + q) : 0.f;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int rr = rb + u;
@@ -238,11 +258,6 @@ __global__ void __launch_bounds__(kPostThreads) heads_bwd64_kernel(
         if (is_loc) {
           ve = sdz[rr][q] + kw * raw_e[u];
           vp = mw * sg[rr][q];
-        } else if (diag) {
-          const float dg = softplus_f(raw_e[u]) + 1e-5f;
-          ve = (sdz[rr][i] * se[rr][i] + kw * (dg - 1.0f / dg)) * sigmoid_f(raw_e[u]);
-          const float dgp = softplus_f(raw_p[u]) + 1e-5f;
-          vp = mw * (sg[rr][i] * sr[rr][i] - 1.0f / dgp) * sigmoid_f(raw_p[u]);
         } else {
           ve = sdz[rr][i] * se[rr][j] + kw * raw_e[u];
           vp = mw * sg[rr][i] * sr[rr][j];
