@@ -813,6 +813,9 @@ struct BwdArgs {
   int debug;                  // PMVAE_FUSED_DEBUG bits (profiling only): 16 no column sums, 32 no dY stores
 };
 
+// (A version with R as a run-time argument and rolled per-Linear loops -- 27 KB of SASS instead of 82 KB -- measured 2 %
+// slower on the power step, 1.281 vs 1.258 ms: the instruction caches are not what paces this kernel, unlike
+// net_bwd_ln_kernel below.)
 template <int R, bool DIN>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 net_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant__ CUtensorMap map_wh,
@@ -1143,7 +1146,7 @@ constexpr int kLnThreads = kThreads + kLnHelpers * 32;      // 384: leaves 168 r
 static_assert(kLnSmemBytes <= 232448, "shared-memory plan exceeds 227 KB");
 
 struct BwdLnArgs {
-  int64_t B; int num_tiles;
+  int64_t B; int num_tiles; int R;
   int k16_h;                  // K = 16 steps of the head contraction (ceil(head_N / 16))
   int din_N, din_cols;        // dIn: MMA N (multiple of 16, 0 = none) and valid columns
   float* dIn;                 // [B, din_cols] fp32
@@ -1154,7 +1157,10 @@ struct BwdLnArgs {
 
 __device__ long long g_ln_trace[1024];      // PMVAE_FUSED_DEBUG bit 8192: clock64 stamps of block 0 (profiling only)
 
-template <int R, bool DIN>
+// R (residual blocks) is a run-time argument and every per-Linear loop is a real loop (one copy of the epilogue and of
+// the helper code): with the chain unrolled over its 2R + 1 Linears the kernel was 400 KB of SASS, far beyond the
+// instruction caches, and half of all warp stalls were instruction fetches (profiles/r02_net_bwd_ln_ncu.md).
+template <bool DIN>
 __global__ void __launch_bounds__(kLnThreads, 1)
 net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant__ CUtensorMap map_wh,
                   const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w0,
@@ -1178,7 +1184,8 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + kLnOffBar + 8 * 37);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-  constexpr int n_hidden = 2 * R + 1;
+  const int R = p.R;
+  const int n_hidden = 2 * R + 1;
   const int nkb_h = (p.k16_h + 3) >> 2;
 
   if (warp == 0 && lane == 0) {
@@ -1246,6 +1253,7 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
         __syncwarp();
         load_w(&map_wh, kb * 64, 0, kWStageBytes);
       }
+#pragma unroll 1
       for (int l = 2 * R; l >= 1; --l) {
         for (int kb = 0; kb < 4; ++kb) load_w(&map_w, kb * 64, (l - 1) * 256, kWStageBytes);
         load_x(l - 1, tile);
@@ -1290,6 +1298,7 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
         mbar_wait(hd_full(slot), (hd_cnt >> 2) & 1u, 8);
         kblock(abuf + slot * kChunkBytes, min(4, p.k16_h - 4 * kb), instr_desc(128, 256, 0, 0), kb == 0, hd_empty(slot), kb == nkb_h - 1);
       }
+#pragma unroll 1
       for (int st = 0; st < 2 * R; ++st) {
         acquire_acc();
         for (int kb = 0; kb < 4; ++kb) {
@@ -1324,7 +1333,6 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
     auto epi = [&](int l, bool first, int64_t g, bool has_consumer) {
       const bool even = (l & 1) == 0;
       const uint4 mq = *reinterpret_cast<const uint4*>(p.masks + (((int64_t)l * p.Bpad + g) * 8 + half * 4));
-      const uint32_t mw[4] = {mq.x, mq.y, mq.z, mq.w};
       const float rstd = p.rstd[(int64_t)l * p.Bpad + g];
       const uint32_t cf_par = (e_cnt & 1u) ^ 1u;      // chunk_free: the previous gradient tile in this chunk has been stored
       const uint32_t x_par = e_cnt & 1u;
@@ -1337,7 +1345,7 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
       if (tr) g_ln_trace[8 * e_cnt + 1] = clock64();
       float S1 = 0.f, S2 = 0.f;
       // ---- pass 1: masked values, row sums; s -> TMEM (even) or bf16 stash in the operand buffer (odd)
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < 4; ++j) {
         uint32_t r[32], so[32];
         tmem_ld32(t_acc + 64 * j, r);
@@ -1354,7 +1362,7 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
         }
         tmem_ld_wait();
         if (tr && e_cnt == 6) g_ln_trace[512 + 8 * j + 2] = clock64();
-        const uint32_t m = mw[j];
+        const uint32_t m = j == 0 ? mq.x : (j == 1 ? mq.y : (j == 2 ? mq.z : mq.w));
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float a0 = ((int32_t)(m << (2 * i)) < 0) ? __uint_as_float(r[2 * i]) : 0.f;
@@ -1393,7 +1401,7 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
       if (tr) g_ln_trace[8 * e_cnt + 3] = clock64();
       const float c1 = (S1 + other[0]) * (1.0f / 256.0f), c2 = (S2 + other[1]) * (1.0f / 256.0f);
       // ---- pass 2: g = rstd (v - c1 - x c2)
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < 4; ++j) {
         uint32_t r[32];
         uint32_t vq[16];
@@ -1446,12 +1454,8 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
 
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int64_t g = (int64_t)tile * 128 + row;
-      epi(2 * R, true, g, true);
-#pragma unroll
-      for (int r = R - 1; r >= 0; --r) {
-        epi(2 * r + 1, false, g, true);
-        epi(2 * r, false, g, DIN || r > 0);
-      }
+#pragma unroll 1
+      for (int l = 2 * R; l >= 0; --l) epi(l, l == 2 * R, g, DIN || l > 0);
       if (DIN) {
         mbar_wait(acc_full, full_par, 6);
         full_par ^= 1u;
@@ -1473,55 +1477,43 @@ net_bwd_ln_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_const
     }
   } else {
     // ===================== helpers (2 warps): warp h owns chunks 2h, 2h + 1 of every gradient tile =====================
+    // one TMA store of the chunk as dY_l, and the bias gradient (column sums of the bf16 values the weight-gradient
+    // GEMM will read), two columns per lane, added to the gradient arena per tile (one atomicAdd per column)
     const int h = warp - (2 + kEpiWarps);
-    float cs[n_hidden][2][2];
-#pragma unroll
-    for (int l = 0; l < n_hidden; ++l) { cs[l][0][0] = cs[l][0][1] = cs[l][1][0] = cs[l][1][1] = 0.f; }
     uint32_t wr_cnt = 0;
-    auto help = [&](int l, int tile, float (&c2)[2][2]) {
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int j = 2 * h + u;
-        const uint32_t src = abuf + j * kChunkBytes;
-        mbar_wait(written(j), wr_cnt & 1u, 11);
-        if (lane == 0) {
-          if (!(p.debug & 2048)) tma_store_2d(&map_dy, src, 64 * j, (int)((int64_t)l * p.Bpad + (int64_t)tile * 128));
-          tma_store_commit();
-        }
-        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < ((p.debug & 1024) ? 0 : 128); r += 2) {
-          const uint32_t w0 = ld_shared_u32(src + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
-          const uint32_t w1 = ld_shared_u32(src + (r + 1) * 128 + ((((lane >> 2) ^ ((r + 1) & 7)) << 4) | ((lane & 3) << 2)));
-          a0 += bf16_lo(w0); a1 += bf16_hi(w0);
-          b0 += bf16_lo(w1); b1 += bf16_hi(w1);
-        }
-        c2[u][0] += a0 + b0; c2[u][1] += a1 + b1;
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(chunk_free(j));
-      }
-      ++wr_cnt;
-    };
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      help(2 * R, tile, cs[2 * R]);
-#pragma unroll
-      for (int r = R - 1; r >= 0; --r) {
-        help(2 * r + 1, tile, cs[2 * r + 1]);
-        help(2 * r, tile, cs[2 * r]);
+#pragma unroll 1
+      for (int l = 2 * R; l >= 0; --l) {
+#pragma unroll 1
+        for (int u = 0; u < 2; ++u) {
+          const int j = 2 * h + u;
+          const uint32_t src = abuf + j * kChunkBytes;
+          mbar_wait(written(j), wr_cnt & 1u, 11);
+          if (lane == 0) {
+            if (!(p.debug & 2048)) tma_store_2d(&map_dy, src, 64 * j, (int)((int64_t)l * p.Bpad + (int64_t)tile * 128));
+            tma_store_commit();
+          }
+          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll 8
+          for (int r = 0; r < ((p.debug & 1024) ? 0 : 128); r += 2) {
+            const uint32_t w0 = ld_shared_u32(src + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+            const uint32_t w1 = ld_shared_u32(src + (r + 1) * 128 + ((((lane >> 2) ^ ((r + 1) & 7)) << 4) | ((lane & 3) << 2)));
+            a0 += bf16_lo(w0); a1 += bf16_hi(w0);
+            b0 += bf16_lo(w1); b1 += bf16_hi(w1);
+          }
+          if (p.db[l]) {
+            atomicAdd(p.db[l] + 64 * j + 2 * lane, a0 + b0);
+            atomicAdd(p.db[l] + 64 * j + 2 * lane + 1, a1 + b1);
+          }
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(chunk_free(j));
+        }
+        ++wr_cnt;
       }
       if (lane == 0) { mbar_arrive(bufa_free); mbar_arrive(bufa_free); }   // both chunks of the tile's last gradient tile stored
     }
     if (lane == 0) tma_store_wait_all();
-#pragma unroll
-    for (int l = 0; l < n_hidden; ++l)
-      if (p.db[l]) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          atomicAdd(p.db[l] + 64 * (2 * h + u) + 2 * lane, cs[l][u][0]);
-          atomicAdd(p.db[l] + 64 * (2 * h + u) + 2 * lane + 1, cs[l][u][1]);
-        }
-      }
   }
 
   tc_fence_before();
@@ -1818,16 +1810,16 @@ int net_backward(const Net& n, const Leaf& head, const NetImages& im, const bf16
   return 1;
 }
 
-template <int R, bool DIN>
+template <bool DIN>
 static int launch_bwd_ln(const CUtensorMap& mdh, const CUtensorMap& mwh, const CUtensorMap& mw, const CUtensorMap& mw0,
                          const CUtensorMap& mdy, const CUtensorMap& mx, const BwdLnArgs& a, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    PMVAE_CUDA(cudaFuncSetAttribute(net_bwd_ln_kernel<R, DIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnSmemBytes));
+    PMVAE_CUDA(cudaFuncSetAttribute(net_bwd_ln_kernel<DIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnSmemBytes));
     attr_set = true;
   }
   const int grid = grid_cap(a.num_tiles < num_sms() ? a.num_tiles : num_sms());
-  net_bwd_ln_kernel<R, DIN><<<grid, kLnThreads, kLnSmemBytes, s>>>(mdh, mwh, mw, mw0, mdy, mx, a);
+  net_bwd_ln_kernel<DIN><<<grid, kLnThreads, kLnSmemBytes, s>>>(mdh, mwh, mw, mw0, mdy, mx, a);
   PMVAE_LAUNCH_CHECK();
   if (a.debug & 8192) {
     static int printed = 0;
@@ -1851,7 +1843,7 @@ static int launch_bwd_ln(const CUtensorMap& mdh, const CUtensorMap& mwh, const C
   return 0;
 }
 
-bool backward_ln_supported(const Net& n, int H, int in_kind) { return ln_train_supported(n, H, in_kind) && n.R <= 5; }
+bool backward_ln_supported(const Net& n, int H, int in_kind) { return ln_train_supported(n, H, in_kind); }
 
 int net_backward_ln(const Net& n, const Leaf& head, const NetImages& im, const bf16* dHead, int64_t ld_dhead, int64_t B,
                     const uint32_t* masks, const bf16* xhat, const float* rstd, int64_t Bpad, bf16* dY, float* grads,
@@ -1876,18 +1868,8 @@ int net_backward_ln(const Net& n, const Leaf& head, const NetImages& im, const b
   PMVAE_TRY(make_map_2d(&mx, xhat, 2, (uint64_t)(2 * n.R + 1) * Bpad, 256, 256, 64, 128));
   if (dIn) PMVAE_TRY(make_map_2d(&mw0, im.w0_n, 2, (uint64_t)im.din_N, 256, 256, 64, (uint32_t)im.din_N));
   else mw0 = mw;
-#define PMVAE_BWD_LN_CASE(RR)                                                                                    \
-  case RR: return dIn ? launch_bwd_ln<RR, true>(mdh, mwh, mw, mw0, mdy, mx, a, s) : launch_bwd_ln<RR, false>(mdh, mwh, mw, mw0, mdy, mx, a, s)
-  switch (n.R) {
-    PMVAE_BWD_LN_CASE(1);
-    PMVAE_BWD_LN_CASE(2);
-    PMVAE_BWD_LN_CASE(3);
-    PMVAE_BWD_LN_CASE(4);
-    PMVAE_BWD_LN_CASE(5);
-  }
-#undef PMVAE_BWD_LN_CASE
-  PMVAE_CHECK(false, "unsupported number of residual blocks");
-  return 1;
+  a.R = n.R;
+  return dIn ? launch_bwd_ln<true>(mdh, mwh, mw, mw0, mdy, mx, a, s) : launch_bwd_ln<false>(mdh, mwh, mw, mw0, mdy, mx, a, s);
 }
 
 }  // namespace fused
