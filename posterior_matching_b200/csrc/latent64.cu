@@ -39,23 +39,26 @@ __device__ __forceinline__ void v_to_ij(int q, int& i, int& j) {
 // index into v of the diagonal element (i, i)
 __device__ __forceinline__ int diag_q(int i) { return i < 32 ? D + 65 * i : 4095 - 65 * i; }
 
-// Stages L (diagonal = softplus(raw) + 1e-5) into Lp[64][65]; sraw[i] = raw diagonal, sinv[i] = 1 / L_ii.
-// Returns this lane's share of sum_i log L_ii.  The 65 loads of a lane are issued in batches of 13 before anything is
-// stored (stores to shared memory would otherwise pin every load behind the previous iteration: one HBM round trip
-// per element), and the transcendental work of the 64 diagonal elements is done once, two per lane, after the copy.
-__device__ __forceinline__ float stage_factor(const float* __restrict__ pr, float* Lp, float* sraw, float* sinv, int lane) {
+// The factor of a row is 65 floats per lane.  `load_row` issues all of them (one HBM round trip instead of one per
+// element or per batch: stores to shared memory in between would pin every load behind the previous one), and the
+// kernels call it for the NEXT row before they start the triangular algebra of the current one, so that the latency
+// is hidden behind ~4 K cycles of dependent solve steps.
+constexpr int kRowVals = M / 32;       // 65
+__device__ __forceinline__ void load_row(const float* __restrict__ pr, float (&buf)[kRowVals], int lane) {
   const float* v = pr + D;
-#pragma unroll 1
-  for (int it0 = 0; it0 < M / 32; it0 += 13) {
-    float buf[13];
 #pragma unroll
-    for (int u = 0; u < 13; ++u) buf[u] = __ldg(v + lane + 32 * (it0 + u));
+  for (int u = 0; u < kRowVals; ++u) buf[u] = __ldg(v + lane + 32 * u);
+}
+
+// Stages L (diagonal = softplus(raw) + 1e-5) from the registers filled by load_row into Lp[64][65]; sraw[i] = raw
+// diagonal, sinv[i] = 1 / L_ii.  Returns this lane's share of sum_i log L_ii.  The transcendental work of the 64
+// diagonal elements is done once, two per lane, after the copy.
+__device__ __forceinline__ float stage_factor(const float (&buf)[kRowVals], float* Lp, float* sraw, float* sinv, int lane) {
 #pragma unroll
-    for (int u = 0; u < 13; ++u) {
-      int i, j;
-      v_to_ij(lane + 32 * (it0 + u), i, j);
-      Lp[i * kPitch + j] = buf[u];
-    }
+  for (int u = 0; u < kRowVals; ++u) {
+    int i, j;
+    v_to_ij(lane + 32 * u, i, j);
+    Lp[i * kPitch + j] = buf[u];
   }
   __syncwarp();
   float logd = 0.f;
@@ -110,11 +113,16 @@ __global__ void __launch_bounds__(kThreads) latent_fwd64_kernel(const float* __r
   float* se = Lp + kLFloats;
   float* sraw = se + D;
   float* sinv = sraw + D;
-  for (int64_t r = (int64_t)blockIdx.x * kWarps + wib; r < B; r += (int64_t)gridDim.x * kWarps) {
+  const int64_t stride = (int64_t)gridDim.x * kWarps;
+  float buf[kRowVals];
+  int64_t r = (int64_t)blockIdx.x * kWarps + wib;
+  if (r < B) load_row(par + r * P, buf, lane);
+  for (; r < B; r += stride) {
     const float* pr = par + r * P;
     __syncwarp();
     se[lane] = eps[r * D + lane]; se[lane + 32] = eps[r * D + lane + 32];
-    float logd = stage_factor(pr, Lp, sraw, sinv, lane);
+    float logd = stage_factor(buf, Lp, sraw, sinv, lane);
+    if (r + stride < B) load_row(par + (r + stride) * P, buf, lane);
     __syncwarp();
     const float mu0 = __ldg(pr + lane), mu1 = __ldg(pr + lane + 32);
     float a0 = mu0, a1 = mu1, fro = 0.f;
@@ -142,10 +150,15 @@ __global__ void __launch_bounds__(kThreads) match_fwd64_kernel(const float* __re
   float* sr = Lp + kLFloats;
   float* sraw = sr + D;
   float* sinv = sraw + D;
-  for (int64_t r = (int64_t)blockIdx.x * kWarps + wib; r < B; r += (int64_t)gridDim.x * kWarps) {
+  const int64_t stride = (int64_t)gridDim.x * kWarps;
+  float buf[kRowVals];
+  int64_t r = (int64_t)blockIdx.x * kWarps + wib;
+  if (r < B) load_row(par_p + r * P, buf, lane);
+  for (; r < B; r += stride) {
     const float* pr = par_p + r * P;
     __syncwarp();
-    float logd = stage_factor(pr, Lp, sraw, sinv, lane);
+    float logd = stage_factor(buf, Lp, sraw, sinv, lane);
+    if (r + stride < B) load_row(par_p + (r + stride) * P, buf, lane);
     __syncwarp();
     const float s0 = z[r * D + lane] - __ldg(pr + lane), s1 = z[r * D + lane + 32] - __ldg(pr + lane + 32);
     const float sumsq = solve_lower(Lp, sinv, s0, s1, sr, lane);
@@ -175,10 +188,15 @@ __global__ void __launch_bounds__(kThreads) solve64_bwd_kernel(const float* __re
   float* sg = sr + D;
   float* sraw = sg + D;
   float* sinv = sraw + D;
-  for (int64_t r = (int64_t)blockIdx.x * kWarps + wib; r < B; r += (int64_t)gridDim.x * kWarps) {
+  const int64_t stride = (int64_t)gridDim.x * kWarps;
+  float buf[kRowVals];
+  int64_t r = (int64_t)blockIdx.x * kWarps + wib;
+  if (r < B) load_row(par_p + r * P, buf, lane);
+  for (; r < B; r += stride) {
     const float* pp = par_p + r * P;
     __syncwarp();
-    stage_factor(pp, Lp, sraw, sinv, lane);
+    stage_factor(buf, Lp, sraw, sinv, lane);
+    if (r + stride < B) load_row(par_p + (r + stride) * P, buf, lane);
     __syncwarp();
     const float s0 = z[r * D + lane] - __ldg(pp + lane), s1 = z[r * D + lane + 32] - __ldg(pp + lane + 32);
     solve_lower(Lp, sinv, s0, s1, sr, lane);
@@ -192,43 +210,51 @@ __global__ void __launch_bounds__(kThreads) solve64_bwd_kernel(const float* __re
   }
 }
 
-constexpr int kPostThreads = 256, kPostRows = 32;
-__global__ void __launch_bounds__(kPostThreads) heads_bwd64_kernel(
+// Thread = a PAIR of adjacent head columns (P and D are even, so a pair never straddles loc | tril), four rows per
+// inner step.  The per-row vectors are staged TRANSPOSED ([element][row], pitch 36 floats) so that the four rows of a
+// step are one LDS.128 per operand; together with the 8-byte loads and 4-byte bf16x2 stores that is 22 memory
+// instructions per (4 rows x 2 columns) where the one-column / one-row form issued 72 - the kernel was bound by the
+// load/store issue rate, not by HBM.
+constexpr int kPostThreads = 256, kPostRows = 32, kPostPitch = kPostRows + 4, kPairs = P / 2;
+constexpr int kPostBlocksX = (kPairs + D + kPostThreads - 1) / kPostThreads;
+__global__ void __launch_bounds__(kPostThreads, 3) heads_bwd64_kernel(
     const float* __restrict__ par_e, const float* __restrict__ par_p, const float* __restrict__ eps,
     const float* __restrict__ dz_total, const float* __restrict__ vec_r, const float* __restrict__ vec_g,
     const float* __restrict__ g_kl, const float* __restrict__ g_match, __nv_bfloat16* __restrict__ dpar_e_b,
     __nv_bfloat16* __restrict__ dpar_p_b, float* __restrict__ db_e, float* __restrict__ db_p, int64_t B) {
-  __shared__ float sdz[kPostRows][D], se[kPostRows][D], sr[kPostRows][D], sg[kPostRows][D], skw[kPostRows], smw[kPostRows];
+  __shared__ __align__(16) float sdz[D][kPostPitch], se[D][kPostPitch], sr[D][kPostPitch], sg[D][kPostPitch];
+  __shared__ __align__(16) float skw[kPostRows], smw[kPostRows];
   const int64_t r0 = (int64_t)blockIdx.y * kPostRows;
   const int nr = (int)((B - r0 < kPostRows) ? (B - r0) : kPostRows);
-  const int q = blockIdx.x * kPostThreads + threadIdx.x;
-  for (int t = threadIdx.x; t < kPostRows * D; t += kPostThreads) {
-    const bool ok = t < nr * D;
-    sdz[t / D][t % D] = ok ? dz_total[r0 * D + t] : 0.f;
-    se[t / D][t % D] = ok ? eps[r0 * D + t] : 0.f;
-    sr[t / D][t % D] = ok ? vec_r[r0 * D + t] : 0.f;
-    sg[t / D][t % D] = ok ? vec_g[r0 * D + t] : 0.f;
+  const int t = blockIdx.x * kPostThreads + threadIdx.x;
+  for (int e = threadIdx.x; e < kPostRows * D; e += kPostThreads) {
+    const bool ok = e < nr * D;
+    const int row = e / D, el = e % D;
+    sdz[el][row] = ok ? dz_total[r0 * D + e] : 0.f;
+    se[el][row] = ok ? eps[r0 * D + e] : 0.f;
+    sr[el][row] = ok ? vec_r[r0 * D + e] : 0.f;
+    sg[el][row] = ok ? vec_g[r0 * D + e] : 0.f;
   }
   if (threadIdx.x < kPostRows) {
     skw[threadIdx.x] = threadIdx.x < nr ? g_kl[r0 + threadIdx.x] : 0.f;
     smw[threadIdx.x] = threadIdx.x < nr ? g_match[r0 + threadIdx.x] : 0.f;
   }
   __syncthreads();
-  // The 64 diagonal elements go through softplus / sigmoid.  They sit 65 columns apart, i.e. one in almost every warp:
-  // handled in line, every warp would pay the transcendental path (one active lane) for every row.  The spare threads
-  // past the last column (9 x 256 = 2304 > 2144) take them instead, thread = diagonal index.
-  float acc_e = 0.f, acc_p = 0.f;
-  if (q >= P) {
-    const int i = q - P;
+  // The 64 diagonal elements go through softplus / sigmoid.  They sit 65 columns apart, i.e. one in every other warp:
+  // handled in line, those warps would pay the transcendental path (one active lane) for every row.  The spare threads
+  // past the last pair take them instead, thread = diagonal index.
+  if (t >= kPairs) {
+    const int i = t - kPairs;
     if (i >= D) return;
     const int qd = D + diag_q(i);
+    float acc_e = 0.f, acc_p = 0.f;
 #pragma unroll 4
     for (int rr = 0; rr < nr; ++rr) {
       const float raw_e = __ldg(par_e + (r0 + rr) * P + qd), raw_p = __ldg(par_p + (r0 + rr) * P + qd);
       const float dg = softplus_f(raw_e) + 1e-5f;
-      const float ve = (sdz[rr][i] * se[rr][i] + skw[rr] * (dg - 1.0f / dg)) * sigmoid_f(raw_e);
+      const float ve = (sdz[i][rr] * se[i][rr] + skw[rr] * (dg - 1.0f / dg)) * sigmoid_f(raw_e);
       const float dgp = softplus_f(raw_p) + 1e-5f;
-      const float vp = smw[rr] * (sg[rr][i] * sr[rr][i] - 1.0f / dgp) * sigmoid_f(raw_p);
+      const float vp = smw[rr] * (sg[i][rr] * sr[i][rr] - 1.0f / dgp) * sigmoid_f(raw_p);
       const __nv_bfloat16 he = __float2bfloat16(ve), hp = __float2bfloat16(vp);
       dpar_e_b[(r0 + rr) * P + qd] = he;
       dpar_p_b[(r0 + rr) * P + qd] = hp;
@@ -239,39 +265,48 @@ __global__ void __launch_bounds__(kPostThreads) heads_bwd64_kernel(
     if (db_p) atomicAdd(db_p + qd, acc_p);
     return;
   }
-  int i = 0, j = 0;
-  if (q >= D) v_to_ij(q - D, i, j);
-  const bool is_loc = q < D;
-  if (!is_loc && i == j) return;                 // diagonal: the spare threads above
-#pragma unroll 1
-  for (int rb = 0; rb < kPostRows; rb += 8) {
-    // all loads of eight rows first, then the arithmetic and the stores
-    float raw_e[8];
+  const int q0 = 2 * t;
+  const bool is_loc = q0 < D;
+  int i0 = q0, j0 = 0, i1 = q0 + 1, j1 = 0;
+  if (!is_loc) { v_to_ij(q0 - D, i0, j0); v_to_ij(q0 + 1 - D, i1, j1); }
+  const bool d0 = !is_loc && i0 == j0, d1 = !is_loc && i1 == j1;     // a diagonal slot: left to the spare threads
+  float ae0 = 0.f, ae1 = 0.f, ap0 = 0.f, ap1 = 0.f;
+  auto el = [](const float4& v, int u) { return u == 0 ? v.x : u == 1 ? v.y : u == 2 ? v.z : v.w; };
+#pragma unroll 2
+  for (int rb = 0; rb < kPostRows; rb += 4) {
+    float2 raw[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) raw_e[u] = (rb + u < nr) ? __ldg(par_e + (r0 + rb + u) * P + q) : 0.f;
+    for (int u = 0; u < 4; ++u)
+      raw[u] = (rb + u < nr) ? __ldg(reinterpret_cast<const float2*>(par_e + (r0 + rb + u) * P + q0)) : make_float2(0.f, 0.f);
+    const float4 kw = *reinterpret_cast<const float4*>(&skw[rb]), mw = *reinterpret_cast<const float4*>(&smw[rb]);
+    const float4 dzA = *reinterpret_cast<const float4*>(&sdz[i0][rb]), dzB = *reinterpret_cast<const float4*>(&sdz[i1][rb]);
+    const float4 gA = *reinterpret_cast<const float4*>(&sg[i0][rb]), gB = *reinterpret_cast<const float4*>(&sg[i1][rb]);
+    float4 eA = *reinterpret_cast<const float4*>(&se[j0][rb]), eB = *reinterpret_cast<const float4*>(&se[j1][rb]);
+    float4 rA = *reinterpret_cast<const float4*>(&sr[j0][rb]), rB = *reinterpret_cast<const float4*>(&sr[j1][rb]);
+    if (is_loc) { eA = eB = rA = rB = make_float4(1.f, 1.f, 1.f, 1.f); }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int rr = rb + u;
-      if (rr < nr) {
-        const float kw = skw[rr], mw = smw[rr];
-        float ve, vp;
-        if (is_loc) {
-          ve = sdz[rr][q] + kw * raw_e[u];
-          vp = mw * sg[rr][q];
-        } else {
-          ve = sdz[rr][i] * se[rr][j] + kw * raw_e[u];
-          vp = mw * sg[rr][i] * sr[rr][j];
+    for (int u = 0; u < 4; ++u) {
+      if (rb + u < nr) {
+        const float k = el(kw, u), m = el(mw, u);
+        const float ve0 = el(dzA, u) * el(eA, u) + k * raw[u].x, ve1 = el(dzB, u) * el(eB, u) + k * raw[u].y;
+        const float vp0 = m * el(gA, u) * el(rA, u), vp1 = m * el(gB, u) * el(rB, u);
+        const __nv_bfloat162 he = __floats2bfloat162_rn(ve0, ve1), hp = __floats2bfloat162_rn(vp0, vp1);
+        __nv_bfloat16* oe = dpar_e_b + (r0 + rb + u) * P + q0;
+        __nv_bfloat16* op = dpar_p_b + (r0 + rb + u) * P + q0;
+        if (!(d0 | d1)) {
+          *reinterpret_cast<__nv_bfloat162*>(oe) = he;
+          *reinterpret_cast<__nv_bfloat162*>(op) = hp;
+        } else {                       // (both can be diagonal: a forward run of v ends where a reversed one starts)
+          if (!d0) { oe[0] = he.x; op[0] = hp.x; }
+          if (!d1) { oe[1] = he.y; op[1] = hp.y; }
         }
-        const __nv_bfloat16 he = __float2bfloat16(ve), hp = __float2bfloat16(vp);
-        dpar_e_b[(r0 + rr) * P + q] = he;
-        dpar_p_b[(r0 + rr) * P + q] = hp;
-        acc_e += __bfloat162float(he);
-        acc_p += __bfloat162float(hp);
+        ae0 += __low2float(he); ae1 += __high2float(he);
+        ap0 += __low2float(hp); ap1 += __high2float(hp);
       }
     }
   }
-  if (db_e) atomicAdd(db_e + q, acc_e);
-  if (db_p) atomicAdd(db_p + q, acc_p);
+  if (db_e) { if (!d0) atomicAdd(db_e + q0, ae0); if (!d1) atomicAdd(db_e + q0 + 1, ae1); }
+  if (db_p) { if (!d0) atomicAdd(db_p + q0, ap0); if (!d1) atomicAdd(db_p + q0 + 1, ap1); }
 }
 
 static int grid_rows(int64_t B, int blocks_per_sm) {
@@ -312,7 +347,7 @@ int latent_bwd64(const float* par_e, const float* par_p, const float* eps, const
   float* vec_g = scratch + 2 * (uint64_t)B * D;
   solve64_bwd_kernel<<<grid_rows(B, 3), kThreads, kSmemBytes, s>>>(par_p, z, dz_dec, g_match, stop_grad, vec_r, vec_g, dz_total, B);
   PMVAE_LAUNCH_CHECK();
-  const dim3 grid((P + kPostThreads - 1) / kPostThreads, (unsigned)((B + kPostRows - 1) / kPostRows));
+  const dim3 grid(kPostBlocksX, (unsigned)((B + kPostRows - 1) / kPostRows));
   heads_bwd64_kernel<<<grid, kPostThreads, 0, s>>>(par_e, par_p, eps, dz_total, vec_r, vec_g, g_kl, g_match, dpar_e_b, dpar_p_b,
                                                    db_e, db_p, B);
   PMVAE_LAUNCH_CHECK();
