@@ -4,11 +4,15 @@
 // fill_triangular map puts every row of L into ONE contiguous run of v:
 //     rows i <= 31 :  L[i][j] = v[64 + 64 i + j]          (forward run)
 //     rows i >= 32 :  L[i][j] = v[4095 - 64 i - j]        (reversed run; v[0..63] is row 63)
-// so the factor is staged straight from global memory (coalesced, consecutive lanes = consecutive elements) into a
-// dense [64][65] tile in shared memory.  The odd pitch makes both access patterns of the triangular algebra
-// bank-conflict free: fixed row / varying column (dot products, back substitution) and fixed column / varying row
-// (forward substitution) -- the general-d kernels of latent.cu address the packed vector with a stride of 64 floats
-// between lanes (32-way conflicts) and pay the index map per element, which made them 47 % of the bsds train step.
+// i.e. v, read as a matrix X of 32.5 rows of 64, holds row a - 1 of L in the left part of its row a and row 63 - a,
+// reversed, in the right part.  The kernels keep exactly that packed image in shared memory (33 rows, pitch 65 floats,
+// 8.6 KB per warp: 16 warps per SM where a dense [64][65] tile allowed 12), so staging is a straight coalesced copy with
+// compile-time offsets, and
+//     L[i][j] = X[i + 1][j]            (i <= 31)          L[i][j] = X[63 - i][63 - j]      (i >= 32).
+// The odd pitch makes both access patterns of the triangular algebra bank-conflict free: fixed row / varying column
+// (dot products, back substitution; contiguous, ascending or descending) and fixed column / varying row (forward
+// substitution; 65 floats apart) -- the general-d kernels of latent.cu address the packed vector with a stride of 64
+// floats between lanes (32-way conflicts) and pay the index map per element, which made them 47 % of the bsds step.
 //
 // Reference sites as in latent.cu: distributions.py:101-113 (TriLGaussian / FillScaleTriL), vae.py:124,130,136-138.
 #include "kernels.h"
@@ -20,10 +24,14 @@ constexpr int D = 64, M = D * (D + 1) / 2, P = D + M;      // 2080, 2144
 constexpr int kPitch = D + 1;
 constexpr int kWarps = 4;                                  // per block
 constexpr int kThreads = kWarps * 32;
-constexpr int kLFloats = D * kPitch;                       // dense factor
+constexpr int kLFloats = 33 * kPitch;                      // packed factor (see above)
 constexpr int kVecs = 4;                                   // per-warp vectors of D floats
 constexpr int kWarpFloats = kLFloats + kVecs * D;
 constexpr size_t kSmemBytes = (size_t)kWarps * kWarpFloats * sizeof(float);
+constexpr int kBlocksPerSm = 5;                            // 38.4 KB and <= 96 registers x 128 threads per block
+
+// offset of L[i][j] (j <= i) in the packed image
+__device__ __forceinline__ int xoff(int i, int j) { return i < 32 ? (i + 1) * kPitch + j : (63 - i) * kPitch + 63 - j; }
 
 // position q of v (0 .. 2079) -> (i, j), j <= i
 __device__ __forceinline__ void v_to_ij(int q, int& i, int& j) {
@@ -50,33 +58,31 @@ __device__ __forceinline__ void load_row(const float* __restrict__ pr, float (&b
   for (int u = 0; u < kRowVals; ++u) buf[u] = __ldg(v + lane + 32 * u);
 }
 
-// Stages L (diagonal = softplus(raw) + 1e-5) from the registers filled by load_row into Lp[64][65]; sraw[i] = raw
-// diagonal, sinv[i] = 1 / L_ii.  Returns this lane's share of sum_i log L_ii.  The transcendental work of the 64
+// Stages L (diagonal = softplus(raw) + 1e-5) from the registers filled by load_row into the packed image Xs; sraw[i] =
+// raw diagonal, sinv[i] = 1 / L_ii.  Returns this lane's share of sum_i log L_ii.  The transcendental work of the 64
 // diagonal elements is done once, two per lane, after the copy.
-__device__ __forceinline__ float stage_factor(const float (&buf)[kRowVals], float* Lp, float* sraw, float* sinv, int lane) {
+__device__ __forceinline__ float stage_factor(const float (&buf)[kRowVals], float* Xs, float* sraw, float* sinv, int lane) {
 #pragma unroll
-  for (int u = 0; u < kRowVals; ++u) {
-    int i, j;
-    v_to_ij(lane + 32 * u, i, j);
-    Lp[i * kPitch + j] = buf[u];
-  }
+  for (int u = 0; u < kRowVals; ++u) Xs[(u >> 1) * kPitch + 32 * (u & 1) + lane] = buf[u];
   __syncwarp();
   float logd = 0.f;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const int i = lane + 32 * h;
-    const float raw = Lp[i * kPitch + i];
+    const int i = lane + 32 * h, o = xoff(i, i);
+    const float raw = Xs[o];
     const float dg = softplus_f(raw) + 1e-5f;
     sraw[i] = raw;
     sinv[i] = 1.0f / dg;
-    Lp[i * kPitch + i] = dg;
+    Xs[o] = dg;
     logd += logf(dg);
   }
   return logd;
 }
 
 // r = L^-1 s (forward substitution, column oriented): lanes own s_k for k = lane, lane + 32; r -> sr[], returns |r|^2.
-__device__ __forceinline__ float solve_lower(const float* Lp, const float* sinv, float s0, float s1, float* sr, int lane) {
+__device__ __forceinline__ float solve_lower(const float* Xs, const float* sinv, float s0, float s1, float* sr, int lane) {
+  const float* c0 = Xs + (lane + 1) * kPitch;           // L[lane][i]      = c0[i]
+  const float* c1 = Xs + (31 - lane) * kPitch + 63;     // L[lane + 32][i] = c1[-i]
   float sumsq = 0.f;
 #pragma unroll 4
   for (int i = 0; i < D; ++i) {
@@ -84,22 +90,29 @@ __device__ __forceinline__ float solve_lower(const float* Lp, const float* sinv,
     const float ri = __shfl_sync(0xffffffffu, src, i & 31) * sinv[i];
     sumsq = fmaf(ri, ri, sumsq);
     if (lane == 0) sr[i] = ri;
-    if (lane > i) s0 = fmaf(-Lp[lane * kPitch + i], ri, s0);
-    if (lane + 32 > i) s1 = fmaf(-Lp[(lane + 32) * kPitch + i], ri, s1);
+    if (lane > i) s0 = fmaf(-c0[i], ri, s0);
+    if (lane + 32 > i) s1 = fmaf(-c1[-i], ri, s1);
   }
   __syncwarp();
   return sumsq;
 }
 
 // g = L^-T t (back substitution): lanes own t_k; g -> sg[]
-__device__ __forceinline__ void solve_upper_t(const float* Lp, const float* sinv, float t0, float t1, float* sg, int lane) {
+__device__ __forceinline__ void solve_upper_t(const float* Xs, const float* sinv, float t0, float t1, float* sg, int lane) {
 #pragma unroll 4
-  for (int i = D - 1; i >= 0; --i) {
-    const float src = (i < 32) ? t0 : t1;
-    const float gi = __shfl_sync(0xffffffffu, src, i & 31) * sinv[i];
+  for (int i = D - 1; i >= 32; --i) {                   // row i >= 32: L[i][j] = row[-j]
+    const float* row = Xs + (63 - i) * kPitch + 63;
+    const float gi = __shfl_sync(0xffffffffu, t1, i & 31) * sinv[i];
     if (lane == 0) sg[i] = gi;
-    if (lane < i) t0 = fmaf(-Lp[i * kPitch + lane], gi, t0);
-    if (lane + 32 < i) t1 = fmaf(-Lp[i * kPitch + lane + 32], gi, t1);
+    t0 = fmaf(-row[-lane], gi, t0);
+    if (lane + 32 < i) t1 = fmaf(-row[-lane - 32], gi, t1);
+  }
+#pragma unroll 4
+  for (int i = 31; i >= 0; --i) {                       // row i <= 31: L[i][j] = row[j]
+    const float* row = Xs + (i + 1) * kPitch;
+    const float gi = __shfl_sync(0xffffffffu, t0, i) * sinv[i];
+    if (lane == 0) sg[i] = gi;
+    if (lane < i) t0 = fmaf(-row[lane], gi, t0);
   }
   __syncwarp();
 }
@@ -126,11 +139,13 @@ __global__ void __launch_bounds__(kThreads) latent_fwd64_kernel(const float* __r
     __syncwarp();
     const float mu0 = __ldg(pr + lane), mu1 = __ldg(pr + lane + 32);
     float a0 = mu0, a1 = mu1, fro = 0.f;
+    const float* c0 = Lp + (lane + 1) * kPitch;
+    const float* c1 = Lp + (31 - lane) * kPitch + 63;
 #pragma unroll 8
     for (int j = 0; j < D; ++j) {
       const float e = se[j];
-      const float l0 = (j <= lane) ? Lp[lane * kPitch + j] : 0.f;
-      const float l1 = (j <= lane + 32) ? Lp[(lane + 32) * kPitch + j] : 0.f;
+      const float l0 = (j <= lane) ? c0[j] : 0.f;
+      const float l1 = (j <= lane + 32) ? c1[-j] : 0.f;
       a0 = fmaf(l0, e, a0); a1 = fmaf(l1, e, a1);
       fro = fmaf(l0, l0, fro); fro = fmaf(l1, l1, fro);
     }
@@ -169,7 +184,8 @@ __global__ void __launch_bounds__(kThreads) match_fwd64_kernel(const float* __re
 
 // ---------------------------------------------------------------- backward of both heads
 // Two kernels.  (1) solve64_bwd_kernel: the triangular algebra of the partial posterior, one warp per row:
-// r = L_p^-1 (z - mu_p), g = L_p^-T r, and dz_total = dz_dec - (stop_grad ? 0 : mw g); writes the three 64-vectors.
+// r = L_p^-1 (z - mu_p), g = L_p^-T r, and dz_total = dz_dec - (stop_grad ? 0 : mw g); writes the three 64-vectors and
+// the 64 diagonal slots of d / d par_p (it holds their raw values and 1 / D_ii, the streaming kernel would re-read them).
 // (2) heads_bwd64_kernel: everything else is elementwise in the P = 2144 head columns, so it streams: thread = column q,
 // block = kPostRows consecutive rows (coalesced reads and bf16 writes, the head bias gradients are one register per
 // thread and output):
@@ -180,7 +196,9 @@ __global__ void __launch_bounds__(kThreads) solve64_bwd_kernel(const float* __re
                                                                const float* __restrict__ dz_dec,
                                                                const float* __restrict__ g_match, int stop_grad,
                                                                float* __restrict__ out_r, float* __restrict__ out_g,
-                                                               float* __restrict__ dz_total, int64_t B) {
+                                                               float* __restrict__ dz_total,
+                                                               __nv_bfloat16* __restrict__ dpar_p_b,
+                                                               float* __restrict__ db_p, int64_t B) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   float* Lp = smem + (size_t)wib * kWarpFloats;
@@ -192,6 +210,8 @@ __global__ void __launch_bounds__(kThreads) solve64_bwd_kernel(const float* __re
   float buf[kRowVals];
   int64_t r = (int64_t)blockIdx.x * kWarps + wib;
   if (r < B) load_row(par_p + r * P, buf, lane);
+  const int qd0 = D + diag_q(lane), qd1 = D + diag_q(lane + 32);
+  float accd0 = 0.f, accd1 = 0.f;
   for (; r < B; r += stride) {
     const float* pp = par_p + r * P;
     __syncwarp();
@@ -207,7 +227,13 @@ __global__ void __launch_bounds__(kThreads) solve64_bwd_kernel(const float* __re
     dz_total[r * D + lane] = v0; dz_total[r * D + lane + 32] = v1;
     out_r[r * D + lane] = sr[lane]; out_r[r * D + lane + 32] = sr[lane + 32];
     out_g[r * D + lane] = sg[lane]; out_g[r * D + lane + 32] = sg[lane + 32];
+    // the diagonal slots of d / d par_p: raw diagonal and 1 / D_ii are at hand here
+    const __nv_bfloat16 h0 = __float2bfloat16(mw * (sg[lane] * sr[lane] - sinv[lane]) * sigmoid_f(sraw[lane]));
+    const __nv_bfloat16 h1 = __float2bfloat16(mw * (sg[lane + 32] * sr[lane + 32] - sinv[lane + 32]) * sigmoid_f(sraw[lane + 32]));
+    dpar_p_b[r * P + qd0] = h0; dpar_p_b[r * P + qd1] = h1;
+    accd0 += __bfloat162float(h0); accd1 += __bfloat162float(h1);
   }
+  if (db_p) { atomicAdd(db_p + qd0, accd0); atomicAdd(db_p + qd1, accd1); }
 }
 
 // Thread = a PAIR of adjacent head columns (P and D are even, so a pair never straddles loc | tril), four rows per
@@ -222,11 +248,20 @@ __global__ void __launch_bounds__(kPostThreads, 3) heads_bwd64_kernel(
     const float* __restrict__ dz_total, const float* __restrict__ vec_r, const float* __restrict__ vec_g,
     const float* __restrict__ g_kl, const float* __restrict__ g_match, __nv_bfloat16* __restrict__ dpar_e_b,
     __nv_bfloat16* __restrict__ dpar_p_b, float* __restrict__ db_e, float* __restrict__ db_p, int64_t B) {
+  (void)par_p;
   __shared__ __align__(16) float sdz[D][kPostPitch], se[D][kPostPitch], sr[D][kPostPitch], sg[D][kPostPitch];
   __shared__ __align__(16) float skw[kPostRows], smw[kPostRows];
   const int64_t r0 = (int64_t)blockIdx.y * kPostRows;
   const int nr = (int)((B - r0 < kPostRows) ? (B - r0) : kPostRows);
   const int t = blockIdx.x * kPostThreads + threadIdx.x;
+  // The streaming loop below keeps at most eight 8-byte loads per thread in flight, which at DRAM latency is ~3 TB/s
+  // for the whole chip (ncu: long-scoreboard stalls, 28% of the warp slots).  Ask L2 for the block's whole tile of
+  // head outputs up front - prefetches hold no register and no scoreboard - so that the demand loads find it there.
+  if (t < kPairs && (threadIdx.x & 15) == 0) {
+#pragma unroll 8
+    for (int rr = 0; rr < nr; ++rr)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(par_e + (r0 + rr) * P + 2 * t));
+  }
   for (int e = threadIdx.x; e < kPostRows * D; e += kPostThreads) {
     const bool ok = e < nr * D;
     const int row = e / D, el = e % D;
@@ -247,23 +282,18 @@ __global__ void __launch_bounds__(kPostThreads, 3) heads_bwd64_kernel(
     const int i = t - kPairs;
     if (i >= D) return;
     const int qd = D + diag_q(i);
-    float acc_e = 0.f, acc_p = 0.f;
+    float acc_e = 0.f;
 #pragma unroll 4
     for (int rr = 0; rr < nr; ++rr) {
-      const float raw_e = __ldg(par_e + (r0 + rr) * P + qd), raw_p = __ldg(par_p + (r0 + rr) * P + qd);
+      const float raw_e = __ldg(par_e + (r0 + rr) * P + qd);
       const float dg = softplus_f(raw_e) + 1e-5f;
       const float ve = (sdz[i][rr] * se[i][rr] + skw[rr] * (dg - 1.0f / dg)) * sigmoid_f(raw_e);
-      const float dgp = softplus_f(raw_p) + 1e-5f;
-      const float vp = smw[rr] * (sg[i][rr] * sr[i][rr] - 1.0f / dgp) * sigmoid_f(raw_p);
-      const __nv_bfloat16 he = __float2bfloat16(ve), hp = __float2bfloat16(vp);
+      const __nv_bfloat16 he = __float2bfloat16(ve);
       dpar_e_b[(r0 + rr) * P + qd] = he;
-      dpar_p_b[(r0 + rr) * P + qd] = hp;
       acc_e += __bfloat162float(he);
-      acc_p += __bfloat162float(hp);
     }
     if (db_e) atomicAdd(db_e + qd, acc_e);
-    if (db_p) atomicAdd(db_p + qd, acc_p);
-    return;
+    return;                                   // (the diagonal of d / d par_p: solve64_bwd_kernel)
   }
   const int q0 = 2 * t;
   const bool is_loc = q0 < D;
@@ -322,7 +352,7 @@ int latent_fwd64(const float* par, const float* eps, float* z, float* kl, int64_
   using namespace l64;
   static bool attr = false;
   if (!attr) { PMVAE_CUDA(cudaFuncSetAttribute(latent_fwd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes)); attr = true; }
-  latent_fwd64_kernel<<<grid_rows(B, 3), kThreads, kSmemBytes, s>>>(par, eps, z, kl, B);
+  latent_fwd64_kernel<<<grid_rows(B, kBlocksPerSm), kThreads, kSmemBytes, s>>>(par, eps, z, kl, B);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -331,7 +361,7 @@ int match_fwd64(const float* par_p, const float* z, float* match, int64_t B, cud
   using namespace l64;
   static bool attr = false;
   if (!attr) { PMVAE_CUDA(cudaFuncSetAttribute(match_fwd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes)); attr = true; }
-  match_fwd64_kernel<<<grid_rows(B, 3), kThreads, kSmemBytes, s>>>(par_p, z, match, B);
+  match_fwd64_kernel<<<grid_rows(B, kBlocksPerSm), kThreads, kSmemBytes, s>>>(par_p, z, match, B);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }
@@ -345,7 +375,8 @@ int latent_bwd64(const float* par_e, const float* par_p, const float* eps, const
   float* dz_total = scratch;
   float* vec_r = scratch + (uint64_t)B * D;
   float* vec_g = scratch + 2 * (uint64_t)B * D;
-  solve64_bwd_kernel<<<grid_rows(B, 3), kThreads, kSmemBytes, s>>>(par_p, z, dz_dec, g_match, stop_grad, vec_r, vec_g, dz_total, B);
+  solve64_bwd_kernel<<<grid_rows(B, kBlocksPerSm), kThreads, kSmemBytes, s>>>(par_p, z, dz_dec, g_match, stop_grad, vec_r, vec_g, dz_total,
+                                                                   dpar_p_b, db_p, B);
   PMVAE_LAUNCH_CHECK();
   const dim3 grid(kPostBlocksX, (unsigned)((B + kPostRows - 1) / kPostRows));
   heads_bwd64_kernel<<<grid, kPostThreads, 0, s>>>(par_e, par_p, eps, dz_total, vec_r, vec_g, g_kl, g_match, dpar_e_b, dpar_p_b,
