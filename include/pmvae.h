@@ -211,6 +211,14 @@ int pmvae_std_normal_log_prob(const float* z, int64_t B, int32_t d, float* out, 
 int pmvae_diag_sample(const float* par, const float* eps, int64_t B, int32_t d, float* z, pmvae_stream_t stream);
 int pmvae_diag_log_prob(const float* par, const float* z, int64_t B, int32_t d, float* out_log_prob,
                         float* out_entropy, pmvae_stream_t stream);
+/* LookaheadPosterior objective (lookahead.py:183-199): par[B,S,2d] = the selected LookaheadBlock
+ * outputs [loc | raw scale] (lookahead.py:14-39), z[K,B,S,d] one-step latent samples, valid[B,S] in {0,1}:
+ *   ll[b] = sum_s valid[b,s] mean_k MultivariateNormalDiag(loc, softplus(raw) + 1e-5).log_prob(z[k,b,s]) / #valid[b]
+ * (0 where no s is valid), and its VJP dpar[B,S,2d] for the cotangent g[B]. */
+int pmvae_lookahead_ll(const float* par, const float* z, const float* valid, int64_t K, int64_t B, int32_t S, int32_t d,
+                       float* out_ll, pmvae_stream_t stream);
+int pmvae_lookahead_ll_backward(const float* par, const float* z, const float* valid, const float* g, int64_t K,
+                                int64_t B, int32_t S, int32_t d, float* dpar, pmvae_stream_t stream);
 
 /* ---- the whole training step as one launch sequence ---------------------------------------------
  * train_pm_vae.py's step (mask draw, eps draw, loss_fn forward, value_and_grad, optax update) enqueued by ONE

@@ -213,3 +213,22 @@ class PRNGSequence:
 
     def take(self, n):
         return [self.next() for _ in range(n)]
+
+
+def permutation(key, n: int):
+    """[R: jax 0.2.26 `jax.random.permutation(key, n)` -> `_shuffle(key, arange(n), 0)`] ceil(3 ln n / ln(2^32 - 1))
+    rounds; each round: key, subkey = split(key); stable sort of the current order by 32 random bits per element
+    drawn from subkey (`lax.sort_key_val`, stable by default)."""
+    x = np.arange(int(n))
+    rounds = int(np.ceil(3 * np.log(max(1, int(n))) / np.log(np.iinfo(np.uint32).max)))
+    key = np.asarray(key, dtype=U32)
+    for _ in range(rounds):
+        ks = split(key, 2)
+        key, sub = ks[0], ks[1]
+        x = x[np.argsort(random_bits(sub, int(n)), kind="stable")]
+    return x
+
+
+def choice_without_replacement(key, n: int, k: int):
+    """[R: jax 0.2.26 `jax.random.choice(key, n, (k,), replace=False)` with p=None] = permutation(key, n)[:k]."""
+    return permutation(key, n)[: int(k)]

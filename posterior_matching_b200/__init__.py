@@ -12,3 +12,4 @@ from .train import HostFeeder, Trainer, get_beta_schedule, cyclical_annealing_sc
 from .evaluate import eval_fn, nrmse_score  # noqa: F401
 from .distributions import AutoregressiveGMM, Bernoulli  # noqa: F401
 from .conv_vae import ConvPosteriorMatchingVAE  # noqa: F401
+from .lookahead import LookaheadBlock, LookaheadPosterior  # noqa: F401

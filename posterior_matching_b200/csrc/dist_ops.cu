@@ -85,6 +85,73 @@ __global__ void __launch_bounds__(256) diag_log_prob_kernel(const float* __restr
   }
 }
 
+
+// ---------------------------------------------------------------- lookahead posteriors (lookahead.py:14-39,183-199)
+// par [B, S, 2d] = the selected LookaheadBlock outputs (loc | raw scale, scale = softplus(raw) + 1e-5),
+// z [K, B, S, d] = one-step latent samples of the model, valid [B, S] in {0, 1}:
+//     ll[b] = sum_s valid[b,s] * mean_k log N(z[k,b,s] ; loc[b,s], diag(scale[b,s])^2) / #valid[b]     (0 if none valid)
+// One block per row b; warp = one (b, s) pair at a time, lanes over the latent dimension.
+__global__ void __launch_bounds__(256) lookahead_ll_kernel(const float* __restrict__ par, const float* __restrict__ z,
+                                                           const float* __restrict__ valid, int64_t K, int64_t B, int S,
+                                                           int d, float* __restrict__ out) {
+  __shared__ float s_sum[8], s_cnt[8];
+  const int64_t b = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float sum = 0.f, cnt = 0.f;
+  for (int s = w; s < S; s += 8) {
+    if (valid[b * S + s] == 0.f) continue;
+    const float* pr = par + (b * S + s) * 2 * d;
+    float acc = 0.f;
+    for (int j = lane; j < d; j += 32) {
+      const float loc = pr[j], sc = softplus_f(pr[d + j]) + 1e-5f, inv = 1.0f / sc;
+      float q = 0.f;
+      for (int64_t k = 0; k < K; ++k) {
+        const float t = (z[((k * B + b) * S + s) * d + j] - loc) * inv;
+        q = fmaf(t, t, q);
+      }
+      acc += -0.5f * q / (float)K - logf(sc) - 0.5f * kLog2Pi;
+    }
+    sum += warp_sum(acc);
+    cnt += 1.f;
+  }
+  if (lane == 0) { s_sum[w] = sum; s_cnt[w] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f, c = 0.f;
+    for (int i = 0; i < 8; ++i) { t += s_sum[i]; c += s_cnt[i]; }
+    out[b] = c > 0.f ? t / c : 0.f;
+  }
+}
+
+// d (sum_b g[b] ll[b]) / d par: thread = one (b, s, j).
+__global__ void __launch_bounds__(256) lookahead_ll_bwd_kernel(const float* __restrict__ par, const float* __restrict__ z,
+                                                               const float* __restrict__ valid,
+                                                               const float* __restrict__ g, int64_t K, int64_t B, int S,
+                                                               int d, float* __restrict__ dpar) {
+  const int64_t n = B * S * d;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(t % d);
+    const int64_t bs = t / d, b = bs / S;
+    float cnt = 0.f;
+    for (int s = 0; s < S; ++s) cnt += valid[b * S + s];
+    float dloc = 0.f, draw = 0.f;
+    if (valid[bs] != 0.f && cnt > 0.f) {
+      const float loc = par[bs * 2 * d + j], raw = par[bs * 2 * d + d + j];
+      const float sc = softplus_f(raw) + 1e-5f, inv = 1.0f / sc;
+      float a1 = 0.f, a2 = 0.f;
+      for (int64_t k = 0; k < K; ++k) {
+        const float u = z[(k * B * S + bs) * d + j] - loc;
+        a1 += u; a2 = fmaf(u, u, a2);
+      }
+      const float coef = g[b] / (cnt * (float)K);
+      dloc = coef * a1 * inv * inv;
+      draw = coef * (a2 * inv * inv * inv - (float)K * inv) * sigmoid_f(raw);
+    }
+    dpar[bs * 2 * d + j] = dloc;
+    dpar[bs * 2 * d + d + j] = draw;
+  }
+}
+
 }  // namespace pmvae
 
 using namespace pmvae;
@@ -143,6 +210,24 @@ int pmvae_diag_log_prob(const float* par, const float* z, int64_t B, int32_t d, 
   PMVAE_CHECK(out_log_prob == nullptr || z != nullptr, "log_prob needs z");
   if (B == 0) return 0;
   diag_log_prob_kernel<<<grid_rows(B, 256), 256, 0, as_stream(stream)>>>(par, z, B, d, out_log_prob, out_entropy);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int pmvae_lookahead_ll(const float* par, const float* z, const float* valid, int64_t K, int64_t B, int32_t S, int32_t d,
+                       float* out_ll, pmvae_stream_t stream) {
+  PMVAE_CHECK(K >= 1 && B >= 0 && S >= 1 && d >= 1 && (B == 0 || (par && z && valid && out_ll)), "bad arguments");
+  if (B == 0) return 0;
+  lookahead_ll_kernel<<<(unsigned)B, 256, 0, as_stream(stream)>>>(par, z, valid, K, B, S, d, out_ll);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+int pmvae_lookahead_ll_backward(const float* par, const float* z, const float* valid, const float* g, int64_t K,
+                                int64_t B, int32_t S, int32_t d, float* dpar, pmvae_stream_t stream) {
+  PMVAE_CHECK(K >= 1 && B >= 0 && S >= 1 && d >= 1 && (B == 0 || (par && z && valid && g && dpar)), "bad arguments");
+  if (B == 0) return 0;
+  lookahead_ll_bwd_kernel<<<grid_rows(B * S * d, 256), 256, 0, as_stream(stream)>>>(par, z, valid, g, K, B, S, d, dpar);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }
