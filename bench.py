@@ -709,7 +709,8 @@ def main():
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
-                tj = json.load(f).get(precision, {})
+                tall = json.load(f)
+                tj = tall.get(f"{precision}:{name}", tall.get(precision, {}))     # per-config entry, else the headline's
             if tj.get("config", name) == name and tj.get("rows", B) == B:
                 traffic = tj.get("dram_bytes_per_launch_train")
                 step_dram = tj.get("step_dram_bytes")

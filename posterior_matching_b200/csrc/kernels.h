@@ -80,11 +80,16 @@ int impute_samples(const float* x, const float* b, const float* loc, int64_t ld_
 
 // ---- latent.cu  (par = raw TriL head output [B, P], P = d + d(d+1)/2)
 int latent_fwd(const float* par, const float* eps, float* z, float* kl, int64_t B, int d, cudaStream_t s);
-int match_fwd(const float* par_p, const float* z, float* match, int64_t B, int d, cudaStream_t s);
+// `saved` (training forward, d = 64 only): three [*, d] vectors at saved, saved + saved_stride, saved + 2 saved_stride that
+// latent_bwd takes back through the same two arguments (match_fwd_saves(d) tells whether the pair is used).
+int match_fwd(const float* par_p, const float* z, float* match, int64_t B, int d, cudaStream_t s, float* saved = nullptr,
+              int64_t saved_stride = 0);
+bool match_fwd_saves(int d);
 int latent_bwd(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
                const float* g_kl, const float* g_match, int stop_grad, float* dpar_e, float* dpar_p,
                __nv_bfloat16* dpar_e_b, __nv_bfloat16* dpar_p_b, int64_t B, int d, cudaStream_t s,
-               float* db_e = nullptr, float* db_p = nullptr, bool* db_done = nullptr, float* dz_scratch = nullptr);
+               float* db_e = nullptr, float* db_p = nullptr, bool* db_done = nullptr, const float* saved = nullptr,
+               int64_t saved_stride = 0);
 bool latent_bwd_bias_fused(int d);
 int tril_sample_bwd(const float* par, const float* eps, const float* dz, const float* g_kl, float* dpar, int64_t B, int d,
                     cudaStream_t s);
@@ -98,11 +103,13 @@ int latent_bwd16(const float* par_e, const float* par_p, const float* eps, const
                  __nv_bfloat16* dpar_p_b, float* db_e, float* db_p, int64_t B, cudaStream_t s);
 // latent64.cu: warp-per-row versions for d = 64 (dense [64][65] factor in shared memory; bf16 gradient outputs only)
 int latent_fwd64(const float* par, const float* eps, float* z, float* kl, int64_t B, cudaStream_t s);
-int match_fwd64(const float* par_p, const float* z, float* match, int64_t B, cudaStream_t s);
-int latent_bwd64(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
-                 const float* g_kl, const float* g_match, int stop_grad, __nv_bfloat16* dpar_e_b,
-                 __nv_bfloat16* dpar_p_b, float* db_e, float* db_p, float* scratch /* [3, B, 64] floats */, int64_t B,
-                 cudaStream_t s);
+// match_fwd64 with save_* != NULL (training forward) also writes r = L_p^-1 (z - mu_p), g = L_p^-T r and the diagonal
+// terms qd, [B, 64] each; latent_bwd64 consumes them instead of re-reading par_p.
+int match_fwd64(const float* par_p, const float* z, float* match, int64_t B, cudaStream_t s, float* save_r = nullptr,
+                float* save_g = nullptr, float* save_qd = nullptr);
+int latent_bwd64(const float* par_e, const float* eps, const float* dz_dec, const float* g_kl, const float* g_match,
+                 int stop_grad, __nv_bfloat16* dpar_e_b, __nv_bfloat16* dpar_p_b, float* db_e, float* db_p,
+                 const float* vec_r, const float* vec_g, const float* vec_qd, int64_t B, cudaStream_t s);
 // z[k,r,:] = mu_r + L_r eps[k,r,:], eps = normal(key, [K, B_total, d]) rows row_start..;
 // base[k,r] = log N(z;0,I) - log q(z) = -0.5|z|^2 + 0.5|eps|^2 + sum log L_ii
 int sample_latents(const float* par, Key2 key, int64_t B, int64_t K, int64_t B_total, int64_t row_start, int d,

@@ -529,11 +529,16 @@ int latent_fwd(const float* par, const float* eps, float* z, float* kl, int64_t 
   return 0;
 }
 
-int match_fwd(const float* par_p, const float* z, float* match, int64_t B, int d, cudaStream_t s) {
+bool match_fwd_saves(int d) { return d == 64 && fast64(); }
+
+int match_fwd(const float* par_p, const float* z, float* match, int64_t B, int d, cudaStream_t s, float* saved,
+              int64_t saved_stride) {
   PMVAE_CHECK(d >= 1 && d <= 64, "latent_dim must be in [1, 64]");
   if (B == 0) return 0;
   if (d == 16 && fast16()) return match_fwd16(par_p, z, match, B, s);
-  if (d == 64 && fast64()) return match_fwd64(par_p, z, match, B, s);
+  if (d == 64 && fast64())
+    return saved ? match_fwd64(par_p, z, match, B, s, saved, saved + saved_stride, saved + 2 * saved_stride)
+                 : match_fwd64(par_p, z, match, B, s);
   const int P = d + d * (d + 1) / 2;
   const size_t spg = (size_t)(P + 4 * d) * sizeof(float);
   DISPATCH_D(match_fwd_kernel, d, B, spg, s, par_p, z, match, B, d);
@@ -547,7 +552,7 @@ bool latent_bwd_bias_fused(int d) { return (d == 16 && fast16()) || (d == 64 && 
 int latent_bwd(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
                const float* g_kl, const float* g_match, int stop_grad, float* dpar_e, float* dpar_p,
                __nv_bfloat16* dpar_e_b, __nv_bfloat16* dpar_p_b, int64_t B, int d, cudaStream_t s, float* db_e,
-               float* db_p, bool* db_done, float* dz_scratch) {
+               float* db_p, bool* db_done, const float* saved, int64_t saved_stride) {
   if (db_done) *db_done = false;
   PMVAE_CHECK(d >= 1 && d <= 64, "latent_dim must be in [1, 64]");
   if (B == 0) return 0;
@@ -555,9 +560,10 @@ int latent_bwd(const float* par_e, const float* par_p, const float* eps, const f
     if (db_done) *db_done = (db_e != nullptr && db_p != nullptr);     // head bias gradients are taken here as well
     return latent_bwd16(par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad, dpar_e_b, dpar_p_b, db_e, db_p, B, s);
   }
-  if (d == 64 && fast64() && dpar_e == nullptr && dpar_p == nullptr && dpar_e_b && dpar_p_b && dz_scratch) {
+  if (d == 64 && fast64() && dpar_e == nullptr && dpar_p == nullptr && dpar_e_b && dpar_p_b && saved) {
     if (db_done) *db_done = (db_e != nullptr && db_p != nullptr);
-    return latent_bwd64(par_e, par_p, eps, z, dz_dec, g_kl, g_match, stop_grad, dpar_e_b, dpar_p_b, db_e, db_p, dz_scratch, B, s);
+    return latent_bwd64(par_e, eps, dz_dec, g_kl, g_match, stop_grad, dpar_e_b, dpar_p_b, db_e, db_p, saved,
+                        saved + saved_stride, saved + 2 * saved_stride, B, s);
   }
   const int P = d + d * (d + 1) / 2;
   const size_t spg = (size_t)(P + 6 * d) * sizeof(float);

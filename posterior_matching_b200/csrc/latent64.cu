@@ -157,14 +157,22 @@ __global__ void __launch_bounds__(kThreads) latent_fwd64_kernel(const float* __r
 }
 
 // ---------------------------------------------------------------- log q(z | x_o) (vae.py:136-138)
+// Training forward (SAVE): the factor is staged here anyway, so the backward's triangular algebra is done on it now and
+// three 64-vectors per row are kept instead of re-reading the 8.6 KB of par_p in the backward:
+//     r = L_p^-1 (z - mu_p),   g = L_p^-T r,   qd_i = (g_i r_i - 1 / D_ii) sigmoid(raw_ii)   (diagonal slots of d / d par_p
+// before the per-row cotangent).
+template <bool SAVE>
 __global__ void __launch_bounds__(kThreads) match_fwd64_kernel(const float* __restrict__ par_p, const float* __restrict__ z,
-                                                               float* __restrict__ match, int64_t B) {
+                                                               float* __restrict__ match, float* __restrict__ out_r,
+                                                               float* __restrict__ out_g, float* __restrict__ out_qd,
+                                                               int64_t B) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   float* Lp = smem + (size_t)wib * kWarpFloats;
   float* sr = Lp + kLFloats;
   float* sraw = sr + D;
   float* sinv = sraw + D;
+  float* sg = sinv + D;
   const int64_t stride = (int64_t)gridDim.x * kWarps;
   float buf[kRowVals];
   int64_t r = (int64_t)blockIdx.x * kWarps + wib;
@@ -179,100 +187,75 @@ __global__ void __launch_bounds__(kThreads) match_fwd64_kernel(const float* __re
     const float sumsq = solve_lower(Lp, sinv, s0, s1, sr, lane);
     logd = warp_sum(logd);
     if (lane == 0) match[r] = -0.5f * sumsq - logd - 0.5f * (float)D * kLog2Pi;
+    if (SAVE) {
+      solve_upper_t(Lp, sinv, sr[lane], sr[lane + 32], sg, lane);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        out_r[r * D + i] = sr[i];
+        out_g[r * D + i] = sg[i];
+        out_qd[r * D + i] = (sg[i] * sr[i] - sinv[i]) * sigmoid_f(sraw[i]);
+      }
+    }
   }
 }
 
 // ---------------------------------------------------------------- backward of both heads
-// Two kernels.  (1) solve64_bwd_kernel: the triangular algebra of the partial posterior, one warp per row:
-// r = L_p^-1 (z - mu_p), g = L_p^-T r, and dz_total = dz_dec - (stop_grad ? 0 : mw g); writes the three 64-vectors and
-// the 64 diagonal slots of d / d par_p (it holds their raw values and 1 / D_ii, the streaming kernel would re-read them).
-// (2) heads_bwd64_kernel: everything else is elementwise in the P = 2144 head columns, so it streams: thread = column q,
+// The triangular algebra of the partial posterior (r, g and the diagonal terms qd) was done by match_fwd64_kernel<true>
+// in the forward; what is left is elementwise in the P = 2144 head columns, so it streams: thread = a pair of columns,
 // block = kPostRows consecutive rows (coalesced reads and bf16 writes, the head bias gradients are one register per
 // thread and output):
 //     d / d par_p: loc -> mw g;  L_ij -> mw g_i r_j;  diagonal -> mw (g_i r_i - 1 / D_ii) sigmoid(raw_ii)
 //     d / d par_e: loc -> dz_i + kw mu_i;  L_ij -> dz_i eps_j + kw L_ij;  diagonal -> (dz_i eps_i + kw (D_ii - 1 / D_ii)) sigmoid(raw_ii)
 // (formulas as latent.cu::latent_bwd_kernel; D_ii = softplus(raw_ii) + 1e-5).
-__global__ void __launch_bounds__(kThreads) solve64_bwd_kernel(const float* __restrict__ par_p, const float* __restrict__ z,
-                                                               const float* __restrict__ dz_dec,
-                                                               const float* __restrict__ g_match, int stop_grad,
-                                                               float* __restrict__ out_r, float* __restrict__ out_g,
-                                                               float* __restrict__ dz_total,
-                                                               __nv_bfloat16* __restrict__ dpar_p_b,
-                                                               float* __restrict__ db_p, int64_t B) {
-  extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  float* Lp = smem + (size_t)wib * kWarpFloats;
-  float* sr = Lp + kLFloats;
-  float* sg = sr + D;
-  float* sraw = sg + D;
-  float* sinv = sraw + D;
-  const int64_t stride = (int64_t)gridDim.x * kWarps;
-  float buf[kRowVals];
-  int64_t r = (int64_t)blockIdx.x * kWarps + wib;
-  if (r < B) load_row(par_p + r * P, buf, lane);
-  const int qd0 = D + diag_q(lane), qd1 = D + diag_q(lane + 32);
-  float accd0 = 0.f, accd1 = 0.f;
-  for (; r < B; r += stride) {
-    const float* pp = par_p + r * P;
-    __syncwarp();
-    stage_factor(buf, Lp, sraw, sinv, lane);
-    if (r + stride < B) load_row(par_p + (r + stride) * P, buf, lane);
-    __syncwarp();
-    const float s0 = z[r * D + lane] - __ldg(pp + lane), s1 = z[r * D + lane + 32] - __ldg(pp + lane + 32);
-    solve_lower(Lp, sinv, s0, s1, sr, lane);
-    solve_upper_t(Lp, sinv, sr[lane], sr[lane + 32], sg, lane);
-    const float mw = g_match[r];
-    float v0 = dz_dec ? dz_dec[r * D + lane] : 0.f, v1 = dz_dec ? dz_dec[r * D + lane + 32] : 0.f;
-    if (!stop_grad) { v0 -= mw * sg[lane]; v1 -= mw * sg[lane + 32]; }
-    dz_total[r * D + lane] = v0; dz_total[r * D + lane + 32] = v1;
-    out_r[r * D + lane] = sr[lane]; out_r[r * D + lane + 32] = sr[lane + 32];
-    out_g[r * D + lane] = sg[lane]; out_g[r * D + lane + 32] = sg[lane + 32];
-    // the diagonal slots of d / d par_p: raw diagonal and 1 / D_ii are at hand here
-    const __nv_bfloat16 h0 = __float2bfloat16(mw * (sg[lane] * sr[lane] - sinv[lane]) * sigmoid_f(sraw[lane]));
-    const __nv_bfloat16 h1 = __float2bfloat16(mw * (sg[lane + 32] * sr[lane + 32] - sinv[lane + 32]) * sigmoid_f(sraw[lane + 32]));
-    dpar_p_b[r * P + qd0] = h0; dpar_p_b[r * P + qd1] = h1;
-    accd0 += __bfloat162float(h0); accd1 += __bfloat162float(h1);
-  }
-  if (db_p) { atomicAdd(db_p + qd0, accd0); atomicAdd(db_p + qd1, accd1); }
-}
-
 // Thread = a PAIR of adjacent head columns (P and D are even, so a pair never straddles loc | tril), four rows per
 // inner step.  The per-row vectors are staged TRANSPOSED ([element][row], pitch 36 floats) so that the four rows of a
-// step are one LDS.128 per operand; together with the 8-byte loads and 4-byte bf16x2 stores that is 22 memory
-// instructions per (4 rows x 2 columns) where the one-column / one-row form issued 72 - the kernel was bound by the
-// load/store issue rate, not by HBM.
+// step are one LDS.128 per operand; with 8-byte loads and 4-byte bf16x2 stores that is a third of the memory
+// instructions of the one-column / one-row form, which was bound by the load/store issue rate.  One kernel per head
+// (ROLE 0: d / d par_e, reads the head output; ROLE 1: d / d par_p, a pure write stream): each needs two of the four
+// vectors, i.e. half the operand registers and half the shared memory of a combined kernel, and runs at its own pace.
 constexpr int kPostThreads = 256, kPostRows = 32, kPostPitch = kPostRows + 4, kPairs = P / 2;
 constexpr int kPostBlocksX = (kPairs + D + kPostThreads - 1) / kPostThreads;
-__global__ void __launch_bounds__(kPostThreads, 3) heads_bwd64_kernel(
-    const float* __restrict__ par_e, const float* __restrict__ par_p, const float* __restrict__ eps,
-    const float* __restrict__ dz_total, const float* __restrict__ vec_r, const float* __restrict__ vec_g,
-    const float* __restrict__ g_kl, const float* __restrict__ g_match, __nv_bfloat16* __restrict__ dpar_e_b,
-    __nv_bfloat16* __restrict__ dpar_p_b, float* __restrict__ db_e, float* __restrict__ db_p, int64_t B) {
-  (void)par_p;
-  __shared__ __align__(16) float sdz[D][kPostPitch], se[D][kPostPitch], sr[D][kPostPitch], sg[D][kPostPitch];
-  __shared__ __align__(16) float skw[kPostRows], smw[kPostRows];
+template <int ROLE>
+__global__ void __launch_bounds__(kPostThreads, 4) heads_bwd64_kernel(
+    const float* __restrict__ par_e, const float* __restrict__ eps, const float* __restrict__ dz_dec, int stop_grad,
+    const float* __restrict__ vec_r, const float* __restrict__ vec_g, const float* __restrict__ vec_qd,
+    const float* __restrict__ g_kl, const float* __restrict__ g_match, __nv_bfloat16* __restrict__ dpar_b,
+    float* __restrict__ db, int64_t B) {
+  // ROLE 0: sa = dz_total, sb = eps, sw = g_kl;   ROLE 1: sa = g, sb = r, sw = g_match
+  // One block = 32 rows x 512 columns; the five column blocks of a row block are adjacent in launch order, so they run
+  // together and share the row vectors and DRAM pages through L2 (a variant where each block looped over many row
+  // blocks, to issue the bias-gradient atomics once, lost that: 2.4x slower with 1.7x the DRAM reads).
+  __shared__ __align__(16) float sa[D][kPostPitch], sb[D][kPostPitch];
+  __shared__ __align__(16) float sw[kPostRows];
   const int64_t r0 = (int64_t)blockIdx.y * kPostRows;
   const int nr = (int)((B - r0 < kPostRows) ? (B - r0) : kPostRows);
   const int t = blockIdx.x * kPostThreads + threadIdx.x;
   // The streaming loop below keeps at most eight 8-byte loads per thread in flight, which at DRAM latency is ~3 TB/s
-  // for the whole chip (ncu: long-scoreboard stalls, 28% of the warp slots).  Ask L2 for the block's whole tile of
-  // head outputs up front - prefetches hold no register and no scoreboard - so that the demand loads find it there.
-  if (t < kPairs && (threadIdx.x & 15) == 0) {
+  // for the whole chip (ncu: long-scoreboard stalls).  Ask L2 for the block's whole tile of head outputs up front -
+  // prefetches hold no register and no scoreboard - so that the demand loads find it there.
+  if (ROLE == 0 && t < kPairs && (threadIdx.x & 15) == 0) {
 #pragma unroll 8
     for (int rr = 0; rr < nr; ++rr)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(par_e + (r0 + rr) * P + 2 * t));
   }
+  if (threadIdx.x < kPostRows) {
+    const float* w = ROLE == 0 ? g_kl : g_match;
+    sw[threadIdx.x] = threadIdx.x < nr ? w[r0 + threadIdx.x] : 0.f;
+  }
   for (int e = threadIdx.x; e < kPostRows * D; e += kPostThreads) {
     const bool ok = e < nr * D;
-    const int row = e / D, el = e % D;
-    sdz[el][row] = ok ? dz_total[r0 * D + e] : 0.f;
-    se[el][row] = ok ? eps[r0 * D + e] : 0.f;
-    sr[el][row] = ok ? vec_r[r0 * D + e] : 0.f;
-    sg[el][row] = ok ? vec_g[r0 * D + e] : 0.f;
-  }
-  if (threadIdx.x < kPostRows) {
-    skw[threadIdx.x] = threadIdx.x < nr ? g_kl[r0 + threadIdx.x] : 0.f;
-    smw[threadIdx.x] = threadIdx.x < nr ? g_match[r0 + threadIdx.x] : 0.f;
+    const int row = e / D, c = e % D;
+    if (ROLE == 0) {
+      // total gradient into z: the decoder's, minus the matching term's unless it carries a stop_gradient (vae.py:136-138)
+      float dzv = (ok && dz_dec) ? dz_dec[r0 * D + e] : 0.f;
+      if (!stop_grad && ok) dzv -= g_match[r0 + row] * vec_g[r0 * D + e];
+      sa[c][row] = dzv;
+      sb[c][row] = ok ? eps[r0 * D + e] : 0.f;
+    } else {
+      sa[c][row] = ok ? vec_g[r0 * D + e] : 0.f;
+      sb[c][row] = ok ? vec_r[r0 * D + e] : 0.f;
+    }
   }
   __syncthreads();
   // The 64 diagonal elements go through softplus / sigmoid.  They sit 65 columns apart, i.e. one in every other warp:
@@ -282,61 +265,67 @@ __global__ void __launch_bounds__(kPostThreads, 3) heads_bwd64_kernel(
     const int i = t - kPairs;
     if (i >= D) return;
     const int qd = D + diag_q(i);
-    float acc_e = 0.f;
+    float acc = 0.f;
 #pragma unroll 4
     for (int rr = 0; rr < nr; ++rr) {
-      const float raw_e = __ldg(par_e + (r0 + rr) * P + qd);
-      const float dg = softplus_f(raw_e) + 1e-5f;
-      const float ve = (sdz[i][rr] * se[i][rr] + skw[rr] * (dg - 1.0f / dg)) * sigmoid_f(raw_e);
-      const __nv_bfloat16 he = __float2bfloat16(ve);
-      dpar_e_b[(r0 + rr) * P + qd] = he;
-      acc_e += __bfloat162float(he);
+      float v;
+      if (ROLE == 0) {
+        const float raw_e = __ldg(par_e + (r0 + rr) * P + qd);
+        const float dg = softplus_f(raw_e) + 1e-5f;
+        v = (sa[i][rr] * sb[i][rr] + sw[rr] * (dg - 1.0f / dg)) * sigmoid_f(raw_e);
+      } else {
+        v = sw[rr] * vec_qd[(r0 + rr) * D + i];
+      }
+      const __nv_bfloat16 h = __float2bfloat16(v);
+      dpar_b[(r0 + rr) * P + qd] = h;
+      acc += __bfloat162float(h);
     }
-    if (db_e) atomicAdd(db_e + qd, acc_e);
-    return;                                   // (the diagonal of d / d par_p: solve64_bwd_kernel)
+    if (db) atomicAdd(db + qd, acc);
+    return;
   }
   const int q0 = 2 * t;
   const bool is_loc = q0 < D;
   int i0 = q0, j0 = 0, i1 = q0 + 1, j1 = 0;
   if (!is_loc) { v_to_ij(q0 - D, i0, j0); v_to_ij(q0 + 1 - D, i1, j1); }
   const bool d0 = !is_loc && i0 == j0, d1 = !is_loc && i1 == j1;     // a diagonal slot: left to the spare threads
-  float ae0 = 0.f, ae1 = 0.f, ap0 = 0.f, ap1 = 0.f;
+  float a0 = 0.f, a1 = 0.f;
   auto el = [](const float4& v, int u) { return u == 0 ? v.x : u == 1 ? v.y : u == 2 ? v.z : v.w; };
 #pragma unroll 2
   for (int rb = 0; rb < kPostRows; rb += 4) {
     float2 raw[4];
+    if (ROLE == 0) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      raw[u] = (rb + u < nr) ? __ldg(reinterpret_cast<const float2*>(par_e + (r0 + rb + u) * P + q0)) : make_float2(0.f, 0.f);
-    const float4 kw = *reinterpret_cast<const float4*>(&skw[rb]), mw = *reinterpret_cast<const float4*>(&smw[rb]);
-    const float4 dzA = *reinterpret_cast<const float4*>(&sdz[i0][rb]), dzB = *reinterpret_cast<const float4*>(&sdz[i1][rb]);
-    const float4 gA = *reinterpret_cast<const float4*>(&sg[i0][rb]), gB = *reinterpret_cast<const float4*>(&sg[i1][rb]);
-    float4 eA = *reinterpret_cast<const float4*>(&se[j0][rb]), eB = *reinterpret_cast<const float4*>(&se[j1][rb]);
-    float4 rA = *reinterpret_cast<const float4*>(&sr[j0][rb]), rB = *reinterpret_cast<const float4*>(&sr[j1][rb]);
-    if (is_loc) { eA = eB = rA = rB = make_float4(1.f, 1.f, 1.f, 1.f); }
+      for (int u = 0; u < 4; ++u)
+        raw[u] = (rb + u < nr) ? __ldg(reinterpret_cast<const float2*>(par_e + (r0 + rb + u) * P + q0)) : make_float2(0.f, 0.f);
+    }
+    const float4 w = *reinterpret_cast<const float4*>(&sw[rb]);
+    const float4 aA = *reinterpret_cast<const float4*>(&sa[i0][rb]), aB = *reinterpret_cast<const float4*>(&sa[i1][rb]);
+    float4 bA = *reinterpret_cast<const float4*>(&sb[j0][rb]), bB = *reinterpret_cast<const float4*>(&sb[j1][rb]);
+    if (is_loc) { bA = bB = make_float4(1.f, 1.f, 1.f, 1.f); }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (rb + u < nr) {
-        const float k = el(kw, u), m = el(mw, u);
-        const float ve0 = el(dzA, u) * el(eA, u) + k * raw[u].x, ve1 = el(dzB, u) * el(eB, u) + k * raw[u].y;
-        const float vp0 = m * el(gA, u) * el(rA, u), vp1 = m * el(gB, u) * el(rB, u);
-        const __nv_bfloat162 he = __floats2bfloat162_rn(ve0, ve1), hp = __floats2bfloat162_rn(vp0, vp1);
-        __nv_bfloat16* oe = dpar_e_b + (r0 + rb + u) * P + q0;
-        __nv_bfloat16* op = dpar_p_b + (r0 + rb + u) * P + q0;
-        if (!(d0 | d1)) {
-          *reinterpret_cast<__nv_bfloat162*>(oe) = he;
-          *reinterpret_cast<__nv_bfloat162*>(op) = hp;
-        } else {                       // (both can be diagonal: a forward run of v ends where a reversed one starts)
-          if (!d0) { oe[0] = he.x; op[0] = hp.x; }
-          if (!d1) { oe[1] = he.y; op[1] = hp.y; }
+        float v0, v1;
+        if (ROLE == 0) {
+          v0 = el(aA, u) * el(bA, u) + el(w, u) * raw[u].x;
+          v1 = el(aB, u) * el(bB, u) + el(w, u) * raw[u].y;
+        } else {
+          v0 = el(w, u) * el(aA, u) * el(bA, u);
+          v1 = el(w, u) * el(aB, u) * el(bB, u);
         }
-        ae0 += __low2float(he); ae1 += __high2float(he);
-        ap0 += __low2float(hp); ap1 += __high2float(hp);
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+        __nv_bfloat16* o = dpar_b + (r0 + rb + u) * P + q0;
+        if (!(d0 | d1)) {
+          *reinterpret_cast<__nv_bfloat162*>(o) = h;
+        } else {                       // (both can be diagonal: a forward run of v ends where a reversed one starts)
+          if (!d0) o[0] = h.x;
+          if (!d1) o[1] = h.y;
+        }
+        a0 += __low2float(h); a1 += __high2float(h);
       }
     }
   }
-  if (db_e) { if (!d0) atomicAdd(db_e + q0, ae0); if (!d1) atomicAdd(db_e + q0 + 1, ae1); }
-  if (db_p) { if (!d0) atomicAdd(db_p + q0, ap0); if (!d1) atomicAdd(db_p + q0 + 1, ap1); }
+  if (db) { if (!d0) atomicAdd(db + q0, a0); if (!d1) atomicAdd(db + q0 + 1, a1); }
 }
 
 static int grid_rows(int64_t B, int blocks_per_sm) {
@@ -357,30 +346,34 @@ int latent_fwd64(const float* par, const float* eps, float* z, float* kl, int64_
   return 0;
 }
 
-int match_fwd64(const float* par_p, const float* z, float* match, int64_t B, cudaStream_t s) {
+int match_fwd64(const float* par_p, const float* z, float* match, int64_t B, cudaStream_t s, float* save_r, float* save_g,
+                float* save_qd) {
   using namespace l64;
   static bool attr = false;
-  if (!attr) { PMVAE_CUDA(cudaFuncSetAttribute(match_fwd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes)); attr = true; }
-  match_fwd64_kernel<<<grid_rows(B, kBlocksPerSm), kThreads, kSmemBytes, s>>>(par_p, z, match, B);
+  if (!attr) {
+    PMVAE_CUDA(cudaFuncSetAttribute(match_fwd64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    PMVAE_CUDA(cudaFuncSetAttribute(match_fwd64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    attr = true;
+  }
+  if (save_r)
+    match_fwd64_kernel<true><<<grid_rows(B, kBlocksPerSm), kThreads, kSmemBytes, s>>>(par_p, z, match, save_r, save_g, save_qd, B);
+  else
+    match_fwd64_kernel<false><<<grid_rows(B, kBlocksPerSm), kThreads, kSmemBytes, s>>>(par_p, z, match, nullptr, nullptr, nullptr, B);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }
 
-int latent_bwd64(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
-                 const float* g_kl, const float* g_match, int stop_grad, __nv_bfloat16* dpar_e_b, __nv_bfloat16* dpar_p_b,
-                 float* db_e, float* db_p, float* scratch /* [3, B, 64] */, int64_t B, cudaStream_t s) {
+// r / g / qd: the three [B, 64] vectors match_fwd64 saved for these rows in the forward.
+int latent_bwd64(const float* par_e, const float* eps, const float* dz_dec, const float* g_kl, const float* g_match,
+                 int stop_grad, __nv_bfloat16* dpar_e_b, __nv_bfloat16* dpar_p_b, float* db_e, float* db_p,
+                 const float* vec_r, const float* vec_g, const float* vec_qd, int64_t B, cudaStream_t s) {
   using namespace l64;
-  static bool attr = false;
-  if (!attr) { PMVAE_CUDA(cudaFuncSetAttribute(solve64_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes)); attr = true; }
-  float* dz_total = scratch;
-  float* vec_r = scratch + (uint64_t)B * D;
-  float* vec_g = scratch + 2 * (uint64_t)B * D;
-  solve64_bwd_kernel<<<grid_rows(B, kBlocksPerSm), kThreads, kSmemBytes, s>>>(par_p, z, dz_dec, g_match, stop_grad, vec_r, vec_g, dz_total,
-                                                                   dpar_p_b, db_p, B);
-  PMVAE_LAUNCH_CHECK();
   const dim3 grid(kPostBlocksX, (unsigned)((B + kPostRows - 1) / kPostRows));
-  heads_bwd64_kernel<<<grid, kPostThreads, 0, s>>>(par_e, par_p, eps, dz_total, vec_r, vec_g, g_kl, g_match, dpar_e_b, dpar_p_b,
-                                                   db_e, db_p, B);
+  heads_bwd64_kernel<0><<<grid, kPostThreads, 0, s>>>(par_e, eps, dz_dec, stop_grad, vec_r, vec_g, vec_qd, g_kl, g_match,
+                                                      dpar_e_b, db_e, B);
+  PMVAE_LAUNCH_CHECK();
+  heads_bwd64_kernel<1><<<grid, kPostThreads, 0, s>>>(par_e, eps, dz_dec, stop_grad, vec_r, vec_g, vec_qd, g_kl, g_match,
+                                                      dpar_p_b, db_p, B);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }

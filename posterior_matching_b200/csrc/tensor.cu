@@ -225,27 +225,30 @@ __global__ void __launch_bounds__(256) in_layer_dinput_kernel(const bf16* __rest
 
 // bf16 image of a net's input, [B, ld] with ld = pad8(K0): in (K0 = D_in) or [in*msk, msk] (K0 = 2 D_in);
 // it is the A operand of the first Linear's weight-gradient GEMM (gW_0 += in^T @ dY_0).
-// One thread per row (the rows are 8 ... 64 elements): no per-element division, contiguous reads and writes per warp.
+// One thread per PAIR of output columns, consecutive threads = consecutive pairs of a row: reads and writes of a warp are
+// contiguous whatever the row length (one thread per row left every load of a warp on a different line: 77 us per
+// launch for the 126-column bsds input, 0.7 TB/s).
 __global__ void __launch_bounds__(256) cast_input_kernel(const float* __restrict__ in, const float* __restrict__ msk,
                                                          int D_in, int K0, int ld, int64_t B, bf16* __restrict__ out) {
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < B; r += (int64_t)gridDim.x * blockDim.x) {
+  const int half_ld = ld >> 1;
+  const int64_t n = B * half_ld;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / half_ld;
+    const int k = 2 * (int)(t - r * half_ld);
     const float* xi = in + r * D_in;
     const float* mi = msk ? msk + r * D_in : nullptr;
-    bf16* o = out + r * ld;
-    for (int k = 0; k < ld; k += 2) {
-      float v[2];
+    float v[2];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int kk = k + e;
-        float t = 0.f;
-        if (kk < K0) {
-          if (mi) t = (kk < D_in) ? xi[kk] * mi[kk] : mi[kk - D_in];
-          else t = xi[kk];
-        }
-        v[e] = t;
+    for (int e = 0; e < 2; ++e) {
+      const int kk = k + e;
+      float u = 0.f;
+      if (kk < K0) {
+        if (mi) u = (kk < D_in) ? xi[kk] * mi[kk] : mi[kk - D_in];
+        else u = xi[kk];
       }
-      *reinterpret_cast<__nv_bfloat162*>(o + k) = __floats2bfloat162_rn(v[0], v[1]);
+      v[e] = u;
     }
+    *reinterpret_cast<__nv_bfloat162*>(out + r * ld + k) = __floats2bfloat162_rn(v[0], v[1]);
   }
 }
 
@@ -504,7 +507,7 @@ static TrainPlanB plan_train_b(const pmvae_config* c, const Layout& L, int64_t B
   p.z = bp.take<float>((uint64_t)B * c->d);
   p.loc = bp.take<float>((uint64_t)B * p.Dp);
   p.dz = bp.take<float>((uint64_t)B * c->d);
-  p.dz2 = bp.take<float>((uint64_t)3 * B * c->d);         // dz_total, r, g of the d = 64 latent backward (two kernels)
+  p.dz2 = bp.take<float>((uint64_t)3 * B * c->d);         // d = 64: r, g, qd saved by match_fwd for latent_bwd ([3][B][d])
   p.wtmp = bp.take<float>((uint64_t)256 * p.Dp);         // padded-pitch dW of the decoder head
   p.dH = bp.take<bf16>((uint64_t)B * 256);
   p.dU = bp.take<bf16>((uint64_t)B * 256);
@@ -681,7 +684,7 @@ static int net_bwd_b(const float* params, float* grads, const Net& n, const Leaf
       PMVAE_TRY(fused::net_backward(n, head, *fim, dHead, ld_dhead, B, sv.masks, sv.Bpad, dY, grads, dIn, s));
     const Leaf& l0 = n.lin[0];
     const int ld0 = pad8(l0.rows);
-    cast_input_kernel<<<grid1d(B, 256), 256, 0, s>>>(in, msk, D_in, l0.rows, ld0, B, in_b);
+    cast_input_kernel<<<grid1d(B * (ld0 / 2), 256), 256, 0, s>>>(in, msk, D_in, l0.rows, ld0, B, in_b);
     PMVAE_LAUNCH_CHECK();
     // every weight gradient of the net in one grouped launch
     tc::TnDesc td[2 * kMaxBlocks + 2];
@@ -782,7 +785,7 @@ int forward_bf16(const pmvae_config* c, const Layout& L, const float* params, co
     PMVAE_TRY(net_fwd_b(params, L.part, p.img.part, L.ppost, p.img.ppost, L.P, xc, b + r0 * D, D, nb,
                         shift_saved(p.part, L.part, r0), p.h, p.ytmp, p.par_p + r0 * L.P, L.P,
                         p.img.f_part_ok ? &p.img.f_part : nullptr, true, s));
-    PMVAE_TRY(match_fwd(p.par_p + r0 * L.P, p.z + r0 * d, out_match + r0, nb, d, s));
+    PMVAE_TRY(match_fwd(p.par_p + r0 * L.P, p.z + r0 * d, out_match + r0, nb, d, s, p.dz2 + r0 * d, B * d));
   }
   return 0;
 }
@@ -817,7 +820,7 @@ int backward_bf16(const pmvae_config* c, const Layout& L, const float* params, c
       bool done = false;
       PMVAE_TRY(latent_bwd(p.par_e + r0 * L.P, p.par_p + r0 * L.P, eps + r0 * d, p.z + r0 * d, p.dz, g_kl + r0,
                            g_match + r0, c->stop_grad, nullptr, nullptr, p.dpar_e_b, p.dpar_p_b, nb, d, s, grads + L.post.b,
-                           grads + L.ppost.b, &done, p.dz2));
+                           grads + L.ppost.b, &done, p.dz2 + r0 * d, B * d));
       PMVAE_CHECK(done == lat_db, "latent_bwd bias-gradient contract changed");
     }
     if (stages & 2)
