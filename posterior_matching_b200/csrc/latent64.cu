@@ -16,6 +16,7 @@
 //
 // Reference sites as in latent.cu: distributions.py:101-113 (TriLGaussian / FillScaleTriL), vae.py:124,130,136-138.
 #include <cstdlib>
+#include <type_traits>
 
 #include "kernels.h"
 
@@ -321,41 +322,49 @@ __global__ void __launch_bounds__(kPostThreads, 4) heads_bwd64_kernel(
       }
       continue;
     }
+    // ncu: this loop is bound by instruction issue and the L1 data stage (31 instructions per thread and row in the
+    // first version), so the full-tile case runs without row guards, with one row pointer and immediate offsets
+    __nv_bfloat16* const orow = dpar_b + r0 * P + q0;
+    const float2* const prow = reinterpret_cast<const float2*>(par_e + r0 * P + q0);
+    auto tile = [&](auto full_tag) {
+      constexpr bool kFull = decltype(full_tag)::value;
 #pragma unroll 2
-    for (int rb = 0; rb < kPostRows; rb += 4) {
-      float2 raw[4];
-      if (ROLE == 0) {
+      for (int rb = 0; rb < kPostRows; rb += 4) {
+        float2 raw[4];
+        if (ROLE == 0) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          raw[u] = (rb + u < nr) ? __ldg(reinterpret_cast<const float2*>(par_e + (r0 + rb + u) * P + q0)) : make_float2(0.f, 0.f);
-      }
-      const float4 w = *reinterpret_cast<const float4*>(&sw[rb]);
-      const float4 aA = *reinterpret_cast<const float4*>(&sa[i0][rb]), aB = *reinterpret_cast<const float4*>(&sa[i1][rb]);
-      float4 bA = *reinterpret_cast<const float4*>(&sb[j0][rb]), bB = *reinterpret_cast<const float4*>(&sb[j1][rb]);
-      if (is_loc) { bA = bB = make_float4(1.f, 1.f, 1.f, 1.f); }
+          for (int u = 0; u < 4; ++u)
+            raw[u] = (kFull || rb + u < nr) ? __ldg(prow + (rb + u) * (P / 2)) : make_float2(0.f, 0.f);
+        }
+        const float4 w = *reinterpret_cast<const float4*>(&sw[rb]);
+        const float4 aA = *reinterpret_cast<const float4*>(&sa[i0][rb]), aB = *reinterpret_cast<const float4*>(&sa[i1][rb]);
+        float4 bA = *reinterpret_cast<const float4*>(&sb[j0][rb]), bB = *reinterpret_cast<const float4*>(&sb[j1][rb]);
+        if (is_loc) { bA = bB = make_float4(1.f, 1.f, 1.f, 1.f); }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (rb + u < nr) {
-          float v0, v1;
-          if (ROLE == 0) {
-            v0 = el(aA, u) * el(bA, u) + el(w, u) * raw[u].x;
-            v1 = el(aB, u) * el(bB, u) + el(w, u) * raw[u].y;
-          } else {
-            v0 = el(w, u) * el(aA, u) * el(bA, u);
-            v1 = el(w, u) * el(aB, u) * el(bB, u);
+        for (int u = 0; u < 4; ++u) {
+          if (kFull || rb + u < nr) {
+            float v0, v1;
+            if (ROLE == 0) {
+              v0 = fmaf(el(aA, u), el(bA, u), el(w, u) * raw[u].x);
+              v1 = fmaf(el(aB, u), el(bB, u), el(w, u) * raw[u].y);
+            } else {
+              v0 = el(w, u) * el(aA, u) * el(bA, u);
+              v1 = el(w, u) * el(aB, u) * el(bB, u);
+            }
+            const __nv_bfloat162 hv = __floats2bfloat162_rn(v0, v1);
+            __nv_bfloat16* o = orow + (rb + u) * P;
+            if (!(d0 | d1)) {
+              *reinterpret_cast<__nv_bfloat162*>(o) = hv;
+            } else {                     // (both can be diagonal: a forward run of v ends where a reversed one starts)
+              if (!d0) o[0] = hv.x;
+              if (!d1) o[1] = hv.y;
+            }
+            a0 += v0; a1 += v1;
           }
-          const __nv_bfloat162 hv = __floats2bfloat162_rn(v0, v1);
-          __nv_bfloat16* o = dpar_b + (r0 + rb + u) * P + q0;
-          if (!(d0 | d1)) {
-            *reinterpret_cast<__nv_bfloat162*>(o) = hv;
-          } else {                       // (both can be diagonal: a forward run of v ends where a reversed one starts)
-            if (!d0) o[0] = hv.x;
-            if (!d1) o[1] = hv.y;
-          }
-          a0 += __low2float(hv); a1 += __high2float(hv);
         }
       }
-    }
+    };
+    if (nr == kPostRows) tile(std::true_type{}); else tile(std::false_type{});
   }
   if (!db) return;
   if (is_diag) {
