@@ -15,7 +15,6 @@
 // floats between lanes (32-way conflicts) and pay the index map per element, which made them 47 % of the bsds step.
 //
 // Reference sites as in latent.cu: distributions.py:101-113 (TriLGaussian / FillScaleTriL), vae.py:124,130,136-138.
-#include <cstdlib>
 #include <type_traits>
 
 #include "kernels.h"
@@ -219,52 +218,40 @@ __global__ void __launch_bounds__(kThreads) match_fwd64_kernel(const float* __re
 // vectors, i.e. half the operand registers and half the shared memory of a combined kernel, and runs at its own pace.
 constexpr int kPostThreads = 256, kPostRows = 32, kPostPitch = kPostRows + 4, kPairs = P / 2;
 constexpr int kPostBlocksX = (kPairs + D + kPostThreads - 1) / kPostThreads;
-template <int ROLE, int NH>
+template <int ROLE>
 __global__ void __launch_bounds__(kPostThreads, 4) heads_bwd64_kernel(
     const float* __restrict__ par_e, const float* __restrict__ eps, const float* __restrict__ dz_dec, int stop_grad,
     const float* __restrict__ vec_r, const float* __restrict__ vec_g, const float* __restrict__ vec_qd,
     const float* __restrict__ g_kl, const float* __restrict__ g_match, __nv_bfloat16* __restrict__ dpar_b,
     float* __restrict__ db, int64_t B) {
   // ROLE 0: sa = dz_total, sb = eps, sw = g_kl;   ROLE 1: sa = g, sb = r, sw = g_match
-  // One block = NH consecutive tiles of 32 rows x 512 columns; the five column blocks of a row range are adjacent in
-  // launch order, so they run together and share the row vectors and DRAM pages through L2 (a variant where each block
-  // strode over the whole batch, to issue the bias-gradient atomics once, lost that: 2.4x slower, 1.7x the DRAM reads).
-  // NH > 1 divides the number of bias-gradient atomics (one per column and block, every block on the same 2144 words).
+  // One block = one tile of 32 rows x 512 columns; the five column blocks of a row range are adjacent in launch order,
+  // so they run together and share the row vectors and DRAM pages through L2.  Measured and dropped: 64-row tiles
+  // (0.66 vs 0.49 ms), 2 / 4 consecutive tiles per block to divide the bias-gradient atomics (0.43 / 0.51 vs 0.40 ms),
+  // blocks striding over the whole batch (2.4x slower, 1.7x the DRAM reads).
   __shared__ __align__(16) float sa[D][kPostPitch], sb[D][kPostPitch];
   __shared__ float sd[kPostRows][D];                 // the diagonal threads' inputs (last column block only)
   __shared__ __align__(16) float sw[kPostRows];
+  const int64_t r0 = (int64_t)blockIdx.y * kPostRows;
+  const int nr = (int)((B - r0 < kPostRows) ? (B - r0) : kPostRows);
   const int t = blockIdx.x * kPostThreads + threadIdx.x;
-  const bool is_diag = t >= kPairs;                 // spare threads past the last pair: thread = diagonal index
-  const int di = t - kPairs;
-  const int qd = (is_diag && di < D) ? D + diag_q(di) : 0;
   const int q0 = 2 * t;
-  const bool is_loc = q0 < D;
-  int i0 = q0, j0 = 0, i1 = q0 + 1, j1 = 0;
-  if (!is_diag && !is_loc) { v_to_ij(q0 - D, i0, j0); v_to_ij(q0 + 1 - D, i1, j1); }
-  if (is_diag) { i0 = i1 = j0 = j1 = 0; }
-  const bool d0 = !is_loc && i0 == j0, d1 = !is_loc && i1 == j1;     // a diagonal slot: left to the spare threads
-  float a0 = 0.f, a1 = 0.f;                         // bias-gradient partial sums over the rows this block sees
-  auto el = [](const float4& v, int u) { return u == 0 ? v.x : u == 1 ? v.y : u == 2 ? v.z : v.w; };
-  constexpr int kFill = kPostRows * D / kPostThreads;     // 8 elements per thread
-#pragma unroll 1
-  for (int h = 0; h < NH; ++h) {
-    const int64_t r0 = ((int64_t)blockIdx.y * NH + h) * kPostRows;
-    if (r0 >= B) break;
-    const int nr = (int)((B - r0 < kPostRows) ? (B - r0) : kPostRows);
-    // The streaming loop below keeps at most eight 8-byte loads per thread in flight, which at DRAM latency is ~3 TB/s
-    // for the whole chip (ncu: long-scoreboard stalls).  Ask L2 for the block's whole tile of head outputs up front -
-    // prefetches hold no register and no scoreboard - so that the demand loads find it there.
-    if (ROLE == 0 && !is_diag && (threadIdx.x & 15) == 0) {
+  // The streaming loop below keeps at most eight 8-byte loads per thread in flight, which at DRAM latency is ~3 TB/s
+  // for the whole chip (ncu: long-scoreboard stalls).  Ask L2 for the block's whole tile of head outputs up front -
+  // prefetches hold no register and no scoreboard - so that the demand loads find it there.
+  if (ROLE == 0 && t < kPairs && (threadIdx.x & 15) == 0) {
 #pragma unroll 8
-      for (int rr = 0; rr < nr; ++rr)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(par_e + (r0 + rr) * P + q0));
-    }
-    // All loads of the staging phase are issued before the first shared-memory store: a load / store loop made one L2
-    // round trip per iteration (the stores may alias the loads as far as the compiler knows), ~5 us per block.
-    float va[kFill], vb[kFill], vd[kFill], vw = 0.f;
+    for (int rr = 0; rr < nr; ++rr)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(par_e + (r0 + rr) * P + q0));
+  }
+  // All loads of the staging phase are issued before the first shared-memory store: a load / store loop made one L2
+  // round trip per iteration (the stores may alias the loads as far as the compiler knows), ~5 us per block.
+  constexpr int kFill = kPostRows * D / kPostThreads;     // 8 elements per thread
+  {
+    float va[kFill], vb[kFill], vd[kFill];
     if (threadIdx.x < kPostRows) {
       const float* w = ROLE == 0 ? g_kl : g_match;
-      vw = threadIdx.x < nr ? w[r0 + threadIdx.x] : 0.f;
+      sw[threadIdx.x] = threadIdx.x < nr ? w[r0 + threadIdx.x] : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < kFill; ++u) {
@@ -281,7 +268,8 @@ __global__ void __launch_bounds__(kPostThreads, 4) heads_bwd64_kernel(
         vb[u] = ok ? vec_r[r0 * D + e] : 0.f;
       }
     }
-    if (blockIdx.x == kPostBlocksX - 1) {
+    const bool last = blockIdx.x == kPostBlocksX - 1;
+    if (last) {
       // what the diagonal threads below read, fetched by the whole block with every load in flight at once
 #pragma unroll
       for (int u = 0; u < kFill; ++u) {
@@ -291,88 +279,90 @@ __global__ void __launch_bounds__(kPostThreads, 4) heads_bwd64_kernel(
         if (row < nr) vd[u] = ROLE == 0 ? __ldg(par_e + (r0 + row) * P + D + diag_q(i)) : vec_qd[(r0 + row) * D + i];
       }
     }
-    if (h > 0) __syncthreads();                      // the previous tile has been consumed
-    if (threadIdx.x < kPostRows) sw[threadIdx.x] = vw;
 #pragma unroll
     for (int u = 0; u < kFill; ++u) {
       const int e = threadIdx.x + u * kPostThreads;
       sa[e % D][e / D] = va[u];
       sb[e % D][e / D] = vb[u];
-      if (blockIdx.x == kPostBlocksX - 1) sd[e / D][e % D] = vd[u];
+      if (last) sd[e / D][e % D] = vd[u];
     }
-    __syncthreads();
-    if (is_diag) {
-      // The 64 diagonal elements go through softplus / sigmoid.  They sit 65 columns apart, i.e. one in every other
-      // warp: handled in line, those warps would pay the transcendental path (one active lane) for every row.
-      if (di < D) {
+  }
+  __syncthreads();
+  // The 64 diagonal elements go through softplus / sigmoid.  They sit 65 columns apart, i.e. one in every other warp:
+  // handled in line, those warps would pay the transcendental path (one active lane) for every row.  The spare threads
+  // past the last pair take them instead, thread = diagonal index.
+  if (t >= kPairs) {
+    const int i = t - kPairs;
+    if (i >= D) return;
+    const int qd = D + diag_q(i);
+    float acc = 0.f;
 #pragma unroll 4
-        for (int rr = 0; rr < nr; ++rr) {
-          float v;
-          if (ROLE == 0) {
-            const float raw_e = sd[rr][di];
-            const float dg = softplus_f(raw_e) + 1e-5f;
-            v = (sa[di][rr] * sb[di][rr] + sw[rr] * (dg - 1.0f / dg)) * sigmoid_f(raw_e);
-          } else {
-            v = sw[rr] * sd[rr][di];
-          }
-          const __nv_bfloat16 hv = __float2bfloat16(v);
-          dpar_b[(r0 + rr) * P + qd] = hv;
-          a0 += __bfloat162float(hv);
-        }
+    for (int rr = 0; rr < nr; ++rr) {
+      float v;
+      if (ROLE == 0) {
+        const float raw_e = sd[rr][i];
+        const float dg = softplus_f(raw_e) + 1e-5f;
+        v = (sa[i][rr] * sb[i][rr] + sw[rr] * (dg - 1.0f / dg)) * sigmoid_f(raw_e);
+      } else {
+        v = sw[rr] * sd[rr][i];
       }
-      continue;
+      const __nv_bfloat16 hv = __float2bfloat16(v);
+      dpar_b[(r0 + rr) * P + qd] = hv;
+      acc += __bfloat162float(hv);
     }
-    // ncu: this loop is bound by instruction issue and the L1 data stage (31 instructions per thread and row in the
-    // first version), so the full-tile case runs without row guards, with one row pointer and immediate offsets
-    __nv_bfloat16* const orow = dpar_b + r0 * P + q0;
-    const float2* const prow = reinterpret_cast<const float2*>(par_e + r0 * P + q0);
-    auto tile = [&](auto full_tag) {
-      constexpr bool kFull = decltype(full_tag)::value;
+    if (db) atomicAdd(db + qd, acc);
+    return;
+  }
+  const bool is_loc = q0 < D;
+  int i0 = q0, j0 = 0, i1 = q0 + 1, j1 = 0;
+  if (!is_loc) { v_to_ij(q0 - D, i0, j0); v_to_ij(q0 + 1 - D, i1, j1); }
+  const bool d0 = !is_loc && i0 == j0, d1 = !is_loc && i1 == j1;     // a diagonal slot: left to the spare threads
+  float a0 = 0.f, a1 = 0.f;                         // bias-gradient partial sums
+  auto el = [](const float4& v, int u) { return u == 0 ? v.x : u == 1 ? v.y : u == 2 ? v.z : v.w; };
+  // ncu: this loop is bound by instruction issue and the L1 data stage (31 instructions per thread and row in the
+  // first version), so the full-tile case runs without row guards, with one row pointer and immediate offsets
+  __nv_bfloat16* const orow = dpar_b + r0 * P + q0;
+  const float2* const prow = reinterpret_cast<const float2*>(par_e + r0 * P + q0);
+  auto tile = [&](auto full_tag) {
+    constexpr bool kFull = decltype(full_tag)::value;
 #pragma unroll 2
-      for (int rb = 0; rb < kPostRows; rb += 4) {
-        float2 raw[4];
-        if (ROLE == 0) {
+    for (int rb = 0; rb < kPostRows; rb += 4) {
+      float2 raw[4];
+      if (ROLE == 0) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            raw[u] = (kFull || rb + u < nr) ? __ldg(prow + (rb + u) * (P / 2)) : make_float2(0.f, 0.f);
-        }
-        const float4 w = *reinterpret_cast<const float4*>(&sw[rb]);
-        const float4 aA = *reinterpret_cast<const float4*>(&sa[i0][rb]), aB = *reinterpret_cast<const float4*>(&sa[i1][rb]);
-        float4 bA = *reinterpret_cast<const float4*>(&sb[j0][rb]), bB = *reinterpret_cast<const float4*>(&sb[j1][rb]);
-        if (is_loc) { bA = bB = make_float4(1.f, 1.f, 1.f, 1.f); }
+        for (int u = 0; u < 4; ++u)
+          raw[u] = (kFull || rb + u < nr) ? __ldg(prow + (rb + u) * (P / 2)) : make_float2(0.f, 0.f);
+      }
+      const float4 w = *reinterpret_cast<const float4*>(&sw[rb]);
+      const float4 aA = *reinterpret_cast<const float4*>(&sa[i0][rb]), aB = *reinterpret_cast<const float4*>(&sa[i1][rb]);
+      float4 bA = *reinterpret_cast<const float4*>(&sb[j0][rb]), bB = *reinterpret_cast<const float4*>(&sb[j1][rb]);
+      if (is_loc) { bA = bB = make_float4(1.f, 1.f, 1.f, 1.f); }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (kFull || rb + u < nr) {
-            float v0, v1;
-            if (ROLE == 0) {
-              v0 = fmaf(el(aA, u), el(bA, u), el(w, u) * raw[u].x);
-              v1 = fmaf(el(aB, u), el(bB, u), el(w, u) * raw[u].y);
-            } else {
-              v0 = el(w, u) * el(aA, u) * el(bA, u);
-              v1 = el(w, u) * el(aB, u) * el(bB, u);
-            }
-            const __nv_bfloat162 hv = __floats2bfloat162_rn(v0, v1);
-            __nv_bfloat16* o = orow + (rb + u) * P;
-            if (!(d0 | d1)) {
-              *reinterpret_cast<__nv_bfloat162*>(o) = hv;
-            } else {                     // (both can be diagonal: a forward run of v ends where a reversed one starts)
-              if (!d0) o[0] = hv.x;
-              if (!d1) o[1] = hv.y;
-            }
-            a0 += v0; a1 += v1;
+      for (int u = 0; u < 4; ++u) {
+        if (kFull || rb + u < nr) {
+          float v0, v1;
+          if (ROLE == 0) {
+            v0 = fmaf(el(aA, u), el(bA, u), el(w, u) * raw[u].x);
+            v1 = fmaf(el(aB, u), el(bB, u), el(w, u) * raw[u].y);
+          } else {
+            v0 = el(w, u) * el(aA, u) * el(bA, u);
+            v1 = el(w, u) * el(aB, u) * el(bB, u);
           }
+          const __nv_bfloat162 hv = __floats2bfloat162_rn(v0, v1);
+          __nv_bfloat16* o = orow + (rb + u) * P;
+          if (!(d0 | d1)) {
+            *reinterpret_cast<__nv_bfloat162*>(o) = hv;
+          } else {                       // (both can be diagonal: a forward run of v ends where a reversed one starts)
+            if (!d0) o[0] = hv.x;
+            if (!d1) o[1] = hv.y;
+          }
+          a0 += v0; a1 += v1;
         }
       }
-    };
-    if (nr == kPostRows) tile(std::true_type{}); else tile(std::false_type{});
-  }
-  if (!db) return;
-  if (is_diag) {
-    if (di < D) atomicAdd(db + qd, a0);
-  } else {
-    if (!d0) atomicAdd(db + q0, a0);
-    if (!d1) atomicAdd(db + q0 + 1, a1);
-  }
+    }
+  };
+  if (nr == kPostRows) tile(std::true_type{}); else tile(std::false_type{});
+  if (db) { if (!d0) atomicAdd(db + q0, a0); if (!d1) atomicAdd(db + q0 + 1, a1); }
 }
 
 static int grid_rows(int64_t B, int blocks_per_sm) {
@@ -415,16 +405,12 @@ int latent_bwd64(const float* par_e, const float* eps, const float* dz_dec, cons
                  int stop_grad, __nv_bfloat16* dpar_e_b, __nv_bfloat16* dpar_p_b, float* db_e, float* db_p,
                  const float* vec_r, const float* vec_g, const float* vec_qd, int64_t B, cudaStream_t s) {
   using namespace l64;
-  static const int nh = [] { const char* e = getenv("PMVAE_HEADS_NH"); const int v = e ? atoi(e) : 1; return (v == 2 || v == 4) ? v : 1; }();   // measured: 1 is best (0.40 + 0.25 ms; 2: 0.43 + 0.25; 4: 0.51 + 0.27)
-  const int64_t n_rb = (B + kPostRows - 1) / kPostRows;
-  const dim3 grid(kPostBlocksX, (unsigned)((n_rb + nh - 1) / nh));
-#define PMVAE_HEADS(ROLE, NH, OUT, DB)                                                                                  \
-  heads_bwd64_kernel<ROLE, NH><<<grid, kPostThreads, 0, s>>>(par_e, eps, dz_dec, stop_grad, vec_r, vec_g, vec_qd, g_kl, \
-                                                             g_match, OUT, DB, B)
-  if (nh == 1) PMVAE_HEADS(0, 1, dpar_e_b, db_e); else if (nh == 2) PMVAE_HEADS(0, 2, dpar_e_b, db_e); else PMVAE_HEADS(0, 4, dpar_e_b, db_e);
+  const dim3 grid(kPostBlocksX, (unsigned)((B + kPostRows - 1) / kPostRows));
+  heads_bwd64_kernel<0><<<grid, kPostThreads, 0, s>>>(par_e, eps, dz_dec, stop_grad, vec_r, vec_g, vec_qd, g_kl, g_match,
+                                                      dpar_e_b, db_e, B);
   PMVAE_LAUNCH_CHECK();
-  if (nh == 1) PMVAE_HEADS(1, 1, dpar_p_b, db_p); else if (nh == 2) PMVAE_HEADS(1, 2, dpar_p_b, db_p); else PMVAE_HEADS(1, 4, dpar_p_b, db_p);
-#undef PMVAE_HEADS
+  heads_bwd64_kernel<1><<<grid, kPostThreads, 0, s>>>(par_e, eps, dz_dec, stop_grad, vec_r, vec_g, vec_qd, g_kl, g_match,
+                                                      dpar_p_b, db_p, B);
   PMVAE_LAUNCH_CHECK();
   return 0;
 }
