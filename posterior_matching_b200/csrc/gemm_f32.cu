@@ -22,9 +22,18 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32Args p) {
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int tx = tid % 16, ty = tid / 16;  // thread tile: rows ty*4.., cols tx*4..
+  // blockIdx.z = batch index * splits + split-K index; a batch member is the same problem at strided pointers
+  const int nsplit = (int)gridDim.z / p.batch;
+  const int bi = (int)blockIdx.z / nsplit, zi = (int)blockIdx.z - bi * nsplit;
+  if (p.batch > 1) {
+    p.A += bi * p.sA; p.B += bi * p.sB; p.C += bi * p.sC;
+    if (p.bias) p.bias += bi * p.sBias;
+    if (p.mask) p.mask += bi * p.sMask;
+    if (p.resid) p.resid += bi * p.sResid;
+  }
   // split-K range
-  const int64_t kchunk = ((p.K + gridDim.z - 1) / gridDim.z + BK - 1) / BK * BK;
-  const int64_t kbeg = (int64_t)blockIdx.z * kchunk;
+  const int64_t kchunk = ((p.K + nsplit - 1) / nsplit + BK - 1) / BK * BK;
+  const int64_t kbeg = (int64_t)zi * kchunk;
   const int64_t kend = min((int64_t)p.K, kbeg + kchunk);
 
   float acc[TM][TN];
@@ -141,10 +150,13 @@ int gemm_f32(const GemmF32Args& a, bool ta, bool tb, cudaStream_t stream) {
   PMVAE_CHECK(a.M >= 0 && a.N > 0 && a.K >= 0, "bad gemm shape");
   if (a.M == 0) return 0;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-  const bool vec = al16(a.A) && al16(a.B) && a.lda % 4 == 0 && a.ldb % 4 == 0;
+  PMVAE_CHECK(a.batch >= 1, "bad batch count");
+  const bool vec = al16(a.A) && al16(a.B) && a.lda % 4 == 0 && a.ldb % 4 == 0 &&
+                   (a.batch == 1 || (a.sA % 4 == 0 && a.sB % 4 == 0));
   int split = a.atomic ? a.split_k : 1;
   if (split < 1) split = 1;
-  dim3 grid((unsigned)ceil_div(a.N, BN), (unsigned)ceil_div(a.M, BM), (unsigned)split);
+  PMVAE_CHECK((int64_t)split * a.batch <= 65535, "batch x split-K exceeds the grid's z extent");
+  dim3 grid((unsigned)ceil_div(a.N, BN), (unsigned)ceil_div(a.M, BM), (unsigned)(split * a.batch));
   PMVAE_CHECK(grid.y <= 65535u * 1u || true, "");
   // blockIdx.y is limited to 65535: M up to 4.1M rows per call
   PMVAE_CHECK(ceil_div(a.M, BM) <= 65535, "M too large for one gemm_f32 launch");

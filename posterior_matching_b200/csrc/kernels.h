@@ -31,6 +31,9 @@ struct GemmF32Args {
   int relu_a = 0;
   int atomic = 0;   // atomicAdd the raw product into C (split-K over gridDim.z)
   int split_k = 1;
+  // `batch` independent problems of the same shape in one launch: member i uses A + i sA, B + i sB, C + i sC, ... (elements)
+  int batch = 1;
+  int64_t sA = 0, sB = 0, sC = 0, sBias = 0, sMask = 0, sResid = 0;
 };
 int gemm_f32(const GemmF32Args& a, bool ta, bool tb, cudaStream_t stream);
 

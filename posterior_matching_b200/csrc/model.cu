@@ -203,8 +203,34 @@ static int lin_fwd(const float* params, const Leaf& lf, const float* in, int64_t
   return gemm_f32(a, false, false, s);
 }
 
+// Head Linear restricted to the diagonal blocks of a (row block, column block) partition: rows [i rb, (i+1) rb) only
+// need columns [i cb, (i+1) cb).  The AutoregressiveGMM batches its d steps as d row blocks and reads, for step i, only
+// the 3 K parameters of dimension i out of the 3 K d the Linear produces (distributions.py:153-166), so 1/d of the head
+// GEMM is ever used; `only` >= 0 computes that one block (the sampler, one step at a time).  Entries outside the
+// blocks are not written.
+static int head_fwd_blocks(const float* params, const Leaf& head, const float* act, int H, int64_t B, int blocks, int only,
+                           float* head_out, cudaStream_t s) {
+  PMVAE_CHECK(blocks >= 1 && head.cols % blocks == 0 && only < blocks && (only >= 0 || B % blocks == 0),
+              "block-diagonal head: sizes do not divide");
+  const int64_t rb = only >= 0 ? B : B / blocks;
+  const int cb = head.cols / blocks;
+  const int i0 = only >= 0 ? only : 0;
+  GemmF32Args a{};                         // one launch: batch member i = block i (or the single block `only`)
+  a.M = rb; a.N = cb; a.K = head.rows;
+  a.A = act; a.lda = H;
+  a.B = params + head.w + (int64_t)i0 * cb; a.ldb = head.cols;
+  a.C = head_out + (int64_t)i0 * cb; a.ldc = head.cols;
+  a.bias = params + head.b + (int64_t)i0 * cb;
+  a.relu_a = 1;
+  if (only < 0) {
+    a.batch = blocks;
+    a.sA = rb * H; a.sB = cb; a.sC = rb * head.cols + cb; a.sBias = cb;
+  }
+  return gemm_f32(a, false, false, s);
+}
+
 static int net_fwd_f32(const float* params, const Net& n, const Leaf& head, int H, const float* in, int64_t B,
-                       const NetSaved& sv, float* head_out, cudaStream_t s) {
+                       const NetSaved& sv, float* head_out, cudaStream_t s, int head_blocks = 1, int head_only = -1) {
   PMVAE_TRY(lin_fwd(params, n.lin[0], in, n.in_dim, 0, B, sv.H[0], nullptr, s));
   if (n.ln) PMVAE_TRY(ln_fwd(sv.H[0], sv.rstd0, nullptr, nullptr, B, H, s));
   for (int r = 0; r < n.R; ++r) {
@@ -217,6 +243,7 @@ static int net_fwd_f32(const float* params, const Net& n, const Leaf& head, int 
       PMVAE_TRY(lin_fwd(params, n.lin[2 * r + 2], sv.U[r], H, 1, B, sv.H[r + 1], sv.H[r], s));
     }
   }
+  if (head_blocks > 1) return head_fwd_blocks(params, head, sv.H[n.R], H, B, head_blocks, head_only, head_out, s);
   return lin_fwd(params, head, sv.H[n.R], H, 1, B, head_out, nullptr, s);
 }
 
@@ -256,11 +283,41 @@ static int lin_bwd_input(const float* params, const Leaf& lf, const float* dY, i
   return gemm_f32(a, false, true, s);
 }
 
+// VJP of head_fwd_blocks (all blocks): dHead is read on the diagonal blocks only.
+static int head_bwd_blocks(const float* params, float* grads, const Leaf& head, const float* act, int H, int64_t B,
+                           int blocks, const float* dHead, float* dH, cudaStream_t s) {
+  PMVAE_CHECK(blocks >= 1 && B % blocks == 0 && head.cols % blocks == 0, "block-diagonal head: sizes do not divide");
+  const int64_t rb = B / blocks;
+  const int cb = head.cols / blocks;
+  GemmF32Args w{};                         // gW[:, block i] += relu(act_i)^T dy_i, all blocks in one launch
+  w.M = head.rows; w.N = cb; w.K = rb;
+  w.A = act; w.lda = H;
+  w.B = dHead; w.ldb = head.cols;
+  w.C = grads + head.w; w.ldc = head.cols;
+  w.relu_a = 1; w.atomic = 1; w.split_k = split_for(head.rows, (int64_t)cb * blocks, rb);
+  w.batch = blocks; w.sA = rb * H; w.sB = rb * head.cols + cb; w.sC = cb;
+  PMVAE_TRY(gemm_f32(w, true, false, s));
+  for (int i = 0; i < blocks; ++i)
+    PMVAE_TRY(colsum_add(dHead + i * rb * head.cols + (int64_t)i * cb, head.cols, grads + head.b + (int64_t)i * cb, rb, cb, s));
+  GemmF32Args x{};                         // dH_i = (dy_i W[:, block i]^T) * (act_i > 0)
+  x.M = rb; x.N = head.rows; x.K = cb;
+  x.A = dHead; x.lda = head.cols;
+  x.B = params + head.w; x.ldb = head.cols;
+  x.C = dH; x.ldc = head.rows;
+  x.mask = act; x.ldmask = H;
+  x.batch = blocks; x.sA = rb * head.cols + cb; x.sB = cb; x.sC = rb * head.rows; x.sMask = rb * H;
+  return gemm_f32(x, false, true, s);
+}
+
 static int net_bwd_f32(const float* params, float* grads, const Net& n, const Leaf& head, int H, const float* in,
                        int64_t B, const NetSaved& sv, const float* dHead, float* dH, float* tmp1, float* tmp2,
-                       float* dIn, cudaStream_t s) {
-  PMVAE_TRY(lin_bwd_params(grads, head, sv.H[n.R], H, 1, dHead, B, s));
-  PMVAE_TRY(lin_bwd_input(params, head, dHead, B, dH, sv.H[n.R], nullptr, s));
+                       float* dIn, cudaStream_t s, int head_blocks = 1) {
+  if (head_blocks > 1) {
+    PMVAE_TRY(head_bwd_blocks(params, grads, head, sv.H[n.R], H, B, head_blocks, dHead, dH, s));
+  } else {
+    PMVAE_TRY(lin_bwd_params(grads, head, sv.H[n.R], H, 1, dHead, B, s));
+    PMVAE_TRY(lin_bwd_input(params, head, dHead, B, dH, sv.H[n.R], nullptr, s));
+  }
   for (int r = n.R - 1; r >= 0; --r) {
     const float* dV = dH;
     if (n.ln) { PMVAE_TRY(ln_bwd(dH, sv.V[r], sv.rstdV[r], tmp1, B, H, s)); dV = tmp1; }
@@ -486,7 +543,7 @@ int argmm_log_prob(const pmvae_argmm_config* c, const float* params, const float
   ArgmmPlan p = plan_argmm(c, L, B, ws);
   PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_argmm_workspace_bytes)");
   PMVAE_TRY(argmm_input(z, ctx, B, c->d, c->C, p.X, s));
-  PMVAE_TRY(net_fwd_f32(params, L.net, L.head, c->H, p.X, (int64_t)c->d * B, p.sv, p.out, s));
+  PMVAE_TRY(net_fwd_f32(params, L.net, L.head, c->H, p.X, (int64_t)c->d * B, p.sv, p.out, s, c->d));
   return argmm_lp(p.out, z, B, c->d, c->n_comp, out, s);
 }
 
@@ -503,9 +560,9 @@ int argmm_backward(const pmvae_argmm_config* c, const float* params, const float
   ArgmmPlan p = plan_argmm(c, L, B, ws);
   PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_argmm_workspace_bytes)");
   const int64_t M = (int64_t)c->d * B;
-  PMVAE_CUDA(cudaMemsetAsync(p.dout, 0, (size_t)M * L.cols * sizeof(float), s));
+  // (argmm_lp_bwd writes, and the block-diagonal head VJP reads, only the 3 K columns of step i in row block i)
   PMVAE_TRY(argmm_lp_bwd(p.out, z, g, B, c->d, c->n_comp, p.dout, p.dzd, s));
-  PMVAE_TRY(net_bwd_f32(params, grads, L.net, L.head, c->H, p.X, M, p.sv, p.dout, p.dH, p.tmp1, p.tmp2, p.dX, s));
+  PMVAE_TRY(net_bwd_f32(params, grads, L.net, L.head, c->H, p.X, M, p.sv, p.dout, p.dH, p.tmp1, p.tmp2, p.dX, s, c->d));
   if (dz || dctx) PMVAE_TRY(argmm_reduce_dx(p.dX, p.dzd, B, c->d, c->C, dz, dctx, s));
   return 0;
 }
@@ -545,7 +602,7 @@ int argmm_sample(const pmvae_argmm_config* c, const float* params, const float* 
   PMVAE_CUDA(cudaMemsetAsync(out, 0, (size_t)M * c->d * sizeof(float), s));
   for (int i = 0; i < c->d; ++i) {
     PMVAE_TRY(argmm_sample_input(out, ctx, M, B, c->d, c->C, i, p.X, s));
-    PMVAE_TRY(net_fwd_f32(params, L.net, L.head, c->H, p.X, M, p.sv, p.out, s));
+    PMVAE_TRY(net_fwd_f32(params, L.net, L.head, c->H, p.X, M, p.sv, p.out, s, c->d, i));
     PMVAE_TRY(argmm_sample_step(p.out, p.eps, p.u, M, B, c->d, c->n_comp, i, out, s));
   }
   return 0;
