@@ -287,7 +287,8 @@ typedef struct pmvae_argmm_config {
   int32_t R;       /* residual_blocks                     */
   int32_t H;       /* hidden_units                        */
   int32_t C;       /* flattened context features          */
-  int32_t reserved[3];
+  int32_t reserved[3]; /* [0] = 1: hidden 256 x 256 Linears on the tcgen05 GEMMs with bf16 operands and fp32
+                        * accumulation (first Linear, mixture head and density algebra stay float32); else 0 */
 } pmvae_argmm_config;
 uint64_t pmvae_argmm_param_count(const pmvae_argmm_config* cfg);
 int pmvae_argmm_layout(const pmvae_argmm_config* cfg, pmvae_leaf* out, int cap);

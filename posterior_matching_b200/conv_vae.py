@@ -96,7 +96,7 @@ class ConvPosteriorMatchingVAE:
         ar_cfg = dict(config.get("partial_posterior_dist_config", {}) or {})
         self.argmm = AutoregressiveGMM(d, ar_cfg.get("num_components", 10), ar_cfg.get("residual_blocks", 2),
                                        ar_cfg.get("hidden_units", 256), context_size=self.part.out_hw ** 2 * self.part.out_c,
-                                       device=self.device)
+                                       device=self.device, precision=precision)
         self.bern = Bernoulli(device=self.device)
         # one flat arena for the conv / head leaves (the AR-GMM keeps its own arena inside `self.argmm`)
         self.leaves = self.enc.leaf_shapes() + [("posterior_dist/linear", (self.enc_feat, self.P), self.P)] + \

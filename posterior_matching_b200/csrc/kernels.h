@@ -104,6 +104,14 @@ int sample_latents16(const float* par, Key2 key, int64_t B, int64_t K, int64_t B
 int latent_bwd16(const float* par_e, const float* par_p, const float* eps, const float* z, const float* dz_dec,
                  const float* g_kl, const float* g_match, int stop_grad, __nv_bfloat16* dpar_e_b,
                  __nv_bfloat16* dpar_p_b, float* db_e, float* db_p, int64_t B, cudaStream_t s);
+// tensor.cu: one hidden 256 x 256 Linear of a float32 net on the tcgen05 GEMMs (bf16 operand copies, fp32 results)
+uint64_t hidden_images_bytes(int n_leaves);
+int hidden_images_pack(const float* params, const struct Leaf* leaves, int n, void* img, const __nv_bfloat16** wn,
+                       const __nv_bfloat16** wt, cudaStream_t s);
+int hidden_fwd_tc(const float* x, const __nv_bfloat16* wt, const float* bias, const float* resid, int64_t M, float* y,
+                  __nv_bfloat16* xb, cudaStream_t s);
+int hidden_bwd_tc(const float* x, const float* dy, const __nv_bfloat16* wn, float* gW, float* dx, const float* resid,
+                  int64_t M, __nv_bfloat16* xb, __nv_bfloat16* dyb, cudaStream_t s);
 // latent64.cu: warp-per-row versions for d = 64 (dense [64][65] factor in shared memory; bf16 gradient outputs only)
 int latent_fwd64(const float* par, const float* eps, float* z, float* kl, int64_t B, cudaStream_t s);
 // match_fwd64 with save_* != NULL (training forward) also writes r = L_p^-1 (z - mu_p), g = L_p^-T r and the diagonal

@@ -229,11 +229,25 @@ static int head_fwd_blocks(const float* params, const Leaf& head, const float* a
   return gemm_f32(a, false, false, s);
 }
 
+// Optional tensor-core route for the hidden H x H Linears (H = 256, no LayerNorm) of a float32-composed net: bf16 images
+// of lin[1 .. 2R] (wn[l - 1], wt[l - 1]) and two bf16 scratch tensors of [rows, 256] (tensor.cu::hidden_*_tc).
+struct HiddenTc {
+  const __nv_bfloat16* wn[2 * kMaxBlocks];
+  const __nv_bfloat16* wt[2 * kMaxBlocks];
+  __nv_bfloat16 *xb, *dyb;
+};
+
 static int net_fwd_f32(const float* params, const Net& n, const Leaf& head, int H, const float* in, int64_t B,
-                       const NetSaved& sv, float* head_out, cudaStream_t s, int head_blocks = 1, int head_only = -1) {
+                       const NetSaved& sv, float* head_out, cudaStream_t s, int head_blocks = 1, int head_only = -1,
+                       const HiddenTc* tcp = nullptr) {
   PMVAE_TRY(lin_fwd(params, n.lin[0], in, n.in_dim, 0, B, sv.H[0], nullptr, s));
   if (n.ln) PMVAE_TRY(ln_fwd(sv.H[0], sv.rstd0, nullptr, nullptr, B, H, s));
   for (int r = 0; r < n.R; ++r) {
+    if (tcp) {
+      PMVAE_TRY(hidden_fwd_tc(sv.H[r], tcp->wt[2 * r], params + n.lin[2 * r + 1].b, nullptr, B, sv.U[r], tcp->xb, s));
+      PMVAE_TRY(hidden_fwd_tc(sv.U[r], tcp->wt[2 * r + 1], params + n.lin[2 * r + 2].b, sv.H[r], B, sv.H[r + 1], tcp->xb, s));
+      continue;
+    }
     PMVAE_TRY(lin_fwd(params, n.lin[2 * r + 1], sv.H[r], H, 1, B, sv.U[r], nullptr, s));
     if (n.ln) {
       PMVAE_TRY(ln_fwd(sv.U[r], sv.rstdU[r], nullptr, nullptr, B, H, s));
@@ -311,7 +325,7 @@ static int head_bwd_blocks(const float* params, float* grads, const Leaf& head, 
 
 static int net_bwd_f32(const float* params, float* grads, const Net& n, const Leaf& head, int H, const float* in,
                        int64_t B, const NetSaved& sv, const float* dHead, float* dH, float* tmp1, float* tmp2,
-                       float* dIn, cudaStream_t s, int head_blocks = 1) {
+                       float* dIn, cudaStream_t s, int head_blocks = 1, const HiddenTc* tcp = nullptr) {
   if (head_blocks > 1) {
     PMVAE_TRY(head_bwd_blocks(params, grads, head, sv.H[n.R], H, B, head_blocks, dHead, dH, s));
   } else {
@@ -319,6 +333,15 @@ static int net_bwd_f32(const float* params, float* grads, const Net& n, const Le
     PMVAE_TRY(lin_bwd_input(params, head, dHead, B, dH, sv.H[n.R], nullptr, s));
   }
   for (int r = n.R - 1; r >= 0; --r) {
+    if (tcp) {
+      const Leaf& l2 = n.lin[2 * r + 2];
+      const Leaf& l1 = n.lin[2 * r + 1];
+      PMVAE_TRY(colsum_add(dH, l2.cols, grads + l2.b, B, l2.cols, s));
+      PMVAE_TRY(hidden_bwd_tc(sv.U[r], dH, tcp->wn[2 * r + 1], grads + l2.w, tmp2, nullptr, B, tcp->xb, tcp->dyb, s));
+      PMVAE_TRY(colsum_add(tmp2, l1.cols, grads + l1.b, B, l1.cols, s));
+      PMVAE_TRY(hidden_bwd_tc(sv.H[r], tmp2, tcp->wn[2 * r], grads + l1.w, dH, dH, B, tcp->xb, tcp->dyb, s));
+      continue;
+    }
     const float* dV = dH;
     if (n.ln) { PMVAE_TRY(ln_bwd(dH, sv.V[r], sv.rstdV[r], tmp1, B, H, s)); dV = tmp1; }
     PMVAE_TRY(lin_bwd_params(grads, n.lin[2 * r + 2], sv.U[r], H, 1, dV, B, s));
@@ -514,8 +537,15 @@ static int build_argmm_layout(const pmvae_argmm_config* c, ArgmmLayout* L) {
 struct ArgmmPlan {
   NetSaved sv;
   float *X, *out, *dout, *dH, *tmp1, *tmp2, *dX, *dzd;
+  void* img;                 // bf16 images of the hidden Linears (tensor-core route only)
+  HiddenTc tc;
+  bool use_tc;
   uint64_t bytes;
 };
+
+// pmvae_argmm_config.reserved[0] = 1: hidden Linears on the tcgen05 GEMMs with bf16 operands (the first Linear, the
+// block-diagonal head and all mixture algebra stay float32)
+static bool argmm_tc(const pmvae_argmm_config* c) { return c->reserved[0] == 1 && c->H == 256 && c->R >= 1; }
 
 static ArgmmPlan plan_argmm(const pmvae_argmm_config* c, const ArgmmLayout& L, int64_t B, void* ws) {
   ArgmmPlan p{};
@@ -530,6 +560,12 @@ static ArgmmPlan plan_argmm(const pmvae_argmm_config* c, const ArgmmLayout& L, i
   p.tmp2 = bp.take<float>((uint64_t)M * c->H);
   p.dX = bp.take<float>((uint64_t)M * L.F);
   p.dzd = bp.take<float>((uint64_t)B * c->d);
+  p.use_tc = argmm_tc(c);
+  if (p.use_tc) {
+    p.img = bp.take<char>(hidden_images_bytes(2 * c->R));
+    p.tc.xb = bp.take<__nv_bfloat16>((uint64_t)M * c->H);
+    p.tc.dyb = bp.take<__nv_bfloat16>((uint64_t)M * c->H);
+  }
   p.bytes = bp.off;
   return p;
 }
@@ -543,7 +579,9 @@ int argmm_log_prob(const pmvae_argmm_config* c, const float* params, const float
   ArgmmPlan p = plan_argmm(c, L, B, ws);
   PMVAE_CHECK(p.bytes <= ws_bytes, "workspace too small (see pmvae_argmm_workspace_bytes)");
   PMVAE_TRY(argmm_input(z, ctx, B, c->d, c->C, p.X, s));
-  PMVAE_TRY(net_fwd_f32(params, L.net, L.head, c->H, p.X, (int64_t)c->d * B, p.sv, p.out, s, c->d));
+  if (p.use_tc) PMVAE_TRY(hidden_images_pack(params, &L.net.lin[1], 2 * c->R, p.img, p.tc.wn, p.tc.wt, s));
+  PMVAE_TRY(net_fwd_f32(params, L.net, L.head, c->H, p.X, (int64_t)c->d * B, p.sv, p.out, s, c->d, -1,
+                        p.use_tc ? &p.tc : nullptr));
   return argmm_lp(p.out, z, B, c->d, c->n_comp, out, s);
 }
 
@@ -562,7 +600,14 @@ int argmm_backward(const pmvae_argmm_config* c, const float* params, const float
   const int64_t M = (int64_t)c->d * B;
   // (argmm_lp_bwd writes, and the block-diagonal head VJP reads, only the 3 K columns of step i in row block i)
   PMVAE_TRY(argmm_lp_bwd(p.out, z, g, B, c->d, c->n_comp, p.dout, p.dzd, s));
-  PMVAE_TRY(net_bwd_f32(params, grads, L.net, L.head, c->H, p.X, M, p.sv, p.dout, p.dH, p.tmp1, p.tmp2, p.dX, s, c->d));
+  // (tensor-core route: the bf16 weight images packed by argmm_log_prob are still in `ws`, like the activations)
+  if (p.use_tc)
+    for (int l = 0; l < 2 * c->R; ++l) {
+      p.tc.wn[l] = reinterpret_cast<const __nv_bfloat16*>(p.img) + (uint64_t)(2 * l) * 256 * 256;
+      p.tc.wt[l] = reinterpret_cast<const __nv_bfloat16*>(p.img) + (uint64_t)(2 * l + 1) * 256 * 256;
+    }
+  PMVAE_TRY(net_bwd_f32(params, grads, L.net, L.head, c->H, p.X, M, p.sv, p.dout, p.dH, p.tmp1, p.tmp2, p.dX, s, c->d,
+                        p.use_tc ? &p.tc : nullptr));
   if (dz || dctx) PMVAE_TRY(argmm_reduce_dx(p.dX, p.dzd, B, c->d, c->C, dz, dctx, s));
   return 0;
 }

@@ -40,7 +40,7 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kSmemBytes = kStages * kStageBytes + 256 /*barriers*/ + kEpiWarps * 32 * kStagePitch * 4 + 1024 /*align slack*/;
 
 // ---------------------------------------------------------------- kernel
-// EPI selects the auxiliary input streams of the NT epilogue: 0 none, 1 fp32 residual,
+// EPI selects the auxiliary input streams of the NT epilogue: 0 none, 1 fp32 residual, 3 bf16 mask then fp32 residual,
 // 2 bf16 relu mask (+ optional bf16 residual).
 template <int KIND, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -231,11 +231,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int i = 0; i < kRowBatch; ++i) {
               const int64_t row = row0 + rb + i;
               const bool ok = col_ok && row < p.M;
-              if (EPI == 2) {
+              if (EPI == 2 || EPI == 3)
                 mk[i] = ok ? __ldg(reinterpret_cast<const uint32_t*>(p.mask_bf16 + row * p.ld_mask + n)) : 0u;
+              if (EPI == 2)
                 rbv[i] = (ok && p.resid_bf16) ? *reinterpret_cast<const uint32_t*>(p.resid_bf16 + row * p.ld_resid_bf16 + n) : 0u;
-              }
-              if (EPI == 1) rf[i] = ok ? *reinterpret_cast<const float2*>(p.resid_f32 + row * p.ld_resid_f32 + n) : make_float2(0.f, 0.f);
+              if (EPI == 1 || EPI == 3)
+                rf[i] = ok ? *reinterpret_cast<const float2*>(p.resid_f32 + row * p.ld_resid_f32 + n) : make_float2(0.f, 0.f);
             }
 #pragma unroll
             for (int i = 0; i < kRowBatch; ++i) {
@@ -243,12 +244,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               if (!(col_ok && row < p.M)) continue;
               float2 v = *reinterpret_cast<const float2*>(stage + (rb + i) * kStagePitch + 2 * lane);
               v.x += bias2.x; v.y += bias2.y;
-              if (EPI == 2) {
+              if (EPI == 2 || EPI == 3) {
                 if (!(bf16_lo(mk[i]) > 0.f)) v.x = 0.f;
                 if (!(bf16_hi(mk[i]) > 0.f)) v.y = 0.f;
-                v.x += bf16_lo(rbv[i]); v.y += bf16_hi(rbv[i]);
               }
-              if (EPI == 1) { v.x += rf[i].x; v.y += rf[i].y; }
+              if (EPI == 2) { v.x += bf16_lo(rbv[i]); v.y += bf16_hi(rbv[i]); }
+              if (EPI == 1 || EPI == 3) { v.x += rf[i].x; v.y += rf[i].y; }   // (EPI 3: mask, then the fp32 residual)
               if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + row * p.ld_out_f32 + n) = v;
               if (p.out_bf16) {
                 if (p.relu_out) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
@@ -541,8 +542,9 @@ int gemm_nt(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Bt, int64_
   CUtensorMap ma, mb;
   PMVAE_TRY(make_map(&ma, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBlockK, kBlockM));
   PMVAE_TRY(make_map(&mb, Bt, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, kBlockK, (uint32_t)ep.n_tile));
-  PMVAE_CHECK(!(ep.resid_f32 && (ep.mask_bf16 || ep.resid_bf16)), "unsupported epilogue combination");
+  PMVAE_CHECK(!(ep.resid_f32 && ep.resid_bf16), "unsupported epilogue combination");
   PMVAE_CHECK(!(ep.resid_bf16 && !ep.mask_bf16), "bf16 residual needs a mask");
+  if (ep.resid_f32 && ep.mask_bf16) return launch<0, 3>(ma, mb, ep, s);
   if (ep.resid_f32) return launch<0, 1>(ma, mb, ep, s);
   if (ep.mask_bf16) return launch<0, 2>(ma, mb, ep, s);
   return launch<0, 0>(ma, mb, ep, s);

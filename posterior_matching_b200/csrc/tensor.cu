@@ -906,6 +906,54 @@ int net_apply_bf16(const pmvae_config* c, const Layout& L, const float* params, 
   return 0;
 }
 
+// ---------------------------------------------------------------- hidden 256 x 256 Linears of a host-composed net
+// (the AutoregressiveGMM of the MNIST config, model.cu): the float32 net keeps its float32 activations; one hidden Linear
+// at a time takes the tcgen05 GEMMs with bf16 copies of its operands (fp32 accumulation, fp32 results).
+uint64_t hidden_images_bytes(int n_leaves) { return (uint64_t)n_leaves * 2 * 256 * 256 * sizeof(bf16); }
+
+// img: hidden_images_bytes(n) of scratch; leaf i -> wn[i] = bf16(W) [256, 256], wt[i] = bf16(W^T)
+int hidden_images_pack(const float* params, const Leaf* leaves, int n, void* img, const bf16** wn, const bf16** wt,
+                       cudaStream_t s) {
+  PMVAE_CHECK(n >= 0 && n <= 48, "too many leaves for one pack launch");
+  if (n == 0) return 0;
+  PackTable tb{};
+  tb.n = n;
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    PMVAE_CHECK(leaves[i].rows == 256 && leaves[i].cols == 256, "hidden Linear images are 256 x 256");
+    PackLeaf& pl = tb.leaf[i];
+    pl.w_off = leaves[i].w; pl.rows = 256; pl.cols = 256; pl.ldn = 256; pl.ldt = 256;
+    pl.wn_off = (uint64_t)(2 * i) * 256 * 256; pl.wt_off = (uint64_t)(2 * i + 1) * 256 * 256;
+    pl.tile0 = tiles; tiles += 64;
+    wn[i] = reinterpret_cast<const bf16*>(img) + pl.wn_off;
+    wt[i] = reinterpret_cast<const bf16*>(img) + pl.wt_off;
+  }
+  tb.total_tiles = tiles;
+  pack_weights_kernel<<<tiles, 256, 0, s>>>(params, reinterpret_cast<bf16*>(img), tb);
+  PMVAE_LAUNCH_CHECK();
+  return 0;
+}
+
+// y[M, 256] = relu(x)[M, 256] @ W + bias (+ resid);  xb: bf16 scratch [M, 256]
+int hidden_fwd_tc(const float* x, const bf16* wt, const float* bias, const float* resid, int64_t M, float* y, bf16* xb,
+                  cudaStream_t s) {
+  PMVAE_TRY(cast_bf16(x, xb, M * 256, 1, s));
+  tc::TcGemmArgs e{};
+  e.bias = bias; e.resid_f32 = resid; e.ld_resid_f32 = 256; e.out_f32 = y; e.ld_out_f32 = 256;
+  return tc::gemm_nt(xb, 256, wt, 256, M, 256, 256, e, s);
+}
+
+// gW[256, 256] += relu(x)^T dy;  dx[M, 256] = (dy @ W^T) * (x > 0) (+ resid; dx may alias resid);  xb, dyb: bf16 scratch
+int hidden_bwd_tc(const float* x, const float* dy, const bf16* wn, float* gW, float* dx, const float* resid, int64_t M,
+                  bf16* xb, bf16* dyb, cudaStream_t s) {
+  PMVAE_TRY(cast_bf16(x, xb, M * 256, 1, s));
+  PMVAE_TRY(cast_bf16(dy, dyb, M * 256, 0, s));
+  PMVAE_TRY(tc::gemm_tn(xb, 256, dyb, 256, 256, 256, M, gW, 256, 1, 0, nullptr, s));
+  tc::TcGemmArgs e{};
+  e.mask_bf16 = xb; e.ld_mask = 256; e.resid_f32 = resid; e.ld_resid_f32 = 256; e.out_f32 = dx; e.ld_out_f32 = 256;
+  return tc::gemm_nt(dyb, 256, wn, 256, M, 256, 256, e, s);
+}
+
 // ---------------------------------------------------------------- single Linear (tests / roofline leg)
 // ws: [x bf16 B*Kp][W^T bf16 Np*Kp]
 int linear_bf16(const float* x, const float* w, const float* bias, int64_t B, int K, int N, int relu_in, float* y,

@@ -69,7 +69,7 @@ class AutoregressiveGMM:
     here to infer it).  `log_prob(z, context)` -> [B]; `backward(g)` -> (parameter gradients, dz, dcontext)."""
 
     def __init__(self, event_size: int, num_components: int = 10, residual_blocks: int = 2, hidden_units: int = 256,
-                 name: Optional[str] = None, *, context_size: int, device=None):
+                 name: Optional[str] = None, *, context_size: int, device=None, precision: str = "fp32"):
         if not torch.cuda.is_available():
             raise RuntimeError("AutoregressiveGMM needs a CUDA device: the hot path has no CPU fallback")
         self.name = name
@@ -78,6 +78,12 @@ class AutoregressiveGMM:
         self.cfg.d, self.cfg.n_comp, self.cfg.R, self.cfg.H, self.cfg.C = (int(event_size), int(num_components),
                                                                             int(residual_blocks), int(hidden_units),
                                                                             int(context_size))
+        # precision="bf16": the hidden 256 x 256 Linears of the ResidualMLP run on the tcgen05 GEMMs with bf16 operands
+        # (fp32 accumulation); the first Linear, the mixture head and all density algebra stay float32
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
+        self.cfg.reserved[0] = 1 if (precision == "bf16" and int(hidden_units) == 256) else 0
         self._cfgp = C.byref(self.cfg)
         n = int(_lib.lib.pmvae_argmm_param_count(self._cfgp))
         if n == 0:

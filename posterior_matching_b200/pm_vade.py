@@ -39,7 +39,7 @@ class PosteriorMatchingVADE:
         ar = dict(config.get("partial_posterior_dist_config", {}) or {})
         self.argmm = AutoregressiveGMM(d, ar.get("num_components", 10), ar.get("residual_blocks", 2),
                                        ar.get("hidden_units", 256), context_size=self.part.out_hw ** 2 * self.part.out_c,
-                                       device=self.device)
+                                       device=self.device, precision=precision)
         # frozen (pre-trained VaDE) leaves and trainable partial-encoder leaves live in two arenas
         self.frozen_leaves = self.enc.leaf_shapes() + [("diagonal_gaussian/linear", (self.enc_feat, 2 * d), 2 * d)]
         self.train_leaves = self.part.leaf_shapes()

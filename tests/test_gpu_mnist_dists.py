@@ -63,6 +63,43 @@ def test_argmm_log_prob_and_gradients(d, K, R, H, Cx, B):
             assert e < 5e-4, (n, k, e)
 
 
+def test_argmm_bf16_hidden_linears_track_the_float64_oracle():
+    """precision="bf16": the hidden 256 x 256 Linears run on the tcgen05 GEMMs with bf16 operands (fp32 accumulation);
+    the log-density and every gradient stay within operand-rounding distance of the oracle, and the same inputs through
+    the float32 route agree with it far more closely (i.e. the flag really switches arithmetic)."""
+    from posterior_matching_b200.distributions import AutoregressiveGMM
+    d, K, R, H, Cx, B = 32, 10, 2, 256, 128, 96
+    spec = DM.ArgmmSpec(d=d, n_comp=K, R=R, H=H, C=Cx)
+    p = DM.argmm_init(spec)
+    for leaf in p.values():
+        for t in leaf.values():
+            t.requires_grad_(True)
+    torch.manual_seed(11)
+    z = torch.randn(B, d, dtype=torch.float64, requires_grad=True)
+    ctx = torch.randn(B, Cx, dtype=torch.float64, requires_grad=True)
+    want = DM.argmm_log_prob(p, spec, z, ctx)
+    g = torch.randn(B, dtype=torch.float64)
+    (want * g).sum().backward()
+    errs = {}
+    for precision in ("fp32", "bf16"):
+        dist = AutoregressiveGMM(d, K, R, H, context_size=Cx, precision=precision)
+        dist.load_params({n: {k: t.detach() for k, t in leaf.items()} for n, leaf in p.items()})
+        got = dist.log_prob(z.detach().float().cuda(), ctx.detach().float().cuda())
+        grads, dz, dctx = dist.backward(g.float().cuda())
+        torch.cuda.synchronize()
+        assert np.isfinite(got.cpu().numpy()).all()
+        e = {"lp": rel_err(got.cpu().numpy(), want.detach().numpy()), "dz": rel_l2(dz.cpu().numpy(), z.grad.numpy()),
+             "dctx": rel_l2(dctx.cpu().numpy(), ctx.grad.numpy())}
+        for n, leaf in p.items():
+            for k, t in leaf.items():
+                e[f"{n}/{k}"] = rel_l2(grads[n][k].cpu().numpy(), t.grad.numpy())
+        errs[precision] = e
+    assert errs["fp32"]["lp"] < 2e-5 and max(v for k, v in errs["fp32"].items() if k != "lp") < 5e-4
+    assert errs["bf16"]["lp"] < 5e-3, errs["bf16"]["lp"]
+    assert max(v for k, v in errs["bf16"].items() if k != "lp") < 1e-1, errs["bf16"]      # operand rounding: ~6 % measured
+    assert errs["bf16"]["dz"] > 10 * errs["fp32"]["dz"]         # the two routes are different arithmetic
+
+
 def test_argmm_rejects_bad_shapes_and_configs():
     from posterior_matching_b200 import _lib
     from posterior_matching_b200.distributions import AutoregressiveGMM
