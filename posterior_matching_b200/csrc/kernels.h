@@ -112,7 +112,7 @@ int hidden_fwd_tc(const float* x, const __nv_bfloat16* wt, const float* bias, co
                   __nv_bfloat16* xb, cudaStream_t s);
 int hidden_bwd_tc(const float* x, const float* dy, const __nv_bfloat16* wn, float* gW, float* dx, const float* resid,
                   int64_t M, __nv_bfloat16* xb, __nv_bfloat16* dyb, cudaStream_t s);
-// latent64.cu: warp-per-row versions for d = 64 (dense [64][65] factor in shared memory; bf16 gradient outputs only)
+// latent64.cu: warp-per-row versions for d = 64 (packed factor image in shared memory; bf16 gradient outputs only)
 int latent_fwd64(const float* par, const float* eps, float* z, float* kl, int64_t B, cudaStream_t s);
 // match_fwd64 with save_* != NULL (training forward) also writes r = L_p^-1 (z - mu_p), g = L_p^-T r and the diagonal
 // terms qd, [B, 64] each; latent_bwd64 consumes them instead of re-reading par_p.

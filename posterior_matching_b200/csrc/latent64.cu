@@ -6,7 +6,7 @@
 //     rows i >= 32 :  L[i][j] = v[4095 - 64 i - j]        (reversed run; v[0..63] is row 63)
 // i.e. v, read as a matrix X of 32.5 rows of 64, holds row a - 1 of L in the left part of its row a and row 63 - a,
 // reversed, in the right part.  The kernels keep exactly that packed image in shared memory (33 rows, pitch 65 floats,
-// 8.6 KB per warp: 16 warps per SM where a dense [64][65] tile allowed 12), so staging is a straight coalesced copy with
+// 8.6 KB per warp: 20 warps per SM where a dense [64][65] tile allowed 12), so staging is a straight coalesced copy with
 // compile-time offsets, and
 //     L[i][j] = X[i + 1][j]            (i <= 31)          L[i][j] = X[63 - i][63 - j]      (i >= 32).
 // The odd pitch makes both access patterns of the triangular algebra bank-conflict free: fixed row / varying column
