@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+from types import SimpleNamespace
 from typing import Any, Dict, Mapping, Optional
 
 import numpy as np
@@ -19,6 +20,7 @@ import torch
 
 from . import _lib, prng
 from .conv import conv2d_backward, conv2d_forward, conv_desc
+from .dist_objects import BernoulliLogits, MultivariateNormalTriL
 from .distributions import AutoregressiveGMM, Bernoulli
 
 
@@ -74,10 +76,15 @@ class ConvPosteriorMatchingVAE:
                  channels: int = 1, precision: str = "fp32"):
         if not torch.cuda.is_available():
             raise RuntimeError("ConvPosteriorMatchingVAE needs a CUDA device: the hot path has no CPU fallback")
-        if (config["encoder_net"], config["decoder_net"], config["posterior_dist"], config["decoder_dist"],
-                config.get("partial_posterior_dist")) != ("ConvEncoder", "ConvDecoder", "TriLGaussian", "Bernoulli",
-                                                          "AutoregressiveGMM"):
-            raise NotImplementedError("this class covers the combination configs/pm_vae_mnist.py uses")
+        if (config["encoder_net"], config["decoder_net"], config["posterior_dist"], config["decoder_dist"]) != (
+                "ConvEncoder", "ConvDecoder", "TriLGaussian", "Bernoulli"):
+            raise NotImplementedError("this class covers ConvEncoder / ConvDecoder / TriLGaussian / Bernoulli models")
+        # vae.py:97-105: the partial posterior defaults to the posterior's type.  AutoregressiveGMM (configs/pm_vae_mnist.py)
+        # is the trainable combination; TriLGaussian (configs/pm_vae_mnist16.py) is served as a FROZEN model: the
+        # distribution-object interface LookaheadPosterior reads (lookahead.py:126-133,219), not __call__ / backward.
+        self.partial_posterior_dist = config.get("partial_posterior_dist", config["posterior_dist"])
+        if self.partial_posterior_dist not in ("AutoregressiveGMM", "TriLGaussian"):
+            raise NotImplementedError(f"partial_posterior_dist {self.partial_posterior_dist!r} is not built")
         self.name = name
         self.device = torch.device("cuda" if device is None else device)
         self.latent_dim = d = int(config["latent_dim"])
@@ -93,24 +100,40 @@ class ConvPosteriorMatchingVAE:
             raise ValueError("decoder does not reproduce the image shape")
         self.P = d + d * (d + 1) // 2
         self.enc_feat = self.enc.out_hw ** 2 * self.enc.out_c
-        ar_cfg = dict(config.get("partial_posterior_dist_config", {}) or {})
-        self.argmm = AutoregressiveGMM(d, ar_cfg.get("num_components", 10), ar_cfg.get("residual_blocks", 2),
-                                       ar_cfg.get("hidden_units", 256), context_size=self.part.out_hw ** 2 * self.part.out_c,
-                                       device=self.device, precision=precision)
+        self.part_feat = self.part.out_hw ** 2 * self.part.out_c
+        self.image_size, self.channels = int(image_size), int(channels)
+        self.feature_shape = (self.image_size, self.image_size, self.channels)
+        self.num_features = self.image_size * self.image_size * self.channels
+        self.cfg = SimpleNamespace(R_enc=0, R_dec=0, R_part=0)     # dropout keys a network call draws: none (networks.py:9-72)
+        self.argmm = None
+        if self.partial_posterior_dist == "AutoregressiveGMM":
+            ar_cfg = dict(config.get("partial_posterior_dist_config", {}) or {})
+            self.argmm = AutoregressiveGMM(d, ar_cfg.get("num_components", 10), ar_cfg.get("residual_blocks", 2),
+                                           ar_cfg.get("hidden_units", 256), context_size=self.part_feat,
+                                           device=self.device, precision=precision)
         self.bern = Bernoulli(device=self.device)
         # one flat arena for the conv / head leaves (the AR-GMM keeps its own arena inside `self.argmm`)
         self.leaves = self.enc.leaf_shapes() + [("posterior_dist/linear", (self.enc_feat, self.P), self.P)] + \
             self.dec.leaf_shapes() + self.part.leaf_shapes()
+        if self.argmm is None:
+            self.leaves.append(("partial_posterior_dist/linear", (self.part_feat, self.P), self.P))
         n = sum(int(np.prod(s)) + nb for _, s, nb in self.leaves)
         self.arena = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.grad_arena = torch.zeros_like(self.arena)
         self.params, self.grads = self._views(self.arena), self._views(self.grad_arena)
-        self.params.update(self.argmm.params)
-        self.grads.update(self.argmm.grads)
-        self.m = [torch.zeros_like(self.arena), torch.zeros_like(self.argmm.arena)]
-        self.v = [torch.zeros_like(self.arena), torch.zeros_like(self.argmm.arena)]
+        self.m, self.v = [torch.zeros_like(self.arena)], [torch.zeros_like(self.arena)]
+        if self.argmm is not None:
+            self.params.update(self.argmm.params)
+            self.grads.update(self.argmm.grads)
+            self.m.append(torch.zeros_like(self.argmm.arena))
+            self.v.append(torch.zeros_like(self.argmm.arena))
         self.step = 0
         self._last = None
+
+    def _need_argmm(self, what: str):
+        if self.argmm is None:
+            raise NotImplementedError(f"{what} with a TriLGaussian partial posterior is not built: this combination is "
+                                      "served as a frozen model (encoder / partial_encoder / decoder objects)")
 
     @classmethod
     def from_config(cls, config: Mapping[str, Any], name: Optional[str] = None, **kw):
@@ -147,6 +170,7 @@ class ConvPosteriorMatchingVAE:
                  total_rows: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """`row_start` / `total_rows`: this call's rows inside a global batch (data parallelism): eps is rows
         [row_start, row_start + B) of normal(key, [total_rows, d]), like PosteriorMatchingVAE.draw_eps."""
+        self._need_argmm("__call__")
         x, b = _f32c(x, self.device), _f32c(b, self.device)
         B, d = x.shape[0], self.latent_dim
         if eps is None:
@@ -227,9 +251,32 @@ class ConvPosteriorMatchingVAE:
         K, B, d = z.shape
         return self.dec.forward(self.params, z.reshape(K * B, 1, 1, d).contiguous())[-1]
 
+    # ---- vae.py:47-53: the sub-modules as distribution objects ------------------------------------------
+    def encoder(self, x: torch.Tensor, is_training: bool = False) -> MultivariateNormalTriL:
+        return MultivariateNormalTriL(self._posterior_par(_f32c(x, self.device)), self.latent_dim)
+
+    def decoder(self, z: torch.Tensor, is_training: bool = False) -> BernoulliLogits:
+        z = _f32c(z, self.device)
+        return BernoulliLogits(self.dec.forward(self.params, z.reshape(z.shape[0], 1, 1, self.latent_dim))[-1])
+
+    def partial_encoder(self, x_o_b: torch.Tensor, is_training: bool = False) -> MultivariateNormalTriL:
+        """q(z | x_o) of a TriLGaussian partial posterior from the channel-concatenated [x_o, b] image (vae.py:132-134)."""
+        if self.argmm is not None:
+            raise NotImplementedError("the AutoregressiveGMM partial posterior has no distribution object: use "
+                                      "`argmm.sample / argmm.log_prob` with `_context(x, b)`")
+        x_o_b = _f32c(x_o_b, self.device)
+        B = x_o_b.shape[0]
+        ctx = self.part.forward(self.params, x_o_b)[-1].reshape(B, self.part_feat)
+        par = torch.empty((B, self.P), dtype=torch.float32, device=self.device)
+        hw = self.params["partial_posterior_dist/linear"]
+        _lib.check(_lib.lib.pmvae_linear(_lib.PREC_F32, ctx.data_ptr(), hw["w"].data_ptr(), hw["b"].data_ptr(), B,
+                                         self.part_feat, self.P, 0, par.data_ptr(), None, 0, _stream()), "pmvae_linear")
+        return MultivariateNormalTriL(par, self.latent_dim)
+
     def impute(self, x_o: torch.Tensor, b: torch.Tensor, num_samples: int = 100, *, rng=None, key=None) -> torch.Tensor:
         """vae.py:146-169 -> [num_samples, B, 28, 28, 1]: z ~ q(z | x_o) (AR-GMM), decoder mean = sigmoid(logits)
         (tfd.Bernoulli.mean), observed pixels kept."""
+        self._need_argmm("impute")
         x_o, b = _f32c(x_o, self.device), _f32c(b, self.device)
         if key is None:
             if rng is None:
@@ -243,6 +290,7 @@ class ConvPosteriorMatchingVAE:
 
     def is_log_prob(self, x: torch.Tensor, b: torch.Tensor, num_samples: int = 100, *, rng=None, keys=None):
         """vae.py:171-226 -> (log p(x), log p(x_u | x_o)), each [B]."""
+        self._need_argmm("is_log_prob")
         x, b = _f32c(x, self.device), _f32c(b, self.device)
         if keys is None:
             if rng is None:
@@ -284,6 +332,7 @@ class ConvPosteriorMatchingVAE:
         cotangents are scaled by 1 / global_rows) and `grad_sync(tensors)` sums the two flat gradient arenas across ranks
         before the update (e.g. one NCCL all-reduce each).  `sync_metrics=False` skips the host read of the batch means
         (returns device tensors instead), so consecutive steps queue without a host round trip."""
+        self._need_argmm("train_step")
         out = self(x, b, is_training=True, rng=rng, eps=eps, row_start=row_start, total_rows=global_rows)
         B = out["kl"].shape[0]
         ones = torch.full((B,), 1.0 / (global_rows or B), device=self.device)

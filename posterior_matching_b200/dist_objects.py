@@ -154,3 +154,15 @@ class Normal:
         _lib.check(_lib.lib.pmvae_normal(_key(seed), eps.numel(), 0, eps.numel(), eps.data_ptr(), _stream()), "pmvae_normal")
         out = self.loc.unsqueeze(0) + torch.exp(self.log_scale) * eps
         return out if lead else out[0]
+
+
+class BernoulliLogits:
+    """tfd.Independent(tfd.Bernoulli(logits)) as the convolutional decoders return it (distributions.py:20-25): `.logits`
+    [B, H, W, C] and `.mean()` = sigmoid(logits) (what `impute` and the lookahead model read, vae.py:165, lookahead.py:
+    132-133); the log-prob operator is `posterior_matching_b200.distributions.Bernoulli`."""
+
+    def __init__(self, logits: torch.Tensor):
+        self.logits = logits
+
+    def mean(self) -> torch.Tensor:
+        return torch.sigmoid(self.logits)

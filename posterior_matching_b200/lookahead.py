@@ -1,5 +1,6 @@
 """`LookaheadPosterior` (reference: posterior_matching/models/lookahead.py:14-227, train_lookahead_posterior.py:47-70;
-SURVEY.md §8f N3) over a feature-vector `PosteriorMatchingVAE`.
+SURVEY.md §8f N3) over a feature-vector `PosteriorMatchingVAE` or a frozen convolutional one with a TriLGaussian partial
+posterior (`ConvPosteriorMatchingVAE`: configs/pm_vae_mnist16.py + configs/lookahead_mnist16.py).
 
 A frozen PM-VAE produces, for every training row, `model_samples` imputations of the unobserved features and from each
 of them one latent sample of q(z | x_o + one more feature) for `lookahead_subsample` candidate features; a second
@@ -24,6 +25,7 @@ import numpy as np
 import torch
 
 from . import _lib, prng
+from .conv_vae import ConvPosteriorMatchingVAE, _ConvStack
 from .dist_objects import MultivariateNormalTriL
 from .vae import PosteriorMatchingVAE, ResidualMLP, _f32c, _stream, get_network
 
@@ -80,6 +82,33 @@ class _LookaheadLLFn(torch.autograd.Function):
         return dpar, None, None
 
 
+class ConvEncoder:
+    """networks.py:9-38 (spec only): `conv_layers` = [(filters, kernel, stride), ...]."""
+
+    def __init__(self, conv_layers, name: Optional[str] = None):
+        self.conv_layers, self.name = [tuple(int(v) for v in l) for l in conv_layers], name
+
+
+class _ConvStackFn(torch.autograd.Function):
+    """A ConvEncoder stack on `pmvae_conv2d_forward / backward` (conv_vae._ConvStack), forward and VJP."""
+
+    @staticmethod
+    def forward(ctx, x, stack, *flat):
+        params = {n: {"w": flat[2 * i], "b": flat[2 * i + 1]} for i, n in enumerate(stack.names)}
+        acts = stack.forward(params, x.contiguous())
+        ctx.stack, ctx.params, ctx.acts = stack, params, acts
+        return acts[-1]
+
+    @staticmethod
+    def backward(ctx, dy):
+        grads = {n: {k: torch.zeros_like(t) for k, t in leaf.items()} for n, leaf in ctx.params.items()}
+        ctx.stack.backward(ctx.params, grads, ctx.acts, dy.contiguous(), need_dx=False)
+        out = [None, None]
+        for n in ctx.stack.names:
+            out += [grads[n]["w"], grads[n]["b"]]
+        return tuple(out)
+
+
 def _layer_norm(h, eps: float = 1e-5):
     """hk.LayerNorm(-1, False, False) (networks.py:118): biased variance, no scale / offset."""
     mu = h.mean(-1, keepdim=True)
@@ -103,24 +132,40 @@ class LookaheadPosterior:
     NET = "lookahead_encoder_net"
     HEAD = "lookahead_posterior/lookahead_block/linear"        # [R] Haiku module path of LookaheadBlock's Linear
 
-    def __init__(self, pm_vae: PosteriorMatchingVAE, lookahead_encoder_net: ResidualMLP, num_features: int,
-                 lookahead_subsample: int = 16, model_samples: int = 64, name: Optional[str] = None):
-        if not isinstance(pm_vae, PosteriorMatchingVAE):
-            raise NotImplementedError("LookaheadPosterior is built over the feature-vector PosteriorMatchingVAE; the "
-                                      "convolutional mnist16 model of configs/lookahead_mnist16.py is not (DESIGN.md)")
+    def __init__(self, pm_vae, lookahead_encoder_net, num_features: int, lookahead_subsample: int = 16,
+                 model_samples: int = 64, name: Optional[str] = None):
+        if not isinstance(pm_vae, (PosteriorMatchingVAE, ConvPosteriorMatchingVAE)):
+            raise TypeError("pm_vae must be a PosteriorMatchingVAE or a ConvPosteriorMatchingVAE")
+        if isinstance(pm_vae, ConvPosteriorMatchingVAE) and pm_vae.argmm is not None:
+            raise NotImplementedError("LookaheadPosterior needs a TriLGaussian partial posterior (q(z | x_o).sample)")
         if int(num_features) != pm_vae.num_features:
             raise ValueError("num_features must match the PM-VAE's")
         self.pm_vae, self.net, self.name = pm_vae, lookahead_encoder_net, name
         self.device = pm_vae.device
+        self.feature_shape = tuple(getattr(pm_vae, "feature_shape", (pm_vae.num_features,)))
         self.block = LookaheadBlock(pm_vae.latent_dim, num_features)
         self._num_features, self._lookahead_subsample, self._model_samples = int(num_features), int(lookahead_subsample), int(model_samples)
         if self._lookahead_subsample > self._num_features:
             raise ValueError("lookahead_subsample exceeds num_features (jax.random.choice without replacement would fail)")
-        H, R = self.net.hidden_units, self.net.residual_blocks
-        self.leaves = [(_lin_name(self.NET, 0), 2 * num_features, H)]
-        self.leaves += [(_lin_name(self.NET, i), H, H) for i in range(1, 2 * R + 1)]
-        self.leaves.append((self.HEAD, H, self.block.num_params * num_features))
-        n = sum(fi * fo + fo for _, fi, fo in self.leaves)
+        # leaves: (Haiku name, weight shape, bias size)
+        self.stack = None
+        if isinstance(self.net, ResidualMLP):
+            if len(self.feature_shape) != 1:
+                raise NotImplementedError("a ResidualMLP lookahead encoder takes feature vectors")
+            H, R = self.net.hidden_units, self.net.residual_blocks
+            self.leaves = [(_lin_name(self.NET, 0), (2 * num_features, H), H)]
+            self.leaves += [(_lin_name(self.NET, i), (H, H), H) for i in range(1, 2 * R + 1)]
+            feat = H
+        elif isinstance(self.net, ConvEncoder):
+            if len(self.feature_shape) != 3 or self.feature_shape[0] != self.feature_shape[1]:
+                raise NotImplementedError("a ConvEncoder lookahead encoder takes square [H, W, C] images")
+            self.stack = _ConvStack(self.NET, self.net.conv_layers, self.feature_shape[0], 2 * self.feature_shape[2], False)
+            self.leaves = list(self.stack.leaf_shapes())
+            feat = self.stack.out_hw ** 2 * self.stack.out_c
+        else:
+            raise NotImplementedError("lookahead_encoder_net must be a ResidualMLP or a ConvEncoder spec")
+        self.leaves.append((self.HEAD, (feat, self.block.num_params * num_features), self.block.num_params * num_features))
+        n = sum(int(np.prod(ws)) + nb for _, ws, nb in self.leaves)
         self.arena = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.grad_arena = torch.zeros_like(self.arena)
         self.m, self.v = torch.zeros_like(self.arena), torch.zeros_like(self.arena)
@@ -132,19 +177,23 @@ class LookaheadPosterior:
     def from_config(cls, config: Mapping[str, Any], pm_vae_config: Mapping[str, Any], name: Optional[str] = None,
                     **pm_vae_kwargs) -> "LookaheadPosterior":
         """lookahead.py:84-120: the lookahead encoder defaults to the PM-VAE's encoder type and config."""
-        pm_vae = PosteriorMatchingVAE.from_config(pm_vae_config, **pm_vae_kwargs)
-        net = get_network(config.get("lookahead_encoder_net", pm_vae_config["encoder_net"]),
-                          config.get("lookahead_encoder_net_config", pm_vae_config.get("encoder_net_config")),
-                          name=cls.NET)
+        pm_vae = PosteriorMatchingVAE.from_config(pm_vae_config, **pm_vae_kwargs)      # conv configs: ConvPosteriorMatchingVAE
+        net_type = config.get("lookahead_encoder_net", pm_vae_config["encoder_net"])
+        net_cfg = config.get("lookahead_encoder_net_config", pm_vae_config.get("encoder_net_config"))
+        if net_type == "ConvEncoder":
+            net = ConvEncoder(**dict(net_cfg or {}), name=cls.NET)
+        else:
+            net = get_network(net_type, net_cfg, name=cls.NET)
         return cls(pm_vae, net, config["num_features"], config.get("lookahead_subsample", 16),
                    config.get("model_samples", 64), name=name)
 
     # ---- parameters ---------------------------------------------------------------------------------
     def _views(self, arena: torch.Tensor) -> Dict[str, Dict[str, torch.Tensor]]:
         out, off = {}, 0
-        for nm, fi, fo in self.leaves:
-            out[nm] = {"w": arena[off:off + fi * fo].view(fi, fo), "b": arena[off + fi * fo:off + fi * fo + fo]}
-            off += fi * fo + fo
+        for nm, ws, nb in self.leaves:
+            nw = int(np.prod(ws))
+            out[nm] = {"w": arena[off:off + nw].view(*ws), "b": arena[off + nw:off + nw + nb]}
+            off += nw + nb
         return out
 
     def init(self, seed: int = 0):
@@ -154,7 +203,7 @@ class LookaheadPosterior:
         for leaf in self.params.values():
             w = torch.empty(leaf["w"].shape, dtype=torch.float32)
             torch.nn.init.trunc_normal_(w, mean=0.0, std=1.0, a=-2.0, b=2.0, generator=g)
-            leaf["w"].copy_(w / math.sqrt(w.shape[0]))
+            leaf["w"].copy_(w / math.sqrt(w[..., 0].numel()))
             leaf["b"].zero_()
         return self.params
 
@@ -173,19 +222,25 @@ class LookaheadPosterior:
     def lookahead_encoder(self, x_o_b: torch.Tensor, params=None) -> torch.Tensor:
         """hk.Sequential([lookahead_encoder_net, LookaheadBlock]) (lookahead.py:77-80) -> raw parameters [B, F, 2d]."""
         p = self.params if params is None else params
-        ln, R = self.net.layer_norm, self.net.residual_blocks
+        x_o_b = _f32c(x_o_b, self.device)
+        if self.stack is not None:
+            flat = [p[n][k] for n in self.stack.names for k in ("w", "b")]
+            h = _ConvStackFn.apply(x_o_b, self.stack, *flat)
+            h = h.reshape(h.shape[0], -1)               # LookaheadBlock: rearrange "b ... -> b (...)" (lookahead.py:25)
+        else:
+            ln, R = self.net.layer_norm, self.net.residual_blocks
 
-        def lin(i, h):
-            leaf = p[_lin_name(self.NET, i)]
-            h = _LinearFn.apply(h, leaf["w"], leaf["b"])
-            return _layer_norm(h) if ln else h
+            def lin(i, h):
+                leaf = p[_lin_name(self.NET, i)]
+                h = _LinearFn.apply(h, leaf["w"], leaf["b"])
+                return _layer_norm(h) if ln else h
 
-        h = lin(0, _f32c(x_o_b, self.device))
-        for r in range(R):
-            res = lin(2 * r + 1, torch.relu(h))
-            res = lin(2 * r + 2, torch.relu(res))
-            h = h + res
-        h = torch.relu(h)
+            h = lin(0, x_o_b)
+            for r in range(R):
+                res = lin(2 * r + 1, torch.relu(h))
+                res = lin(2 * r + 2, torch.relu(res))
+                h = h + res
+            h = torch.relu(h)
         out = _LinearFn.apply(h, p[self.HEAD]["w"], p[self.HEAD]["b"])
         return out.view(out.shape[0], self._num_features, self.block.num_params)
 
@@ -206,7 +261,7 @@ class LookaheadPosterior:
     def model_one_step_samples(self, x: torch.Tensor, b: torch.Tensor, rng):
         """The frozen-model half of `__call__`: (subsampled_inds [S], valid_mask [B,S], model_one_step_z [K,B,S,d])."""
         pm, F, K, S = self.pm_vae, self._num_features, self._model_samples, self._lookahead_subsample
-        d = pm.latent_dim
+        d, shape = pm.latent_dim, self.feature_shape
         x, b = _f32c(x, self.device), _f32c(b, self.device)
         B = x.shape[0]
         seq = prng.PRNGSequence(rng)
@@ -214,16 +269,17 @@ class LookaheadPosterior:
         po_posterior = pm.partial_encoder(torch.cat([x_o, b], dim=-1))
         seq.skip(pm.cfg.R_part)
         z = po_posterior.sample(seed=seq.next(), sample_shape=K)                      # [K, B, d]
-        dec_mean = pm.decoder(z.view(K * B, d)).mean().view(K, B, F)
+        dec_mean = pm.decoder(z.view(K * B, d)).mean().reshape(K, B, *shape)
         seq.skip(pm.cfg.R_dec)
-        x_samples = torch.where((b == 1).unsqueeze(0), x_o.unsqueeze(0), dec_mean)     # [K, B, F]
+        x_samples = torch.where((b == 1).unsqueeze(0), x_o.unsqueeze(0), dec_mean)     # [K, B, *shape]
         inds = self._choice(seq.next(), F, S)
-        one_hots = torch.eye(F, device=self.device)[inds]                              # [S, F]
-        b_look = torch.maximum(b.unsqueeze(1), one_hots.unsqueeze(0))                  # [B, S, F]
-        x_look = (x_samples.unsqueeze(2) * b_look.unsqueeze(0)).reshape(K * B * S, F)
-        valid = ((b.unsqueeze(1) + one_hots.unsqueeze(0)).amax(dim=-1) < 2).to(torch.float32)
+        one_hots = torch.eye(F, device=self.device)[inds].view(S, *shape)              # lookahead.py:139-150
+        b_look = torch.maximum(b.unsqueeze(1), one_hots.unsqueeze(0))                  # [B, S, *shape]
+        x_look = (x_samples.unsqueeze(2) * b_look.unsqueeze(0)).reshape(K * B * S, *shape)
+        valid = ((b.unsqueeze(1) + one_hots.unsqueeze(0)).flatten(2).amax(dim=-1) < 2).to(torch.float32)
         keys = prng.split(seq.next(), K)
-        par = pm.net_apply(2, x_look, b_look.unsqueeze(0).expand(K, B, S, F).reshape(K * B * S, F))
+        b_rep = b_look.unsqueeze(0).expand(K, *b_look.shape).reshape(K * B * S, *shape)
+        par = pm.partial_encoder(torch.cat([x_look, b_rep], dim=-1)).parameters
         par = par.view(K, B * S, -1)
         z1 = torch.empty((K, B * S, d), dtype=torch.float32, device=self.device)
         for k in range(K):                     # jax.vmap(model_sample) over the K keys: one [B*S, d] draw per key
@@ -242,9 +298,9 @@ class LookaheadPosterior:
         return ll.view(1, -1)
 
     def expected_info_gains(self, x: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-        """lookahead.py:204-227 for one instance x [F], b [F] -> [F]; -inf where the feature is already observed."""
-        pm, F, d = self.pm_vae, self._num_features, self.pm_vae.latent_dim
-        x, b = _f32c(x, self.device).view(1, F), _f32c(b, self.device).view(1, F)
+        """lookahead.py:204-227 for one instance x, b of the feature shape -> [F]; -inf where the feature is observed."""
+        pm, F, d, shape = self.pm_vae, self._num_features, self.pm_vae.latent_dim, self.feature_shape
+        x, b = _f32c(x, self.device).view(1, *shape), _f32c(b, self.device).view(1, *shape)
         with torch.no_grad():
             current_ent = pm.encoder(x).entropy()                                      # [1]
             raw = self.lookahead_encoder(torch.cat([x * b, b], dim=-1)).view(F, 2 * d).contiguous()
@@ -252,7 +308,7 @@ class LookaheadPosterior:
             _lib.check(_lib.lib.pmvae_diag_log_prob(raw.data_ptr(), None, F, d, None, ents.data_ptr(), _stream()),
                        "pmvae_diag_log_prob")
             gains = current_ent - ents
-            return torch.where(b.view(F) == 0, gains, torch.full_like(gains, -math.inf))
+            return torch.where(b.reshape(F) == 0, gains, torch.full_like(gains, -math.inf))
 
     # ---- train_lookahead_posterior.py:47-70 -----------------------------------------------------------
     def loss_and_grads(self, x, b, *, rng):

@@ -95,3 +95,58 @@ def test_lookahead_train_step_and_info_gains():
     assert got_g.shape == (spec.D,)
     assert torch.isinf(got_g[:2]).all() and (got_g[:2] < 0).all()
     assert torch.allclose(got_g[2:], want_g[2:], rtol=1e-4, atol=1e-4)
+
+
+MNIST16_ENC = [(32, 3, 1), (32, 3, 2), (64, 3, 2), (64, 1, 1)]                 # configs/pm_vae_mnist16.py:24-29
+MNIST16_DEC = [(64, 8, 1), (64, 5, 2), (32, 5, 1), (32, 5, 1), (1, 3, 1)]      # :31-38
+
+
+def test_lookahead_over_the_convolutional_mnist16_model():
+    """configs/lookahead_mnist16.py: a frozen ConvEncoder / ConvDecoder PM-VAE with TriLGaussian posteriors (latent 10,
+    16 x 16 x 1 images) and a ConvEncoder lookahead net (the PM-VAE encoder's config by default, lookahead.py:107-113)."""
+    from posterior_matching_b200.lookahead import LookaheadPosterior
+    from posterior_matching_b200.conv_vae import ConvPosteriorMatchingVAE
+    K, S, B = 3, 6, 4
+    spec = OL.ConvLookSpec(16, 1, 10, MNIST16_ENC, MNIST16_DEC, MNIST16_ENC)
+    p, lp = OL.conv_init(spec)
+    cfg = {"latent_dim": 10, "encoder_net": "ConvEncoder", "decoder_net": "ConvDecoder", "posterior_dist": "TriLGaussian",
+           "decoder_dist": "Bernoulli", "encoder_net_config": {"conv_layers": MNIST16_ENC},
+           "decoder_net_config": {"conv_layers": MNIST16_DEC}}
+    look = LookaheadPosterior.from_config({"num_features": 256, "lookahead_subsample": S, "model_samples": K}, cfg,
+                                          image_size=16)
+    assert isinstance(look.pm_vae, ConvPosteriorMatchingVAE) and look.pm_vae.argmm is None
+    with pytest.raises(NotImplementedError):
+        look.pm_vae(torch.zeros(1, 16, 16, 1), torch.zeros(1, 16, 16, 1), rng=(0, 1))     # frozen combination
+    look.pm_vae.load_params(p)
+    look.load_params(lp)
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand(B, 16, 16, 1, generator=g, dtype=torch.float64) < 0.3).double()
+    b = (torch.rand(B, 16, 16, 1, generator=g, dtype=torch.float64) < 0.15).double()
+    b[0] = 1.0
+    key = oprng.PRNGKey(31)
+    rng = tuple(int(v) for v in key)
+    loss_o, ll_o, g_o, (inds_o, valid_o, z1_o) = OL.conv_loss_and_grads(p, lp, spec, x, b, key, K, S)
+    xc, bc = x.float().cuda(), b.float().cuda()
+    inds, valid, z1 = look.model_one_step_samples(xc, bc, rng)
+    torch.cuda.synchronize()
+    assert inds.cpu().tolist() == list(inds_o)
+    assert torch.equal(valid.cpu().double(), valid_o)
+    assert rel_l2(z1.cpu().numpy(), z1_o.numpy()) < 1e-3
+    ll = look(xc, bc, rng=rng)
+    assert ll.shape == (1, B) and float(ll[0, 0]) == 0.0
+    assert rel_err(ll[0].detach().cpu().numpy(), ll_o.numpy()) < 2e-3
+    loss, grads = look.loss_and_grads(xc, bc, rng=rng)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(loss_o)) < 2e-3 * max(1.0, abs(float(loss_o)))
+    for n in g_o:
+        for k in ("w", "b"):
+            assert rel_l2(grads[n][k].cpu().numpy(), g_o[n][k].numpy()) < 1e-2, (n, k)
+    out = look.train_step(xc, bc, rng=rng)
+    assert np.isfinite(out["loss"]) and look.step == 1
+    look.load_params(lp)
+    bi = b[1].clone()
+    want_g = OL.conv_expected_info_gains(p, lp, spec, x[1], bi)
+    got_g = look.expected_info_gains(x[1].float().cuda(), bi.float().cuda()).cpu().double()
+    obs = bi.reshape(-1) == 1
+    assert got_g.shape == (256,) and torch.isinf(got_g[obs]).all()
+    assert torch.allclose(got_g[~obs], want_g[~obs], rtol=1e-3, atol=1e-3)
