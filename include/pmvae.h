@@ -199,6 +199,11 @@ int pmvae_impute(const pmvae_config* cfg, const float* params, const float* x, c
  *   pmvae_std_normal_log_prob  the prior MultivariateNormalDiag(0, 1).log_prob(z) (vae.py:55-57), out[B] */
 int pmvae_tril_log_prob(const float* par, const float* z, int64_t B, int32_t d, float* out, pmvae_stream_t stream);
 int pmvae_tril_entropy(const float* par, int64_t B, int32_t d, float* out, pmvae_stream_t stream);
+/* VJP of pmvae_tril_log_prob for the cotangent g[B]: dpar[B, d + d(d+1)/2] and (optionally) dz[B, d] -- what a
+ * TriLGaussian partial posterior contributes to the backward pass of vae.py:136-138 when it sits on host-composed
+ * networks (configs/pm_vae_mnist16.py).  ws: (B P + B d + B) floats of scratch. */
+int pmvae_tril_log_prob_backward(const float* par, const float* z, const float* g, int64_t B, int32_t d, float* dpar,
+                                 float* dz, void* ws, uint64_t ws_bytes, pmvae_stream_t stream);
 int pmvae_tril_sample(const float* par, const uint32_t key[2], int64_t B, int64_t K, int64_t B_total,
                       int64_t row_start, int32_t d, float* z, float* log_ratio, pmvae_stream_t stream);
 int pmvae_normal_log_prob(const float* x, const float* loc, const float* log_scale /* device scalar */,

@@ -143,6 +143,7 @@ _SIGS = {
     "pmvae_diag_sample": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "pmvae_diag_log_prob": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "pmvae_impute": (_i32, [_cfgp, _vp, _vp, _vp, _i64, _i64, _u32p, _i64, _i64, _vp, _vp, _vp, _u64, _vp]),
+    "pmvae_tril_log_prob_backward": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _u64, _vp]),
     "pmvae_lookahead_ll": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     "pmvae_lookahead_ll_backward": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
 }

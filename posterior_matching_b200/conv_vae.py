@@ -1,4 +1,4 @@
-"""PosteriorMatchingVAE for configs/pm_vae_mnist.py, composed on the host from libpmvae operators
+"""PosteriorMatchingVAE for configs/pm_vae_mnist.py and configs/pm_vae_mnist16.py, composed on the host from libpmvae operators
 (reference: posterior_matching/models/vae.py:34-144 with ConvEncoder / ConvDecoder networks.py:9-72,
 TriLGaussian, Bernoulli and AutoregressiveGMM heads).
 
@@ -79,9 +79,8 @@ class ConvPosteriorMatchingVAE:
         if (config["encoder_net"], config["decoder_net"], config["posterior_dist"], config["decoder_dist"]) != (
                 "ConvEncoder", "ConvDecoder", "TriLGaussian", "Bernoulli"):
             raise NotImplementedError("this class covers ConvEncoder / ConvDecoder / TriLGaussian / Bernoulli models")
-        # vae.py:97-105: the partial posterior defaults to the posterior's type.  AutoregressiveGMM (configs/pm_vae_mnist.py)
-        # is the trainable combination; TriLGaussian (configs/pm_vae_mnist16.py) is served as a FROZEN model: the
-        # distribution-object interface LookaheadPosterior reads (lookahead.py:126-133,219), not __call__ / backward.
+        # vae.py:97-105: the partial posterior defaults to the posterior's type: AutoregressiveGMM in configs/pm_vae_mnist.py,
+        # TriLGaussian in configs/pm_vae_mnist16.py (the model LookaheadPosterior is trained over, lookahead_mnist16.py)
         self.partial_posterior_dist = config.get("partial_posterior_dist", config["posterior_dist"])
         if self.partial_posterior_dist not in ("AutoregressiveGMM", "TriLGaussian"):
             raise NotImplementedError(f"partial_posterior_dist {self.partial_posterior_dist!r} is not built")
@@ -130,11 +129,6 @@ class ConvPosteriorMatchingVAE:
         self.step = 0
         self._last = None
 
-    def _need_argmm(self, what: str):
-        if self.argmm is None:
-            raise NotImplementedError(f"{what} with a TriLGaussian partial posterior is not built: this combination is "
-                                      "served as a frozen model (encoder / partial_encoder / decoder objects)")
-
     @classmethod
     def from_config(cls, config: Mapping[str, Any], name: Optional[str] = None, **kw):
         return cls(config, name=name, **kw)
@@ -170,7 +164,6 @@ class ConvPosteriorMatchingVAE:
                  total_rows: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """`row_start` / `total_rows`: this call's rows inside a global batch (data parallelism): eps is rows
         [row_start, row_start + B) of normal(key, [total_rows, d]), like PosteriorMatchingVAE.draw_eps."""
-        self._need_argmm("__call__")
         x, b = _f32c(x, self.device), _f32c(b, self.device)
         B, d = x.shape[0], self.latent_dim
         if eps is None:
@@ -198,20 +191,48 @@ class ConvPosteriorMatchingVAE:
         xob = torch.cat([x * b, b], dim=-1).contiguous()
         part_acts = self.part.forward(self.params, xob)
         ctx = part_acts[-1].reshape(B, -1)
-        match = self.argmm.log_prob(z, ctx)
-        self._last = (x, eps, feat, par, z, enc_acts, dec_acts, part_acts, B)
+        par_p = None
+        if self.argmm is not None:
+            match = self.argmm.log_prob(z, ctx)
+        else:
+            par_p = self._linear(ctx, "partial_posterior_dist/linear", self.part_feat)
+            match = torch.empty(B, dtype=torch.float32, device=self.device)
+            _lib.check(_lib.lib.pmvae_tril_log_prob(par_p.data_ptr(), z.data_ptr(), B, d, match.data_ptr(), S),
+                       "pmvae_tril_log_prob")
+        self._last = (x, eps, feat, par, z, enc_acts, dec_acts, part_acts, B, ctx, par_p)
         return {"reconstruction_ll": rec, "kl": kl, "matching_ll": match}
+
+    def _linear(self, h: torch.Tensor, leaf: str, fan_in: int) -> torch.Tensor:
+        """One hk.Linear head on [B, fan_in] features -> [B, P] raw TriLGaussian parameters."""
+        B = h.shape[0]
+        out = torch.empty((B, self.P), dtype=torch.float32, device=self.device)
+        hw = self.params[leaf]
+        _lib.check(_lib.lib.pmvae_linear(_lib.PREC_F32, h.data_ptr(), hw["w"].data_ptr(), hw["b"].data_ptr(), B, fan_in,
+                                         self.P, 0, out.data_ptr(), None, 0, _stream()), "pmvae_linear")
+        return out
 
     def backward(self, g_rec: torch.Tensor, g_kl: torch.Tensor, g_match: torch.Tensor):
         """VJP of the last __call__ for per-row cotangents -> `self.grads` (overwritten)."""
         if self._last is None:
             raise RuntimeError("backward() needs a preceding __call__")
-        x, eps, feat, par, z, enc_acts, dec_acts, part_acts, B = self._last
+        x, eps, feat, par, z, enc_acts, dec_acts, part_acts, B, ctx, par_p = self._last
         d, S = self.latent_dim, _stream()
         self.grad_arena.zero_()
         g_rec, g_kl, g_match = (_f32c(t, self.device) for t in (g_rec, g_kl, g_match))
-        # partial posterior (AR-GMM): parameter grads, dz, dcontext -> partial encoder
-        _, dz_match, dctx = self.argmm.backward(g_match)
+        # partial posterior: parameter grads, dz, dcontext -> partial encoder
+        if self.argmm is not None:
+            _, dz_match, dctx = self.argmm.backward(g_match)
+        else:
+            dpar_p, dz_match = torch.empty_like(par_p), torch.empty_like(z)
+            ws = torch.empty(B * (self.P + d + 1), dtype=torch.float32, device=self.device)
+            _lib.check(_lib.lib.pmvae_tril_log_prob_backward(par_p.data_ptr(), z.data_ptr(), g_match.data_ptr(), B, d,
+                                                             dpar_p.data_ptr(), dz_match.data_ptr(), ws.data_ptr(),
+                                                             ws.numel() * 4, S), "pmvae_tril_log_prob_backward")
+            hw, hg = self.params["partial_posterior_dist/linear"], self.grads["partial_posterior_dist/linear"]
+            dctx = torch.empty_like(ctx)
+            _lib.check(_lib.lib.pmvae_linear_backward(ctx.contiguous().data_ptr(), hw["w"].data_ptr(), dpar_p.data_ptr(), B,
+                                                      self.part_feat, self.P, 0, dctx.data_ptr(), hg["w"].data_ptr(),
+                                                      hg["b"].data_ptr(), S), "pmvae_linear_backward")
         self.part.backward(self.params, self.grads, part_acts, dctx.view_as(part_acts[-1]).contiguous(), need_dx=False)
         # decoder: Bernoulli -> conv-transpose stack -> dz
         dlogits = self.bern.backward(g_rec).view_as(dec_acts[-1]).contiguous()
@@ -267,16 +288,11 @@ class ConvPosteriorMatchingVAE:
         x_o_b = _f32c(x_o_b, self.device)
         B = x_o_b.shape[0]
         ctx = self.part.forward(self.params, x_o_b)[-1].reshape(B, self.part_feat)
-        par = torch.empty((B, self.P), dtype=torch.float32, device=self.device)
-        hw = self.params["partial_posterior_dist/linear"]
-        _lib.check(_lib.lib.pmvae_linear(_lib.PREC_F32, ctx.data_ptr(), hw["w"].data_ptr(), hw["b"].data_ptr(), B,
-                                         self.part_feat, self.P, 0, par.data_ptr(), None, 0, _stream()), "pmvae_linear")
-        return MultivariateNormalTriL(par, self.latent_dim)
+        return MultivariateNormalTriL(self._linear(ctx, "partial_posterior_dist/linear", self.part_feat), self.latent_dim)
 
     def impute(self, x_o: torch.Tensor, b: torch.Tensor, num_samples: int = 100, *, rng=None, key=None) -> torch.Tensor:
         """vae.py:146-169 -> [num_samples, B, 28, 28, 1]: z ~ q(z | x_o) (AR-GMM), decoder mean = sigmoid(logits)
         (tfd.Bernoulli.mean), observed pixels kept."""
-        self._need_argmm("impute")
         x_o, b = _f32c(x_o, self.device), _f32c(b, self.device)
         if key is None:
             if rng is None:
@@ -284,13 +300,15 @@ class ConvPosteriorMatchingVAE:
             key = prng.PRNGSequence(rng).next()        # conv nets draw no dropout keys
         x_o = x_o * b
         K, B = int(num_samples), x_o.shape[0]
-        z = self.argmm.sample(self._context(x_o, b), K, key=key)
+        if self.argmm is not None:
+            z = self.argmm.sample(self._context(x_o, b), K, key=key)
+        else:
+            z = self.partial_encoder(torch.cat([x_o, b], dim=-1)).sample(seed=key, sample_shape=K)
         mean = torch.sigmoid(self._decode_logits(z)).view(K, *x_o.shape)
         return torch.where(b.unsqueeze(0) != 0, x_o.unsqueeze(0), mean)
 
     def is_log_prob(self, x: torch.Tensor, b: torch.Tensor, num_samples: int = 100, *, rng=None, keys=None):
         """vae.py:171-226 -> (log p(x), log p(x_u | x_o)), each [B]."""
-        self._need_argmm("is_log_prob")
         x, b = _f32c(x, self.device), _f32c(b, self.device)
         if keys is None:
             if rng is None:
@@ -308,15 +326,23 @@ class ConvPosteriorMatchingVAE:
                                               ratio.data_ptr(), S), "pmvae_tril_sample")
         xk = x.reshape(1, B, D).expand(K, B, D).reshape(K * B, D).contiguous()
         ll = self.bern.log_prob(self._decode_logits(z).reshape(K * B, D), xk).view(K, B) + ratio
-        # z' ~ q(z | x_o): AR-GMM samples, their log-density, the prior, and the observed-pixel likelihood
-        z_xo = self.argmm.sample(ctx, K, key=keys[1])
-        ctx_k = ctx.unsqueeze(0).expand(K, B, ctx.shape[1]).reshape(K * B, -1).contiguous()
-        log_q = self.argmm.log_prob(z_xo.reshape(K * B, d), ctx_k).view(K, B)
-        log_pz = torch.empty(K * B, dtype=torch.float32, device=self.device)
-        _lib.check(_lib.lib.pmvae_std_normal_log_prob(z_xo.data_ptr(), K * B, d, log_pz.data_ptr(), S),
-                   "pmvae_std_normal_log_prob")
+        # z' ~ q(z | x_o): samples, log p(z') - log q(z' | x_o), and the observed-pixel likelihood
         bk = b.reshape(1, B, D).expand(K, B, D).reshape(K * B, D).contiguous()
-        ll_o = self.bern.log_prob(self._decode_logits(z_xo).reshape(K * B, D), xk, bk).view(K, B) + log_pz.view(K, B) - log_q
+        if self.argmm is not None:
+            z_xo = self.argmm.sample(ctx, K, key=keys[1])
+            ctx_k = ctx.unsqueeze(0).expand(K, B, ctx.shape[1]).reshape(K * B, -1).contiguous()
+            log_q = self.argmm.log_prob(z_xo.reshape(K * B, d), ctx_k).view(K, B)
+            log_pz = torch.empty(K * B, dtype=torch.float32, device=self.device)
+            _lib.check(_lib.lib.pmvae_std_normal_log_prob(z_xo.data_ptr(), K * B, d, log_pz.data_ptr(), S),
+                       "pmvae_std_normal_log_prob")
+            ratio_o = log_pz.view(K, B) - log_q
+        else:
+            par_p = self._linear(ctx, "partial_posterior_dist/linear", self.part_feat)
+            z_xo = torch.empty((K, B, d), dtype=torch.float32, device=self.device)
+            ratio_o = torch.empty((K, B), dtype=torch.float32, device=self.device)
+            _lib.check(_lib.lib.pmvae_tril_sample(par_p.data_ptr(), _lib.key_arg(keys[1]), B, K, B, 0, d, z_xo.data_ptr(),
+                                                  ratio_o.data_ptr(), S), "pmvae_tril_sample")
+        ll_o = self.bern.log_prob(self._decode_logits(z_xo).reshape(K * B, D), xk, bk).view(K, B) + ratio_o
         ll, ll_o = ll.contiguous(), ll_o.contiguous()
         out = torch.empty((2, B), dtype=torch.float32, device=self.device)
         _lib.check(_lib.lib.pmvae_logmeanexp_rows(ll.data_ptr(), None, out[0].data_ptr(), B, K, S), "pmvae_logmeanexp_rows")
@@ -332,16 +358,17 @@ class ConvPosteriorMatchingVAE:
         cotangents are scaled by 1 / global_rows) and `grad_sync(tensors)` sums the two flat gradient arenas across ranks
         before the update (e.g. one NCCL all-reduce each).  `sync_metrics=False` skips the host read of the batch means
         (returns device tensors instead), so consecutive steps queue without a host round trip."""
-        self._need_argmm("train_step")
         out = self(x, b, is_training=True, rng=rng, eps=eps, row_start=row_start, total_rows=global_rows)
         B = out["kl"].shape[0]
         ones = torch.full((B,), 1.0 / (global_rows or B), device=self.device)
         self.backward(-ones, ones, -matching_coef * ones)
+        arenas = [(self.arena, self.grad_arena)]
+        if self.argmm is not None:
+            arenas.append((self.argmm.arena, self.argmm.grad_arena))
         if grad_sync is not None:
-            grad_sync([self.grad_arena, self.argmm.grad_arena])
+            grad_sync([g for _, g in arenas])
         lr = float(lr_schedule(self.step)) if lr_schedule else 1e-3
-        for arena, grads, m, v in ((self.arena, self.grad_arena, self.m[0], self.v[0]),
-                                   (self.argmm.arena, self.argmm.grad_arena, self.m[1], self.v[1])):
+        for (arena, grads), m, v in zip(arenas, self.m, self.v):
             _lib.check(_lib.lib.pmvae_adamw_flat(arena.data_ptr(), grads.data_ptr(), m.data_ptr(), v.data_ptr(),
                                                  arena.numel(), self.step, lr, 0.0, adam[0], adam[1], adam[2], _stream()),
                        "pmvae_adamw_flat")

@@ -232,4 +232,23 @@ int pmvae_lookahead_ll_backward(const float* par, const float* z, const float* v
   return 0;
 }
 
+int pmvae_tril_log_prob_backward(const float* par, const float* z, const float* g, int64_t B, int32_t d, float* dpar,
+                                 float* dz, void* ws, uint64_t ws_bytes, pmvae_stream_t stream) {
+  PMVAE_CHECK(B >= 0 && d >= 1 && d <= 64 && (B == 0 || (par && z && g && dpar && ws)), "bad arguments");
+  if (B == 0) return 0;
+  const int64_t P = d + (int64_t)d * (d + 1) / 2;
+  const uint64_t need = (uint64_t)(B * P + B * d + B) * sizeof(float);
+  PMVAE_CHECK(ws_bytes >= need, "workspace too small: (B P + B d + B) floats");
+  cudaStream_t s = as_stream(stream);
+  // The two-head backward kernel with an inert "encoder" head: eps = 0 and g_kl = 0 leave d / d(loc of that head) =
+  // the total gradient into z, which without a decoder term and without stop_gradient is exactly -g * L^-T L^-1 (z - mu).
+  float* tmp = reinterpret_cast<float*>(ws);            // [B, P] gradient of the inert head
+  float* zeros = tmp + B * P;                           // eps [B, d] and g_kl [B]
+  PMVAE_CUDA(cudaMemsetAsync(zeros, 0, (size_t)(B * d + B) * sizeof(float), s));
+  PMVAE_TRY(latent_bwd(par, par, zeros, z, nullptr, zeros + B * d, g, 0, tmp, dpar, nullptr, nullptr, B, d, s));
+  if (dz) PMVAE_CUDA(cudaMemcpy2DAsync(dz, (size_t)d * sizeof(float), tmp, (size_t)P * sizeof(float), (size_t)d * sizeof(float),
+                                       (size_t)B, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
 }  // extern "C"
