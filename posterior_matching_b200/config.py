@@ -102,5 +102,38 @@ def mnist_config() -> ConfigDict:
     })
 
 
+def mnist16_config() -> ConfigDict:
+    """configs/pm_vae_mnist16.py: the model `LookaheadPosterior` is trained over (TriLGaussian posterior and, by the
+    fallback of vae.py:97-105, partial posterior)."""
+    return ConfigDict({
+        "data": {"dataset": "mnist16", "train_split": "train", "validation_split": "test",
+                 "train_batch_size": 128, "val_batch_size": 128, "mask_generator": "UniformMaskGenerator",
+                 "mask_generator_kwargs": {"bounds": (0.0, 0.2)}},
+        "model": {"latent_dim": 10, "encoder_net": "ConvEncoder", "decoder_net": "ConvDecoder",
+                  "posterior_dist": "TriLGaussian", "decoder_dist": "Bernoulli",
+                  "encoder_net_config": {"conv_layers": [(32, 3, 1), (32, 3, 2), (64, 3, 2), (64, 1, 1)]},
+                  "decoder_net_config": {"conv_layers": [(64, 8, 1), (64, 5, 2), (32, 5, 1), (32, 5, 1), (1, 3, 1)]}},
+        "steps": 200000, "validation_freq": 10000,
+        "lr_schedule": {"init_value": 0.001, "decay_rate": 0.9, "transition_steps": 5000},
+    })
+
+
+def lookahead_mnist16_config() -> ConfigDict:
+    """configs/lookahead_mnist16.py (train_lookahead_posterior.py reads `pm_vae_dir` for the frozen model)."""
+    return ConfigDict({
+        "data": {"dataset": "mnist16", "train_split": "train", "validation_split": "test",
+                 "train_batch_size": 32, "val_batch_size": 32, "mask_generator": "UniformMaskGenerator",
+                 "mask_generator_kwargs": {"bounds": (0.0, 0.20)}},
+        "pm_vae_dir": "runs/pm-vae-mnist16-20220302-160842",
+        "model": {"lookahead_subsample": 16, "model_samples": 64},
+        "steps": 40000, "validation_freq": 5000,
+        "lr_schedule": {"init_value": 0.001, "decay_rate": 0.9, "transition_steps": 5000},
+    })
+
+
 def pm_vae_config(name: str) -> ConfigDict:
-    return mnist_config() if name == "mnist" else uci_config(name)
+    if name == "mnist":
+        return mnist_config()
+    if name == "mnist16":
+        return mnist16_config()
+    return uci_config(name)

@@ -81,15 +81,50 @@ class MNISTMaskGenerator(MaskGenerator):
         return out
 
 
+class UniformMaskGenerator(MaskGenerator):
+    """masking.py:50-81: per row, a number q of observed features drawn uniformly (from [int(d lo), int(d lo) + int(d hi))
+    with `bounds=(lo, hi)`, else from [0, d)), then q features chosen without replacement -- the generator of
+    configs/pm_vae_mnist16.py / lookahead_mnist16.py.  On the threefry stream: q from uniform(split(key)[0]) by global
+    row, the subset = the q smallest of d random 32-bit words per row (split(key)[1], global element index); the sort is
+    a library call (rows of a few hundred elements, outside the hot path)."""
+
+    def __init__(self, bounds=None, **kwargs):
+        super().__init__(**kwargs)
+        self._bounds = None if bounds is None else (float(bounds[0]), float(bounds[1]))
+
+    def call(self, shape, key, row_start, total_rows):
+        rows = shape[0]
+        d = 1
+        for s in shape[1:]:
+            d *= s
+        total = rows if total_rows is None else int(total_rows)
+        kq, kb = prng.split(key, 2)
+        u = torch.empty(rows, dtype=torch.float32, device=self._device)
+        _lib.check(_lib.lib.pmvae_uniform(_lib.key_arg(kq), total, row_start, rows, u.data_ptr(), _stream()), "pmvae_uniform")
+        if self._bounds is None:
+            lo, span = 0, d
+        else:
+            lo, span = int(d * self._bounds[0]), int(d * self._bounds[1])
+        q = lo + torch.clamp((u * span).floor().to(torch.int64), max=max(span - 1, 0))
+        bits = torch.empty((rows, d), dtype=torch.int32, device=self._device)
+        _lib.check(_lib.lib.pmvae_random_bits(_lib.key_arg(kb), total * d, row_start * d, rows * d, bits.data_ptr(), _stream()),
+                   "pmvae_random_bits")
+        order = torch.sort(bits.to(torch.int64) & 0xFFFFFFFF, dim=1, stable=True).indices
+        picked = (torch.arange(d, device=self._device).unsqueeze(0) < q.unsqueeze(1)).to(torch.float32)
+        out = torch.zeros((rows, d), dtype=torch.float32, device=self._device)
+        out.scatter_(1, order, picked)
+        return out.view(shape)
+
+
 _GENERATORS = {
     "BernoulliMaskGenerator": BernoulliMaskGenerator,
     "MNISTMaskGenerator": MNISTMaskGenerator,
+    "UniformMaskGenerator": UniformMaskGenerator,
 }
 
 
 def get_mask_generator(mask_generator_name: str, **kwargs) -> MaskGenerator:
-    """masking.py:328-335 (only the generators the five PM-VAE configs name are on the
-    hot path; the others raise)."""
+    """masking.py:328-335 (the generators the PM-VAE / lookahead configs name; the others raise)."""
     if mask_generator_name not in _GENERATORS:
         raise KeyError(f"{mask_generator_name} is outside the PM-VAE hot path (SURVEY.md §2)")
     return _GENERATORS[mask_generator_name](**kwargs)

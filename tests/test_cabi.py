@@ -98,6 +98,24 @@ def test_config_files_keep_the_reference_surface(name):
         assert cfg.model.partial_posterior_dist == "AutoregressiveGMM" and cfg.data.train_batch_size == 256
 
 
+def test_mnist16_and_lookahead_config_files():
+    """configs/pm_vae_mnist16.py and configs/lookahead_mnist16.py carry the reference's keys and values."""
+    mods = {}
+    for fname in ("pm_vae_mnist16", "lookahead_mnist16"):
+        spec = importlib.util.spec_from_file_location(f"cfg_{fname}", os.path.join(ROOT, "configs", f"{fname}.py"))
+        mods[fname] = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mods[fname])
+    cfg = mods["pm_vae_mnist16"].get_config()
+    assert cfg.data.dataset == "mnist16" and cfg.data.mask_generator == "UniformMaskGenerator"
+    assert tuple(cfg.data.mask_generator_kwargs.bounds) == (0.0, 0.2) and cfg.data.train_batch_size == 128
+    assert cfg.model.latent_dim == 10 and "partial_posterior_dist" not in cfg.model      # falls back to posterior_dist
+    assert [tuple(l) for l in cfg.model.encoder_net_config.conv_layers] == [(32, 3, 1), (32, 3, 2), (64, 3, 2), (64, 1, 1)]
+    assert [tuple(l) for l in cfg.model.decoder_net_config.conv_layers][0] == (64, 8, 1) and cfg.steps == 200000
+    look = mods["lookahead_mnist16"].get_config()
+    assert look.model.lookahead_subsample == 16 and look.model.model_samples == 64 and look.steps == 40000
+    assert look.data.train_batch_size == 32 and "pm_vae_dir" in look and look.lr_schedule.decay_rate == 0.9
+
+
 def test_device_entry_points_fail_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():

@@ -81,7 +81,7 @@ def test_bernoulli_mask_generator_stream_is_seeded_and_advances():
     assert torch.equal(m1, b((128, 8))) and not torch.equal(m1, m2)
     assert abs(float(m1.mean()) - 0.5) < 0.1
     with pytest.raises(KeyError):
-        get_mask_generator("UniformMaskGenerator")
+        get_mask_generator("MixtureMaskGenerator")      # (masking.py:328-335 names more generators than the configs use)
 
 
 def test_mnist_mask_bit_exact_and_reference_distribution(golden_dir):
@@ -111,3 +111,29 @@ def test_mnist_mask_bit_exact_and_reference_distribution(golden_dir):
         ref = np.ones((28, 28), dtype=np.float32)
         ref[y1:y2, x1:x2] = 0
         assert np.all(m[cats == c] == ref)
+
+
+def test_uniform_mask_generator_counts_and_subsets():
+    """masking.py:50-81 on the device: per row a count q in [int(d lo), int(d lo) + int(d hi)) of observed features, chosen
+    without replacement; seeded, advancing, shardable by rows."""
+    from posterior_matching_b200 import get_mask_generator
+    gen = get_mask_generator("UniformMaskGenerator", bounds=(0.0, 0.2), seed=5)
+    m = gen((512, 16, 16, 1))
+    assert m.shape == (512, 16, 16, 1) and set(torch.unique(m).tolist()) <= {0.0, 1.0}
+    q = m.view(512, -1).sum(1)
+    assert int(q.min()) >= 0 and int(q.max()) <= int(256 * 0.2) - 1        # l + choice(h): at most h - 1 above l
+    assert q.float().std() > 5                                            # the count itself is spread over its range
+    # every feature is picked about equally often
+    freq = m.view(512, -1).mean(0)
+    assert float(freq.max()) < 0.25 and float(freq.min()) > 0.01
+    # same seed -> same stream; the stream advances; a row shard equals the rows of the whole batch
+    gen2 = get_mask_generator("UniformMaskGenerator", bounds=(0.0, 0.2), seed=5)
+    assert torch.equal(gen2((512, 16, 16, 1)), m)
+    assert not torch.equal(gen2((512, 16, 16, 1)), m)
+    key = (1, 2)
+    whole = gen((64, 21), key=key)
+    part = gen((16, 21), key=key, row_start=32, total_rows=64)
+    assert torch.equal(whole[32:48], part)
+    # no bounds: q in [0, d)
+    free = get_mask_generator("UniformMaskGenerator", seed=1)((256, 30))
+    assert int(free.sum(1).max()) <= 29
