@@ -6,12 +6,13 @@ A frozen PM-VAE produces, for every training row, `model_samples` imputations of
 of them one latent sample of q(z | x_o + one more feature) for `lookahead_subsample` candidate features; a second
 encoder (`lookahead_encoder_net` + `LookaheadBlock`) learns one diagonal-Gaussian "lookahead posterior" per feature to
 match those samples.  The work is almost entirely in the frozen model: K * B * S rows through the partial encoder
-(the fused tcgen05 chains behind `pmvae_net_apply`) and the TriL sampling kernels; the trained encoder sees B rows.
-Its Linears run through `pmvae_linear` / `pmvae_linear_backward` and the objective through `pmvae_lookahead_ll`
+(the fused tcgen05 chains behind `pmvae_net_apply`, or the convolution operators of conv_vae.py) and the TriL sampling
+kernels; the trained encoder sees B rows.  Its Linears run through `pmvae_linear` / `pmvae_linear_backward`, a
+ConvEncoder lookahead net through `pmvae_conv2d_forward / backward`, and the objective through `pmvae_lookahead_ll`
 (csrc/dist_ops.cu); torch.autograd only strings those operators together (relu / LayerNorm / adds on [B, H]).
 
 Key order of one call, as Haiku hands them out (`hk.next_rng_key()`; every ResidualMLP block draws a dropout key even at
-rate 0, networks.py:124) [R: restated from the reference's call order, no JAX here to replay it]:
+rate 0, networks.py:124; the convolutional networks draw none) [R: restated from the reference's call order, no JAX here to replay it]:
     R_part keys (partial encoder) | z sample | R_dec keys (decoder) | choice | split -> K sample keys | ...
 `jax.random.choice(key, F, (S,), replace=False)` is `permutation(key, F)[:S]`: one `sort_key_val` round per
 ceil(3 ln F / ln(2^32 - 1)) with 32 random bits per element from `split(key)[1]` [R: jax 0.2.26 `_shuffle`].
