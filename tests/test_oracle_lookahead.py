@@ -56,3 +56,21 @@ def test_lookahead_objective_rules():
     assert inds2.tolist() == inds.tolist() and torch.equal(z1, z1b)
     g = OL.expected_info_gains(p, lp, spec, R, False, x[2], b[2])
     assert torch.isinf(g[b[2] == 1]).all() and torch.isfinite(g[b[2] == 0]).all()
+
+
+def test_lookahead_oracle_matches_its_committed_fixture():
+    """tests/golden/lookahead_golden.npz (make_lookahead_golden.py): the restated key order, choice without replacement
+    and objective are frozen against silent drift."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lookahead_golden.npz"))
+    spec = spec_of("gas")
+    p = conditioned_params(spec)
+    lp = OL.init_params(spec, 2, 32)
+    x, b, _ = make_inputs(spec, 6, seed=1)
+    loss, ll, grads, (inds, valid, z1) = OL.loss_and_grads(p, lp, spec, 2, False, x, b, P.PRNGKey(77), 4, 5)
+    assert inds.tolist() == g["inds"].tolist() and np.array_equal(valid.numpy(), g["valid"])
+    assert np.allclose(z1.numpy(), g["z1"], rtol=1e-12, atol=1e-12) and np.allclose(ll.numpy(), g["ll"], rtol=1e-12)
+    assert abs(float(loss) - float(g["loss"])) < 1e-12
+    assert np.allclose(grads[OL.HEAD]["b"].numpy(), g["g_head_b"], rtol=1e-10, atol=1e-14)
+    assert P.permutation(P.PRNGKey(3), 21).tolist() == g["perm21"].tolist()
+    assert P.permutation(P.PRNGKey(4), 784)[:16].tolist() == g["perm784_head"].tolist()
